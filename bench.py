@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- ST-block (full STGCN) forward+backward throughput, samples/s (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+A "step" = zero_grad + forward + MSE loss + backward of the whole model on one synthetic batch (the body of the
+reference's main.py:165-168 without the optimizer), plus the gradient all-reduce when N > 1.
+Prints ONE JSON line on rank 0 (contract in the task statement; extra keys: roofline, cpu_baseline, clocks, e2e).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BLOCKS = [[1], [64, 16, 64], [64, 16, 64], [128, 128], [1]]
+WORKLOADS = {
+    # name: (gso file tag, graph conv kind, Ks, default per-GPU batch, description)
+    "pemsd7m": ("pemsd7m", "cheb_graph_conv", 3, 256, "PeMSD7-M N=228 Kt=3 Ks=3 ChebGraphConv T=12"),
+    "metrla": ("metrla", "graph_conv", 3, 512, "METR-LA N=207 GraphConv Kt=3 T=12"),
+    "pemsbay": ("pemsbay", "cheb_graph_conv", 3, 128, "PEMS-BAY N=325 ChebGraphConv Ks=3 Kt=3 T=12"),
+}
+
+
+# ---- algorithmic work per sample (SURVEY.md §8d closed form; MAC = 2 FLOP) ---------------------------------------
+def flops_per_sample(n, kind, ks, blocks=BLOCKS, kt=3, n_his=12):
+    """Returns (fwd, fwd+bwd, per-stage dict of fwd+bwd FLOPs)."""
+    stages = {}
+    fwd = 0.0
+    tot = 0.0
+    T = n_his
+    n_st = len(blocks) - 3
+    for l in range(n_st):
+        c0 = blocks[l][-1]
+        c1, c2, c3 = blocks[l + 1]
+        T1, T2 = T - kt + 1, T - 2 * (kt - 1)
+        tc1 = 2.0 * (2 * c1) * c0 * kt * T1 * n
+        al = 2.0 * c2 * c1 * T1 * n if c1 > c2 else 0.0
+        if kind == "cheb_graph_conv":
+            nn_ = (ks - 1) * 2.0 * n * n * c2 * T1
+            mix = 2.0 * ks * c2 * c2 * T1 * n
+        else:
+            nn_ = 2.0 * n * n * c2 * T1
+            mix = 2.0 * c2 * c2 * T1 * n
+        tc2 = 2.0 * (2 * c3) * c2 * kt * T2 * n
+        first = l == 0
+        # backward: 2x every weight-bearing GEMM (dgrad + wgrad), 1x the node contraction; no dX for block 0's tc1
+        f = tc1 + al + nn_ + mix + tc2
+        b = (1.0 if first else 2.0) * tc1 + 2 * al + nn_ + 2 * mix + 2 * tc2
+        stages[f"st{l}"] = dict(tc1=tc1 * (2 if first else 3), align=3 * al, gso=2 * nn_, mix=3 * mix, tc2=3 * tc2)
+        fwd += f
+        tot += f + b
+        T = T2
+    ko = T
+    if ko > 1:
+        c0, (o0, o1), ce = blocks[-3][-1], blocks[-2], blocks[-1][0]
+        tco = 2.0 * (2 * o0) * c0 * ko * n
+        fc1 = 2.0 * o0 * o1 * n
+        fc2 = 2.0 * o1 * ce * n
+        fwd += tco + fc1 + fc2
+        tot += 3 * (tco + fc1 + fc2)
+        stages["out"] = dict(tc1=3 * tco, fc=3 * (fc1 + fc2))
+    return fwd, tot, stages
+
+
+def bytes_per_sample(n, dtype_bytes, blocks=BLOCKS, kt=3, n_his=12):
+    """Compulsory traffic with whole-block fusion + recompute: per block |in|+|out| forward,
+    |in|+|dout|+|din| backward (no din for block 0)."""
+    T = n_his
+    total = 0
+    n_st = len(blocks) - 3
+    sizes = [blocks[0][-1] * T * n]
+    for l in range(n_st):
+        T -= 2 * (kt - 1)
+        sizes.append(blocks[l + 1][-1] * T * n)
+    sizes.append(blocks[-1][0] * n)
+    for i in range(len(sizes) - 1):
+        total += sizes[i] + sizes[i + 1]                 # fwd
+        total += sizes[i] + sizes[i + 1] + (sizes[i] if i > 0 else 0)   # bwd
+    return total * dtype_bytes
+
+
+# ---- clocks sampler ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- CPU reference arm (oracle port; the Python reference itself cannot travel to the GPU box) --------------------
+def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None):
+    """Times the oracle's restatement of the reference step (same ATen ops as the reference: conv2d, einsum->bmm,
+    layer_norm, autograd) on all host cores.  Returns dict(samples_per_s, ms_per_step, cores, steps)."""
+    from oracle import stgcn_oracle as O
+    tag, kind, ks, _, _ = WORKLOADS[workload]
+    gso = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
+                                                f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
+    n = gso.shape[0]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    params = {k: v.requires_grad_(True) for k, v in
+              O.init_params(blocks=BLOCKS, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 1, 12, n, generator=gen)
+    y = torch.randn(batch, n, generator=gen)
+    cfg = dict(blocks=BLOCKS, kt=3, n_his=12, act="glu", kind=kind, p_drop=droprate, training=True)
+
+    def step():
+        for p in params.values():
+            p.grad = None
+        loss = O.mse_step(x, y, params, gso, **cfg)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    times = []
+    t_start = time.perf_counter()
+    for i in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and i >= 2:
+            break
+    total = sum(times)
+    return dict(samples_per_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
+                steps=len(times), batch=batch)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pemsd7m", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's BASELINE batch)")
+    ap.add_argument("--precision", default=os.environ.get("STGCN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--droprate", type=float, default=0.0,
+                    help="dropout p for BOTH arms (0 = the stricter CPU comparison, BASELINE.md §2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    tag, kind, ks, default_b, desc = WORKLOADS[a.workload]
+    B = a.batch or default_b
+    steps, warmup = a.steps, max(a.warmup, 3)
+
+    cfg_common = {"workload": f"{desc} batch={B}/GPU fwd+bwd+MSE, dropout {a.droprate}", "per_gpu_batch": B,
+                  "global_batch": B * max(world, 1), "droprate": a.droprate}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cpu_b = min(B, 64)
+        r = cpu_reference_run(a.workload, cpu_b, steps, warmup, a.droprate)
+        sample = (f"{r['steps']} steps of B={cpu_b} (a bounded sample of the B={B} workload), oracle port of the "
+                  f"reference step (same ATen ops), {r['cores']} host threads")
+        line = {"impl": "reference", "metric": "ST-block fwd+bwd samples/sec", "value": r["samples_per_s"],
+                "unit": "samples/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": cfg_common,
+                "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"],
+                                 "kind": "port", "sample": sample},
+                "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        ge.build()
+    if world > 1:
+        dist.barrier()
+    import stgcn_b200
+    from stgcn_b200 import models, _lib as L
+    from stgcn_b200.dist import FlatGradAllReducer
+    from oracle import stgcn_oracle as O   # parameter init only (same shapes/keys as the reference)
+    stgcn_b200.set_precision(a.precision)
+
+    gso = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
+                                                f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
+    n = gso.shape[0]
+    args = SimpleNamespace(Kt=3, Ks=ks, act_func="glu", graph_conv_type=kind, gso=gso.to(dev), enable_bias=True,
+                           droprate=a.droprate, n_his=12)
+    cls = models.STGCNChebGraphConv if kind == "cheb_graph_conv" else models.STGCNGraphConv
+    model = cls(args, BLOCKS, n).to(dev)
+    model.load_state_dict(O.init_params(blocks=BLOCKS, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0))
+    model.train()
+    reducer = FlatGradAllReducer(model)
+
+    # synthetic inputs: a pool of distinct batches cycled through so no step re-reads a hot input
+    POOL = 4
+    gen = torch.Generator().manual_seed(1234 + rank)
+    xs_host = [torch.randn(B, 1, 12, n, generator=gen).pin_memory() for _ in range(POOL)]
+    ys_host = [torch.randn(B, n, generator=gen).pin_memory() for _ in range(POOL)]
+    xs = [t.to(dev) for t in xs_host]
+    ys = [t.to(dev) for t in ys_host]
+    lib = L.lib()
+    loss_buf = torch.zeros(1, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(x, y):
+        model.zero_grad(set_to_none=True)
+        pred = model(x).reshape(B, -1)                      # (B,1,1,N) view -> (B,N), main.py:166
+        dpred = torch.empty_like(pred)
+        L.check(lib.stgcn_mse_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), 1.0, loss_buf.data_ptr(),
+                                      dpred.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        pred.backward(dpred)
+        reducer()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(warmup):
+        step(xs[i % POOL], ys[i % POOL])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    ms_total = timed(lambda i: step(xs[i % POOL], ys[i % POOL]), steps)
+    launches = L.launch_count() - n0
+    value = B * world * steps / (ms_total / 1e3)
+
+    # e2e: host (pinned) buffers in, loss out, copies inside the timed region, through the public module API
+    x_dev, y_dev = torch.empty_like(xs[0]), torch.empty_like(ys[0])
+
+    def e2e_step(i):
+        x_dev.copy_(xs_host[i % POOL], non_blocking=True)
+        y_dev.copy_(ys_host[i % POOL], non_blocking=True)
+        step(x_dev, y_dev)
+        loss_host.copy_(loss_buf, non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, steps)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = B * world * steps / (ms_e2e / 1e3)
+    h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 4
+
+    # live per-kernel CUDA-event profile of the same step (separate short pass so the timed loop is unperturbed)
+    roofline, top = None, []
+    fwd_f, tot_f, stages = flops_per_sample(n, kind, ks)
+    peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+        peaks["source"] = "MEASURED_PEAKS.json"
+    if rank == 0 and not a.no_profile:
+        psteps = 3
+        L.profile_begin()
+        for i in range(psteps):
+            step(xs[i % POOL], ys[i % POOL])
+        prof = L.profile_end()
+        tot_ms = sum(v[1] for v in prof.values())
+        rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
+        top = [{"key": k, "launches_per_step": v[0] / psteps, "ms_per_step": v[1] / psteps,
+                "share": v[1] / tot_ms} for k, v in rows[:8]]
+        # dominant kernel: algorithmic FLOPs of the stage it implements / its measured time
+        k0, (c0, ms0) = rows[0]
+        stage_flops = _stage_flops_for_key(k0, stages, B)
+        per_launch_ms = ms0 / c0
+        launches_per_step = c0 / psteps
+        if stage_flops:
+            ach = stage_flops / launches_per_step / (per_launch_ms * 1e-3) / 1e12
+            peak = peaks["bf16_tflops_sustained"]
+            roofline = {"kernel": k0, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                        "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
+                        "avg_launch_ms": per_launch_ms, "share_of_step": ms0 / tot_ms}
+    step_tflops = tot_f * value / world / 1e12          # per GPU
+    roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
+                     "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
+                     "flops_per_sample": tot_f, "alg_bytes_per_sample": bytes_per_sample(n, 4 if a.precision == "fp32" else 2),
+                     "peak_source": peaks["source"]}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        r = cpu_reference_run(a.workload, 32, 60, 3, a.droprate, budget_s=15.0)
+        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
+                        "sample": f"{r['steps']} steps of B=32 (BASELINE configs[0] batch), oracle port of the "
+                                  f"reference step on {r['cores']} host threads, dropout {a.droprate}"}
+
+    if rank == 0:
+        line = {"metric": "ST-block fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+                "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+                "config": {**cfg_common, "precision": a.precision,
+                           "l2": f"{POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
+                           "parallelism": f"dp{world}"},
+                "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / steps},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
+                "cpu_baseline": cpu_baseline, "top_kernels": top}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _stage_flops_for_key(key, stages, B):
+    """FLOPs per step (all launches under this op tag) for a '<stage>.<op>.<dir>:kernel' profile key; used only to
+    convert the dominant kernel's measured time into achieved TFLOP/s."""
+    tagk = key.split(":")[0].split(".")
+    if len(tagk) < 3 or tagk[0] not in stages:
+        return None
+    st, op, direction = tagk[0], tagk[1], tagk[2]
+    s = stages[st]
+    kern = key.split(":")[1]
+    if op in ("tc1", "tc2"):
+        total = s[op]                      # fwd+bwd of this conv
+        first = st == "st0" and op == "tc1"
+        parts = 2 if first else 3
+        if "tapgemm" in kern or "umma" in kern:
+            return total / parts * B       # one GEMM-equivalent (fwd, or dgrad in bwd)
+        if "wgrad" in kern:
+            return total / parts * B
+    if op == "gc" and "gso" in kern:
+        return s["gso"] / 2 * B
+    if op == "fc":
+        return s["fc"] / 3 * B
+    return None
+
+
+if __name__ == "__main__":
+    main()

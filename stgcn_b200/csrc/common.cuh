@@ -1,0 +1,138 @@
+// common.cuh -- error handling, launch accounting, workspace carving, small device helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <atomic>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <mutex>
+
+#include "../../include/stgcn_b200.h"
+
+namespace stgcn {
+
+// ---- errors: C++ exceptions inside, int status at the C boundary -------------------------
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+extern thread_local char g_last_error[512];
+extern std::atomic<uint64_t> g_launches;
+
+inline void set_error(const char* msg) {
+  std::snprintf(g_last_error, sizeof(g_last_error), "%s", msg);
+}
+
+#define STGCN_CHECK(cond, code, msg)                                       \
+  do {                                                                     \
+    if (!(cond)) throw ::stgcn::Error((code), std::string(msg) + " [" #cond "]"); \
+  } while (0)
+
+#define STGCN_CUDA(expr)                                                   \
+  do {                                                                     \
+    cudaError_t _e = (expr);                                               \
+    if (_e != cudaSuccess)                                                 \
+      throw ::stgcn::Error((int)_e, std::string(#expr ": ") + cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---- optional per-launch CUDA-event profiler (stgcn_profile_begin/end) ----------------------
+// When enabled every launch is bracketed by two events recorded on the launching stream; the
+// records are aggregated per "<op tag>:<kernel>" key when the profile is collected.
+struct ProfRec { std::string key; cudaEvent_t a, b; };
+struct Profiler {
+  std::atomic<bool> on{false};
+  std::mutex mu;
+  std::vector<ProfRec> recs;
+};
+extern Profiler g_prof;
+extern thread_local const char* g_tag;     // current op label (set by the host-side op code)
+
+struct Tag {                               // RAII label for the launches of one logical op
+  const char* prev;
+  explicit Tag(const char* t) : prev(g_tag) { g_tag = t; }
+  ~Tag() { g_tag = prev; }
+};
+
+inline cudaEvent_t prof_begin(cudaStream_t s) {
+  cudaEvent_t a;
+  cudaEventCreate(&a);
+  cudaEventRecord(a, s);
+  return a;
+}
+inline void prof_end(const char* kernel, cudaEvent_t a, cudaStream_t s) {
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, s);
+  std::string key = std::string(g_tag ? g_tag : "-") + ":" + kernel;
+  std::lock_guard<std::mutex> lk(g_prof.mu);
+  g_prof.recs.push_back(ProfRec{key, a, b});
+}
+
+// Every kernel launch goes through this: counts it and checks the launch status.
+#define STGCN_LAUNCH(kernel, grid, block, smem, stream, ...)               \
+  do {                                                                     \
+    bool _prof = ::stgcn::g_prof.on.load(std::memory_order_relaxed);       \
+    cudaEvent_t _ea = nullptr;                                             \
+    if (_prof) _ea = ::stgcn::prof_begin(stream);                          \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
+    if (_prof) ::stgcn::prof_end(#kernel, _ea, stream);                    \
+    ::stgcn::g_launches.fetch_add(1, std::memory_order_relaxed);           \
+    STGCN_CUDA(cudaPeekAtLastError());                                     \
+  } while (0)
+
+template <class F>
+int guarded(F&& f) {
+  try {
+    f();
+    return STGCN_OK;
+  } catch (const Error& e) {
+    set_error(e.what());
+    return e.code ? e.code : STGCN_E_INVALID;
+  } catch (const std::exception& e) {
+    set_error(e.what());
+    return STGCN_E_INVALID;
+  } catch (...) {
+    set_error("unknown error");
+    return STGCN_E_INVALID;
+  }
+}
+
+// ---- bump allocator over a caller-provided buffer ---------------------------------------
+struct Arena {
+  char* base;
+  size_t cap, off, peak = 0;
+  bool dry;   // dry run: only measure
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), dry(p == nullptr) {}
+  static size_t align_up(size_t v) { return (v + 255) & ~size_t(255); }
+  template <class T>
+  T* take(size_t n) {
+    size_t o = off;
+    off = align_up(off + n * sizeof(T));
+    if (off > peak) peak = off;
+    if (dry) return nullptr;
+    if (off > cap) throw Error(STGCN_E_WORKSPACE, "workspace/saved buffer too small");
+    return reinterpret_cast<T*>(base + o);
+  }
+};
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ----------------------------------------------------------------------
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+
+// Counter-based dropout keep-mask: splitmix64 finaliser over (seed, element index).
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  float u = (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);   // 24 random bits -> [0,1)
+  return u >= p_drop;
+}
+
+}  // namespace stgcn

@@ -1,0 +1,471 @@
+// ops_fp32.cuh -- host orchestration of the fp32 parity path: each op carves its buffers from
+// caller-provided arenas, then enqueues the SIMT kernels of simt_kernels.cuh on the stream.
+// "dry" arenas (null base) only measure: the *_sizes entry points run the same code paths.
+#pragma once
+#include "simt_kernels.cuh"
+
+namespace stgcn {
+namespace fp32 {
+
+using namespace simt;
+
+struct Ctx {
+  Arena& ws;
+  cudaStream_t stream;
+  bool dry() const { return ws.dry; }
+};
+
+inline void zero(float* p, size_t n, cudaStream_t s) {
+  if (n) STGCN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), s));
+}
+inline void copy(float* dst, const float* src, size_t n, cudaStream_t s) {
+  if (n) STGCN_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+struct ScopedMark {   // releases scratch taken inside a scope
+  Arena& a; size_t mark;
+  explicit ScopedMark(Arena& ar) : a(ar), mark(ar.off) {}
+  ~ScopedMark() { a.off = mark; }
+};
+
+// ============================ gated temporal convolution =====================================
+struct TconvGeom {
+  long long rows_in, rows_out;
+  int T_out, W;
+  bool gated, folded, linear;
+};
+inline TconvGeom tconv_geom(const stgcn_tconv_desc& d) {
+  STGCN_CHECK(d.B >= 0 && d.N > 0 && d.c_in > 0 && d.c_out > 0 && d.Kt >= 1, STGCN_E_INVALID, "bad tconv desc");
+  STGCN_CHECK(d.act >= STGCN_ACT_GLU && d.act <= STGCN_ACT_LINEAR, STGCN_E_UNSUPPORTED,
+              "ERROR: The activation function is not implemented.");
+  STGCN_CHECK(d.T >= d.Kt, STGCN_E_INVALID, "Kernel size can't be greater than actual input size (T < Kt)");
+  TconvGeom g;
+  g.T_out = d.T - d.Kt + 1;
+  g.rows_in = (long long)d.B * d.T * d.N;
+  g.rows_out = (long long)d.B * g.T_out * d.N;
+  g.gated = d.act == STGCN_ACT_GLU || d.act == STGCN_ACT_GTU;
+  g.W = g.gated ? 2 * d.c_out : d.c_out;
+  g.linear = d.act == STGCN_ACT_LINEAR;   // bare conv: no residual at all
+  g.folded = !g.linear && d.c_in > d.c_out;   // residual 1x1 conv folded into tap Kt-1 of the linear half
+  return g;
+}
+inline size_t tconv_saved_floats(const stgcn_tconv_desc& d) { auto g = tconv_geom(d); return (size_t)g.rows_out * g.W; }
+
+// z_saved: [rows_out, W] pre-activations
+inline void tconv_fwd(const stgcn_tconv_desc& d, const float* x, const stgcn_tconv_params& p, float* y, float* z_saved,
+                      Ctx c) {
+  TconvGeom g = tconv_geom(d);
+  ScopedMark sm(c.ws);
+  float* wt = c.ws.take<float>((size_t)d.Kt * d.c_in * g.W);
+  float* bias = c.ws.take<float>(g.W);
+  if (c.dry()) return;
+  STGCN_CHECK(p.conv_w && p.conv_b, STGCN_E_INVALID, "tconv: missing conv weight/bias");
+  // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]
+  launch_gather3(p.conv_w, wt, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
+  launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
+  if (g.folded) {
+    STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "tconv: c_in > c_out needs align conv parameters");
+    // tap Kt-1, linear half: wt[((Kt-1)*c_in + c)*W + o] += align_w[o][c]  
+    STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, c.stream,
+                 wt + (size_t)(d.Kt - 1) * d.c_in * g.W, g.W, p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
+    launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
+  }
+  TapArgs t{};
+  t.in = x; t.wt = wt; t.bias = bias; t.out = z_saved; t.rows = g.rows_out;
+  t.Cin = d.c_in; t.Co = g.W; t.ntaps = d.Kt; t.ldo = g.W; t.accumulate = 0;
+  t.map = RowMap{g.T_out, d.T, d.N, 1, 0};
+  launch_tapgemm(t, c.stream);
+  GateArgs ga{};
+  ga.z = z_saved; ga.xin = x; ga.y = y; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out; ga.W = g.W;
+  ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
+  launch_gate_any(d.act, false, ga, c.stream);
+}
+
+inline void tconv_bwd(const stgcn_tconv_desc& d, const float* x, const float* z_saved, const float* dy,
+                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, float* dx, Ctx c) {
+  TconvGeom g = tconv_geom(d);
+  ScopedMark sm(c.ws);
+  const int Kw = d.Kt * d.c_in;
+  float* dz = c.ws.take<float>((size_t)g.rows_out * g.W);
+  float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
+  float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
+  if (c.dry()) return;
+  GateArgs ga{};
+  ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
+  ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
+  launch_gate_any(d.act, true, ga, c.stream);
+
+  bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
+  if (want_w) {
+    zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
+    WgradArgs w{};
+    w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
+    w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0};
+    launch_wgrad(w, c.stream);
+    // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]
+    if (gr.conv_w) launch_gather3(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W, 0, c.stream);
+    if (gr.conv_b) launch_gather3(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
+    if (g.folded) {
+      if (gr.align_w)
+        launch_gather3(dwt, gr.align_w, 1, d.c_out, d.c_in, (long long)(d.Kt - 1) * d.c_in * g.W, 0, 1, g.W, 0, c.stream);
+      if (gr.align_b) launch_gather3(dwt, gr.align_b, 1, 1, d.c_out, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
+    }
+  }
+  if (dx) {
+    // wd[(k*W + o)*c_in + c] = conv_w[o][c][k]
+    launch_gather3(p.conv_w, wd, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
+    if (g.folded)
+      launch_gather3(p.align_w, wd + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
+    TapArgs t{};
+    t.in = dz; t.wt = wd; t.bias = nullptr; t.out = dx; t.rows = g.rows_in;
+    t.Cin = g.W; t.Co = d.c_in; t.ntaps = d.Kt; t.ldo = d.c_in; t.accumulate = 0;
+    t.map = RowMap{d.T, g.T_out, d.N, -1, 0};
+    launch_tapgemm(t, c.stream);
+    if (!g.folded && !g.linear) {
+      int cres = d.c_in < d.c_out ? d.c_in : d.c_out;
+      long long n = g.rows_out * cres;
+      if (n) STGCN_LAUNCH(residual_add_kernel, ceil_div(n, 256), 256, 0, c.stream, dz, dx, g.rows_out, cres, g.W,
+                          d.c_in, d.Kt, g.T_out, d.T, d.N);
+    }
+  }
+}
+
+// ============================ graph convolution layer ========================================
+inline int gconv_stack_depth(const stgcn_gconv_desc& d) { return d.gconv == STGCN_GCONV_CHEB ? d.Ks : 2; }
+inline void gconv_check(const stgcn_gconv_desc& d) {
+  STGCN_CHECK(d.B >= 0 && d.T > 0 && d.N > 0 && d.c_in > 0 && d.c_out > 0, STGCN_E_INVALID, "bad gconv desc");
+  STGCN_CHECK(d.gconv == STGCN_GCONV_CHEB || d.gconv == STGCN_GCONV_GCN, STGCN_E_UNSUPPORTED, "unknown graph_conv_type");
+  if (d.gconv == STGCN_GCONV_CHEB)
+    STGCN_CHECK(d.Ks >= 1, STGCN_E_INVALID,
+                "ERROR: the graph convolution kernel size Ks has to be a positive integer");
+}
+inline size_t gconv_saved_floats(const stgcn_gconv_desc& d) {
+  gconv_check(d);
+  return (size_t)gconv_stack_depth(d) * d.B * d.T * d.N * d.c_out;
+}
+
+// stack: [depth][rows, C]; stack[0] = aligned input, stack[k] = T_k(L) stack[0] (cheb) / L stack[0] (gcn)
+inline void gconv_fwd(const stgcn_gconv_desc& d, const float* x, const stgcn_gconv_params& p, float* y, float* stack,
+                      Ctx c) {
+  gconv_check(d);
+  ScopedMark sm(c.ws);
+  const long long rows = (long long)d.B * d.T * d.N;
+  const int C = d.c_out;
+  const size_t plane = (size_t)rows * C;
+  float* wat = c.ws.take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
+  if (c.dry()) return;
+  STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
+  float* x0 = stack;
+  if (d.c_in > C) {
+    STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
+    launch_gather3(p.align_w, wat, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // wat[c][o] = align_w[o][c]
+    TapArgs t{};
+    t.in = x; t.wt = wat; t.bias = p.align_b; t.out = x0; t.rows = rows; t.Cin = d.c_in; t.Co = C; t.ntaps = 1;
+    t.ldo = C; t.map = RowMap{d.T, d.T, d.N, 0, 0};
+    launch_tapgemm(t, c.stream);
+  } else {
+    launch_copy_cols(x, x0, rows, d.c_in, d.c_in, C, 0, c.stream);
+  }
+  GsoArgs g{};
+  g.M = p.gso; g.trans = 0; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
+  TapArgs t{};
+  t.bias = p.b; t.out = y; t.rows = rows; t.Cin = C; t.Co = C; t.ldo = C;
+  if (d.gconv == STGCN_GCONV_CHEB) {
+    for (int k = 1; k < d.Ks; ++k) {
+      g.in = stack + (size_t)(k - 1) * plane; g.out = stack + (size_t)k * plane;
+      if (k == 1) { g.alpha = 1.f; g.aux = nullptr; g.beta = 0.f; }
+      else { g.alpha = 2.f; g.aux = stack + (size_t)(k - 2) * plane; g.beta = -1.f; }
+      launch_gso(g, c.stream);
+    }
+    t.in = stack; t.wt = p.w; t.ntaps = d.Ks; t.map = RowMap{d.T, d.T, d.N, 0, rows};
+  } else {
+    g.in = x0; g.out = stack + plane; g.alpha = 1.f; g.aux = nullptr; g.beta = 0.f;
+    launch_gso(g, c.stream);
+    t.in = stack + plane; t.wt = p.w; t.ntaps = 1; t.map = RowMap{d.T, d.T, d.N, 0, 0};
+  }
+  launch_tapgemm(t, c.stream);
+  STGCN_LAUNCH(add_relu_kernel, ceil_div(plane, 256), 256, 0, c.stream, y, d.residual ? x0 : nullptr, y, (long long)plane, d.relu);
+}
+
+inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* stack, const float* y, const float* dy,
+                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, float* dx, Ctx c) {
+  gconv_check(d);
+  ScopedMark sm(c.ws);
+  const long long rows = (long long)d.B * d.T * d.N;
+  const int C = d.c_out;
+  const size_t plane = (size_t)rows * C;
+  const int depth = gconv_stack_depth(d);
+  const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
+  float* dg = c.ws.take<float>(plane);
+  float* dst = c.ws.take<float>((size_t)depth * plane);
+  float* wT = c.ws.take<float>((size_t)ntw * C * C);
+  float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
+  float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
+  if (c.dry()) return;
+  STGCN_LAUNCH(relu_bwd_kernel, ceil_div(plane, 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
+
+  GsoArgs g{};
+  g.M = p.gso; g.trans = 1; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
+  TapArgs t{};
+  t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
+  t.map = RowMap{d.T, d.T, d.N, 0, 0};
+  WgradArgs w{};
+  w.dz = dg; w.dwt = dwt; w.rows = rows; w.Cin = C; w.Co = C; w.ldz = C; w.bias_row = 1;
+  zero(dwt, (size_t)(ntw * C + 1) * C, c.stream);
+
+  if (d.gconv == STGCN_GCONV_CHEB) {
+    // wT[k][j][i] = w[k][i][j];  d stack[k] = dG W_k^T
+    launch_gather3(p.w, wT, d.Ks, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
+    for (int k = 0; k < d.Ks; ++k) {
+      t.wt = wT + (size_t)k * C * C; t.out = dst + (size_t)k * plane;
+      launch_tapgemm(t, c.stream);
+    }
+    if (gr.w || gr.b) {
+      w.in = stack; w.ntaps = d.Ks; w.map = RowMap{d.T, d.T, d.N, 0, rows};
+      launch_wgrad(w, c.stream);
+    }
+    // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
+    for (int k = d.Ks - 1; k >= 2; --k) {
+      g.in = dst + (size_t)k * plane; g.out = dst + (size_t)(k - 1) * plane; g.aux = g.out; g.alpha = 2.f; g.beta = 1.f;
+      launch_gso(g, c.stream);
+      STGCN_LAUNCH(axpy_kernel, ceil_div(plane, 256), 256, 0, c.stream, -1.f, dst + (size_t)k * plane,
+                   dst + (size_t)(k - 2) * plane, (long long)plane);
+    }
+    if (d.Ks >= 2) {
+      g.in = dst + plane; g.out = dst; g.aux = dst; g.alpha = 1.f; g.beta = 1.f;
+      launch_gso(g, c.stream);
+    }
+    if (d.residual) STGCN_LAUNCH(axpy_kernel, ceil_div(plane, 256), 256, 0, c.stream, 1.f, dg, dst, (long long)plane);
+  } else {
+    launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
+    t.wt = wT; t.out = dst + plane;
+    launch_tapgemm(t, c.stream);
+    if (gr.w || gr.b) {
+      w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
+      launch_wgrad(w, c.stream);
+    }
+    g.in = dst + plane; g.out = dst; g.aux = d.residual ? dg : nullptr; g.alpha = 1.f; g.beta = 1.f;
+    launch_gso(g, c.stream);
+  }
+  if (gr.w) launch_gather3(dwt, gr.w, 1, 1, ntw * C * C, 0, 0, 0, 1, 0, c.stream);
+  if (gr.b) launch_gather3(dwt, gr.b, 1, 1, C, (long long)ntw * C * C, 0, 0, 1, 0, c.stream);
+
+  // dst[0] now holds the gradient w.r.t. the aligned input
+  if (d.c_in > C) {
+    if (gr.align_w || gr.align_b) {
+      zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
+      WgradArgs wa{};
+      wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
+      wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0};
+      launch_wgrad(wa, c.stream);
+      if (gr.align_w) launch_gather3(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C, 0, c.stream);
+      if (gr.align_b) launch_gather3(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1, 0, c.stream);
+    }
+    if (dx) {
+      TapArgs ta{};
+      ta.in = dst; ta.wt = p.align_w; ta.bias = nullptr; ta.out = dx; ta.rows = rows; ta.Cin = C; ta.Co = d.c_in;
+      ta.ntaps = 1; ta.ldo = d.c_in; ta.map = RowMap{d.T, d.T, d.N, 0, 0};
+      launch_tapgemm(ta, c.stream);
+    }
+  } else if (dx) {
+    launch_copy_cols(dst, dx, rows, C, C, d.c_in, 0, c.stream);
+  }
+}
+
+// ============================ LayerNorm (+ dropout) ==========================================
+inline void lnorm_check(const stgcn_lnorm_desc& d) {
+  STGCN_CHECK(d.B >= 0 && d.T > 0 && d.N > 0 && d.C > 0, STGCN_E_INVALID, "bad lnorm desc");
+  STGCN_CHECK(d.p_drop >= 0.f && d.p_drop < 1.f, STGCN_E_INVALID, "dropout probability must be in [0,1)");
+}
+inline size_t lnorm_saved_floats(const stgcn_lnorm_desc& d) { return (size_t)2 * d.B * d.T; }
+
+inline void lnorm_fwd(const stgcn_lnorm_desc& d, const float* x, const float* w, const float* b, float* y,
+                      float* stats, uint64_t seed, cudaStream_t s, bool dry) {
+  lnorm_check(d);
+  if (dry) return;
+  long long G = (long long)d.B * d.T;
+  if (G == 0) return;
+  STGCN_LAUNCH(ln_fwd_kernel, (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, d.N * d.C, d.eps, d.training,
+               d.p_drop, seed);
+}
+inline void lnorm_bwd(const stgcn_lnorm_desc& d, const float* x, const float* stats, const float* dy, const float* w,
+                      float* dw, float* db, float* dx, uint64_t seed, cudaStream_t s, bool dry) {
+  lnorm_check(d);
+  if (dry) return;
+  long long G = (long long)d.B * d.T;
+  int M = d.N * d.C;
+  if (dw) zero(dw, M, s);
+  if (db) zero(db, M, s);
+  if (G == 0) return;
+  if (dx) STGCN_LAUNCH(ln_bwd_kernel, (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
+  if (dw || db) {
+    int xb = ceil_div(M, 256);
+    int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 8) / xb));
+    int gpc = ceil_div(G, ychunks);
+    ychunks = ceil_div(G, gpc);
+    STGCN_LAUNCH(ln_param_grad_kernel, dim3(xb, ychunks), 256, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc,
+                 d.training, d.p_drop, seed);
+  }
+}
+
+// ============================ ST-conv block ==================================================
+struct StGeom {
+  int T1, T2;
+  long long rows0, rows1, rows2;
+  stgcn_tconv_desc tc1, tc2;
+  stgcn_gconv_desc gc;
+  stgcn_lnorm_desc ln;
+};
+inline StGeom st_geom(const stgcn_stblock_desc& d) {
+  STGCN_CHECK(d.Kt >= 1 && d.T >= 2 * (d.Kt - 1) + 1, STGCN_E_INVALID,
+              "Kernel size can't be greater than actual input size (T too short for two temporal convs)");
+  StGeom g;
+  g.T1 = d.T - d.Kt + 1; g.T2 = g.T1 - d.Kt + 1;
+  g.rows0 = (long long)d.B * d.T * d.N; g.rows1 = (long long)d.B * g.T1 * d.N; g.rows2 = (long long)d.B * g.T2 * d.N;
+  g.tc1 = stgcn_tconv_desc{d.B, d.T, d.N, d.c_in, d.c1, d.Kt, d.act, d.precision};
+  g.gc = stgcn_gconv_desc{d.B, g.T1, d.N, d.c1, d.c2, d.Ks, d.gconv, 1, 1, d.precision};
+  g.tc2 = stgcn_tconv_desc{d.B, g.T1, d.N, d.c2, d.c3, d.Kt, d.act, d.precision};
+  g.ln = stgcn_lnorm_desc{d.B, g.T2, d.N, d.c3, d.training, d.p_drop, d.eps, d.precision};
+  return g;
+}
+struct StSaved { float *z1, *h1, *stack, *h2, *z2, *h3, *stats; };
+inline StSaved st_saved(const stgcn_stblock_desc& d, const StGeom& g, Arena& sv) {
+  StSaved s;
+  s.z1 = sv.take<float>(tconv_saved_floats(g.tc1));
+  s.h1 = sv.take<float>((size_t)g.rows1 * d.c1);
+  s.stack = sv.take<float>(gconv_saved_floats(g.gc));
+  s.h2 = sv.take<float>((size_t)g.rows1 * d.c2);
+  s.z2 = sv.take<float>(tconv_saved_floats(g.tc2));
+  s.h3 = sv.take<float>((size_t)g.rows2 * d.c3);
+  s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
+  return s;
+}
+
+inline void stblock_fwd(const stgcn_stblock_desc& d, const float* x, const stgcn_stblock_params& p, float* y,
+                        Arena& sv, Ctx c, uint64_t seed) {
+  StGeom g = st_geom(d);
+  StSaved s = st_saved(d, g, sv);
+  const bool first = d.c_in == 1;   // label only: distinguishes the two blocks of the default model in profiles
+  { Tag t(first ? "st0.tc1.fwd" : "st1.tc1.fwd"); tconv_fwd(g.tc1, x, p.tc1, s.h1, s.z1, c); }
+  { Tag t(first ? "st0.gc.fwd" : "st1.gc.fwd"); gconv_fwd(g.gc, s.h1, p.gc, s.h2, s.stack, c); }
+  { Tag t(first ? "st0.tc2.fwd" : "st1.tc2.fwd"); tconv_fwd(g.tc2, s.h2, p.tc2, s.h3, s.z2, c); }
+  { Tag t(first ? "st0.ln.fwd" : "st1.ln.fwd"); lnorm_fwd(g.ln, s.h3, p.ln_w, p.ln_b, y, s.stats, seed, c.stream, c.dry()); }
+}
+
+inline void stblock_bwd(const stgcn_stblock_desc& d, const float* x, Arena& sv, const float* dy,
+                        const stgcn_stblock_params& p, const stgcn_stblock_grads& gr, float* dx, Ctx c, uint64_t seed) {
+  StGeom g = st_geom(d);
+  StSaved s = st_saved(d, g, sv);
+  ScopedMark sm(c.ws);
+  float* dh3 = c.ws.take<float>((size_t)g.rows2 * d.c3);
+  float* dh2 = c.ws.take<float>((size_t)g.rows1 * d.c2);
+  float* dh1 = c.ws.take<float>((size_t)g.rows1 * d.c1);
+  const bool first = d.c_in == 1;
+  { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd"); lnorm_bwd(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
+  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c); }
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
+  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c); }
+}
+
+// ============================ output block ===================================================
+struct OutGeom {
+  int T1;
+  long long rows1;
+  stgcn_tconv_desc tc;
+  stgcn_lnorm_desc ln;
+};
+inline OutGeom out_geom(const stgcn_outblock_desc& d) {
+  STGCN_CHECK(d.c1 > 0 && d.c_end > 0, STGCN_E_INVALID, "bad outblock desc");
+  OutGeom g;
+  g.tc = stgcn_tconv_desc{d.B, d.T, d.N, d.c_in, d.c0, d.Ko, d.act, d.precision};
+  TconvGeom tg = tconv_geom(g.tc);
+  g.T1 = tg.T_out; g.rows1 = tg.rows_out;
+  g.ln = stgcn_lnorm_desc{d.B, g.T1, d.N, d.c0, 0, 0.f, d.eps, d.precision};   // dropout sits after fc1 here
+  return g;
+}
+struct OutSaved { float *z, *h, *stats, *l, *f1, *r; };
+inline OutSaved out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Arena& sv) {
+  OutSaved s;
+  s.z = sv.take<float>(tconv_saved_floats(g.tc));
+  s.h = sv.take<float>((size_t)g.rows1 * d.c0);
+  s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
+  s.l = sv.take<float>((size_t)g.rows1 * d.c0);
+  s.f1 = sv.take<float>((size_t)g.rows1 * d.c1);
+  s.r = sv.take<float>((size_t)g.rows1 * d.c1);
+  return s;
+}
+
+inline void outblock_fwd(const stgcn_outblock_desc& d, const float* x, const stgcn_outblock_params& p, float* y,
+                         Arena& sv, Ctx c, uint64_t seed) {
+  OutGeom g = out_geom(d);
+  OutSaved s = out_saved(d, g, sv);
+  { Tag t("out.tc1.fwd"); tconv_fwd(g.tc, x, p.tc1, s.h, s.z, c); }
+  { Tag t("out.ln.fwd"); lnorm_fwd(g.ln, s.h, p.ln_w, p.ln_b, s.l, s.stats, 0, c.stream, c.dry()); }
+  Tag t_fc("out.fc.fwd");
+  ScopedMark sm(c.ws);
+  float* w1t = c.ws.take<float>((size_t)d.c0 * d.c1);
+  float* w2t = c.ws.take<float>((size_t)d.c1 * d.c_end);
+  if (c.dry()) return;
+  STGCN_CHECK(p.fc1_w && p.fc2_w, STGCN_E_INVALID, "outblock: missing fc weights");
+  launch_gather3(p.fc1_w, w1t, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);      // w1t[c][o] = fc1_w[o][c]
+  launch_gather3(p.fc2_w, w2t, 1, d.c1, d.c_end, 0, 0, 1, d.c1, 0, c.stream);
+  TapArgs t{};
+  t.in = s.l; t.wt = w1t; t.bias = p.fc1_b; t.out = s.f1; t.rows = g.rows1; t.Cin = d.c0; t.Co = d.c1; t.ntaps = 1;
+  t.ldo = d.c1; t.map = RowMap{g.T1, g.T1, d.N, 0, 0};
+  launch_tapgemm(t, c.stream);
+  long long n1 = g.rows1 * d.c1;
+  if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel, ceil_div(n1, 256), 256, 0, c.stream, s.f1, s.r, n1, d.training, d.p_drop, seed);
+  t.in = s.r; t.wt = w2t; t.bias = p.fc2_b; t.out = y; t.Cin = d.c1; t.Co = d.c_end; t.ldo = d.c_end;
+  launch_tapgemm(t, c.stream);
+}
+
+inline void outblock_bwd(const stgcn_outblock_desc& d, const float* x, Arena& sv, const float* dy,
+                         const stgcn_outblock_params& p, const stgcn_outblock_grads& gr, float* dx, Ctx c,
+                         uint64_t seed) {
+  OutGeom g = out_geom(d);
+  OutSaved s = out_saved(d, g, sv);
+  ScopedMark sm(c.ws);
+  float* dr = c.ws.take<float>((size_t)g.rows1 * d.c1);
+  float* df1 = c.ws.take<float>((size_t)g.rows1 * d.c1);
+  float* dl = c.ws.take<float>((size_t)g.rows1 * d.c0);
+  float* dh = c.ws.take<float>((size_t)g.rows1 * d.c0);
+  float* dw2 = c.ws.take<float>((size_t)(d.c1 + 1) * d.c_end);
+  float* dw1 = c.ws.take<float>((size_t)(d.c0 + 1) * d.c1);
+  if (!c.dry()) {
+    Tag t_fc("out.fc.bwd");
+    RowMap rm{g.T1, g.T1, d.N, 0, 0};
+    // fc2
+    TapArgs t{};
+    t.in = dy; t.wt = p.fc2_w; t.bias = nullptr; t.out = dr; t.rows = g.rows1; t.Cin = d.c_end; t.Co = d.c1;
+    t.ntaps = 1; t.ldo = d.c1; t.map = rm;
+    launch_tapgemm(t, c.stream);
+    if (gr.fc2_w || gr.fc2_b) {
+      zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
+      WgradArgs w{};
+      w.in = s.r; w.dz = dy; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
+      w.bias_row = 1; w.map = rm;
+      launch_wgrad(w, c.stream);
+      if (gr.fc2_w) launch_gather3(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end, 0, c.stream);
+      if (gr.fc2_b) launch_gather3(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1, 0, c.stream);
+    }
+    long long n1 = g.rows1 * d.c1;
+    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel, ceil_div(n1, 256), 256, 0, c.stream, dr, s.f1, df1, n1, d.training, d.p_drop, seed);
+    // fc1
+    t.in = df1; t.wt = p.fc1_w; t.out = dl; t.Cin = d.c1; t.Co = d.c0; t.ldo = d.c0;
+    launch_tapgemm(t, c.stream);
+    if (gr.fc1_w || gr.fc1_b) {
+      zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.stream);
+      WgradArgs w{};
+      w.in = s.l; w.dz = df1; w.dwt = dw1; w.rows = g.rows1; w.Cin = d.c0; w.Co = d.c1; w.ntaps = 1; w.ldz = d.c1;
+      w.bias_row = 1; w.map = rm;
+      launch_wgrad(w, c.stream);
+      if (gr.fc1_w) launch_gather3(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1, 0, c.stream);
+      if (gr.fc1_b) launch_gather3(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1, 0, c.stream);
+    }
+  }
+  { Tag t("out.ln.bwd"); lnorm_bwd(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
+  { Tag t("out.tc1.bwd"); tconv_bwd(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c); }
+}
+
+}  // namespace fp32
+}  // namespace stgcn

@@ -1,0 +1,679 @@
+// simt_kernels.cuh -- fp32 CUDA-core kernels of the parity path (precision == STGCN_PREC_FP32).
+//
+// Data layout everywhere: activations are row-major [rows, C] with rows = (b, t, n) and the
+// channel axis innermost ("channels-last"), i.e. the memory order of the reference's own
+// permuted (B,T,N,C) tensors (layers.py:145,255).  In that layout every stage of the ST block is
+// a GEMM over rows:
+//   * temporal (Kt,1) convolution  = "tap GEMM": Kt row-shifted copies of the input tile times
+//     per-tap weight slices (layers.py:52-57,89);  its data-gradient is the same GEMM with
+//     negative shifts and a validity mask; 1x1 align convs / nn.Linear are the 1-tap case
+//     (layers.py:16, 270-271); the Chebyshev weight contraction is a Ks-tap GEMM over the stacked
+//     x_k tensors (layers.py:163-165).
+//   * node contraction  out[g,h,:] = alpha * sum_i L[h,i] x[g,i,:] + beta * aux[g,h,:]
+//     (layers.py:154-161), one [N x N] x [N x (groups*C)] GEMM.
+//   * weight gradients = GEMMs whose contraction axis is the row axis, split over CTAs and
+//     reduced with fp32 atomics.
+#pragma once
+#include "common.cuh"
+
+namespace stgcn {
+namespace simt {
+
+constexpr int BK = 16;
+constexpr int NT = 256;
+
+// Row geometry of a tap GEMM.  Output row r = (b, t, n), t < T_out.  Tap k reads input row
+// (b, t + t_shift*k, n) of a [B, T_in, N] tensor (invalid -> contributes 0), displaced by
+// k * tap_row_stride rows (stacked operands).
+struct RowMap {
+  int T_out, T_in, N;
+  int t_shift;
+  long long tap_row_stride;
+};
+
+struct TapArgs {
+  const float* in;     // [*, Cin]
+  const float* wt;     // [ntaps*Cin, Co], Co contiguous
+  const float* bias;   // [Co] or nullptr
+  float* out;          // [rows, ldo]
+  long long rows;
+  int Cin, Co, ntaps, ldo;
+  int accumulate;      // out += result
+  RowMap map;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs a) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == NT, "tile/thread mismatch");
+  constexpr int A_PER = BM * BK / NT;
+  constexpr int B_PER = (BK * BN + NT - 1) / NT;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const long long row0 = (long long)blockIdx.x * BM;
+  const int col0 = blockIdx.y * BN;
+  const int Ktot = a.ntaps * a.Cin;
+  const long long TN_out = (long long)a.map.T_out * a.map.N;
+  const long long TN_in = (long long)a.map.T_in * a.map.N;
+  const long long tap_step = (long long)a.map.t_shift * a.map.N + a.map.tap_row_stride;
+
+  // per-thread A rows (fixed across K chunks)
+  long long a_base[A_PER];
+  int a_t[A_PER];
+#pragma unroll
+  for (int j = 0; j < A_PER; ++j) {
+    int e = tid + j * NT;
+    int m = e / BK;
+    long long r = row0 + m;
+    if (r < a.rows) {
+      long long b = r / TN_out;
+      long long rem = r - b * TN_out;
+      a_t[j] = (int)(rem / a.map.N);
+      a_base[j] = b * TN_in + rem;
+    } else {
+      a_t[j] = -1000000;
+      a_base[j] = 0;
+    }
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < Ktot; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      int e = tid + j * NT;
+      int kk = e % BK, m = e / BK;
+      int gk = k0 + kk;
+      float v = 0.f;
+      if (gk < Ktot) {
+        int tap = gk / a.Cin;
+        int c = gk - tap * a.Cin;
+        int ti = a_t[j] + a.map.t_shift * tap;
+        if (ti >= 0 && ti < a.map.T_in) v = __ldg(a.in + (a_base[j] + tap * tap_step) * a.Cin + c);
+      }
+      As[kk][m] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int e = tid + j * NT;
+      if (e < BK * BN) {
+        int n = e % BN, kk = e / BN;
+        int gk = k0 + kk, o = col0 + n;
+        Bs[kk][n] = (gk < Ktot && o < a.Co) ? __ldg(a.wt + (long long)gk * a.Co + o) : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    long long r = row0 + ty * TM + i;
+    if (r >= a.rows) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int o = col0 + tx * TN + j;
+      if (o >= a.Co) continue;
+      float v = acc[i][j] + (a.bias ? __ldg(a.bias + o) : 0.f);
+      float* p = a.out + r * a.ldo + o;
+      if (a.accumulate) v += *p;
+      *p = v;
+    }
+  }
+}
+
+inline void launch_tapgemm(const TapArgs& a, cudaStream_t s) {
+  if (a.rows == 0 || a.Co == 0) return;
+  if (a.Co <= 16) {
+    dim3 grid(ceil_div(a.rows, 128), ceil_div(a.Co, 16));
+    STGCN_LAUNCH((tapgemm_kernel<128, 16, 2, 4>), grid, NT, 0, s, a);
+  } else {
+    dim3 grid(ceil_div(a.rows, 64), ceil_div(a.Co, 64));
+    STGCN_LAUNCH((tapgemm_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+  }
+}
+
+// ---- node contraction ---------------------------------------------------------------------
+struct GsoArgs {
+  const float* M;      // [N, N] row-major
+  int trans;           // 0: out[h] = sum_i M[h,i] x[i];  1: uses M[i,h]
+  const float* in;     // [G, N, C]
+  const float* aux;    // [G, N, C] or nullptr
+  float* out;          // [G, N, C]
+  int N, C;
+  long long G;
+  float alpha, beta;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) gso_kernel(GsoArgs a) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == NT, "tile/thread mismatch");
+  constexpr int A_PER = BM * BK / NT;
+  constexpr int B_PER = BK * BN / NT;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const long long col0 = (long long)blockIdx.x * BN;   // flattened (g, c)
+  const int h0 = blockIdx.y * BM;
+  const long long Jtot = a.G * a.C;
+
+  long long b_base[B_PER];
+#pragma unroll
+  for (int j = 0; j < B_PER; ++j) {
+    int e = tid + j * NT;
+    int n = e % BN;
+    long long J = col0 + n;
+    if (J < Jtot) {
+      long long g = J / a.C;
+      int c = (int)(J - g * a.C);
+      b_base[j] = g * a.N * a.C + c;
+    } else {
+      b_base[j] = -1;
+    }
+  }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < a.N; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      int e = tid + j * NT;
+      int kk, m;
+      if (a.trans) { m = e % BM; kk = e / BM; } else { kk = e % BK; m = e / BK; }
+      int h = h0 + m, i = k0 + kk;
+      float v = 0.f;
+      if (h < a.N && i < a.N) v = a.trans ? __ldg(a.M + (long long)i * a.N + h) : __ldg(a.M + (long long)h * a.N + i);
+      As[kk][m] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int e = tid + j * NT;
+      int n = e % BN, kk = e / BN;
+      int i = k0 + kk;
+      Bs[kk][n] = (b_base[j] >= 0 && i < a.N) ? __ldg(a.in + b_base[j] + (long long)i * a.C) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int j = 0; j < TN; ++j) {
+    long long J = col0 + tx * TN + j;
+    if (J >= Jtot) continue;
+    long long g = J / a.C;
+    int c = (int)(J - g * a.C);
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      int h = h0 + ty * TM + i;
+      if (h >= a.N) continue;
+      long long idx = (g * a.N + h) * a.C + c;
+      float v = a.alpha * acc[i][j];
+      if (a.aux) v += a.beta * a.aux[idx];
+      a.out[idx] = v;
+    }
+  }
+}
+
+inline void launch_gso(const GsoArgs& a, cudaStream_t s) {
+  if (a.G == 0) return;
+  dim3 grid(ceil_div(a.G * a.C, 64), ceil_div(a.N, 64));
+  STGCN_LAUNCH((gso_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+}
+
+// ---- weight gradient: dwt[(tap,c) | bias row][o] += sum_r in[row(r,tap), c] * dz[r, o] ----
+struct WgradArgs {
+  const float* in;     // [*, Cin]
+  const float* dz;     // [rows, ldz]
+  float* dwt;          // [ntaps*Cin (+1), Co], pre-zeroed, atomically accumulated
+  long long rows;
+  int Cin, Co, ntaps, ldz;
+  int bias_row;        // 1: extra last row = column sums of dz (bias gradient)
+  int rows_per_cta;
+  RowMap map;
+};
+
+template <int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
+  constexpr int TX = BN / TN, TY = BM / TM;
+  static_assert(TX * TY == NT, "tile/thread mismatch");
+  constexpr int A_PER = BM * BK / NT;
+  constexpr int B_PER = BK * BN / NT;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int m0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
+  const long long r_begin = (long long)blockIdx.z * a.rows_per_cta;
+  const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
+  const int Kw = a.ntaps * a.Cin;
+  const int Mtot = Kw + (a.bias_row ? 1 : 0);
+  const long long TN_out = (long long)a.map.T_out * a.map.N;
+  const long long TN_in = (long long)a.map.T_in * a.map.N;
+  const long long tap_step = (long long)a.map.t_shift * a.map.N + a.map.tap_row_stride;
+
+  // A-operand columns handled by this thread: m = e % BM is fixed per j
+  int a_tap[A_PER], a_c[A_PER];
+#pragma unroll
+  for (int j = 0; j < A_PER; ++j) {
+    int e = tid + j * NT;
+    int mm = m0 + e % BM;
+    if (mm < Kw) { a_tap[j] = mm / a.Cin; a_c[j] = mm - a_tap[j] * a.Cin; }
+    else if (mm == Kw && a.bias_row) { a_tap[j] = -1; a_c[j] = 0; }
+    else { a_tap[j] = -2; a_c[j] = 0; }
+  }
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  for (long long k0 = r_begin; k0 < r_end; k0 += BK) {
+#pragma unroll
+    for (int j = 0; j < A_PER; ++j) {
+      int e = tid + j * NT;
+      int m = e % BM, kk = e / BM;
+      long long r = k0 + kk;
+      float v = 0.f;
+      if (r < r_end && a_tap[j] >= -1) {
+        if (a_tap[j] == -1) {
+          v = 1.f;
+        } else {
+          long long b = r / TN_out;
+          long long rem = r - b * TN_out;
+          int ti = (int)(rem / a.map.N) + a.map.t_shift * a_tap[j];
+          if (ti >= 0 && ti < a.map.T_in)
+            v = __ldg(a.in + (b * TN_in + rem + a_tap[j] * tap_step) * a.Cin + a_c[j]);
+        }
+      }
+      As[kk][m] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < B_PER; ++j) {
+      int e = tid + j * NT;
+      int n = e % BN, kk = e / BN;
+      long long r = k0 + kk;
+      int o = col0 + n;
+      Bs[kk][n] = (r < r_end && o < a.Co) ? __ldg(a.dz + r * a.ldz + o) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    int mm = m0 + ty * TM + i;
+    if (mm >= Mtot) continue;
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      int o = col0 + tx * TN + j;
+      if (o < a.Co) atomicAdd(a.dwt + (long long)mm * a.Co + o, acc[i][j]);
+    }
+  }
+}
+
+inline void launch_wgrad(WgradArgs a, cudaStream_t s) {
+  if (a.rows == 0 || a.Co == 0) return;
+  int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
+  int tiles;
+  dim3 grid;
+  if (a.Co <= 16) {
+    tiles = ceil_div(Mtot, 128) * ceil_div(a.Co, 16);
+  } else {
+    tiles = ceil_div(Mtot, 64) * ceil_div(a.Co, 64);
+  }
+  // aim for ~4 CTAs per SM in total, at least 512 rows per CTA
+  long long want = (148 * 4 + tiles - 1) / tiles;
+  long long rpc = (a.rows + want - 1) / want;
+  if (rpc < 512) rpc = 512;
+  rpc = (rpc + BK - 1) / BK * BK;
+  a.rows_per_cta = (int)rpc;
+  int chunks = ceil_div(a.rows, rpc);
+  if (a.Co <= 16) {
+    grid = dim3(ceil_div(Mtot, 128), ceil_div(a.Co, 16), chunks);
+    STGCN_LAUNCH((wgrad_kernel<128, 16, 2, 4>), grid, NT, 0, s, a);
+  } else {
+    grid = dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks);
+    STGCN_LAUNCH((wgrad_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+  }
+}
+
+// ---- gating / activation of the temporal conv (layers.py:92-115) ---------------------------
+struct GateArgs {
+  const float* z;      // [rows, W]   pre-activation (W = 2*Cout for glu/gtu, Cout otherwise)
+  const float* xin;    // [*, Cin]    layer input (residual source), or nullptr when folded
+  const float* dy;     // bwd: [rows, Cout]
+  float* y;            // fwd: [rows, Cout]
+  float* dz;           // bwd: [rows, W]
+  long long rows;
+  int Cin, Cout, W, Kt;
+  int T_out, T_in, N;
+  int explicit_res;    // 1: residual = xin[(b,t+Kt-1,n), j] for j < Cin (zero pad / identity)
+};
+
+__device__ __forceinline__ float gate_residual(const GateArgs& a, long long r, int j) {
+  if (!a.explicit_res || j >= a.Cin) return 0.f;
+  long long TN_out = (long long)a.T_out * a.N;
+  long long b = r / TN_out;
+  long long rem = r - b * TN_out;
+  long long row = b * a.T_in * a.N + rem + (long long)(a.Kt - 1) * a.N;
+  return __ldg(a.xin + row * a.Cin + j);
+}
+
+template <int ACT>
+__global__ void gate_fwd_kernel(GateArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * a.Cout) return;
+  long long r = idx / a.Cout;
+  int j = (int)(idx - r * a.Cout);
+  float res = gate_residual(a, r, j);
+  float p = a.z[r * a.W + j] + res;
+  float out;
+  if (ACT == STGCN_ACT_GLU) {
+    out = p * sigmoidf_(a.z[r * a.W + a.Cout + j]);
+  } else if (ACT == STGCN_ACT_GTU) {
+    out = tanhf(p) * sigmoidf_(a.z[r * a.W + a.Cout + j]);
+  } else if (ACT == STGCN_ACT_RELU) {
+    out = fmaxf(p, 0.f);
+  } else if (ACT == STGCN_ACT_SILU) {
+    out = p * sigmoidf_(p);
+  } else {
+    out = p;
+  }
+  a.y[idx] = out;
+}
+
+template <int ACT>
+__global__ void gate_bwd_kernel(GateArgs a) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * a.Cout) return;
+  long long r = idx / a.Cout;
+  int j = (int)(idx - r * a.Cout);
+  float res = gate_residual(a, r, j);
+  float p = a.z[r * a.W + j] + res;
+  float g = a.dy[idx];
+  if (ACT == STGCN_ACT_GLU) {
+    float s = sigmoidf_(a.z[r * a.W + a.Cout + j]);
+    a.dz[r * a.W + j] = g * s;
+    a.dz[r * a.W + a.Cout + j] = g * p * s * (1.f - s);
+  } else if (ACT == STGCN_ACT_GTU) {
+    float s = sigmoidf_(a.z[r * a.W + a.Cout + j]);
+    float th = tanhf(p);
+    a.dz[r * a.W + j] = g * s * (1.f - th * th);
+    a.dz[r * a.W + a.Cout + j] = g * th * s * (1.f - s);
+  } else if (ACT == STGCN_ACT_RELU) {
+    a.dz[r * a.W + j] = p > 0.f ? g : 0.f;
+  } else if (ACT == STGCN_ACT_SILU) {
+    float s = sigmoidf_(p);
+    a.dz[r * a.W + j] = g * (s + p * s * (1.f - s));
+  } else {
+    a.dz[r * a.W + j] = g;
+  }
+}
+
+// dx[(b, t+Kt-1, n), j] += dz[(b,t,n), j]  for j < min(Cin, Cout)  (gradient of the explicit residual)
+__global__ void residual_add_kernel(const float* dz, float* dx, long long rows, int Cres, int W, int Cin, int Kt,
+                                    int T_out, int T_in, int N) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Cres) return;
+  long long r = idx / Cres;
+  int j = (int)(idx - r * Cres);
+  long long TN_out = (long long)T_out * N;
+  long long b = r / TN_out;
+  long long rem = r - b * TN_out;
+  long long row = b * T_in * N + rem + (long long)(Kt - 1) * N;
+  dx[row * Cin + j] += dz[r * W + j];
+}
+
+template <int ACT>
+inline void launch_gate(bool bwd, const GateArgs& a, cudaStream_t s) {
+  long long n = a.rows * a.Cout;
+  if (n == 0) return;
+  if (bwd) STGCN_LAUNCH((gate_bwd_kernel<ACT>), ceil_div(n, 256), 256, 0, s, a);
+  else     STGCN_LAUNCH((gate_fwd_kernel<ACT>), ceil_div(n, 256), 256, 0, s, a);
+}
+
+inline void launch_gate_any(int act, bool bwd, const GateArgs& a, cudaStream_t s) {
+  switch (act) {
+    case STGCN_ACT_GLU:  launch_gate<STGCN_ACT_GLU>(bwd, a, s); break;
+    case STGCN_ACT_GTU:  launch_gate<STGCN_ACT_GTU>(bwd, a, s); break;
+    case STGCN_ACT_RELU: launch_gate<STGCN_ACT_RELU>(bwd, a, s); break;
+    case STGCN_ACT_SILU: launch_gate<STGCN_ACT_SILU>(bwd, a, s); break;
+    case STGCN_ACT_LINEAR: launch_gate<STGCN_ACT_LINEAR>(bwd, a, s); break;
+    default: throw Error(STGCN_E_UNSUPPORTED, "activation not implemented");
+  }
+}
+
+// ---- small elementwise / layout kernels ----------------------------------------------------
+// out[i0][i1][i2] (contiguous) (+)= in[off + i0*s0 + i1*s1 + i2*s2]
+__global__ void gather3_kernel(const float* in, float* out, int d0, int d1, int d2, long long off,
+                               long long s0, long long s1, long long s2, int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long tot = (long long)d0 * d1 * d2;
+  if (idx >= tot) return;
+  int i2 = (int)(idx % d2);
+  long long q = idx / d2;
+  int i1 = (int)(q % d1);
+  int i0 = (int)(q / d1);
+  float v = in[off + i0 * s0 + i1 * s1 + i2 * s2];
+  if (accumulate) out[idx] += v; else out[idx] = v;
+}
+inline void launch_gather3(const float* in, float* out, int d0, int d1, int d2, long long off, long long s0,
+                           long long s1, long long s2, int accumulate, cudaStream_t s) {
+  long long tot = (long long)d0 * d1 * d2;
+  if (tot == 0) return;
+  STGCN_LAUNCH(gather3_kernel, ceil_div(tot, 256), 256, 0, s, in, out, d0, d1, d2, off, s0, s1, s2, accumulate);
+}
+
+// out[i*ldo + j] += in[i*si + j*sj]   (strided block accumulate; used to fold 1x1 align weights)
+__global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, int d1, long long si, long long sj) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= d0 * d1) return;
+  int i = idx / d1, j = idx - i * d1;
+  out[(long long)i * ldo + j] += in[i * si + j * sj];
+}
+
+// out[r, j] = j < Cin ? in[r*ldi + j] : 0   for j < Cout   (zero-pad or column slice copy)
+__global__ void copy_cols_kernel(const float* in, float* out, long long rows, int Cin, int ldi, int Cout, int accumulate) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * Cout) return;
+  long long r = idx / Cout;
+  int j = (int)(idx - r * Cout);
+  float v = j < Cin ? in[r * ldi + j] : 0.f;
+  if (accumulate) out[idx] += v; else out[idx] = v;
+}
+inline void launch_copy_cols(const float* in, float* out, long long rows, int Cin, int ldi, int Cout, int accumulate,
+                             cudaStream_t s) {
+  if (rows * Cout == 0) return;
+  STGCN_LAUNCH(copy_cols_kernel, ceil_div(rows * Cout, 256), 256, 0, s, in, out, rows, Cin, ldi, Cout, accumulate);
+}
+
+// y = relu?(g + a)
+__global__ void add_relu_kernel(const float* g, const float* a, float* y, long long n, int relu) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = g[i] + (a ? a[i] : 0.f);
+  y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+// dg = relu ? dy * (y > 0) : dy
+__global__ void relu_bwd_kernel(const float* dy, const float* y, float* dg, long long n, int relu) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dg[i] = (!relu || y[i] > 0.f) ? dy[i] : 0.f;
+}
+// y += alpha * x
+__global__ void axpy_kernel(float alpha, const float* x, float* y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  y[i] += alpha * x[i];
+}
+// y = relu(x), with optional dropout; and its backward
+__global__ void relu_dropout_fwd_kernel(const float* x, float* y, long long n, int training, float p, uint64_t seed) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = fmaxf(x[i], 0.f);
+  if (training && p > 0.f) v = dropout_keep(seed, (uint64_t)i, p) ? v / (1.f - p) : 0.f;
+  y[i] = v;
+}
+__global__ void relu_dropout_bwd_kernel(const float* dy, const float* x, float* dx, long long n, int training, float p,
+                                        uint64_t seed) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = x[i] > 0.f ? dy[i] : 0.f;
+  if (training && p > 0.f) g = dropout_keep(seed, (uint64_t)i, p) ? g / (1.f - p) : 0.f;
+  dx[i] = g;
+}
+
+// ---- LayerNorm over the joint (N, C) axes of each (b, t) group (layers.py:246,255) ----------
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  __syncthreads();   // protect red[] reuse
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  int nw = (blockDim.x + 31) >> 5;
+  float t = (threadIdx.x < nw) ? red[threadIdx.x] : 0.f;
+  if (w == 0) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (l == 0) red[0] = t;
+  }
+  __syncthreads();
+  return red[0];
+}
+
+__global__ void __launch_bounds__(512) ln_fwd_kernel(const float* x, const float* w, const float* b, float* y,
+                                                     float* mean, float* rstd, int M, float eps, int training,
+                                                     float p, uint64_t seed) {
+  __shared__ float red[32];
+  long long g = blockIdx.x;
+  const float* xp = x + g * M;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s += xp[i];
+  float mu = block_sum(s, red) / M;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { float d = xp[i] - mu; q += d * d; }
+  float var = block_sum(q, red) / M;
+  float rs = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { mean[g] = mu; rstd[g] = rs; }
+  bool drop = training && p > 0.f;
+  float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float v = (xp[i] - mu) * rs * w[i] + b[i];
+    if (drop) v = dropout_keep(seed, (uint64_t)(g * M + i), p) ? v * keep_scale : 0.f;
+    y[g * M + i] = v;
+  }
+}
+
+__global__ void __launch_bounds__(512) ln_bwd_kernel(const float* x, const float* dy, const float* w, const float* mean,
+                                                     const float* rstd, float* dx, int M, int training, float p,
+                                                     uint64_t seed) {
+  __shared__ float red[32];
+  long long g = blockIdx.x;
+  const float* xp = x + g * M;
+  const float* dp = dy + g * M;
+  float mu = mean[g], rs = rstd[g];
+  bool drop = training && p > 0.f;
+  float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float d = dp[i];
+    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
+    float gi = d * w[i];
+    float xh = (xp[i] - mu) * rs;
+    s1 += gi; s2 += gi * xh;
+  }
+  s1 = block_sum(s1, red) / M;
+  s2 = block_sum(s2, red) / M;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float d = dp[i];
+    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
+    float gi = d * w[i];
+    float xh = (xp[i] - mu) * rs;
+    dx[g * M + i] = rs * (gi - s1 - xh * s2);
+  }
+}
+
+// dw[i] += sum_g dy'[g,i] * xhat[g,i];  db[i] += sum_g dy'[g,i]   (pre-zeroed, atomics over group chunks)
+__global__ void ln_param_grad_kernel(const float* x, const float* dy, const float* mean, const float* rstd, float* dw,
+                                     float* db, int M, long long G, int groups_per_cta, int training, float p,
+                                     uint64_t seed) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  long long g0 = (long long)blockIdx.y * groups_per_cta;
+  long long g1 = min(G, g0 + groups_per_cta);
+  bool drop = training && p > 0.f;
+  float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
+  float aw = 0.f, ab = 0.f;
+  for (long long g = g0; g < g1; ++g) {
+    float d = dy[g * M + i];
+    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
+    aw += d * (x[g * M + i] - mean[g]) * rstd[g];
+    ab += d;
+  }
+  if (dw) atomicAdd(dw + i, aw);
+  if (db) atomicAdd(db + i, ab);
+}
+
+// loss = mean((pred-target)^2); dpred = 2 (pred-target)/n * scale
+__global__ void mse_kernel(const float* pred, const float* target, long long n, float scale, float* loss, float* dpred) {
+  __shared__ float red[32];
+  float s = 0.f;
+  float inv = 1.f / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float d = pred[i] - target[i];
+    s += d * d;
+    if (dpred) dpred[i] = 2.f * d * inv * scale;
+  }
+  float t = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(loss, t * inv);
+}
+
+}  // namespace simt
+}  // namespace stgcn

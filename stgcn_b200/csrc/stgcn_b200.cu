@@ -1,0 +1,267 @@
+// stgcn_b200.cu -- C-ABI exports of libstgcn_b200.so (see include/stgcn_b200.h).
+#include "ops_fp32.cuh"
+
+namespace stgcn {
+thread_local char g_last_error[512] = "";
+std::atomic<uint64_t> g_launches{0};
+Profiler g_prof;
+thread_local const char* g_tag = nullptr;
+}  // namespace stgcn
+
+using namespace stgcn;
+
+namespace {
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline void need_fp32(int precision) {
+  STGCN_CHECK(precision == STGCN_PREC_FP32, STGCN_E_UNSUPPORTED, "only STGCN_PREC_FP32 is implemented for this entry point");
+}
+inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
+}  // namespace
+
+extern "C" {
+
+int stgcn_version(void) { return STGCN_ABI_VERSION; }
+const char* stgcn_last_error(void) { return g_last_error; }
+uint64_t stgcn_launch_count(void) { return g_launches.load(); }
+
+int stgcn_profile_begin(void) {
+  return guarded([&] {
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    for (auto& r : g_prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.recs.clear();
+    g_prof.on.store(true);
+  });
+}
+int stgcn_profile_end(char* buf, size_t cap, size_t* needed) {
+  return guarded([&] {
+    g_prof.on.store(false);
+    STGCN_CUDA(cudaDeviceSynchronize());
+    std::lock_guard<std::mutex> lk(g_prof.mu);
+    std::vector<std::string> keys;
+    std::vector<double> ms;
+    std::vector<long> cnt;
+    for (auto& r : g_prof.recs) {
+      float t = 0.f;
+      cudaEventElapsedTime(&t, r.a, r.b);
+      size_t i = 0;
+      for (; i < keys.size(); ++i) if (keys[i] == r.key) break;
+      if (i == keys.size()) { keys.push_back(r.key); ms.push_back(0); cnt.push_back(0); }
+      ms[i] += t; cnt[i] += 1;
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    g_prof.recs.clear();
+    std::string out;
+    char line[640];
+    for (size_t i = 0; i < keys.size(); ++i) {
+      std::snprintf(line, sizeof(line), "%s\t%ld\t%.6f\n", keys[i].c_str(), cnt[i], ms[i]);
+      out += line;
+    }
+    if (needed) *needed = out.size() + 1;
+    if (buf && cap) {
+      size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+      std::memcpy(buf, out.data(), n);
+      buf[n] = 0;
+    }
+  });
+}
+
+// ---------------------------------------------------------------- tconv
+int stgcn_tconv_sizes(const stgcn_tconv_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
+  return guarded([&] {
+    STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
+    need_fp32(d->precision);
+    Arena ws(nullptr, 0);
+    fp32::Ctx c{ws, nullptr};
+    stgcn_tconv_params p{};
+    stgcn_tconv_grads g{};
+    fp32::tconv_fwd(*d, nullptr, p, nullptr, nullptr, c);
+    fp32::tconv_bwd(*d, nullptr, nullptr, nullptr, p, g, nullptr, c);
+    if (saved_bytes) *saved_bytes = Arena::align_up(fp32::tconv_saved_floats(*d) * sizeof(float));
+    if (workspace_bytes) *workspace_bytes = ws.peak;
+  });
+}
+int stgcn_tconv_fwd(const stgcn_tconv_desc* d, const void* x, const stgcn_tconv_params* p, void* y, void* saved,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes);
+    fp32::tconv_fwd(*d, (const float*)x, *p, (float*)y, (float*)saved, fp32::Ctx{ws, as_stream(stream)});
+  });
+}
+int stgcn_tconv_bwd(const stgcn_tconv_desc* d, const void* x, const void* saved, const void* dy,
+                    const stgcn_tconv_params* p, const stgcn_tconv_grads* g, void* dx, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes);
+    fp32::tconv_bwd(*d, (const float*)x, (const float*)saved, (const float*)dy, *p, *g, (float*)dx,
+                    fp32::Ctx{ws, as_stream(stream)});
+  });
+}
+
+// ---------------------------------------------------------------- gconv
+// public saved layout: [stack][y copy]
+int stgcn_gconv_sizes(const stgcn_gconv_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
+  return guarded([&] {
+    STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
+    need_fp32(d->precision);
+    Arena ws(nullptr, 0);
+    fp32::Ctx c{ws, nullptr};
+    stgcn_gconv_params p{};
+    stgcn_gconv_grads g{};
+    fp32::gconv_fwd(*d, nullptr, p, nullptr, nullptr, c);
+    fp32::gconv_bwd(*d, nullptr, nullptr, nullptr, nullptr, p, g, nullptr, c);
+    Arena sv(nullptr, 0);
+    sv.take<float>(fp32::gconv_saved_floats(*d));
+    sv.take<float>((size_t)d->B * d->T * d->N * d->c_out);
+    if (saved_bytes) *saved_bytes = sv.peak;
+    if (workspace_bytes) *workspace_bytes = ws.peak;
+  });
+}
+int stgcn_gconv_fwd(const stgcn_gconv_desc* d, const void* x, const stgcn_gconv_params* p, void* y, void* saved,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes);
+    Arena sv(saved, (size_t)-1);
+    float* stack = sv.take<float>(fp32::gconv_saved_floats(*d));
+    size_t ny = (size_t)d->B * d->T * d->N * d->c_out;
+    float* ycopy = sv.take<float>(ny);
+    fp32::gconv_fwd(*d, (const float*)x, *p, (float*)y, stack, fp32::Ctx{ws, as_stream(stream)});
+    fp32::copy(ycopy, (const float*)y, ny, as_stream(stream));
+  });
+}
+int stgcn_gconv_bwd(const stgcn_gconv_desc* d, const void* x, const void* saved, const void* dy,
+                    const stgcn_gconv_params* p, const stgcn_gconv_grads* g, void* dx, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes);
+    Arena sv(const_cast<void*>(saved), (size_t)-1);
+    float* stack = sv.take<float>(fp32::gconv_saved_floats(*d));
+    float* ycopy = sv.take<float>((size_t)d->B * d->T * d->N * d->c_out);
+    fp32::gconv_bwd(*d, (const float*)x, stack, ycopy, (const float*)dy, *p, *g, (float*)dx,
+                    fp32::Ctx{ws, as_stream(stream)});
+  });
+}
+
+// ---------------------------------------------------------------- lnorm
+int stgcn_lnorm_sizes(const stgcn_lnorm_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
+  return guarded([&] {
+    STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
+    need_fp32(d->precision);
+    fp32::lnorm_check(*d);
+    if (saved_bytes) *saved_bytes = Arena::align_up(fp32::lnorm_saved_floats(*d) * sizeof(float));
+    if (workspace_bytes) *workspace_bytes = 256;
+  });
+}
+int stgcn_lnorm_fwd(const stgcn_lnorm_desc* d, const void* x, const float* w, const float* b, void* y, void* saved,
+                    uint64_t dropout_seed, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && x && w && b && y && saved, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    fp32::lnorm_fwd(*d, (const float*)x, w, b, (float*)y, (float*)saved, dropout_seed, as_stream(stream), false);
+  });
+}
+int stgcn_lnorm_bwd(const stgcn_lnorm_desc* d, const void* x, const void* saved, const void* dy, const float* w,
+                    float* dw, float* db, void* dx, void* workspace, size_t workspace_bytes, uint64_t dropout_seed,
+                    void* stream) {
+  (void)workspace; (void)workspace_bytes;
+  return guarded([&] {
+    STGCN_CHECK(d && x && saved && dy && w, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    fp32::lnorm_bwd(*d, (const float*)x, (const float*)saved, (const float*)dy, w, dw, db, (float*)dx, dropout_seed,
+                    as_stream(stream), false);
+  });
+}
+
+// ---------------------------------------------------------------- ST block
+int stgcn_stblock_sizes(const stgcn_stblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
+  return guarded([&] {
+    STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
+    need_fp32(d->precision);
+    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
+    fp32::Ctx c{ws, nullptr};
+    stgcn_stblock_params p{};
+    stgcn_stblock_grads g{};
+    fp32::stblock_fwd(*d, nullptr, p, nullptr, sv, c, 0);
+    fp32::stblock_bwd(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0);
+    if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
+    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
+  });
+}
+int stgcn_stblock_fwd(const stgcn_stblock_desc* d, const void* x, const stgcn_stblock_params* p, void* y, void* saved,
+                      void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
+    fp32::stblock_fwd(*d, (const float*)x, *p, (float*)y, sv, fp32::Ctx{ws, as_stream(stream)}, dropout_seed);
+  });
+}
+int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* saved, const void* dy,
+                      const stgcn_stblock_params* p, const stgcn_stblock_grads* g, void* dx, void* workspace,
+                      size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
+    fp32::stblock_bwd(*d, (const float*)x, sv, (const float*)dy, *p, *g, (float*)dx, fp32::Ctx{ws, as_stream(stream)},
+                      dropout_seed);
+  });
+}
+
+// ---------------------------------------------------------------- output block
+int stgcn_outblock_sizes(const stgcn_outblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
+  return guarded([&] {
+    STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
+    need_fp32(d->precision);
+    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
+    fp32::Ctx c{ws, nullptr};
+    stgcn_outblock_params p{};
+    stgcn_outblock_grads g{};
+    fp32::outblock_fwd(*d, nullptr, p, nullptr, sv, c, 0);
+    fp32::outblock_bwd(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0);
+    if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
+    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
+  });
+}
+int stgcn_outblock_fwd(const stgcn_outblock_desc* d, const void* x, const stgcn_outblock_params* p, void* y,
+                       void* saved, void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
+    fp32::outblock_fwd(*d, (const float*)x, *p, (float*)y, sv, fp32::Ctx{ws, as_stream(stream)}, dropout_seed);
+  });
+}
+int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* saved, const void* dy,
+                       const stgcn_outblock_params* p, const stgcn_outblock_grads* g, void* dx, void* workspace,
+                       size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
+    need_fp32(d->precision);
+    Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
+    fp32::outblock_bwd(*d, (const float*)x, sv, (const float*)dy, *p, *g, (float*)dx, fp32::Ctx{ws, as_stream(stream)},
+                       dropout_seed);
+  });
+}
+
+// ---------------------------------------------------------------- loss
+int stgcn_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float loss_scale, float* loss, float* dpred,
+                      void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(pred && target && loss && n > 0, STGCN_E_INVALID, "null argument");
+    cudaStream_t s = as_stream(stream);
+    STGCN_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), s));
+    int blocks = ceil_div(n, 256 * 8);
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    STGCN_LAUNCH(simt::mse_kernel, blocks, 256, 0, s, pred, target, (long long)n, loss_scale, loss, dpred);
+  });
+}
+
+}  // extern "C"
