@@ -143,7 +143,7 @@ class ClockSampler:
 
 
 # ---- CPU reference arm (oracle port; the Python reference itself cannot travel to the GPU box) --------------------
-def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None):
+def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, threads=0):
     """Times the oracle's restatement of the reference step (same ATen ops as the reference: conv2d, einsum->bmm,
     layer_norm, autograd) on all host cores.  Returns dict(samples_per_s, ms_per_step, cores, steps)."""
     from oracle import stgcn_oracle as O
@@ -151,8 +151,10 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None):
     gso = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
                                                 f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
     n = gso.shape[0]
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
     params = {k: v.requires_grad_(True) for k, v in
               O.init_params(blocks=BLOCKS, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
     gen = torch.Generator().manual_seed(0)
@@ -167,6 +169,23 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None):
         loss.backward()
         return loss
 
+    # Use the thread count that is FASTEST for the reference's step on this host (many small ATen ops: on the GPU box all 128
+    # hardware threads were far slower than a moderate count in the first measurement, profiles/bench_r01_fp32_first.json).
+    cores, best = avail, None
+    if threads:
+        cores = threads
+    else:
+        for cand in sorted({min(c, avail) for c in (4, 8, 16, 32, 64, avail)}):
+            torch.set_num_threads(cand)
+            step()
+            t0 = time.perf_counter()
+            step()
+            dt = time.perf_counter() - t0
+            if best is None or dt < best:
+                best, cores = dt, cand
+            elif dt > 1.5 * best:
+                break
+    torch.set_num_threads(cores)
     for _ in range(warmup):
         step()
     times = []
@@ -179,7 +198,7 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None):
             break
     total = sum(times)
     return dict(samples_per_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                steps=len(times), batch=batch)
+                steps=len(times), batch=batch, host_threads_available=avail)
 
 
 def main():
@@ -211,10 +230,11 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cpu_b = min(B, 64)
+        cpu_b = min(B, 32)
         r = cpu_reference_run(a.workload, cpu_b, steps, warmup, a.droprate)
         sample = (f"{r['steps']} steps of B={cpu_b} (a bounded sample of the B={B} workload), oracle port of the "
-                  f"reference step (same ATen ops), {r['cores']} host threads")
+                  f"reference step (same ATen ops), {r['cores']} host threads (fastest of a sweep; "
+                  f"{r['host_threads_available']} available)")
         line = {"impl": "reference", "metric": "ST-block fwd+bwd samples/sec", "value": r["samples_per_s"],
                 "unit": "samples/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -361,7 +381,8 @@ def main():
         r = cpu_reference_run(a.workload, 32, 60, 3, a.droprate, budget_s=15.0)
         cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
                         "sample": f"{r['steps']} steps of B=32 (BASELINE configs[0] batch), oracle port of the "
-                                  f"reference step on {r['cores']} host threads, dropout {a.droprate}"}
+                                  f"reference step on {r['cores']} host threads (fastest of a sweep; "
+                                  f"{r['host_threads_available']} available), dropout {a.droprate}"}
 
     if rank == 0:
         line = {"metric": "ST-block fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,

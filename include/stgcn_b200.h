@@ -197,6 +197,12 @@ int stgcn_outblock_bwd(const stgcn_outblock_desc*, const void* x, const void* sa
                        const stgcn_outblock_params*, const stgcn_outblock_grads*, void* dx,
                        void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream);
 
+/* ---- diagnostics ---------------------------------------------------------------------- */
+/* Minimal tcgen05 GEMM (bf16 operands, fp32 TMEM accumulate) exercising the operand layouts of the
+ * production kernels; see csrc/umma_selftest.cuh for the modes.  Used by tests only.         */
+int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M, int N, int K,
+                        uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, void* stream);
+
 /* ---- training-step helpers (main.py:166-168) ------------------------------------------ */
 /* loss = mean((pred - target)^2) over n elements, written to *loss (device, fp32);
  * dpred = 2 (pred - target) / n * loss_scale.  Replaces nn.MSELoss fwd+bwd (main.py:136,167-168). */

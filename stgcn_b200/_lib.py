@@ -116,6 +116,8 @@ _SIGNATURES = [
     ("stgcn_outblock_fwd", C.c_int, [_P(OutblockDesc), _fp, _P(OutblockParams), _fp, _fp, _fp, _sz, C.c_uint64, _fp]),
     ("stgcn_outblock_bwd", C.c_int, [_P(OutblockDesc), _fp, _fp, _fp, _P(OutblockParams), _P(OutblockGrads), _fp,
                                      _fp, _sz, C.c_uint64, _fp]),
+    ("stgcn_umma_selftest", C.c_int, [C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
+                                      C.c_uint32, C.c_uint32, _fp]),
     ("stgcn_mse_fwd_bwd", C.c_int, [_fp, _fp, C.c_int64, C.c_float, _fp, _fp, _fp]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

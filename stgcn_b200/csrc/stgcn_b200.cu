@@ -1,5 +1,6 @@
 // stgcn_b200.cu -- C-ABI exports of libstgcn_b200.so (see include/stgcn_b200.h).
 #include "ops_fp32.cuh"
+#include "umma_selftest.cuh"
 
 namespace stgcn {
 thread_local char g_last_error[512] = "";
@@ -248,6 +249,15 @@ int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* 
     Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
     fp32::outblock_bwd(*d, (const float*)x, sv, (const float*)dy, *p, *g, (float*)dx, fp32::Ctx{ws, as_stream(stream)},
                        dropout_seed);
+  });
+}
+
+// ---------------------------------------------------------------- diagnostics
+int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M, int N, int K, uint32_t lbo_a,
+                        uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(A && B && C, STGCN_E_INVALID, "null argument");
+    umma::run_selftest(mode, A, B, C, M, N, K, lbo_a, sbo_a, lbo_b, sbo_b, as_stream(stream));
   });
 }
 
