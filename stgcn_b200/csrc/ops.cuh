@@ -1,11 +1,12 @@
-// ops_fp32.cuh -- host orchestration of the fp32 parity path: each op carves its buffers from
+// ops.cuh -- host orchestration of the modular path, templated on the activation storage type T
+// (float: parity path; __nv_bfloat16: throughput path): each op carves its buffers from
 // caller-provided arenas, then enqueues the SIMT kernels of simt_kernels.cuh on the stream.
 // "dry" arenas (null base) only measure: the *_sizes entry points run the same code paths.
 #pragma once
 #include "simt_kernels.cuh"
 
 namespace stgcn {
-namespace fp32 {
+namespace ops {
 
 using namespace simt;
 
@@ -18,8 +19,9 @@ struct Ctx {
 inline void zero(float* p, size_t n, cudaStream_t s) {
   if (n) STGCN_CUDA(cudaMemsetAsync(p, 0, n * sizeof(float), s));
 }
-inline void copy(float* dst, const float* src, size_t n, cudaStream_t s) {
-  if (n) STGCN_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+template <class T>
+inline void copy(T* dst, const T* src, size_t n, cudaStream_t s) {
+  if (n) STGCN_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToDevice, s));
 }
 
 struct ScopedMark {   // releases scratch taken inside a scope
@@ -49,11 +51,11 @@ inline TconvGeom tconv_geom(const stgcn_tconv_desc& d) {
   g.folded = !g.linear && d.c_in > d.c_out;   // residual 1x1 conv folded into tap Kt-1 of the linear half
   return g;
 }
-inline size_t tconv_saved_floats(const stgcn_tconv_desc& d) { auto g = tconv_geom(d); return (size_t)g.rows_out * g.W; }
+inline size_t tconv_saved_elems(const stgcn_tconv_desc& d) { auto g = tconv_geom(d); return (size_t)g.rows_out * g.W; }
 
 // z_saved: [rows_out, W] pre-activations
-inline void tconv_fwd(const stgcn_tconv_desc& d, const float* x, const stgcn_tconv_params& p, float* y, float* z_saved,
-                      Ctx c) {
+template <class T>
+inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_params& p, T* y, T* z_saved, Ctx c) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   float* wt = c.ws.take<float>((size_t)d.Kt * d.c_in * g.W);
@@ -70,27 +72,28 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const float* x, const stgcn_tco
                  wt + (size_t)(d.Kt - 1) * d.c_in * g.W, g.W, p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
     launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
   }
-  TapArgs t{};
+  TapArgs<T> t{};
   t.in = x; t.wt = wt; t.bias = bias; t.out = z_saved; t.rows = g.rows_out;
   t.Cin = d.c_in; t.Co = g.W; t.ntaps = d.Kt; t.ldo = g.W; t.accumulate = 0;
   t.map = RowMap{g.T_out, d.T, d.N, 1, 0};
   launch_tapgemm(t, c.stream);
-  GateArgs ga{};
+  GateArgs<T> ga{};
   ga.z = z_saved; ga.xin = x; ga.y = y; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out; ga.W = g.W;
   ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
   launch_gate_any(d.act, false, ga, c.stream);
 }
 
-inline void tconv_bwd(const stgcn_tconv_desc& d, const float* x, const float* z_saved, const float* dy,
-                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, float* dx, Ctx c) {
+template <class T>
+inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, const T* dy,
+                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
-  float* dz = c.ws.take<float>((size_t)g.rows_out * g.W);
+  T* dz = c.ws.take<T>((size_t)g.rows_out * g.W);
   float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
   float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
   if (c.dry()) return;
-  GateArgs ga{};
+  GateArgs<T> ga{};
   ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
   ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
   launch_gate_any(d.act, true, ga, c.stream);
@@ -98,7 +101,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const float* x, const float* z_
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   if (want_w) {
     zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
-    WgradArgs w{};
+    WgradArgs<T> w{};
     w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
     w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0};
     launch_wgrad(w, c.stream);
@@ -116,7 +119,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const float* x, const float* z_
     launch_gather3(p.conv_w, wd, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
     if (g.folded)
       launch_gather3(p.align_w, wd + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
-    TapArgs t{};
+    TapArgs<T> t{};
     t.in = dz; t.wt = wd; t.bias = nullptr; t.out = dx; t.rows = g.rows_in;
     t.Cin = g.W; t.Co = d.c_in; t.ntaps = d.Kt; t.ldo = d.c_in; t.accumulate = 0;
     t.map = RowMap{d.T, g.T_out, d.N, -1, 0};
@@ -124,7 +127,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const float* x, const float* z_
     if (!g.folded && !g.linear) {
       int cres = d.c_in < d.c_out ? d.c_in : d.c_out;
       long long n = g.rows_out * cres;
-      if (n) STGCN_LAUNCH(residual_add_kernel, ceil_div(n, 256), 256, 0, c.stream, dz, dx, g.rows_out, cres, g.W,
+      if (n) STGCN_LAUNCH(residual_add_kernel<T>, ceil_div(n, 256), 256, 0, c.stream, dz, dx, g.rows_out, cres, g.W,
                           d.c_in, d.Kt, g.T_out, d.T, d.N);
     }
   }
@@ -139,14 +142,14 @@ inline void gconv_check(const stgcn_gconv_desc& d) {
     STGCN_CHECK(d.Ks >= 1, STGCN_E_INVALID,
                 "ERROR: the graph convolution kernel size Ks has to be a positive integer");
 }
-inline size_t gconv_saved_floats(const stgcn_gconv_desc& d) {
+inline size_t gconv_saved_elems(const stgcn_gconv_desc& d) {
   gconv_check(d);
   return (size_t)gconv_stack_depth(d) * d.B * d.T * d.N * d.c_out;
 }
 
 // stack: [depth][rows, C]; stack[0] = aligned input, stack[k] = T_k(L) stack[0] (cheb) / L stack[0] (gcn)
-inline void gconv_fwd(const stgcn_gconv_desc& d, const float* x, const stgcn_gconv_params& p, float* y, float* stack,
-                      Ctx c) {
+template <class T>
+inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_params& p, T* y, T* stack, Ctx c) {
   gconv_check(d);
   ScopedMark sm(c.ws);
   const long long rows = (long long)d.B * d.T * d.N;
@@ -155,20 +158,20 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const float* x, const stgcn_gco
   float* wat = c.ws.take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
-  float* x0 = stack;
+  T* x0 = stack;
   if (d.c_in > C) {
     STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
     launch_gather3(p.align_w, wat, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // wat[c][o] = align_w[o][c]
-    TapArgs t{};
+    TapArgs<T> t{};
     t.in = x; t.wt = wat; t.bias = p.align_b; t.out = x0; t.rows = rows; t.Cin = d.c_in; t.Co = C; t.ntaps = 1;
     t.ldo = C; t.map = RowMap{d.T, d.T, d.N, 0, 0};
     launch_tapgemm(t, c.stream);
   } else {
     launch_copy_cols(x, x0, rows, d.c_in, d.c_in, C, 0, c.stream);
   }
-  GsoArgs g{};
+  GsoArgs<T> g{};
   g.M = p.gso; g.trans = 0; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
-  TapArgs t{};
+  TapArgs<T> t{};
   t.bias = p.b; t.out = y; t.rows = rows; t.Cin = C; t.Co = C; t.ldo = C;
   if (d.gconv == STGCN_GCONV_CHEB) {
     for (int k = 1; k < d.Ks; ++k) {
@@ -184,11 +187,12 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const float* x, const stgcn_gco
     t.in = stack + plane; t.wt = p.w; t.ntaps = 1; t.map = RowMap{d.T, d.T, d.N, 0, 0};
   }
   launch_tapgemm(t, c.stream);
-  STGCN_LAUNCH(add_relu_kernel, ceil_div(plane, 256), 256, 0, c.stream, y, d.residual ? x0 : nullptr, y, (long long)plane, d.relu);
+  STGCN_LAUNCH(add_relu_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, (const T*)y, (const T*)(d.residual ? x0 : nullptr), y, (long long)plane, d.relu);
 }
 
-inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* stack, const float* y, const float* dy,
-                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, float* dx, Ctx c) {
+template <class T>
+inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, const T* y, const T* dy,
+                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c) {
   gconv_check(d);
   ScopedMark sm(c.ws);
   const long long rows = (long long)d.B * d.T * d.N;
@@ -196,20 +200,20 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* st
   const size_t plane = (size_t)rows * C;
   const int depth = gconv_stack_depth(d);
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
-  float* dg = c.ws.take<float>(plane);
-  float* dst = c.ws.take<float>((size_t)depth * plane);
+  T* dg = c.ws.take<T>(plane);
+  T* dst = c.ws.take<T>((size_t)depth * plane);
   float* wT = c.ws.take<float>((size_t)ntw * C * C);
   float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
   if (c.dry()) return;
-  STGCN_LAUNCH(relu_bwd_kernel, ceil_div(plane, 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
+  STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
-  GsoArgs g{};
+  GsoArgs<T> g{};
   g.M = p.gso; g.trans = 1; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
-  TapArgs t{};
+  TapArgs<T> t{};
   t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
   t.map = RowMap{d.T, d.T, d.N, 0, 0};
-  WgradArgs w{};
+  WgradArgs<T> w{};
   w.dz = dg; w.dwt = dwt; w.rows = rows; w.Cin = C; w.Co = C; w.ldz = C; w.bias_row = 1;
   zero(dwt, (size_t)(ntw * C + 1) * C, c.stream);
 
@@ -228,14 +232,14 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* st
     for (int k = d.Ks - 1; k >= 2; --k) {
       g.in = dst + (size_t)k * plane; g.out = dst + (size_t)(k - 1) * plane; g.aux = g.out; g.alpha = 2.f; g.beta = 1.f;
       launch_gso(g, c.stream);
-      STGCN_LAUNCH(axpy_kernel, ceil_div(plane, 256), 256, 0, c.stream, -1.f, dst + (size_t)k * plane,
+      STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, -1.f, (const T*)(dst + (size_t)k * plane),
                    dst + (size_t)(k - 2) * plane, (long long)plane);
     }
     if (d.Ks >= 2) {
       g.in = dst + plane; g.out = dst; g.aux = dst; g.alpha = 1.f; g.beta = 1.f;
       launch_gso(g, c.stream);
     }
-    if (d.residual) STGCN_LAUNCH(axpy_kernel, ceil_div(plane, 256), 256, 0, c.stream, 1.f, dg, dst, (long long)plane);
+    if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
   } else {
     launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
     t.wt = wT; t.out = dst + plane;
@@ -254,7 +258,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* st
   if (d.c_in > C) {
     if (gr.align_w || gr.align_b) {
       zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
-      WgradArgs wa{};
+      WgradArgs<T> wa{};
       wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
       wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0};
       launch_wgrad(wa, c.stream);
@@ -262,13 +266,13 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const float* x, const float* st
       if (gr.align_b) launch_gather3(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1, 0, c.stream);
     }
     if (dx) {
-      TapArgs ta{};
+      TapArgs<T> ta{};
       ta.in = dst; ta.wt = p.align_w; ta.bias = nullptr; ta.out = dx; ta.rows = rows; ta.Cin = C; ta.Co = d.c_in;
       ta.ntaps = 1; ta.ldo = d.c_in; ta.map = RowMap{d.T, d.T, d.N, 0, 0};
       launch_tapgemm(ta, c.stream);
     }
   } else if (dx) {
-    launch_copy_cols(dst, dx, rows, C, C, d.c_in, 0, c.stream);
+    launch_copy_cols((const T*)dst, dx, rows, C, C, d.c_in, 0, c.stream);
   }
 }
 
@@ -279,17 +283,19 @@ inline void lnorm_check(const stgcn_lnorm_desc& d) {
 }
 inline size_t lnorm_saved_floats(const stgcn_lnorm_desc& d) { return (size_t)2 * d.B * d.T; }
 
-inline void lnorm_fwd(const stgcn_lnorm_desc& d, const float* x, const float* w, const float* b, float* y,
+template <class T>
+inline void lnorm_fwd(const stgcn_lnorm_desc& d, const T* x, const float* w, const float* b, T* y,
                       float* stats, uint64_t seed, cudaStream_t s, bool dry) {
   lnorm_check(d);
   if (dry) return;
   long long G = (long long)d.B * d.T;
   if (G == 0) return;
-  STGCN_LAUNCH(ln_fwd_kernel, (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, d.N * d.C, d.eps, d.training,
+  STGCN_LAUNCH(ln_fwd_kernel<T>, (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, d.N * d.C, d.eps, d.training,
                d.p_drop, seed);
 }
-inline void lnorm_bwd(const stgcn_lnorm_desc& d, const float* x, const float* stats, const float* dy, const float* w,
-                      float* dw, float* db, float* dx, uint64_t seed, cudaStream_t s, bool dry) {
+template <class T>
+inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats, const T* dy, const float* w,
+                      float* dw, float* db, T* dx, uint64_t seed, cudaStream_t s, bool dry) {
   lnorm_check(d);
   if (dry) return;
   long long G = (long long)d.B * d.T;
@@ -297,13 +303,13 @@ inline void lnorm_bwd(const stgcn_lnorm_desc& d, const float* x, const float* st
   if (dw) zero(dw, M, s);
   if (db) zero(db, M, s);
   if (G == 0) return;
-  if (dx) STGCN_LAUNCH(ln_bwd_kernel, (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
+  if (dx) STGCN_LAUNCH(ln_bwd_kernel<T>, (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
   if (dw || db) {
     int xb = ceil_div(M, 256);
     int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 8) / xb));
     int gpc = ceil_div(G, ychunks);
     ychunks = ceil_div(G, gpc);
-    STGCN_LAUNCH(ln_param_grad_kernel, dim3(xb, ychunks), 256, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc,
+    STGCN_LAUNCH(ln_param_grad_kernel<T>, dim3(xb, ychunks), 256, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc,
                  d.training, d.p_drop, seed);
   }
 }
@@ -328,43 +334,47 @@ inline StGeom st_geom(const stgcn_stblock_desc& d) {
   g.ln = stgcn_lnorm_desc{d.B, g.T2, d.N, d.c3, d.training, d.p_drop, d.eps, d.precision};
   return g;
 }
-struct StSaved { float *z1, *h1, *stack, *h2, *z2, *h3, *stats; };
-inline StSaved st_saved(const stgcn_stblock_desc& d, const StGeom& g, Arena& sv) {
-  StSaved s;
-  s.z1 = sv.take<float>(tconv_saved_floats(g.tc1));
-  s.h1 = sv.take<float>((size_t)g.rows1 * d.c1);
-  s.stack = sv.take<float>(gconv_saved_floats(g.gc));
-  s.h2 = sv.take<float>((size_t)g.rows1 * d.c2);
-  s.z2 = sv.take<float>(tconv_saved_floats(g.tc2));
-  s.h3 = sv.take<float>((size_t)g.rows2 * d.c3);
+template <class T>
+struct StSaved { T *z1, *h1, *stack, *h2, *z2, *h3; float* stats; };
+template <class T>
+inline StSaved<T> st_saved(const stgcn_stblock_desc& d, const StGeom& g, Arena& sv) {
+  StSaved<T> s;
+  s.z1 = sv.take<T>(tconv_saved_elems(g.tc1));
+  s.h1 = sv.take<T>((size_t)g.rows1 * d.c1);
+  s.stack = sv.take<T>(gconv_saved_elems(g.gc));
+  s.h2 = sv.take<T>((size_t)g.rows1 * d.c2);
+  s.z2 = sv.take<T>(tconv_saved_elems(g.tc2));
+  s.h3 = sv.take<T>((size_t)g.rows2 * d.c3);
   s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
   return s;
 }
 
-inline void stblock_fwd(const stgcn_stblock_desc& d, const float* x, const stgcn_stblock_params& p, float* y,
+template <class T>
+inline void stblock_fwd(const stgcn_stblock_desc& d, const T* x, const stgcn_stblock_params& p, T* y,
                         Arena& sv, Ctx c, uint64_t seed) {
   StGeom g = st_geom(d);
-  StSaved s = st_saved(d, g, sv);
+  StSaved<T> s = st_saved<T>(d, g, sv);
   const bool first = d.c_in == 1;   // label only: distinguishes the two blocks of the default model in profiles
-  { Tag t(first ? "st0.tc1.fwd" : "st1.tc1.fwd"); tconv_fwd(g.tc1, x, p.tc1, s.h1, s.z1, c); }
-  { Tag t(first ? "st0.gc.fwd" : "st1.gc.fwd"); gconv_fwd(g.gc, s.h1, p.gc, s.h2, s.stack, c); }
-  { Tag t(first ? "st0.tc2.fwd" : "st1.tc2.fwd"); tconv_fwd(g.tc2, s.h2, p.tc2, s.h3, s.z2, c); }
-  { Tag t(first ? "st0.ln.fwd" : "st1.ln.fwd"); lnorm_fwd(g.ln, s.h3, p.ln_w, p.ln_b, y, s.stats, seed, c.stream, c.dry()); }
+  { Tag t(first ? "st0.tc1.fwd" : "st1.tc1.fwd"); tconv_fwd<T>(g.tc1, x, p.tc1, s.h1, s.z1, c); }
+  { Tag t(first ? "st0.gc.fwd" : "st1.gc.fwd"); gconv_fwd<T>(g.gc, s.h1, p.gc, s.h2, s.stack, c); }
+  { Tag t(first ? "st0.tc2.fwd" : "st1.tc2.fwd"); tconv_fwd<T>(g.tc2, s.h2, p.tc2, s.h3, s.z2, c); }
+  { Tag t(first ? "st0.ln.fwd" : "st1.ln.fwd"); lnorm_fwd<T>(g.ln, s.h3, p.ln_w, p.ln_b, y, s.stats, seed, c.stream, c.dry()); }
 }
 
-inline void stblock_bwd(const stgcn_stblock_desc& d, const float* x, Arena& sv, const float* dy,
-                        const stgcn_stblock_params& p, const stgcn_stblock_grads& gr, float* dx, Ctx c, uint64_t seed) {
+template <class T>
+inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, const T* dy,
+                        const stgcn_stblock_params& p, const stgcn_stblock_grads& gr, T* dx, Ctx c, uint64_t seed) {
   StGeom g = st_geom(d);
-  StSaved s = st_saved(d, g, sv);
+  StSaved<T> s = st_saved<T>(d, g, sv);
   ScopedMark sm(c.ws);
-  float* dh3 = c.ws.take<float>((size_t)g.rows2 * d.c3);
-  float* dh2 = c.ws.take<float>((size_t)g.rows1 * d.c2);
-  float* dh1 = c.ws.take<float>((size_t)g.rows1 * d.c1);
+  T* dh3 = c.ws.take<T>((size_t)g.rows2 * d.c3);
+  T* dh2 = c.ws.take<T>((size_t)g.rows1 * d.c2);
+  T* dh1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
   const bool first = d.c_in == 1;
-  { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd"); lnorm_bwd(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
-  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c); }
-  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
-  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c); }
+  { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd"); lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
+  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c); }
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
+  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c); }
 }
 
 // ============================ output block ===================================================
@@ -383,24 +393,28 @@ inline OutGeom out_geom(const stgcn_outblock_desc& d) {
   g.ln = stgcn_lnorm_desc{d.B, g.T1, d.N, d.c0, 0, 0.f, d.eps, d.precision};   // dropout sits after fc1 here
   return g;
 }
-struct OutSaved { float *z, *h, *stats, *l, *f1, *r; };
-inline OutSaved out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Arena& sv) {
-  OutSaved s;
-  s.z = sv.take<float>(tconv_saved_floats(g.tc));
-  s.h = sv.take<float>((size_t)g.rows1 * d.c0);
+template <class T>
+struct OutSaved { T *z, *h, *l, *f1, *r; float* stats; };
+template <class T>
+inline OutSaved<T> out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Arena& sv) {
+  OutSaved<T> s;
+  s.z = sv.take<T>(tconv_saved_elems(g.tc));
+  s.h = sv.take<T>((size_t)g.rows1 * d.c0);
   s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
-  s.l = sv.take<float>((size_t)g.rows1 * d.c0);
-  s.f1 = sv.take<float>((size_t)g.rows1 * d.c1);
-  s.r = sv.take<float>((size_t)g.rows1 * d.c1);
+  s.l = sv.take<T>((size_t)g.rows1 * d.c0);
+  s.f1 = sv.take<T>((size_t)g.rows1 * d.c1);
+  s.r = sv.take<T>((size_t)g.rows1 * d.c1);
   return s;
 }
 
-inline void outblock_fwd(const stgcn_outblock_desc& d, const float* x, const stgcn_outblock_params& p, float* y,
+// y (and dy in the backward) are ALWAYS fp32: the model output feeds the loss (main.py:166-167).
+template <class T>
+inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_outblock_params& p, float* y,
                          Arena& sv, Ctx c, uint64_t seed) {
   OutGeom g = out_geom(d);
-  OutSaved s = out_saved(d, g, sv);
-  { Tag t("out.tc1.fwd"); tconv_fwd(g.tc, x, p.tc1, s.h, s.z, c); }
-  { Tag t("out.ln.fwd"); lnorm_fwd(g.ln, s.h, p.ln_w, p.ln_b, s.l, s.stats, 0, c.stream, c.dry()); }
+  OutSaved<T> s = out_saved<T>(d, g, sv);
+  { Tag t("out.tc1.fwd"); tconv_fwd<T>(g.tc, x, p.tc1, s.h, s.z, c); }
+  { Tag t("out.ln.fwd"); lnorm_fwd<T>(g.ln, s.h, p.ln_w, p.ln_b, s.l, s.stats, 0, c.stream, c.dry()); }
   Tag t_fc("out.fc.fwd");
   ScopedMark sm(c.ws);
   float* w1t = c.ws.take<float>((size_t)d.c0 * d.c1);
@@ -409,53 +423,67 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const float* x, const stg
   STGCN_CHECK(p.fc1_w && p.fc2_w, STGCN_E_INVALID, "outblock: missing fc weights");
   launch_gather3(p.fc1_w, w1t, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);      // w1t[c][o] = fc1_w[o][c]
   launch_gather3(p.fc2_w, w2t, 1, d.c1, d.c_end, 0, 0, 1, d.c1, 0, c.stream);
-  TapArgs t{};
+  TapArgs<T> t{};
   t.in = s.l; t.wt = w1t; t.bias = p.fc1_b; t.out = s.f1; t.rows = g.rows1; t.Cin = d.c0; t.Co = d.c1; t.ntaps = 1;
   t.ldo = d.c1; t.map = RowMap{g.T1, g.T1, d.N, 0, 0};
   launch_tapgemm(t, c.stream);
   long long n1 = g.rows1 * d.c1;
-  if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel, ceil_div(n1, 256), 256, 0, c.stream, s.f1, s.r, n1, d.training, d.p_drop, seed);
-  t.in = s.r; t.wt = w2t; t.bias = p.fc2_b; t.out = y; t.Cin = d.c1; t.Co = d.c_end; t.ldo = d.c_end;
-  launch_tapgemm(t, c.stream);
+  if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
+  TapArgs<T, float> t2{};
+  t2.in = s.r; t2.wt = w2t; t2.bias = p.fc2_b; t2.out = y; t2.rows = g.rows1; t2.Cin = d.c1; t2.Co = d.c_end;
+  t2.ntaps = 1; t2.ldo = d.c_end; t2.map = t.map;
+  launch_tapgemm(t2, c.stream);
 }
 
-inline void outblock_bwd(const stgcn_outblock_desc& d, const float* x, Arena& sv, const float* dy,
-                         const stgcn_outblock_params& p, const stgcn_outblock_grads& gr, float* dx, Ctx c,
+template <class T>
+inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, const float* dy,
+                         const stgcn_outblock_params& p, const stgcn_outblock_grads& gr, T* dx, Ctx c,
                          uint64_t seed) {
   OutGeom g = out_geom(d);
-  OutSaved s = out_saved(d, g, sv);
+  OutSaved<T> s = out_saved<T>(d, g, sv);
   ScopedMark sm(c.ws);
-  float* dr = c.ws.take<float>((size_t)g.rows1 * d.c1);
-  float* df1 = c.ws.take<float>((size_t)g.rows1 * d.c1);
-  float* dl = c.ws.take<float>((size_t)g.rows1 * d.c0);
-  float* dh = c.ws.take<float>((size_t)g.rows1 * d.c0);
+  T* dr = c.ws.take<T>((size_t)g.rows1 * d.c1);
+  T* df1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
+  T* dl = c.ws.take<T>((size_t)g.rows1 * d.c0);
+  T* dh = c.ws.take<T>((size_t)g.rows1 * d.c0);
+  T* dyT = c.ws.take<T>(sizeof(T) == sizeof(float) ? 0 : (size_t)g.rows1 * d.c_end);
   float* dw2 = c.ws.take<float>((size_t)(d.c1 + 1) * d.c_end);
   float* dw1 = c.ws.take<float>((size_t)(d.c0 + 1) * d.c1);
   if (!c.dry()) {
     Tag t_fc("out.fc.bwd");
     RowMap rm{g.T1, g.T1, d.N, 0, 0};
-    // fc2
-    TapArgs t{};
-    t.in = dy; t.wt = p.fc2_w; t.bias = nullptr; t.out = dr; t.rows = g.rows1; t.Cin = d.c_end; t.Co = d.c1;
-    t.ntaps = 1; t.ldo = d.c1; t.map = rm;
-    launch_tapgemm(t, c.stream);
+    // fc2 (dy is fp32; the wgrad kernel wants it in the activation type)
+    TapArgs<float, T> t0{};
+    t0.in = dy; t0.wt = p.fc2_w; t0.bias = nullptr; t0.out = dr; t0.rows = g.rows1; t0.Cin = d.c_end; t0.Co = d.c1;
+    t0.ntaps = 1; t0.ldo = d.c1; t0.map = rm;
+    launch_tapgemm(t0, c.stream);
+    const T* dy_t;
+    if constexpr (sizeof(T) == sizeof(float)) {
+      dy_t = reinterpret_cast<const T*>(dy);
+    } else {
+      long long ne = g.rows1 * d.c_end;
+      if (ne) STGCN_LAUNCH(convert_kernel, ceil_div(ne, 256), 256, 0, c.stream, dy, dyT, ne);
+      dy_t = dyT;
+    }
+    TapArgs<T> t{};
+    t.bias = nullptr; t.rows = g.rows1; t.ntaps = 1; t.map = rm;
     if (gr.fc2_w || gr.fc2_b) {
       zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
-      WgradArgs w{};
-      w.in = s.r; w.dz = dy; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
+      WgradArgs<T> w{};
+      w.in = s.r; w.dz = dy_t; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
       w.bias_row = 1; w.map = rm;
       launch_wgrad(w, c.stream);
       if (gr.fc2_w) launch_gather3(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end, 0, c.stream);
       if (gr.fc2_b) launch_gather3(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1, 0, c.stream);
     }
     long long n1 = g.rows1 * d.c1;
-    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel, ceil_div(n1, 256), 256, 0, c.stream, dr, s.f1, df1, n1, d.training, d.p_drop, seed);
+    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, (const T*)s.f1, df1, n1, d.training, d.p_drop, seed);
     // fc1
     t.in = df1; t.wt = p.fc1_w; t.out = dl; t.Cin = d.c1; t.Co = d.c0; t.ldo = d.c0;
     launch_tapgemm(t, c.stream);
     if (gr.fc1_w || gr.fc1_b) {
       zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.stream);
-      WgradArgs w{};
+      WgradArgs<T> w{};
       w.in = s.l; w.dz = df1; w.dwt = dw1; w.rows = g.rows1; w.Cin = d.c0; w.Co = d.c1; w.ntaps = 1; w.ldz = d.c1;
       w.bias_row = 1; w.map = rm;
       launch_wgrad(w, c.stream);
@@ -463,9 +491,9 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const float* x, Arena& sv
       if (gr.fc1_b) launch_gather3(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1, 0, c.stream);
     }
   }
-  { Tag t("out.ln.bwd"); lnorm_bwd(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
-  { Tag t("out.tc1.bwd"); tconv_bwd(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c); }
+  { Tag t("out.ln.bwd"); lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
+  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c); }
 }
 
-}  // namespace fp32
+}  // namespace ops
 }  // namespace stgcn

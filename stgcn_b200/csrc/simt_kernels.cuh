@@ -22,6 +22,13 @@ namespace simt {
 constexpr int BK = 16;
 constexpr int NT = 256;
 
+// activation storage type T: float (parity path) or __nv_bfloat16 (throughput path); math is always fp32
+using bf16 = __nv_bfloat16;
+__device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
 // Row geometry of a tap GEMM.  Output row r = (b, t, n), t < T_out.  Tap k reads input row
 // (b, t + t_shift*k, n) of a [B, T_in, N] tensor (invalid -> contributes 0), displaced by
 // k * tap_row_stride rows (stacked operands).
@@ -31,19 +38,20 @@ struct RowMap {
   long long tap_row_stride;
 };
 
+template <class TI, class TO = TI>
 struct TapArgs {
-  const float* in;     // [*, Cin]
+  const TI* in;        // [*, Cin]
   const float* wt;     // [ntaps*Cin, Co], Co contiguous
   const float* bias;   // [Co] or nullptr
-  float* out;          // [rows, ldo]
+  TO* out;             // [rows, ldo]
   long long rows;
   int Cin, Co, ntaps, ldo;
   int accumulate;      // out += result
   RowMap map;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs a) {
+template <class TI, class TO, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs<TI, TO> a) {
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -96,7 +104,7 @@ __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs a) {
         int tap = gk / a.Cin;
         int c = gk - tap * a.Cin;
         int ti = a_t[j] + a.map.t_shift * tap;
-        if (ti >= 0 && ti < a.map.T_in) v = __ldg(a.in + (a_base[j] + tap * tap_step) * a.Cin + c);
+        if (ti >= 0 && ti < a.map.T_in) v = ldf(a.in + (a_base[j] + tap * tap_step) * a.Cin + c);
       }
       As[kk][m] = v;
     }
@@ -134,38 +142,40 @@ __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs a) {
       int o = col0 + tx * TN + j;
       if (o >= a.Co) continue;
       float v = acc[i][j] + (a.bias ? __ldg(a.bias + o) : 0.f);
-      float* p = a.out + r * a.ldo + o;
-      if (a.accumulate) v += *p;
-      *p = v;
+      TO* p = a.out + r * a.ldo + o;
+      if (a.accumulate) v += ldf(p);
+      stf(p, v);
     }
   }
 }
 
-inline void launch_tapgemm(const TapArgs& a, cudaStream_t s) {
+template <class TI, class TO>
+inline void launch_tapgemm(const TapArgs<TI, TO>& a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
   if (a.Co <= 16) {
     dim3 grid(ceil_div(a.rows, 128), ceil_div(a.Co, 16));
-    STGCN_LAUNCH((tapgemm_kernel<128, 16, 2, 4>), grid, NT, 0, s, a);
+    STGCN_LAUNCH((tapgemm_kernel<TI, TO, 128, 16, 2, 4>), grid, NT, 0, s, a);
   } else {
     dim3 grid(ceil_div(a.rows, 64), ceil_div(a.Co, 64));
-    STGCN_LAUNCH((tapgemm_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+    STGCN_LAUNCH((tapgemm_kernel<TI, TO, 64, 64, 4, 4>), grid, NT, 0, s, a);
   }
 }
 
 // ---- node contraction ---------------------------------------------------------------------
+template <class T>
 struct GsoArgs {
   const float* M;      // [N, N] row-major
   int trans;           // 0: out[h] = sum_i M[h,i] x[i];  1: uses M[i,h]
-  const float* in;     // [G, N, C]
-  const float* aux;    // [G, N, C] or nullptr
-  float* out;          // [G, N, C]
+  const T* in;         // [G, N, C]
+  const T* aux;        // [G, N, C] or nullptr
+  T* out;              // [G, N, C]
   int N, C;
   long long G;
   float alpha, beta;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(NT) gso_kernel(GsoArgs a) {
+template <class T, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) gso_kernel(GsoArgs<T> a) {
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -214,7 +224,7 @@ __global__ void __launch_bounds__(NT) gso_kernel(GsoArgs a) {
       int e = tid + j * NT;
       int n = e % BN, kk = e / BN;
       int i = k0 + kk;
-      Bs[kk][n] = (b_base[j] >= 0 && i < a.N) ? __ldg(a.in + b_base[j] + (long long)i * a.C) : 0.f;
+      Bs[kk][n] = (b_base[j] >= 0 && i < a.N) ? ldf(a.in + b_base[j] + (long long)i * a.C) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -243,22 +253,24 @@ __global__ void __launch_bounds__(NT) gso_kernel(GsoArgs a) {
       if (h >= a.N) continue;
       long long idx = (g * a.N + h) * a.C + c;
       float v = a.alpha * acc[i][j];
-      if (a.aux) v += a.beta * a.aux[idx];
-      a.out[idx] = v;
+      if (a.aux) v += a.beta * ldf(a.aux + idx);
+      stf(a.out + idx, v);
     }
   }
 }
 
-inline void launch_gso(const GsoArgs& a, cudaStream_t s) {
+template <class T>
+inline void launch_gso(const GsoArgs<T>& a, cudaStream_t s) {
   if (a.G == 0) return;
   dim3 grid(ceil_div(a.G * a.C, 64), ceil_div(a.N, 64));
-  STGCN_LAUNCH((gso_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+  STGCN_LAUNCH((gso_kernel<T, 64, 64, 4, 4>), grid, NT, 0, s, a);
 }
 
 // ---- weight gradient: dwt[(tap,c) | bias row][o] += sum_r in[row(r,tap), c] * dz[r, o] ----
+template <class T>
 struct WgradArgs {
-  const float* in;     // [*, Cin]
-  const float* dz;     // [rows, ldz]
+  const T* in;         // [*, Cin]
+  const T* dz;         // [rows, ldz]
   float* dwt;          // [ntaps*Cin (+1), Co], pre-zeroed, atomically accumulated
   long long rows;
   int Cin, Co, ntaps, ldz;
@@ -267,8 +279,8 @@ struct WgradArgs {
   RowMap map;
 };
 
-template <int BM, int BN, int TM, int TN>
-__global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
+template <class T, int BM, int BN, int TM, int TN>
+__global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -317,7 +329,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
           long long rem = r - b * TN_out;
           int ti = (int)(rem / a.map.N) + a.map.t_shift * a_tap[j];
           if (ti >= 0 && ti < a.map.T_in)
-            v = __ldg(a.in + (b * TN_in + rem + a_tap[j] * tap_step) * a.Cin + a_c[j]);
+            v = ldf(a.in + (b * TN_in + rem + a_tap[j] * tap_step) * a.Cin + a_c[j]);
         }
       }
       As[kk][m] = v;
@@ -328,7 +340,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
       int n = e % BN, kk = e / BN;
       long long r = k0 + kk;
       int o = col0 + n;
-      Bs[kk][n] = (r < r_end && o < a.Co) ? __ldg(a.dz + r * a.ldz + o) : 0.f;
+      Bs[kk][n] = (r < r_end && o < a.Co) ? ldf(a.dz + r * a.ldz + o) : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -357,7 +369,8 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs a) {
   }
 }
 
-inline void launch_wgrad(WgradArgs a, cudaStream_t s) {
+template <class T>
+inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
   int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
   int tiles;
@@ -376,48 +389,50 @@ inline void launch_wgrad(WgradArgs a, cudaStream_t s) {
   int chunks = ceil_div(a.rows, rpc);
   if (a.Co <= 16) {
     grid = dim3(ceil_div(Mtot, 128), ceil_div(a.Co, 16), chunks);
-    STGCN_LAUNCH((wgrad_kernel<128, 16, 2, 4>), grid, NT, 0, s, a);
+    STGCN_LAUNCH((wgrad_kernel<T, 128, 16, 2, 4>), grid, NT, 0, s, a);
   } else {
     grid = dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks);
-    STGCN_LAUNCH((wgrad_kernel<64, 64, 4, 4>), grid, NT, 0, s, a);
+    STGCN_LAUNCH((wgrad_kernel<T, 64, 64, 4, 4>), grid, NT, 0, s, a);
   }
 }
 
 // ---- gating / activation of the temporal conv (layers.py:92-115) ---------------------------
+template <class T>
 struct GateArgs {
-  const float* z;      // [rows, W]   pre-activation (W = 2*Cout for glu/gtu, Cout otherwise)
-  const float* xin;    // [*, Cin]    layer input (residual source), or nullptr when folded
-  const float* dy;     // bwd: [rows, Cout]
-  float* y;            // fwd: [rows, Cout]
-  float* dz;           // bwd: [rows, W]
+  const T* z;          // [rows, W]   pre-activation (W = 2*Cout for glu/gtu, Cout otherwise)
+  const T* xin;        // [*, Cin]    layer input (residual source), or nullptr when folded
+  const T* dy;         // bwd: [rows, Cout]
+  T* y;                // fwd: [rows, Cout]
+  T* dz;               // bwd: [rows, W]
   long long rows;
   int Cin, Cout, W, Kt;
   int T_out, T_in, N;
   int explicit_res;    // 1: residual = xin[(b,t+Kt-1,n), j] for j < Cin (zero pad / identity)
 };
 
-__device__ __forceinline__ float gate_residual(const GateArgs& a, long long r, int j) {
+template <class T>
+__device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r, int j) {
   if (!a.explicit_res || j >= a.Cin) return 0.f;
   long long TN_out = (long long)a.T_out * a.N;
   long long b = r / TN_out;
   long long rem = r - b * TN_out;
   long long row = b * a.T_in * a.N + rem + (long long)(a.Kt - 1) * a.N;
-  return __ldg(a.xin + row * a.Cin + j);
+  return ldf(a.xin + row * a.Cin + j);
 }
 
-template <int ACT>
-__global__ void gate_fwd_kernel(GateArgs a) {
+template <class T, int ACT>
+__global__ void gate_fwd_kernel(GateArgs<T> a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = idx / a.Cout;
   int j = (int)(idx - r * a.Cout);
   float res = gate_residual(a, r, j);
-  float p = a.z[r * a.W + j] + res;
+  float p = ldf(a.z + r * a.W + j) + res;
   float out;
   if (ACT == STGCN_ACT_GLU) {
-    out = p * sigmoidf_(a.z[r * a.W + a.Cout + j]);
+    out = p * sigmoidf_(ldf(a.z + r * a.W + a.Cout + j));
   } else if (ACT == STGCN_ACT_GTU) {
-    out = tanhf(p) * sigmoidf_(a.z[r * a.W + a.Cout + j]);
+    out = tanhf(p) * sigmoidf_(ldf(a.z + r * a.W + a.Cout + j));
   } else if (ACT == STGCN_ACT_RELU) {
     out = fmaxf(p, 0.f);
   } else if (ACT == STGCN_ACT_SILU) {
@@ -425,39 +440,40 @@ __global__ void gate_fwd_kernel(GateArgs a) {
   } else {
     out = p;
   }
-  a.y[idx] = out;
+  stf(a.y + idx, out);
 }
 
-template <int ACT>
-__global__ void gate_bwd_kernel(GateArgs a) {
+template <class T, int ACT>
+__global__ void gate_bwd_kernel(GateArgs<T> a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = idx / a.Cout;
   int j = (int)(idx - r * a.Cout);
   float res = gate_residual(a, r, j);
-  float p = a.z[r * a.W + j] + res;
-  float g = a.dy[idx];
+  float p = ldf(a.z + r * a.W + j) + res;
+  float g = ldf(a.dy + idx);
   if (ACT == STGCN_ACT_GLU) {
-    float s = sigmoidf_(a.z[r * a.W + a.Cout + j]);
-    a.dz[r * a.W + j] = g * s;
-    a.dz[r * a.W + a.Cout + j] = g * p * s * (1.f - s);
+    float s = sigmoidf_(ldf(a.z + r * a.W + a.Cout + j));
+    stf(a.dz + r * a.W + j, g * s);
+    stf(a.dz + r * a.W + a.Cout + j, g * p * s * (1.f - s));
   } else if (ACT == STGCN_ACT_GTU) {
-    float s = sigmoidf_(a.z[r * a.W + a.Cout + j]);
+    float s = sigmoidf_(ldf(a.z + r * a.W + a.Cout + j));
     float th = tanhf(p);
-    a.dz[r * a.W + j] = g * s * (1.f - th * th);
-    a.dz[r * a.W + a.Cout + j] = g * th * s * (1.f - s);
+    stf(a.dz + r * a.W + j, g * s * (1.f - th * th));
+    stf(a.dz + r * a.W + a.Cout + j, g * th * s * (1.f - s));
   } else if (ACT == STGCN_ACT_RELU) {
-    a.dz[r * a.W + j] = p > 0.f ? g : 0.f;
+    stf(a.dz + r * a.W + j, p > 0.f ? g : 0.f);
   } else if (ACT == STGCN_ACT_SILU) {
     float s = sigmoidf_(p);
-    a.dz[r * a.W + j] = g * (s + p * s * (1.f - s));
+    stf(a.dz + r * a.W + j, g * (s + p * s * (1.f - s)));
   } else {
-    a.dz[r * a.W + j] = g;
+    stf(a.dz + r * a.W + j, g);
   }
 }
 
 // dx[(b, t+Kt-1, n), j] += dz[(b,t,n), j]  for j < min(Cin, Cout)  (gradient of the explicit residual)
-__global__ void residual_add_kernel(const float* dz, float* dx, long long rows, int Cres, int W, int Cin, int Kt,
+template <class T>
+__global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres, int W, int Cin, int Kt,
                                     int T_out, int T_in, int N) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cres) return;
@@ -467,24 +483,25 @@ __global__ void residual_add_kernel(const float* dz, float* dx, long long rows, 
   long long b = r / TN_out;
   long long rem = r - b * TN_out;
   long long row = b * T_in * N + rem + (long long)(Kt - 1) * N;
-  dx[row * Cin + j] += dz[r * W + j];
+  stf(dx + row * Cin + j, ldf(dx + row * Cin + j) + ldf(dz + r * W + j));
 }
 
-template <int ACT>
-inline void launch_gate(bool bwd, const GateArgs& a, cudaStream_t s) {
+template <class T, int ACT>
+inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   long long n = a.rows * a.Cout;
   if (n == 0) return;
-  if (bwd) STGCN_LAUNCH((gate_bwd_kernel<ACT>), ceil_div(n, 256), 256, 0, s, a);
-  else     STGCN_LAUNCH((gate_fwd_kernel<ACT>), ceil_div(n, 256), 256, 0, s, a);
+  if (bwd) STGCN_LAUNCH((gate_bwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
+  else     STGCN_LAUNCH((gate_fwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
 }
 
-inline void launch_gate_any(int act, bool bwd, const GateArgs& a, cudaStream_t s) {
+template <class T>
+inline void launch_gate_any(int act, bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   switch (act) {
-    case STGCN_ACT_GLU:  launch_gate<STGCN_ACT_GLU>(bwd, a, s); break;
-    case STGCN_ACT_GTU:  launch_gate<STGCN_ACT_GTU>(bwd, a, s); break;
-    case STGCN_ACT_RELU: launch_gate<STGCN_ACT_RELU>(bwd, a, s); break;
-    case STGCN_ACT_SILU: launch_gate<STGCN_ACT_SILU>(bwd, a, s); break;
-    case STGCN_ACT_LINEAR: launch_gate<STGCN_ACT_LINEAR>(bwd, a, s); break;
+    case STGCN_ACT_GLU:  launch_gate<T, STGCN_ACT_GLU>(bwd, a, s); break;
+    case STGCN_ACT_GTU:  launch_gate<T, STGCN_ACT_GTU>(bwd, a, s); break;
+    case STGCN_ACT_RELU: launch_gate<T, STGCN_ACT_RELU>(bwd, a, s); break;
+    case STGCN_ACT_SILU: launch_gate<T, STGCN_ACT_SILU>(bwd, a, s); break;
+    case STGCN_ACT_LINEAR: launch_gate<T, STGCN_ACT_LINEAR>(bwd, a, s); break;
     default: throw Error(STGCN_E_UNSUPPORTED, "activation not implemented");
   }
 }
@@ -519,54 +536,69 @@ __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, i
 }
 
 // out[r, j] = j < Cin ? in[r*ldi + j] : 0   for j < Cout   (zero-pad or column slice copy)
-__global__ void copy_cols_kernel(const float* in, float* out, long long rows, int Cin, int ldi, int Cout, int accumulate) {
+template <class T>
+__global__ void copy_cols_kernel(const T* in, T* out, long long rows, int Cin, int ldi, int Cout, int accumulate) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cout) return;
   long long r = idx / Cout;
   int j = (int)(idx - r * Cout);
-  float v = j < Cin ? in[r * ldi + j] : 0.f;
-  if (accumulate) out[idx] += v; else out[idx] = v;
+  float v = j < Cin ? ldf(in + r * ldi + j) : 0.f;
+  if (accumulate) v += ldf(out + idx);
+  stf(out + idx, v);
 }
-inline void launch_copy_cols(const float* in, float* out, long long rows, int Cin, int ldi, int Cout, int accumulate,
+template <class T>
+inline void launch_copy_cols(const T* in, T* out, long long rows, int Cin, int ldi, int Cout, int accumulate,
                              cudaStream_t s) {
   if (rows * Cout == 0) return;
-  STGCN_LAUNCH(copy_cols_kernel, ceil_div(rows * Cout, 256), 256, 0, s, in, out, rows, Cin, ldi, Cout, accumulate);
+  STGCN_LAUNCH(copy_cols_kernel<T>, ceil_div(rows * Cout, 256), 256, 0, s, in, out, rows, Cin, ldi, Cout, accumulate);
+}
+
+// dtype conversion of an activation tensor
+template <class TI, class TO>
+__global__ void convert_kernel(const TI* in, TO* out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) stf(out + i, ldf(in + i));
 }
 
 // y = relu?(g + a)
-__global__ void add_relu_kernel(const float* g, const float* a, float* y, long long n, int relu) {
+template <class T>
+__global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int relu) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = g[i] + (a ? a[i] : 0.f);
-  y[i] = relu ? fmaxf(v, 0.f) : v;
+  float v = ldf(g + i) + (a ? ldf(a + i) : 0.f);
+  stf(y + i, relu ? fmaxf(v, 0.f) : v);
 }
 // dg = relu ? dy * (y > 0) : dy
-__global__ void relu_bwd_kernel(const float* dy, const float* y, float* dg, long long n, int relu) {
+template <class T>
+__global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int relu) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  dg[i] = (!relu || y[i] > 0.f) ? dy[i] : 0.f;
+  stf(dg + i, (!relu || ldf(y + i) > 0.f) ? ldf(dy + i) : 0.f);
 }
 // y += alpha * x
-__global__ void axpy_kernel(float alpha, const float* x, float* y, long long n) {
+template <class T>
+__global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  y[i] += alpha * x[i];
+  stf(y + i, ldf(y + i) + alpha * ldf(x + i));
 }
 // y = relu(x), with optional dropout; and its backward
-__global__ void relu_dropout_fwd_kernel(const float* x, float* y, long long n, int training, float p, uint64_t seed) {
+template <class T>
+__global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int training, float p, uint64_t seed) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = fmaxf(x[i], 0.f);
+  float v = fmaxf(ldf(x + i), 0.f);
   if (training && p > 0.f) v = dropout_keep(seed, (uint64_t)i, p) ? v / (1.f - p) : 0.f;
-  y[i] = v;
+  stf(y + i, v);
 }
-__global__ void relu_dropout_bwd_kernel(const float* dy, const float* x, float* dx, long long n, int training, float p,
+template <class T>
+__global__ void relu_dropout_bwd_kernel(const T* dy, const T* x, T* dx, long long n, int training, float p,
                                         uint64_t seed) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float g = x[i] > 0.f ? dy[i] : 0.f;
+  float g = ldf(x + i) > 0.f ? ldf(dy + i) : 0.f;
   if (training && p > 0.f) g = dropout_keep(seed, (uint64_t)i, p) ? g / (1.f - p) : 0.f;
-  dx[i] = g;
+  stf(dx + i, g);
 }
 
 // ---- LayerNorm over the joint (N, C) axes of each (b, t) group (layers.py:246,255) ----------
@@ -588,60 +620,63 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-__global__ void __launch_bounds__(512) ln_fwd_kernel(const float* x, const float* w, const float* b, float* y,
+template <class T>
+__global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w, const float* b, T* y,
                                                      float* mean, float* rstd, int M, float eps, int training,
                                                      float p, uint64_t seed) {
   __shared__ float red[32];
   long long g = blockIdx.x;
-  const float* xp = x + g * M;
+  const T* xp = x + g * M;
   float s = 0.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) s += xp[i];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) s += ldf(xp + i);
   float mu = block_sum(s, red) / M;
   float q = 0.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) { float d = xp[i] - mu; q += d * d; }
+  for (int i = threadIdx.x; i < M; i += blockDim.x) { float d = ldf(xp + i) - mu; q += d * d; }
   float var = block_sum(q, red) / M;
   float rs = rsqrtf(var + eps);
   if (threadIdx.x == 0) { mean[g] = mu; rstd[g] = rs; }
   bool drop = training && p > 0.f;
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float v = (xp[i] - mu) * rs * w[i] + b[i];
+    float v = (ldf(xp + i) - mu) * rs * w[i] + b[i];
     if (drop) v = dropout_keep(seed, (uint64_t)(g * M + i), p) ? v * keep_scale : 0.f;
-    y[g * M + i] = v;
+    stf(y + g * M + i, v);
   }
 }
 
-__global__ void __launch_bounds__(512) ln_bwd_kernel(const float* x, const float* dy, const float* w, const float* mean,
-                                                     const float* rstd, float* dx, int M, int training, float p,
+template <class T>
+__global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
+                                                     const float* rstd, T* dx, int M, int training, float p,
                                                      uint64_t seed) {
   __shared__ float red[32];
   long long g = blockIdx.x;
-  const float* xp = x + g * M;
-  const float* dp = dy + g * M;
+  const T* xp = x + g * M;
+  const T* dp = dy + g * M;
   float mu = mean[g], rs = rstd[g];
   bool drop = training && p > 0.f;
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float d = dp[i];
+    float d = ldf(dp + i);
     if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
     float gi = d * w[i];
-    float xh = (xp[i] - mu) * rs;
+    float xh = (ldf(xp + i) - mu) * rs;
     s1 += gi; s2 += gi * xh;
   }
   s1 = block_sum(s1, red) / M;
   s2 = block_sum(s2, red) / M;
   for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float d = dp[i];
+    float d = ldf(dp + i);
     if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
     float gi = d * w[i];
-    float xh = (xp[i] - mu) * rs;
-    dx[g * M + i] = rs * (gi - s1 - xh * s2);
+    float xh = (ldf(xp + i) - mu) * rs;
+    stf(dx + g * M + i, rs * (gi - s1 - xh * s2));
   }
 }
 
 // dw[i] += sum_g dy'[g,i] * xhat[g,i];  db[i] += sum_g dy'[g,i]   (pre-zeroed, atomics over group chunks)
-__global__ void ln_param_grad_kernel(const float* x, const float* dy, const float* mean, const float* rstd, float* dw,
+template <class T>
+__global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean, const float* rstd, float* dw,
                                      float* db, int M, long long G, int groups_per_cta, int training, float p,
                                      uint64_t seed) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -652,9 +687,9 @@ __global__ void ln_param_grad_kernel(const float* x, const float* dy, const floa
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   float aw = 0.f, ab = 0.f;
   for (long long g = g0; g < g1; ++g) {
-    float d = dy[g * M + i];
+    float d = ldf(dy + g * M + i);
     if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
-    aw += d * (x[g * M + i] - mean[g]) * rstd[g];
+    aw += d * (ldf(x + g * M + i) - mean[g]) * rstd[g];
     ab += d;
   }
   if (dw) atomicAdd(dw + i, aw);

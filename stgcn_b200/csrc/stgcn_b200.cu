@@ -1,5 +1,5 @@
 // stgcn_b200.cu -- C-ABI exports of libstgcn_b200.so (see include/stgcn_b200.h).
-#include "ops_fp32.cuh"
+#include "ops.cuh"
 #include "umma_selftest.cuh"
 
 namespace stgcn {
@@ -13,9 +13,18 @@ using namespace stgcn;
 
 namespace {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-inline void need_fp32(int precision) {
-  STGCN_CHECK(precision == STGCN_PREC_FP32, STGCN_E_UNSUPPORTED, "only STGCN_PREC_FP32 is implemented for this entry point");
+inline void need_prec(int precision) {
+  STGCN_CHECK(precision == STGCN_PREC_FP32 || precision == STGCN_PREC_BF16, STGCN_E_UNSUPPORTED, "unknown precision mode");
 }
+using bf16 = __nv_bfloat16;
+// run `body` with T bound to the activation storage type of this precision mode
+#define STGCN_DISPATCH(precision, ...)                                         \
+  do {                                                                         \
+    need_prec(precision);                                                      \
+    if ((precision) == STGCN_PREC_FP32) { using T = float; __VA_ARGS__; }      \
+    else { using T = bf16; __VA_ARGS__; }                                      \
+  } while (0)
+inline size_t elem_size(int precision) { return precision == STGCN_PREC_FP32 ? sizeof(float) : sizeof(bf16); }
 inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
 }  // namespace
 
@@ -70,14 +79,13 @@ int stgcn_profile_end(char* buf, size_t cap, size_t* needed) {
 int stgcn_tconv_sizes(const stgcn_tconv_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    need_fp32(d->precision);
     Arena ws(nullptr, 0);
-    fp32::Ctx c{ws, nullptr};
+    ops::Ctx c{ws, nullptr};
     stgcn_tconv_params p{};
     stgcn_tconv_grads g{};
-    fp32::tconv_fwd(*d, nullptr, p, nullptr, nullptr, c);
-    fp32::tconv_bwd(*d, nullptr, nullptr, nullptr, p, g, nullptr, c);
-    if (saved_bytes) *saved_bytes = Arena::align_up(fp32::tconv_saved_floats(*d) * sizeof(float));
+    STGCN_DISPATCH(d->precision, ops::tconv_fwd<T>(*d, nullptr, p, nullptr, nullptr, c);
+                   ops::tconv_bwd<T>(*d, nullptr, nullptr, nullptr, p, g, nullptr, c));
+    if (saved_bytes) *saved_bytes = Arena::align_up(ops::tconv_saved_elems(*d) * elem_size(d->precision));
     if (workspace_bytes) *workspace_bytes = ws.peak;
   });
 }
@@ -85,9 +93,8 @@ int stgcn_tconv_fwd(const stgcn_tconv_desc* d, const void* x, const stgcn_tconv_
                     void* workspace, size_t workspace_bytes, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes);
-    fp32::tconv_fwd(*d, (const float*)x, *p, (float*)y, (float*)saved, fp32::Ctx{ws, as_stream(stream)});
+    STGCN_DISPATCH(d->precision, ops::tconv_fwd<T>(*d, (const T*)x, *p, (T*)y, (T*)saved, ops::Ctx{ws, as_stream(stream)}));
   });
 }
 int stgcn_tconv_bwd(const stgcn_tconv_desc* d, const void* x, const void* saved, const void* dy,
@@ -95,10 +102,9 @@ int stgcn_tconv_bwd(const stgcn_tconv_desc* d, const void* x, const void* saved,
                     size_t workspace_bytes, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes);
-    fp32::tconv_bwd(*d, (const float*)x, (const float*)saved, (const float*)dy, *p, *g, (float*)dx,
-                    fp32::Ctx{ws, as_stream(stream)});
+    STGCN_DISPATCH(d->precision, ops::tconv_bwd<T>(*d, (const T*)x, (const T*)saved, (const T*)dy, *p, *g, (T*)dx,
+                                                   ops::Ctx{ws, as_stream(stream)}));
   });
 }
 
@@ -107,16 +113,14 @@ int stgcn_tconv_bwd(const stgcn_tconv_desc* d, const void* x, const void* saved,
 int stgcn_gconv_sizes(const stgcn_gconv_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    need_fp32(d->precision);
     Arena ws(nullptr, 0);
-    fp32::Ctx c{ws, nullptr};
+    ops::Ctx c{ws, nullptr};
     stgcn_gconv_params p{};
     stgcn_gconv_grads g{};
-    fp32::gconv_fwd(*d, nullptr, p, nullptr, nullptr, c);
-    fp32::gconv_bwd(*d, nullptr, nullptr, nullptr, nullptr, p, g, nullptr, c);
     Arena sv(nullptr, 0);
-    sv.take<float>(fp32::gconv_saved_floats(*d));
-    sv.take<float>((size_t)d->B * d->T * d->N * d->c_out);
+    STGCN_DISPATCH(d->precision, ops::gconv_fwd<T>(*d, nullptr, p, nullptr, nullptr, c);
+                   ops::gconv_bwd<T>(*d, nullptr, nullptr, nullptr, nullptr, p, g, nullptr, c);
+                   sv.take<T>(ops::gconv_saved_elems(*d)); sv.take<T>((size_t)d->B * d->T * d->N * d->c_out));
     if (saved_bytes) *saved_bytes = sv.peak;
     if (workspace_bytes) *workspace_bytes = ws.peak;
   });
@@ -125,14 +129,12 @@ int stgcn_gconv_fwd(const stgcn_gconv_desc* d, const void* x, const stgcn_gconv_
                     void* workspace, size_t workspace_bytes, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes);
     Arena sv(saved, (size_t)-1);
-    float* stack = sv.take<float>(fp32::gconv_saved_floats(*d));
     size_t ny = (size_t)d->B * d->T * d->N * d->c_out;
-    float* ycopy = sv.take<float>(ny);
-    fp32::gconv_fwd(*d, (const float*)x, *p, (float*)y, stack, fp32::Ctx{ws, as_stream(stream)});
-    fp32::copy(ycopy, (const float*)y, ny, as_stream(stream));
+    STGCN_DISPATCH(d->precision, T* stack = sv.take<T>(ops::gconv_saved_elems(*d)); T* ycopy = sv.take<T>(ny);
+                   ops::gconv_fwd<T>(*d, (const T*)x, *p, (T*)y, stack, ops::Ctx{ws, as_stream(stream)});
+                   ops::copy<T>(ycopy, (const T*)y, ny, as_stream(stream)));
   });
 }
 int stgcn_gconv_bwd(const stgcn_gconv_desc* d, const void* x, const void* saved, const void* dy,
@@ -140,13 +142,12 @@ int stgcn_gconv_bwd(const stgcn_gconv_desc* d, const void* x, const void* saved,
                     size_t workspace_bytes, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes);
     Arena sv(const_cast<void*>(saved), (size_t)-1);
-    float* stack = sv.take<float>(fp32::gconv_saved_floats(*d));
-    float* ycopy = sv.take<float>((size_t)d->B * d->T * d->N * d->c_out);
-    fp32::gconv_bwd(*d, (const float*)x, stack, ycopy, (const float*)dy, *p, *g, (float*)dx,
-                    fp32::Ctx{ws, as_stream(stream)});
+    STGCN_DISPATCH(d->precision, T* stack = sv.take<T>(ops::gconv_saved_elems(*d));
+                   T* ycopy = sv.take<T>((size_t)d->B * d->T * d->N * d->c_out);
+                   ops::gconv_bwd<T>(*d, (const T*)x, stack, ycopy, (const T*)dy, *p, *g, (T*)dx,
+                                     ops::Ctx{ws, as_stream(stream)}));
   });
 }
 
@@ -154,9 +155,9 @@ int stgcn_gconv_bwd(const stgcn_gconv_desc* d, const void* x, const void* saved,
 int stgcn_lnorm_sizes(const stgcn_lnorm_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    need_fp32(d->precision);
-    fp32::lnorm_check(*d);
-    if (saved_bytes) *saved_bytes = Arena::align_up(fp32::lnorm_saved_floats(*d) * sizeof(float));
+    need_prec(d->precision);
+    ops::lnorm_check(*d);
+    if (saved_bytes) *saved_bytes = Arena::align_up(ops::lnorm_saved_floats(*d) * sizeof(float));
     if (workspace_bytes) *workspace_bytes = 256;
   });
 }
@@ -164,8 +165,8 @@ int stgcn_lnorm_fwd(const stgcn_lnorm_desc* d, const void* x, const float* w, co
                     uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && x && w && b && y && saved, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
-    fp32::lnorm_fwd(*d, (const float*)x, w, b, (float*)y, (float*)saved, dropout_seed, as_stream(stream), false);
+    STGCN_DISPATCH(d->precision, ops::lnorm_fwd<T>(*d, (const T*)x, w, b, (T*)y, (float*)saved, dropout_seed,
+                                                   as_stream(stream), false));
   });
 }
 int stgcn_lnorm_bwd(const stgcn_lnorm_desc* d, const void* x, const void* saved, const void* dy, const float* w,
@@ -174,9 +175,8 @@ int stgcn_lnorm_bwd(const stgcn_lnorm_desc* d, const void* x, const void* saved,
   (void)workspace; (void)workspace_bytes;
   return guarded([&] {
     STGCN_CHECK(d && x && saved && dy && w, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
-    fp32::lnorm_bwd(*d, (const float*)x, (const float*)saved, (const float*)dy, w, dw, db, (float*)dx, dropout_seed,
-                    as_stream(stream), false);
+    STGCN_DISPATCH(d->precision, ops::lnorm_bwd<T>(*d, (const T*)x, (const float*)saved, (const T*)dy, w, dw, db, (T*)dx,
+                                                   dropout_seed, as_stream(stream), false));
   });
 }
 
@@ -184,13 +184,12 @@ int stgcn_lnorm_bwd(const stgcn_lnorm_desc* d, const void* x, const void* saved,
 int stgcn_stblock_sizes(const stgcn_stblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    need_fp32(d->precision);
     Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
-    fp32::Ctx c{ws, nullptr};
+    ops::Ctx c{ws, nullptr};
     stgcn_stblock_params p{};
     stgcn_stblock_grads g{};
-    fp32::stblock_fwd(*d, nullptr, p, nullptr, sv, c, 0);
-    fp32::stblock_bwd(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0);
+    STGCN_DISPATCH(d->precision, ops::stblock_fwd<T>(*d, nullptr, p, nullptr, sv, c, 0);
+                   ops::stblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0));
     if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
     if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
   });
@@ -199,9 +198,9 @@ int stgcn_stblock_fwd(const stgcn_stblock_desc* d, const void* x, const stgcn_st
                       void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
-    fp32::stblock_fwd(*d, (const float*)x, *p, (float*)y, sv, fp32::Ctx{ws, as_stream(stream)}, dropout_seed);
+    STGCN_DISPATCH(d->precision,
+                   ops::stblock_fwd<T>(*d, (const T*)x, *p, (T*)y, sv, ops::Ctx{ws, as_stream(stream)}, dropout_seed));
   });
 }
 int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* saved, const void* dy,
@@ -209,10 +208,9 @@ int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* sa
                       size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
-    fp32::stblock_bwd(*d, (const float*)x, sv, (const float*)dy, *p, *g, (float*)dx, fp32::Ctx{ws, as_stream(stream)},
-                      dropout_seed);
+    STGCN_DISPATCH(d->precision, ops::stblock_bwd<T>(*d, (const T*)x, sv, (const T*)dy, *p, *g, (T*)dx,
+                                                     ops::Ctx{ws, as_stream(stream)}, dropout_seed));
   });
 }
 
@@ -220,13 +218,12 @@ int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* sa
 int stgcn_outblock_sizes(const stgcn_outblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    need_fp32(d->precision);
     Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
-    fp32::Ctx c{ws, nullptr};
+    ops::Ctx c{ws, nullptr};
     stgcn_outblock_params p{};
     stgcn_outblock_grads g{};
-    fp32::outblock_fwd(*d, nullptr, p, nullptr, sv, c, 0);
-    fp32::outblock_bwd(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0);
+    STGCN_DISPATCH(d->precision, ops::outblock_fwd<T>(*d, nullptr, p, nullptr, sv, c, 0);
+                   ops::outblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0));
     if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
     if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
   });
@@ -235,9 +232,9 @@ int stgcn_outblock_fwd(const stgcn_outblock_desc* d, const void* x, const stgcn_
                        void* saved, void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
-    fp32::outblock_fwd(*d, (const float*)x, *p, (float*)y, sv, fp32::Ctx{ws, as_stream(stream)}, dropout_seed);
+    STGCN_DISPATCH(d->precision, ops::outblock_fwd<T>(*d, (const T*)x, *p, (float*)y, sv,
+                                                      ops::Ctx{ws, as_stream(stream)}, dropout_seed));
   });
 }
 int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* saved, const void* dy,
@@ -245,10 +242,9 @@ int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* 
                        size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    need_fp32(d->precision);
     Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
-    fp32::outblock_bwd(*d, (const float*)x, sv, (const float*)dy, *p, *g, (float*)dx, fp32::Ctx{ws, as_stream(stream)},
-                       dropout_seed);
+    STGCN_DISPATCH(d->precision, ops::outblock_bwd<T>(*d, (const T*)x, sv, (const float*)dy, *p, *g, (T*)dx,
+                                                      ops::Ctx{ws, as_stream(stream)}, dropout_seed));
   });
 }
 

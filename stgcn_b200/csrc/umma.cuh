@@ -41,8 +41,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+#ifndef STGCN_MBAR_SPIN_LIMIT
+#define STGCN_MBAR_SPIN_LIMIT (1u << 26)
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > STGCN_MBAR_SPIN_LIMIT) {
+      printf("stgcn: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -77,18 +77,24 @@ def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _act_dtype() -> torch.dtype:
+    """Storage type of activations crossing the C ABI in the current precision mode."""
+    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+
+
 def _require_cuda(x: torch.Tensor, what: str) -> None:
     if not x.is_cuda:
         raise RuntimeError(f"stgcn_b200.{what}: expected a CUDA tensor (this framework has no CPU path), got {x.device}")
-    if x.dtype != torch.float32:
-        raise RuntimeError(f"stgcn_b200.{what}: expected float32 input, got {x.dtype}")
+    if x.dtype not in (torch.float32, _act_dtype()):
+        raise RuntimeError(f"stgcn_b200.{what}: expected float32 (or {_act_dtype()}) input, got {x.dtype}")
     if x.dim() != 4:
         raise RuntimeError(f"stgcn_b200.{what}: expected a 4-D (B, C, T, N) tensor, got shape {tuple(x.shape)}")
 
 
 def _channels_last(x: torch.Tensor) -> torch.Tensor:
-    """(B,C,T,N) tensor -> contiguous (B,T,N,C) buffer (no copy if x already is a permuted view of one)."""
-    return x.permute(0, 2, 3, 1).contiguous()
+    """(B,C,T,N) tensor -> contiguous (B,T,N,C) buffer in the activation dtype of the current precision mode
+    (no copy if x already is a permuted view of such a buffer)."""
+    return x.permute(0, 2, 3, 1).to(_act_dtype()).contiguous()
 
 
 def _as_bctn(y_cl: torch.Tensor) -> torch.Tensor:
@@ -126,7 +132,7 @@ class _TconvFn(torch.autograd.Function):
         dev = x_cl.device
         saved = torch.empty(sv_bytes, dtype=torch.uint8, device=dev)
         ws = _workspace(dev, ws_bytes)
-        y = torch.empty((B, T - Kt + 1, N, c_out), dtype=torch.float32, device=dev)
+        y = torch.empty((B, T - Kt + 1, N, c_out), dtype=x_cl.dtype, device=dev)
         params = L.TconvParams(_ptr(conv_w), _ptr(conv_b), _ptr(align_w), _ptr(align_b))
         L.check(lib.stgcn_tconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _stream(dev)))
@@ -147,7 +153,7 @@ class _TconvFn(torch.autograd.Function):
         ws = _workspace(dev, ws_bytes)
         params = L.TconvParams(_ptr(conv_w), _ptr(conv_b), _ptr(align_w), _ptr(align_b))
         grads = L.TconvGrads(*[_ptr(t) for t in g])
-        dy = dy.contiguous()
+        dy = dy.to(x_cl.dtype).contiguous()
         L.check(lib.stgcn_tconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
                                     C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
         return (dx, None, *g)
@@ -163,7 +169,7 @@ class _GconvFn(torch.autograd.Function):
         dev = x_cl.device
         saved = torch.empty(sv_bytes, dtype=torch.uint8, device=dev)
         ws = _workspace(dev, ws_bytes)
-        y = torch.empty((B, T, N, c_out), dtype=torch.float32, device=dev)
+        y = torch.empty((B, T, N, c_out), dtype=x_cl.dtype, device=dev)
         params = L.GconvParams(_ptr(align_w), _ptr(align_b), _ptr(w), _ptr(b), _ptr(gso))
         L.check(lib.stgcn_gconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
                                     ws.data_ptr(), ws.numel(), _stream(dev)))
@@ -183,7 +189,7 @@ class _GconvFn(torch.autograd.Function):
         ws = _workspace(dev, ws_bytes)
         params = L.GconvParams(_ptr(align_w), _ptr(align_b), _ptr(w), _ptr(b), _ptr(gso))
         grads = L.GconvGrads(*[_ptr(t) for t in g])
-        dy = dy.contiguous()
+        dy = dy.to(x_cl.dtype).contiguous()
         L.check(lib.stgcn_gconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
                                     C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
         return (dx, None, None, *g)
@@ -215,7 +221,7 @@ class _LnormFn(torch.autograd.Function):
         dx = torch.empty_like(x_cl) if need[0] else None
         dw = torch.empty_like(w) if need[2] else None
         db = torch.empty_like(w) if need[3] else None
-        dy = dy.contiguous()
+        dy = dy.to(x_cl.dtype).contiguous()
         L.check(lib.stgcn_lnorm_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(), w.data_ptr(),
                                     _ptr(dw), _ptr(db), _ptr(dx), None, 0, ctx.seed, _stream(dev)))
         return dx, None, dw, db
@@ -242,7 +248,7 @@ class _STBlockFn(torch.autograd.Function):
         dev = x_cl.device
         saved = torch.empty(sv_bytes, dtype=torch.uint8, device=dev)
         ws = _workspace(dev, ws_bytes)
-        y = torch.empty((B, T - 2 * (Kt - 1), N, c3), dtype=torch.float32, device=dev)
+        y = torch.empty((B, T - 2 * (Kt - 1), N, c3), dtype=x_cl.dtype, device=dev)
         seed = _next_seed() if (training and p_drop > 0) else 0
         cparams = _STBlockFn._pack(params, gso)
         L.check(lib.stgcn_stblock_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(cparams), y.data_ptr(), saved.data_ptr(),
@@ -270,7 +276,7 @@ class _STBlockFn(torch.autograd.Function):
         gp = [_ptr(t) for t in g]
         grads = L.StblockGrads(L.TconvGrads(*gp[0:4]), L.GconvGrads(*gp[4:8]), L.TconvGrads(*gp[8:12]), gp[12], gp[13])
         cparams = _STBlockFn._pack(params, gso)
-        dy = dy.contiguous()
+        dy = dy.to(x_cl.dtype).contiguous()
         L.check(lib.stgcn_stblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
                                       C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
                                       _stream(dev)))
@@ -317,7 +323,7 @@ class _OutBlockFn(torch.autograd.Function):
         gp = [_ptr(t) for t in g]
         grads = L.OutblockGrads(L.TconvGrads(*gp[0:4]), *gp[4:10])
         cparams = _OutBlockFn._pack(params)
-        dy = dy.contiguous()
+        dy = dy.float().contiguous()
         L.check(lib.stgcn_outblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
                                        C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
                                        _stream(dev)))
