@@ -3,7 +3,10 @@
 // caller-provided arenas, then enqueues the SIMT kernels of simt_kernels.cuh on the stream.
 // "dry" arenas (null base) only measure: the *_sizes entry points run the same code paths.
 #pragma once
+#include <type_traits>
+
 #include "simt_kernels.cuh"
+#include "umma_tap.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -60,8 +63,33 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
   ScopedMark sm(c.ws);
   float* wt = c.ws.take<float>((size_t)d.Kt * d.c_in * g.W);
   float* bias = c.ws.take<float>(g.W);
+  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * d.c_in * g.W : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.conv_w && p.conv_b, STGCN_E_INVALID, "tconv: missing conv weight/bias");
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    // ---- tcgen05 path: conv + bias + gate/residual fused in one kernel (umma_tap.cuh)
+    umma::TapProblem q{};
+    q.in = x; q.w = wbf; q.bias = bias; q.B = d.B; q.N = d.N; q.T_src = d.T; q.T_out = g.T_out; q.Kt = d.Kt; q.t0 = 0;
+    q.Cin = d.c_in; q.Co = g.W; q.epi = umma::EPI_GATE; q.act = d.act; q.Cout = d.c_out;
+    const bool explicit_res = !(g.folded || g.linear);
+    q.aux = explicit_res ? x : nullptr; q.aux_dt = d.Kt - 1; q.T_aux = d.T; q.C_aux = d.c_in;
+    q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
+    q.out = y; q.ld_out = d.c_out; q.out_z = z_saved;
+    if (d.B > 0 && umma::tap_supported(q)) {
+      // window-ordered K-major weights: wt[(j*W + o)*c_in + c] = conv_w[o][c][j] (+ align fold on tap Kt-1)
+      launch_gather3(p.conv_w, wt, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
+      launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
+      if (g.folded) {
+        STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "tconv: c_in > c_out needs align conv parameters");
+        launch_gather3(p.align_w, wt + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
+        launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
+      }
+      long long nw = (long long)d.Kt * g.W * d.c_in;
+      STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wt, wbf, nw);
+      umma::launch_tap(q, c.stream);
+      return;
+    }
+  }
   // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]
   launch_gather3(p.conv_w, wt, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
   launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
@@ -92,6 +120,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   T* dz = c.ws.take<T>((size_t)g.rows_out * g.W);
   float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
   float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
+  simt::bf16* wdbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
   if (c.dry()) return;
   GateArgs<T> ga{};
   ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
@@ -112,6 +141,28 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
       if (gr.align_w)
         launch_gather3(dwt, gr.align_w, 1, d.c_out, d.c_in, (long long)(d.Kt - 1) * d.c_in * g.W, 0, 1, g.W, 0, c.stream);
       if (gr.align_b) launch_gather3(dwt, gr.align_b, 1, 1, d.c_out, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
+    }
+  }
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (dx) {
+      umma::TapProblem q{};
+      q.in = dz; q.w = wdbf; q.bias = nullptr; q.B = d.B; q.N = d.N; q.T_src = g.T_out; q.T_out = d.T; q.Kt = d.Kt;
+      q.t0 = -(d.Kt - 1); q.Cin = g.W; q.Co = d.c_in; q.epi = umma::EPI_LINEAR; q.act = 0; q.Cout = 0;
+      const bool explicit_res = !(g.folded || g.linear);
+      q.aux = explicit_res ? dz : nullptr; q.aux_dt = -(d.Kt - 1); q.T_aux = g.T_out; q.C_aux = g.W;
+      q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
+      q.out = dx; q.ld_out = d.c_in; q.out_z = nullptr;
+      if (d.B > 0 && umma::tap_supported(q)) {
+        // window-ordered weights of the transposed conv: wd[(j*c_in + c)*W + o] = conv_w[o][c][Kt-1-j]
+        launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
+        if (g.folded)   // align conv acts at tap Kt-1, i.e. window position j = 0
+          STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, c.stream, wd, g.W,
+                       p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
+        long long nw = (long long)d.Kt * g.W * d.c_in;
+        STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wd, wdbf, nw);
+        umma::launch_tap(q, c.stream);
+        dx = nullptr;   // done
+      }
     }
   }
   if (dx) {

@@ -1,0 +1,350 @@
+// umma_tap.cuh -- tcgen05 "tap GEMM" for the bf16 path: the gated temporal convolution
+// (layers.py:87-120), its data gradient, and 1-tap linear maps, as one persistent warp-specialised kernel.
+//
+//   out[(b, t_o, n), o] = bias[o] + sum_{j<Kt} sum_{c<Cin} in[(b, t_o + j + t0, n), c] * W_j[o, c]   (+ aux)
+//
+// Work item = (sample b, tile of 128 vertices).  For one item the CTA streams the time slices
+// in[b, ti, n0:n0+128, :] (ti = 0..T_src-1) through a ring of shared-memory stages with TMA
+// (4-D tensor map over the channels-last (B,T,N,C) tensor; vertices past N are zero-filled by TMA) and
+// slides a Kt-wide window over them: output step t_o accumulates Kt x (Cin/16) tcgen05.mma
+// (M = 128 vertices, N = CoT output channels, K = 16) into a TMEM accumulator, so every input
+// byte is read from L2 once and reused by Kt taps.  Weights W_j (bf16, K-major) stay resident in
+// shared memory for the life of the CTA.  Two TMEM accumulators are ping-ponged between the MMA
+// issuer and the epilogue warps.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
+// lane) + TMEM allocation, warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31: one
+// vertex row per thread).
+//
+// Epilogues:
+//   EPI_LINEAR: out = acc + bias (+ aux rows: residual / residual-gradient), stored bf16
+//   EPI_GATE  : z = acc + bias stored (saved for backward); h = act(z, residual) stored
+#pragma once
+#include "umma.cuh"
+#include "simt_kernels.cuh"
+
+namespace stgcn {
+namespace umma {
+
+using simt::bf16;
+enum { EPI_LINEAR = 0, EPI_GATE = 1 };
+constexpr int kMaxStages = 8;
+constexpr int kTapThreads = 192;
+
+struct TapParams {
+  int B, N, T_src, T_out, Kt, t0;
+  int Cin, KB, nKB, CoT, S;
+  uint32_t swz, sbo;          // operand swizzle mode and 8-row group stride (bytes)
+  uint32_t tile_bytes, w_bytes;
+  int act, Cout, W;           // gate: output channels and pre-activation width
+  const float* bias;          // [Co] fp32 or nullptr
+  const bf16* aux;            // [B, T_aux, N, C_aux] or nullptr
+  int aux_dt, T_aux, C_aux, aux_cols;
+  bf16* out;                  // linear: [rows_out, ld_out] ; gate: h [rows_out, Cout]
+  int ld_out, co_valid;
+  bf16* out_z;                // gate: z [rows_out, W]
+  int n_items, n_node_tiles;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void store16_bf16(bf16* dst, const float* v) {
+  uint4 a, b;
+  a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);  a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
+  b.x = pack_bf16x2(v[8], v[9]);  b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+  reinterpret_cast<uint4*>(dst)[0] = a;
+  reinterpret_cast<uint4*>(dst)[1] = b;
+}
+__device__ __forceinline__ void load16_bf16(const bf16* src, float* v) {
+  uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
+  const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(kTapThreads, 1)
+umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TapParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* w_s = smem;
+  uint8_t* ring = smem + p.w_bytes;       // w_bytes is a multiple of 1024
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co0 = blockIdx.y * p.CoT;
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * p.CoT) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&wfull, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      tma_prefetch_desc(&tmX);
+      tma_prefetch_desc(&tmW);
+      mbar_arrive_expect_tx(&wfull, p.w_bytes);
+      const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2;
+      for (int j = 0; j < p.Kt; ++j)
+        for (int kb = 0; kb < p.nKB; ++kb) tma_load_3d(w_s + (size_t)(j * p.nKB + kb) * wblk, &tmW, &wfull, kb * p.KB, co0, j);
+      uint32_t g = 0;
+      const uint32_t ablk = 128u * p.KB * 2;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
+        for (int ti = 0; ti < p.T_src; ++ti, ++g) {
+          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], p.tile_bytes);
+          uint8_t* dst = ring + (size_t)s * p.tile_bytes;
+          for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =============================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.CoT, 0, 0);
+      const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2, ablk = 128u * p.KB * 2;
+      const int nk16 = p.KB / 16;
+      mbar_wait(&wfull, 0);
+      uint32_t g_base = 0, acc_cnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
+          const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
+          mbar_wait(&tempty[ab], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + ab * p.CoT;
+          uint32_t accumulate = 0;
+          for (int j = 0; j < p.Kt; ++j) {
+            const int ti = t_o + j + p.t0;
+            if (ti < 0 || ti >= p.T_src) continue;
+            const uint32_t g = g_base + ti, s = g % p.S, ph = (g / p.S) & 1;
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes);
+            const uint32_t b_base = smem_u32(w_s + (size_t)j * p.nKB * wblk);
+            for (int kb = 0; kb < p.nKB; ++kb)
+              for (int k = 0; k < nk16; ++k) {
+                const uint64_t da = make_smem_desc(a_base + kb * ablk + k * 32, 16, p.sbo, p.swz);
+                const uint64_t db = make_smem_desc(b_base + kb * wblk + k * 32, 16, p.sbo, p.swz);
+                mma_bf16_ss(d_tmem, da, db, idesc, accumulate);
+                accumulate = 1;
+              }
+          }
+          mma_commit(&tfull[ab]);
+          // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
+          const int t_rel = t_o + p.t0;
+          if (t_rel >= 0 && t_rel < p.T_src) mma_commit(&empty[(g_base + t_rel) % p.S]);
+          if (t_o == p.T_out - 1)
+            for (int ti = (t_rel + 1 > 0 ? t_rel + 1 : 0); ti < p.T_src; ++ti) mma_commit(&empty[(g_base + ti) % p.S]);
+        }
+        g_base += p.T_src;
+      }
+    }
+  } else {
+    // =========================== epilogue warps ==========================
+    const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;
+    uint32_t acc_cnt = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
+      const int n = n0 + row;
+      const bool valid = n < p.N;
+      for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
+        const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
+        mbar_wait(&tfull[ab], aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
+        const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
+        const int t_aux = t_o + p.aux_dt;
+        const bool aux_ok = p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
+        const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
+
+        if (EPI == EPI_LINEAR) {
+          for (int c0 = 0; c0 < p.CoT; c0 += 16) {
+            uint32_t r[16];
+            tmem_ld_32x32b_x16(t_addr + c0, r);
+            tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co0 + c0 + i) : 0.f);
+            if (aux_row && co0 + c0 < p.aux_cols) {
+              float av[16];
+              load16_bf16(aux_row + co0 + c0, av);
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (co0 + c0 + i < p.aux_cols) v[i] += av[i];
+            }
+            if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
+          }
+        } else {
+          const bool gated = p.W == 2 * p.Cout;
+          for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+            uint32_t rp[16], rq[16];
+            tmem_ld_32x32b_x16(t_addr + c0, rp);
+            if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + c0, rq);
+            tmem_ld_wait();
+            float zp[16], zq[16], res[16], h[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              zp[i] = __uint_as_float(rp[i]) + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
+              zq[i] = gated ? __uint_as_float(rq[i]) + (p.bias ? __ldg(p.bias + p.Cout + c0 + i) : 0.f) : 0.f;
+              res[i] = 0.f;
+            }
+            if (aux_row && c0 < p.aux_cols) {
+              if (c0 + 16 <= p.C_aux) {
+                load16_bf16(aux_row + c0, res);
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                  if (c0 + i >= p.aux_cols) res[i] = 0.f;
+              } else {
+                for (int i = 0; i < 16; ++i) res[i] = (c0 + i < p.aux_cols) ? __bfloat162float(aux_row[c0 + i]) : 0.f;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float u = zp[i] + res[i];
+              float o;
+              if (p.act == STGCN_ACT_GLU) o = u * sigmoidf_(zq[i]);
+              else if (p.act == STGCN_ACT_GTU) o = tanhf(u) * sigmoidf_(zq[i]);
+              else if (p.act == STGCN_ACT_RELU) o = fmaxf(u, 0.f);
+              else if (p.act == STGCN_ACT_SILU) o = u * sigmoidf_(u);
+              else o = u;
+              h[i] = o;
+            }
+            if (valid) {
+              store16_bf16(p.out_z + orow * p.W + c0, zp);
+              if (gated) store16_bf16(p.out_z + orow * p.W + p.Cout + c0, zq);
+              store16_bf16(p.out + orow * p.Cout + c0, h);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct TapProblem {
+  const bf16* in;          // [B, T_src, N, Cin]
+  const bf16* w;           // [Kt][Co][Cin] bf16, already in window order (W_j)
+  const float* bias;       // [Co] or nullptr
+  int B, N, T_src, T_out, Kt, t0, Cin, Co;
+  int epi, act, Cout;      // gate: Co == W
+  const bf16* aux; int aux_dt, T_aux, C_aux, aux_cols;
+  bf16* out; int ld_out;
+  bf16* out_z;
+};
+
+constexpr size_t kSmemBudget = 225 * 1024;
+
+struct TapPlan { bool ok; int KB, nKB, CoT, nCoT, S; uint32_t swz, sbo, tile_bytes, w_bytes; size_t smem; };
+
+inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate) {
+  TapPlan pl{};
+  pl.ok = false;
+  if (Cin % 16 || Co % 16 || Cin < 16 || Co < 16) return pl;
+  pl.KB = Cin >= 64 ? 64 : Cin;
+  if (Cin % pl.KB) return pl;
+  if (pl.KB != 16 && pl.KB != 32 && pl.KB != 64) return pl;
+  pl.nKB = Cin / pl.KB;
+  pl.swz = pl.KB == 64 ? SWZ_128B : (pl.KB == 32 ? SWZ_64B : SWZ_32B);
+  pl.sbo = 8u * pl.KB * 2;
+  pl.tile_bytes = 128u * Cin * 2;
+  const int live = Kt < T_src ? Kt : T_src;
+  // N tile: the gate epilogue needs the whole width in one CTA; otherwise halve until the weights + ring fit
+  for (int CoT = Co > 256 ? 256 : Co; CoT >= 16; CoT /= 2) {
+    if (Co % CoT || CoT % 16) { if (gate) break; continue; }
+    if (gate && CoT != Co) break;
+    size_t wb = (size_t)Kt * CoT * Cin * 2;
+    wb = (wb + 1023) & ~size_t(1023);
+    if (wb + (size_t)live * pl.tile_bytes > kSmemBudget) continue;
+    int S = (int)((kSmemBudget - wb) / pl.tile_bytes);
+    if (S > kMaxStages) S = kMaxStages;
+    if (S < live) continue;
+    pl.CoT = CoT; pl.nCoT = Co / CoT; pl.S = S; pl.w_bytes = (uint32_t)wb;
+    pl.smem = wb + (size_t)S * pl.tile_bytes + 1024;
+    pl.ok = true;
+    return pl;
+  }
+  return pl;
+}
+
+inline bool tap_supported(const TapProblem& q) {
+  if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
+  if (q.T_out < 1 || q.T_src < 1 || q.N < 1 || q.B < 1) return false;
+  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE).ok;
+}
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    STGCN_CUDA(cudaGetDevice(&dev));
+    STGCN_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
+  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE);
+  STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma tap GEMM: unsupported shape");
+  const CUtensorMapSwizzle tsw = pl.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (pl.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  uint64_t xd[4] = {(uint64_t)q.Cin, (uint64_t)q.N, (uint64_t)q.T_src, (uint64_t)q.B};
+  uint64_t xs[3] = {(uint64_t)q.Cin * 2, (uint64_t)q.N * q.Cin * 2, (uint64_t)q.T_src * q.N * q.Cin * 2};
+  uint32_t xb[4] = {(uint32_t)pl.KB, 128, 1, 1};
+  CUtensorMap tmX = make_tmap_bf16(q.in, 4, xd, xs, xb, tsw);
+  uint64_t wd[3] = {(uint64_t)q.Cin, (uint64_t)q.Co, (uint64_t)q.Kt};
+  uint64_t wsd[2] = {(uint64_t)q.Cin * 2, (uint64_t)q.Co * q.Cin * 2};
+  uint32_t wb[3] = {(uint32_t)pl.KB, (uint32_t)pl.CoT, 1};
+  CUtensorMap tmW = make_tmap_bf16(q.w, 3, wd, wsd, wb, tsw);
+
+  TapParams p{};
+  p.B = q.B; p.N = q.N; p.T_src = q.T_src; p.T_out = q.T_out; p.Kt = q.Kt; p.t0 = q.t0;
+  p.Cin = q.Cin; p.KB = pl.KB; p.nKB = pl.nKB; p.CoT = pl.CoT; p.S = pl.S; p.swz = pl.swz; p.sbo = pl.sbo;
+  p.tile_bytes = pl.tile_bytes; p.w_bytes = pl.w_bytes;
+  p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
+  p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
+  p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z;
+  p.n_node_tiles = (q.N + 127) / 128;
+  p.n_items = q.B * p.n_node_tiles;
+  int gx = p.n_items < sm_count() / pl.nCoT ? p.n_items : sm_count() / pl.nCoT;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, pl.nCoT);
+  if (q.epi == EPI_GATE) {
+    STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    STGCN_LAUNCH(umma_tap_kernel<EPI_GATE>, grid, kTapThreads, pl.smem, stream, tmX, tmW, p);
+  } else {
+    STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    STGCN_LAUNCH(umma_tap_kernel<EPI_LINEAR>, grid, kTapThreads, pl.smem, stream, tmX, tmW, p);
+  }
+}
+
+}  // namespace umma
+}  // namespace stgcn

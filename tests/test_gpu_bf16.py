@@ -83,3 +83,38 @@ def test_bf16_full_size_model(dataset, kind, B, cuda_device):
     errs = {k: rel_l2(named[k].grad.cpu(), v.grad) for k, v in p64.items() if v.grad is not None}
     assert max(errs.values()) < GRAD_TOL, max(errs.items(), key=lambda kv: kv[1])
     assert sorted(errs.values())[len(errs) // 2] < 3e-2
+
+
+@pytest.mark.parametrize("c_in,c_out,kt,T", [(64, 64, 3, 8), (16, 64, 3, 10), (64, 128, 4, 4), (32, 32, 2, 6),
+                                              (128, 64, 3, 7)])
+@pytest.mark.parametrize("act", ["glu", "relu"])
+def test_bf16_tcgen05_temporal_conv(c_in, c_out, kt, T, act, cuda_device):
+    """Shapes served by the tcgen05 tap-GEMM kernel (csrc/umma_tap.cuh).  Oracle evaluated on the same
+    bf16-rounded inputs/weights, so the remaining error is accumulation order + bf16 output rounding."""
+    from stgcn_b200 import layers
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(c_in + c_out + kt)
+    B, N = 3, 228
+    p = {}
+    O._tconv_params(p, "t.", kt, c_in, c_out, act, gen)
+    layer = layers.TemporalConvLayer(kt, c_in, c_out, N, act).to(dev)
+    layer.load_state_dict({k[2:]: v for k, v in p.items()}, strict=True)
+    x = torch.randn(B, c_in, T, N, generator=gen)
+    xg = x.to(dev).requires_grad_(True)
+    y = layer(xg)
+    assert y.dtype == torch.bfloat16
+    rb = lambda t: t.bfloat16().float()
+    pr = {k: rb(v).requires_grad_(True) if "causal_conv.weight" in k or "align" in k else v.clone().requires_grad_(True)
+          for k, v in p.items()}
+    xr = rb(x).requires_grad_(True)
+    yr = O.temporal_gated_conv(xr, pr, "t.", kt, c_out, act)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel_l2(y.float().cpu(), yr) < 6e-3
+    dy = torch.randn(yr.shape, generator=gen)
+    y.backward(dy.to(dev).bfloat16())
+    yr.backward(rb(dy))
+    assert rel_l2(xg.grad.cpu(), xr.grad) < 2e-2
+    named = dict(layer.named_parameters())
+    for k, v in pr.items():
+        if v.grad is not None:
+            assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < 2e-2, k
