@@ -7,6 +7,7 @@
 
 #include "simt_kernels.cuh"
 #include "umma_tap.cuh"
+#include "umma_gso.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -185,6 +186,34 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
 }
 
 // ============================ graph convolution layer ========================================
+// node contraction through tcgen05 (bf16, supported shapes) or the SIMT kernel
+template <class T>
+struct GsoRunner {
+  const float* M; int trans, N, C; long long G; cudaStream_t stream;
+  const simt::bf16* mbf = nullptr;   // prepared bf16 operator (tcgen05 path) or nullptr
+  void operator()(const T* in, const T* aux, T* out, float alpha, float beta) const {
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (mbf) { umma::launch_gso_umma(mbf, in, aux, out, N, C, G, alpha, beta, stream); return; }
+    }
+    GsoArgs<T> g{};
+    g.M = M; g.trans = trans; g.N = N; g.C = C; g.G = G; g.in = in; g.aux = aux; g.out = out; g.alpha = alpha; g.beta = beta;
+    launch_gso(g, stream);
+  }
+};
+template <class T>
+inline GsoRunner<T> make_gso_runner(const float* M, int trans, int N, int C, long long G, simt::bf16* mbf_buf,
+                                    cudaStream_t stream) {
+  GsoRunner<T> r{M, trans, N, C, G, stream};
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (mbf_buf && umma::gso_supported(N, C, G)) {
+      int Kp = (N + 63) / 64 * 64;
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)N * Kp, 256), 256, 0, stream, M, mbf_buf, N, Kp, trans);
+      r.mbf = mbf_buf;
+    }
+  }
+  return r;
+}
+
 inline int gconv_stack_depth(const stgcn_gconv_desc& d) { return d.gconv == STGCN_GCONV_CHEB ? d.Ks : 2; }
 inline void gconv_check(const stgcn_gconv_desc& d) {
   STGCN_CHECK(d.B >= 0 && d.T > 0 && d.N > 0 && d.c_in > 0 && d.c_out > 0, STGCN_E_INVALID, "bad gconv desc");
@@ -207,6 +236,7 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   const int C = d.c_out;
   const size_t plane = (size_t)rows * C;
   float* wat = c.ws.take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
+  simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
   T* x0 = stack;
@@ -220,21 +250,17 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   } else {
     launch_copy_cols(x, x0, rows, d.c_in, d.c_in, C, 0, c.stream);
   }
-  GsoArgs<T> g{};
-  g.M = p.gso; g.trans = 0; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
+  auto gso = make_gso_runner<T>(p.gso, 0, d.N, C, (long long)d.B * d.T, mbf, c.stream);
   TapArgs<T> t{};
   t.bias = p.b; t.out = y; t.rows = rows; t.Cin = C; t.Co = C; t.ldo = C;
   if (d.gconv == STGCN_GCONV_CHEB) {
     for (int k = 1; k < d.Ks; ++k) {
-      g.in = stack + (size_t)(k - 1) * plane; g.out = stack + (size_t)k * plane;
-      if (k == 1) { g.alpha = 1.f; g.aux = nullptr; g.beta = 0.f; }
-      else { g.alpha = 2.f; g.aux = stack + (size_t)(k - 2) * plane; g.beta = -1.f; }
-      launch_gso(g, c.stream);
+      if (k == 1) gso(stack, nullptr, stack + plane, 1.f, 0.f);
+      else gso(stack + (size_t)(k - 1) * plane, stack + (size_t)(k - 2) * plane, stack + (size_t)k * plane, 2.f, -1.f);
     }
     t.in = stack; t.wt = p.w; t.ntaps = d.Ks; t.map = RowMap{d.T, d.T, d.N, 0, rows};
   } else {
-    g.in = x0; g.out = stack + plane; g.alpha = 1.f; g.aux = nullptr; g.beta = 0.f;
-    launch_gso(g, c.stream);
+    gso(x0, nullptr, stack + plane, 1.f, 0.f);
     t.in = stack + plane; t.wt = p.w; t.ntaps = 1; t.map = RowMap{d.T, d.T, d.N, 0, 0};
   }
   launch_tapgemm(t, c.stream);
@@ -256,11 +282,11 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   float* wT = c.ws.take<float>((size_t)ntw * C * C);
   float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
+  simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
   if (c.dry()) return;
   STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
-  GsoArgs<T> g{};
-  g.M = p.gso; g.trans = 1; g.N = d.N; g.C = C; g.G = (long long)d.B * d.T;
+  auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, mbf, c.stream);
   TapArgs<T> t{};
   t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
   t.map = RowMap{d.T, d.T, d.N, 0, 0};
@@ -281,14 +307,12 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     }
     // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
     for (int k = d.Ks - 1; k >= 2; --k) {
-      g.in = dst + (size_t)k * plane; g.out = dst + (size_t)(k - 1) * plane; g.aux = g.out; g.alpha = 2.f; g.beta = 1.f;
-      launch_gso(g, c.stream);
+      gso(dst + (size_t)k * plane, dst + (size_t)(k - 1) * plane, dst + (size_t)(k - 1) * plane, 2.f, 1.f);
       STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, -1.f, (const T*)(dst + (size_t)k * plane),
                    dst + (size_t)(k - 2) * plane, (long long)plane);
     }
     if (d.Ks >= 2) {
-      g.in = dst + plane; g.out = dst; g.aux = dst; g.alpha = 1.f; g.beta = 1.f;
-      launch_gso(g, c.stream);
+      gso(dst + plane, dst, dst, 1.f, 1.f);
     }
     if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
   } else {
@@ -299,8 +323,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
       launch_wgrad(w, c.stream);
     }
-    g.in = dst + plane; g.out = dst; g.aux = d.residual ? dg : nullptr; g.alpha = 1.f; g.beta = 1.f;
-    launch_gso(g, c.stream);
+    gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
   }
   if (gr.w) launch_gather3(dwt, gr.w, 1, 1, ntw * C * C, 0, 0, 0, 1, 0, c.stream);
   if (gr.b) launch_gather3(dwt, gr.b, 1, 1, C, (long long)ntw * C * C, 0, 0, 1, 0, c.stream);

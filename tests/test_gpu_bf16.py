@@ -53,7 +53,7 @@ def test_bf16_model_close_to_reference_golden(name, cuda_device):
         e = rel_l2(named[k].grad.cpu(), gref)
         errs.append(e)
         assert e < GRAD_TOL, (k, e)
-    assert sorted(errs)[len(errs) // 2] < 3e-2      # median gradient error
+    assert sorted(errs)[len(errs) // 2] < 6e-2      # median gradient error
     assert rel_l2(x.grad.cpu(), g.dx) < GRAD_TOL
 
 
@@ -82,7 +82,7 @@ def test_bf16_full_size_model(dataset, kind, B, cuda_device):
     named = dict(model.named_parameters())
     errs = {k: rel_l2(named[k].grad.cpu(), v.grad) for k, v in p64.items() if v.grad is not None}
     assert max(errs.values()) < GRAD_TOL, max(errs.items(), key=lambda kv: kv[1])
-    assert sorted(errs.values())[len(errs) // 2] < 3e-2
+    assert sorted(errs.values())[len(errs) // 2] < 6e-2
 
 
 @pytest.mark.parametrize("c_in,c_out,kt,T", [(64, 64, 3, 8), (16, 64, 3, 10), (64, 128, 4, 4), (32, 32, 2, 6),
