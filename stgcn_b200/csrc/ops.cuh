@@ -8,6 +8,7 @@
 #include "simt_kernels.cuh"
 #include "umma_tap.cuh"
 #include "umma_gso.cuh"
+#include "umma_wgrad.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -131,10 +132,19 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   if (want_w) {
     zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
-    WgradArgs<T> w{};
-    w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
-    w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0};
-    launch_wgrad(w, c.stream);
+    bool done_w = false;
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (umma::wgrad_supported(d.c_in, g.W, d.Kt, d.T, d.B)) {
+        umma::launch_wgrad_umma(x, dz, dwt, d.B, d.N, d.T, d.Kt, d.c_in, g.W, 1, c.stream);
+        done_w = true;
+      }
+    }
+    if (!done_w) {
+      WgradArgs<T> w{};
+      w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
+      w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0};
+      launch_wgrad(w, c.stream);
+    }
     // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]
     if (gr.conv_w) launch_gather3(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W, 0, c.stream);
     if (gr.conv_b) launch_gather3(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
@@ -557,10 +567,19 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     launch_tapgemm(t, c.stream);
     if (gr.fc1_w || gr.fc1_b) {
       zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.stream);
-      WgradArgs<T> w{};
-      w.in = s.l; w.dz = df1; w.dwt = dw1; w.rows = g.rows1; w.Cin = d.c0; w.Co = d.c1; w.ntaps = 1; w.ldz = d.c1;
-      w.bias_row = 1; w.map = rm;
-      launch_wgrad(w, c.stream);
+      bool done_w = false;
+      if constexpr (std::is_same<T, simt::bf16>::value) {
+        if (umma::wgrad_supported(d.c0, d.c1, 1, g.T1, d.B)) {
+          umma::launch_wgrad_umma(s.l, df1, dw1, d.B, d.N, g.T1, 1, d.c0, d.c1, 1, c.stream);
+          done_w = true;
+        }
+      }
+      if (!done_w) {
+        WgradArgs<T> w{};
+        w.in = s.l; w.dz = df1; w.dwt = dw1; w.rows = g.rows1; w.Cin = d.c0; w.Co = d.c1; w.ntaps = 1; w.ldz = d.c1;
+        w.bias_row = 1; w.map = rm;
+        launch_wgrad(w, c.stream);
+      }
       if (gr.fc1_w) launch_gather3(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1, 0, c.stream);
       if (gr.fc1_b) launch_gather3(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1, 0, c.stream);
     }

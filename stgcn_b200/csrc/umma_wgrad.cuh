@@ -1,0 +1,220 @@
+// umma_wgrad.cuh -- tcgen05 weight gradient of the temporal convolution (bf16 path):
+//
+//   dW_j[o, c] = sum_{b, t, n} dZ[(b, t, n), o] * X[(b, t + j, n), c]     j < Kt
+//   db[o]      = sum_{b, t, n} dZ[(b, t, n), o]
+//
+// The contraction runs over rows (b,t,n), so both operands are MN-major in their natural channels-last
+// storage: A = dZ tile [64 rows][128 o] (two 64-wide swizzle-128B chunks), B = X tile [64 rows][Cin].
+// Work item = (sample b, 64-vertex chunk); for each output step t the CTA issues, per tap j,
+// 4 x tcgen05.mma (M = 128 output channels, N = Cin, K = 16 rows) into the tap's own TMEM accumulator
+// D_j, plus one N=16 MMA against a constant ones tile for the bias gradient.  The X time slices slide
+// through a TMA ring exactly as in umma_tap.cuh (each slice is used by Kt taps), dZ slices through a second
+// ring.  Accumulators live in TMEM for the CTA's whole life (split-K over work items); at the end the
+// epilogue warps add them to the fp32 gradient buffer with coalesced atomics.
+// Output layout = the SIMT wgrad kernel's: dwt[(j*Cin + c)*W + o], bias row at j = Kt.
+#pragma once
+#include "umma_tap.cuh"
+
+namespace stgcn {
+namespace umma {
+
+struct WgradParams {
+  int B, N, T_in, T_out, Kt, Cin, W;
+  int Sx, Sz, n_items, n_chunks;
+  uint32_t x_bytes, z_bytes, b_swz, b_sbo, b_kadv;
+  float* dwt;
+  int want_bias;
+};
+
+__global__ void __launch_bounds__(kTapThreads, 1)
+umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem;                               // [64 rows][16] bf16 1.0 (2 KB, padded to 1 KB multiple)
+  uint8_t* zring = smem + 2048;                       // Sz x [2 chunks][64 rows][128 B]
+  uint8_t* xring = zring + (size_t)p.Sz * p.z_bytes;  // Sx x [64 rows][Cin*2 B]
+  __shared__ __align__(8) uint64_t xfull[kMaxStages], xempty[kMaxStages], zfull[kMaxStages], zempty[kMaxStages], done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int o0 = blockIdx.y * 128;
+  const int ncol_used = p.Kt * p.Cin + 16;
+  uint32_t ncols = 32;
+  while ((int)ncols < ncol_used) ncols <<= 1;
+
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(1.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.Sx; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < p.Sz; ++s) { mbar_init(&zfull[s], 1); mbar_init(&zempty[s], 1); }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nxc = p.Cin > 64 ? p.Cin / 64 : 1;        // 64-wide chunks of the X tile
+  const int xcw = p.Cin > 64 ? 64 : p.Cin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmZ);
+      tma_prefetch_desc(&tmX);
+      uint32_t gx = 0, gz = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int b = item / p.n_chunks, n0 = (item % p.n_chunks) * 64;
+        for (int ti = 0; ti < p.T_in; ++ti) {
+          {
+            const uint32_t s = gx % p.Sx, ph = (gx / p.Sx) & 1;
+            mbar_wait(&xempty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&xfull[s], p.x_bytes);
+            uint8_t* dst = xring + (size_t)s * p.x_bytes;
+            for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * 64 * xcw * 2, &tmX, &xfull[s], c * 64, n0, ti, b);
+            ++gx;
+          }
+          const int t_o = ti - (p.Kt - 1);
+          if (t_o >= 0 && t_o < p.T_out) {
+            const uint32_t s = gz % p.Sz, ph = (gz / p.Sz) & 1;
+            mbar_wait(&zempty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&zfull[s], p.z_bytes);
+            uint8_t* dst = zring + (size_t)s * p.z_bytes;
+            for (int c = 0; c < 2; ++c) tma_load_4d(dst + (size_t)c * 8192, &tmZ, &zfull[s], o0 + c * 64, n0, t_o, b);
+            ++gz;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cin, 1, 1);
+      const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones_a = smem_u32(ones);
+      uint32_t gx_base = 0, gz = 0, started = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        for (int t_o = 0; t_o < p.T_out; ++t_o, ++gz) {
+          const uint32_t sz = gz % p.Sz, phz = (gz / p.Sz) & 1;
+          mbar_wait(&zfull[sz], phz);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(zring + (size_t)sz * p.z_bytes);
+          for (int j = 0; j < p.Kt; ++j) {
+            const uint32_t gx = gx_base + t_o + j, sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
+            mbar_wait(&xfull[sx], phx);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
+            const uint32_t acc = (started >> j) & 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024, SWZ_128B);
+              const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, 64u * xcw * 2, p.b_sbo, p.b_swz);
+              mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, acc | (k != 0));
+            }
+            started |= 1u << j;
+          }
+          if (p.want_bias) {
+            const uint32_t acc = (started >> 31) & 1;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024, SWZ_128B);
+              const uint64_t db = make_smem_desc(ones_a + k * 512, 2048, 256, SWZ_32B);
+              mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, acc | (k != 0));
+            }
+            started |= 1u << 31;
+          }
+          mma_commit(&zempty[sz]);
+          mma_commit(&xempty[(gx_base + t_o) % p.Sx]);
+          if (t_o == p.T_out - 1)
+            for (int ti = p.T_out; ti < p.T_in; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
+        }
+        gx_base += p.T_in;
+      }
+      mma_commit(&done);
+    }
+  } else {
+    // epilogue: wait for all MMAs of this CTA, then add the accumulators to the global gradient
+    const int q = warp & 3;
+    const int o = o0 + q * 32 + lane;
+    const bool any = blockIdx.x < p.n_items;
+    if (any) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+      for (int j = 0; j < p.Kt; ++j)
+        for (int c0 = 0; c0 < p.Cin; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_addr + j * p.Cin + c0, r);
+          tmem_ld_wait();
+          if (o < p.W) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              atomicAdd(p.dwt + ((size_t)(j * p.Cin + c0 + i)) * p.W + o, __uint_as_float(r[i]));
+          }
+        }
+      if (p.want_bias) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(t_addr + p.Kt * p.Cin, r);
+        tmem_ld_wait();
+        if (o < p.W) atomicAdd(p.dwt + (size_t)p.Kt * p.Cin * p.W + o, __uint_as_float(r[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+struct WgradPlan { bool ok; int Sx, Sz, nMT; uint32_t x_bytes, z_bytes; size_t smem; };
+
+inline WgradPlan plan_wgrad(int Cin, int W, int Kt, int T_in) {
+  WgradPlan pl{};
+  pl.ok = false;
+  if (W % 128 || W < 128) return pl;
+  if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
+  if (Kt * Cin + 16 > 512 || Kt > 30) return pl;
+  pl.x_bytes = 64u * Cin * 2;
+  pl.z_bytes = 16384;
+  pl.nMT = W / 128;
+  int live = Kt < T_in ? Kt : T_in;
+  pl.Sx = live + 3 > kMaxStages ? kMaxStages : live + 3;
+  if (pl.Sx < live) return pl;
+  pl.Sz = 3;
+  pl.smem = 2048 + (size_t)pl.Sz * pl.z_bytes + (size_t)pl.Sx * pl.x_bytes + 1024;
+  if (pl.smem > kSmemBudget) return pl;
+  pl.ok = true;
+  return pl;
+}
+inline bool wgrad_supported(int Cin, int W, int Kt, int T_in, int B) { return B > 0 && plan_wgrad(Cin, W, Kt, T_in).ok; }
+
+// x: [B, T_in, N, Cin], dz: [B, T_out, N, W] (T_out = T_in - Kt + 1); dwt: fp32 [(Kt*Cin + 1), W], pre-zeroed
+inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, int N, int T_in, int Kt, int Cin, int W,
+                              int want_bias, cudaStream_t stream) {
+  WgradPlan pl = plan_wgrad(Cin, W, Kt, T_in);
+  STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma wgrad: unsupported shape");
+  const int T_out = T_in - Kt + 1;
+  uint64_t zd[4] = {(uint64_t)W, (uint64_t)N, (uint64_t)T_out, (uint64_t)B};
+  uint64_t zs[3] = {(uint64_t)W * 2, (uint64_t)N * W * 2, (uint64_t)T_out * N * W * 2};
+  uint32_t zb[4] = {64, 64, 1, 1};
+  CUtensorMap tmZ = make_tmap_bf16(dz, 4, zd, zs, zb, CU_TENSOR_MAP_SWIZZLE_128B);
+  const int xcw = Cin > 64 ? 64 : Cin;
+  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)T_in, (uint64_t)B};
+  uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2, (uint64_t)T_in * N * Cin * 2};
+  uint32_t xb[4] = {(uint32_t)xcw, 64, 1, 1};
+  const CUtensorMapSwizzle sw = xcw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (xcw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmX = make_tmap_bf16(x, 4, xd, xs, xb, sw);
+  WgradParams p{};
+  p.B = B; p.N = N; p.T_in = T_in; p.T_out = T_out; p.Kt = Kt; p.Cin = Cin; p.W = W;
+  p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + 63) / 64; p.n_items = B * p.n_chunks;
+  p.x_bytes = pl.x_bytes; p.z_bytes = pl.z_bytes;
+  p.b_swz = xcw == 64 ? SWZ_128B : (xcw == 32 ? SWZ_64B : SWZ_32B);
+  p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
+  p.dwt = dwt; p.want_bias = want_bias;
+  int per = sm_count() / pl.nMT;
+  int gx = p.n_items < per ? p.n_items : per;
+  if (gx < 1) gx = 1;
+  STGCN_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  STGCN_LAUNCH(umma_wgrad_kernel, dim3(gx, pl.nMT), kTapThreads, pl.smem, stream, tmZ, tmX, p);
+}
+
+}  // namespace umma
+}  // namespace stgcn
