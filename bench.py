@@ -358,7 +358,7 @@ def main():
         tot_ms = sum(v[1] for v in prof.values())
         rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
         top = [{"key": k, "launches_per_step": v[0] / psteps, "ms_per_step": v[1] / psteps,
-                "share": v[1] / tot_ms} for k, v in rows[:8]]
+                "share": v[1] / tot_ms} for k, v in rows[:60]]
         # dominant kernel: algorithmic FLOPs of the stage it implements / its measured time
         k0, (c0, ms0) = rows[0]
         stage_flops = _stage_flops_for_key(k0, stages, B)

@@ -102,6 +102,18 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
                  wt + (size_t)(d.Kt - 1) * d.c_in * g.W, g.W, p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
     launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
   }
+  if (g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt)) {
+    // first-layer special (tiny K): fused conv + bias + gate, one pass
+    SmallCArgs<T> sa{};
+    sa.x = x; sa.wt = wt; sa.bias = bias; sa.z = z_saved; sa.h = y; sa.rows = g.rows_out; sa.Cin = d.c_in;
+    sa.Cout = d.c_out; sa.W = g.W; sa.Kt = d.Kt; sa.T_out = g.T_out; sa.T_in = d.T; sa.N = d.N; sa.act = d.act;
+    sa.explicit_res = (g.folded || g.linear) ? 0 : 1;
+    size_t smem = (size_t)(d.Kt * d.c_in + 1) * g.W * sizeof(float);
+    long long total = g.rows_out * (d.c_out / 8);
+    int blocks = (int)std::min<long long>(ceil_div(total, 256), 148 * 16);
+    STGCN_LAUNCH(smallc_conv_gate_fwd_kernel<T>, blocks, 256, smem, c.stream, sa);
+    return;
+  }
   TapArgs<T> t{};
   t.in = x; t.wt = wt; t.bias = bias; t.out = z_saved; t.rows = g.rows_out;
   t.Cin = d.c_in; t.Co = g.W; t.ntaps = d.Kt; t.ldo = g.W; t.accumulate = 0;
@@ -124,17 +136,34 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
   simt::bf16* wdbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
   if (c.dry()) return;
-  GateArgs<T> ga{};
-  ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
-  ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
-  launch_gate_any(d.act, true, ga, c.stream);
-
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
-  if (want_w) {
+  const bool smallc = g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
+  if (smallc) {
+    // first-layer special: gate backward fused with the weight gradient (dz only materialised when dx is wanted)
     zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
-    bool done_w = false;
+    SmallCArgs<T> sa{};
+    sa.x = x; sa.z = const_cast<T*>(z_saved); sa.dh = dy; sa.dz = dx ? dz : nullptr; sa.dwt = dwt; sa.rows = g.rows_out;
+    sa.Cin = d.c_in; sa.Cout = d.c_out; sa.W = g.W; sa.Kt = d.Kt; sa.T_out = g.T_out; sa.T_in = d.T; sa.N = d.N;
+    sa.act = d.act; sa.explicit_res = (g.folded || g.linear) ? 0 : 1;
+    const int threads = d.c_out >= 256 ? 256 : 256 / d.c_out * d.c_out;
+    const int lanes = threads / d.c_out;
+    long long rpc = (g.rows_out + 148 * 8 - 1) / (148 * 8);
+    if (rpc < 64) rpc = 64;
+    sa.rows_per_cta = (int)rpc;
+    size_t smem = (size_t)lanes * 2 * (Kw + 1) * d.c_out * sizeof(float);
+    STGCN_CUDA(cudaFuncSetAttribute(smallc_gate_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, ceil_div(g.rows_out, rpc), threads, smem, c.stream, sa);
+  } else {
+    GateArgs<T> ga{};
+    ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
+    ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
+    launch_gate_any(d.act, true, ga, c.stream);
+  }
+  if (want_w) {
+    if (!smallc) zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
+    bool done_w = smallc;
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      if (umma::wgrad_supported(d.c_in, g.W, d.Kt, d.T, d.B)) {
+      if (!done_w && umma::wgrad_supported(d.c_in, g.W, d.Kt, d.T, d.B)) {
         umma::launch_wgrad_umma(x, dz, dwt, d.B, d.N, d.T, d.Kt, d.c_in, g.W, 1, c.stream);
         done_w = true;
       }

@@ -284,9 +284,11 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
-  constexpr int B_PER = BK * BN / NT;
+  constexpr int B_PER = (BK * BN + NT - 1) / NT;
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN + 4];
+  __shared__ long long row_base[BK];   // input row of tap 0 for each K row of the chunk (-1: past the end)
+  __shared__ int row_t[BK];
   const int tid = threadIdx.x;
   const int tx = tid % TX, ty = tid / TX;
   const int m0 = blockIdx.x * BM, col0 = blockIdx.y * BN;
@@ -315,21 +317,31 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
   for (long long k0 = r_begin; k0 < r_end; k0 += BK) {
+    if (tid < BK) {      // one row decode per K row (not per element): the divisions dominated this kernel
+      long long r = k0 + tid;
+      if (r < r_end) {
+        long long b = r / TN_out;
+        long long rem = r - b * TN_out;
+        row_t[tid] = (int)(rem / a.map.N);
+        row_base[tid] = b * TN_in + rem;
+      } else {
+        row_t[tid] = 0;
+        row_base[tid] = -1;
+      }
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < A_PER; ++j) {
       int e = tid + j * NT;
       int m = e % BM, kk = e / BM;
-      long long r = k0 + kk;
       float v = 0.f;
-      if (r < r_end && a_tap[j] >= -1) {
+      const long long rb = row_base[kk];
+      if (rb >= 0 && a_tap[j] >= -1) {
         if (a_tap[j] == -1) {
           v = 1.f;
         } else {
-          long long b = r / TN_out;
-          long long rem = r - b * TN_out;
-          int ti = (int)(rem / a.map.N) + a.map.t_shift * a_tap[j];
-          if (ti >= 0 && ti < a.map.T_in)
-            v = ldf(a.in + (b * TN_in + rem + a_tap[j] * tap_step) * a.Cin + a_c[j]);
+          int ti = row_t[kk] + a.map.t_shift * a_tap[j];
+          if (ti >= 0 && ti < a.map.T_in) v = ldf(a.in + (rb + a_tap[j] * tap_step) * a.Cin + a_c[j]);
         }
       }
       As[kk][m] = v;
@@ -337,10 +349,12 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
 #pragma unroll
     for (int j = 0; j < B_PER; ++j) {
       int e = tid + j * NT;
-      int n = e % BN, kk = e / BN;
-      long long r = k0 + kk;
-      int o = col0 + n;
-      Bs[kk][n] = (r < r_end && o < a.Co) ? ldf(a.dz + r * a.ldz + o) : 0.f;
+      if (e < BK * BN) {
+        int n = e % BN, kk = e / BN;
+        long long r = k0 + kk;
+        int o = col0 + n;
+        Bs[kk][n] = (r < r_end && o < a.Co) ? ldf(a.dz + r * a.ldz + o) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
@@ -372,27 +386,27 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
 template <class T>
 inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
-  int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
-  int tiles;
-  dim3 grid;
-  if (a.Co <= 16) {
-    tiles = ceil_div(Mtot, 128) * ceil_div(a.Co, 16);
-  } else {
-    tiles = ceil_div(Mtot, 64) * ceil_div(a.Co, 64);
-  }
-  // aim for ~4 CTAs per SM in total, at least 512 rows per CTA
-  long long want = (148 * 4 + tiles - 1) / tiles;
+  const int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
+  // tile shape by output shape: skinny in Co (<=16), skinny in M (<=16, e.g. the first layer's Cin = 1), or square
+  int mode, tiles;
+  if (a.Co <= 16) { mode = Mtot <= 64 ? 0 : 1; tiles = ceil_div(Mtot, mode == 0 ? 64 : 128); }
+  else if (Mtot <= 16) { mode = 2; tiles = ceil_div(a.Co, 64); }
+  else { mode = 3; tiles = ceil_div(Mtot, 64) * ceil_div(a.Co, 64); }
+  // aim for ~8 CTAs per SM in total, at least 256 rows per CTA
+  long long want = (148 * 8 + tiles - 1) / tiles;
   long long rpc = (a.rows + want - 1) / want;
-  if (rpc < 512) rpc = 512;
+  if (rpc < 256) rpc = 256;
   rpc = (rpc + BK - 1) / BK * BK;
   a.rows_per_cta = (int)rpc;
-  int chunks = ceil_div(a.rows, rpc);
-  if (a.Co <= 16) {
-    grid = dim3(ceil_div(Mtot, 128), ceil_div(a.Co, 16), chunks);
-    STGCN_LAUNCH((wgrad_kernel<T, 128, 16, 2, 4>), grid, NT, 0, s, a);
+  const int chunks = ceil_div(a.rows, rpc);
+  if (mode == 0) {
+    STGCN_LAUNCH((wgrad_kernel<T, 64, 16, 1, 4>), dim3(ceil_div(Mtot, 64), 1, chunks), NT, 0, s, a);
+  } else if (mode == 1) {
+    STGCN_LAUNCH((wgrad_kernel<T, 128, 16, 2, 4>), dim3(ceil_div(Mtot, 128), 1, chunks), NT, 0, s, a);
+  } else if (mode == 2) {
+    STGCN_LAUNCH((wgrad_kernel<T, 16, 64, 1, 4>), dim3(1, ceil_div(a.Co, 64), chunks), NT, 0, s, a);
   } else {
-    grid = dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks);
-    STGCN_LAUNCH((wgrad_kernel<T, 64, 64, 4, 4>), grid, NT, 0, s, a);
+    STGCN_LAUNCH((wgrad_kernel<T, 64, 64, 4, 4>), dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks), NT, 0, s, a);
   }
 }
 
@@ -504,6 +518,170 @@ inline void launch_gate_any(int act, bool bwd, const GateArgs<T>& a, cudaStream_
     case STGCN_ACT_LINEAR: launch_gate<T, STGCN_ACT_LINEAR>(bwd, a, s); break;
     default: throw Error(STGCN_E_UNSUPPORTED, "activation not implemented");
   }
+}
+
+// ---- first-layer special: temporal conv with a tiny input width (Cin <= 4; the model input has Cin = 1) ------
+// The GEMM has K = Kt*Cin <= 16, so it is bandwidth work: one fused pass computes conv + bias + gate and writes the
+// saved pre-activation Z and the output H (8 output channels per thread, 16/32-byte stores).
+template <class T>
+struct SmallCArgs {
+  const T* x;          // [B, T_in, N, Cin]
+  const float* wt;     // [(k*Cin + c)][W]
+  const float* bias;   // [W]
+  T* z;                // [rows, W]
+  T* h;                // [rows, Cout]
+  const T* dh;         // bwd: [rows, Cout]
+  T* dz;               // bwd (optional): [rows, W]
+  float* dwt;          // bwd: [(Kt*Cin + 1)][W], pre-zeroed
+  long long rows;
+  int Cin, Cout, W, Kt, T_out, T_in, N, act, explicit_res, rows_per_cta;
+};
+
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 a;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  a.x = *reinterpret_cast<uint32_t*>(&t0); a.y = *reinterpret_cast<uint32_t*>(&t1);
+  a.z = *reinterpret_cast<uint32_t*>(&t2); a.w = *reinterpret_cast<uint32_t*>(&t3);
+  *reinterpret_cast<uint4*>(p) = a;
+}
+
+__device__ __forceinline__ float act_fwd(int act, float u, float q) {
+  if (act == STGCN_ACT_GLU) return u * sigmoidf_(q);
+  if (act == STGCN_ACT_GTU) return tanhf(u) * sigmoidf_(q);
+  if (act == STGCN_ACT_RELU) return fmaxf(u, 0.f);
+  if (act == STGCN_ACT_SILU) return u * sigmoidf_(u);
+  return u;
+}
+// gradients of act_fwd w.r.t. (u, q) times g
+__device__ __forceinline__ void act_bwd(int act, float u, float q, float g, float& du, float& dq) {
+  dq = 0.f;
+  if (act == STGCN_ACT_GLU) { float s = sigmoidf_(q); du = g * s; dq = g * u * s * (1.f - s); }
+  else if (act == STGCN_ACT_GTU) { float s = sigmoidf_(q), th = tanhf(u); du = g * s * (1.f - th * th); dq = g * th * s * (1.f - s); }
+  else if (act == STGCN_ACT_RELU) { du = u > 0.f ? g : 0.f; }
+  else if (act == STGCN_ACT_SILU) { float s = sigmoidf_(u); du = g * (s + u * s * (1.f - s)); }
+  else { du = g; }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T> a) {
+  extern __shared__ float sm[];          // wt [K][W] then bias [W]
+  const int K = a.Kt * a.Cin;
+  for (int i = threadIdx.x; i < K * a.W; i += blockDim.x) sm[i] = a.wt[i];
+  for (int i = threadIdx.x; i < a.W; i += blockDim.x) sm[K * a.W + i] = a.bias[i];
+  __syncthreads();
+  const float* w = sm;
+  const float* bs = sm + K * a.W;
+  const int groups = a.Cout / 8;
+  const bool gated = a.W == 2 * a.Cout;
+  const long long total = a.rows * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / groups;
+    const int j0 = (int)(idx - r * groups) * 8;
+    const long long TN_out = (long long)a.T_out * a.N;
+    const long long b = r / TN_out;
+    const long long rem = r - b * TN_out;
+    const long long in0 = b * a.T_in * a.N + rem;
+    float zp[8], zq[8], hv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zp[i] = bs[j0 + i]; zq[i] = gated ? bs[a.Cout + j0 + i] : 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      if (kk < K) {
+        const int k = kk / a.Cin, c = kk - k * a.Cin;
+        const float xk = ldf(a.x + (in0 + (long long)k * a.N) * a.Cin + c);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          zp[i] = fmaf(xk, w[kk * a.W + j0 + i], zp[i]);
+          if (gated) zq[i] = fmaf(xk, w[kk * a.W + a.Cout + j0 + i], zq[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float res = (a.explicit_res && j0 + i < a.Cin) ? ldf(a.x + (in0 + (long long)(a.Kt - 1) * a.N) * a.Cin + j0 + i) : 0.f;
+      hv[i] = act_fwd(a.act, zp[i] + res, zq[i]);
+    }
+    store8(a.z + r * a.W + j0, zp);
+    if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
+    store8(a.h + r * a.Cout + j0, hv);
+  }
+}
+
+// Fused gate-backward + weight gradient for the same layer: per CTA a row range, thread = (channel j, row lane);
+// dW[(k,c)][o] and db[o] accumulate in registers, are reduced across the row lanes in shared memory and added to the
+// global buffer with one atomic per element per CTA.  Optionally also materialises dz (when dx is needed).
+template <class T>
+__global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a) {
+  extern __shared__ float red[];         // [lanes][2][K+1][Cout]
+  const int K = a.Kt * a.Cin;
+  const bool gated = a.W == 2 * a.Cout;
+  const int lanes = blockDim.x / a.Cout;
+  const int j = threadIdx.x % a.Cout, rl = threadIdx.x / a.Cout;
+  float accp[17], accq[17];
+#pragma unroll
+  for (int i = 0; i < 17; ++i) { accp[i] = 0.f; accq[i] = 0.f; }
+  const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+  const long long r1 = min(a.rows, r0 + a.rows_per_cta);
+  const long long TN_out = (long long)a.T_out * a.N;
+  if (rl < lanes) {
+    for (long long r = r0 + rl; r < r1; r += lanes) {
+      const long long b = r / TN_out;
+      const long long rem = r - b * TN_out;
+      const long long in0 = b * a.T_in * a.N + rem;
+      const float res = (a.explicit_res && j < a.Cin) ? ldf(a.x + (in0 + (long long)(a.Kt - 1) * a.N) * a.Cin + j) : 0.f;
+      const float u = ldf(a.z + r * a.W + j) + res;
+      const float q = gated ? ldf(a.z + r * a.W + a.Cout + j) : 0.f;
+      float du, dq;
+      act_bwd(a.act, u, q, ldf(a.dh + r * a.Cout + j), du, dq);
+      if (a.dz) {
+        stf(a.dz + r * a.W + j, du);
+        if (gated) stf(a.dz + r * a.W + a.Cout + j, dq);
+      }
+#pragma unroll
+      for (int kk = 0; kk < 16; ++kk) {
+        if (kk < K) {
+          const int k = kk / a.Cin, c = kk - k * a.Cin;
+          const float xk = ldf(a.x + (in0 + (long long)k * a.N) * a.Cin + c);
+          accp[kk] = fmaf(xk, du, accp[kk]);
+          accq[kk] = fmaf(xk, dq, accq[kk]);
+        }
+      }
+      accp[16] += du;      // bias gradient
+      accq[16] += dq;
+    }
+  }
+  // reduce over row lanes
+  const int stride = (K + 1) * a.Cout;
+  if (rl < lanes) {
+#pragma unroll
+    for (int kk = 0; kk < 17; ++kk) {
+      const int slot = kk == 16 ? K : kk;        // bias row sits right after the K weight rows
+      if (kk == 16 || kk < K) {
+        red[(rl * 2 + 0) * stride + slot * a.Cout + j] = accp[kk];
+        red[(rl * 2 + 1) * stride + slot * a.Cout + j] = accq[kk];
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 2 * stride; e += blockDim.x) {
+    const int half = e / stride, rest = e - half * stride;
+    if (half == 1 && !gated) continue;
+    float v = 0.f;
+    for (int l = 0; l < lanes; ++l) v += red[(l * 2 + half) * stride + rest];
+    const int kk = rest / a.Cout, jj = rest - kk * a.Cout;
+    atomicAdd(a.dwt + (long long)kk * a.W + half * a.Cout + jj, v);
+  }
+}
+
+template <class T>
+inline bool smallc_supported(int Cin, int Cout, int W, int Kt) {
+  return Cin <= 4 && Kt * Cin <= 16 && Cout % 8 == 0 && Cout <= 256 && W <= 512 && (256 % Cout == 0 || Cout == 256);
 }
 
 // ---- small elementwise / layout kernels ----------------------------------------------------

@@ -12,9 +12,9 @@
 // shared memory for the life of the CTA.  Two TMEM accumulators are ping-ponged between the MMA
 // issuer and the epilogue warps.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
-// lane) + TMEM allocation, warps 2..5 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31: one
-// vertex row per thread).
+// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
+// lane) + TMEM allocation, warps 2..9 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31: one
+// vertex row per thread; the two warps of a lane quarter take alternate 16-column chunks).
 //
 // Epilogues:
 //   EPI_LINEAR: out = acc + bias (+ aux rows: residual / residual-gradient), stored bf16
@@ -29,7 +29,9 @@ namespace umma {
 using simt::bf16;
 enum { EPI_LINEAR = 0, EPI_GATE = 1 };
 constexpr int kMaxStages = 8;
-constexpr int kTapThreads = 192;
+constexpr int kTapThreads = 192;       // gso / wgrad kernels: 4 epilogue warps
+constexpr int kTapEpiWarps = 8;        // tap kernel: two epilogue warps per TMEM lane quarter (column halves)
+constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps;
 
 struct TapParams {
   int B, N, T_src, T_out, Kt, t0;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void load16_bf16(const bf16* src, float* v) {
 }
 
 template <int EPI>
-__global__ void __launch_bounds__(kTapThreads, 1)
+__global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TapParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -77,16 +79,18 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* ring = smem + p.w_bytes;       // w_bytes is a multiple of 1024
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.CoT;
+  for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
   uint32_t ncols = 32;
   while ((int)ncols < 2 * p.CoT) ncols <<= 1;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&wfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTapEpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
@@ -161,6 +165,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else {
     // =========================== epilogue warps ==========================
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;           // which alternate 16-column chunks this warp handles
     const int row = q * 32 + lane;
     uint32_t acc_cnt = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -178,13 +183,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
 
         if (EPI == EPI_LINEAR) {
-          for (int c0 = 0; c0 < p.CoT; c0 += 16) {
+          for (int c0 = half * 16; c0 < p.CoT; c0 += 32) {
             uint32_t r[16];
             tmem_ld_32x32b_x16(t_addr + c0, r);
             tmem_ld_wait();
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? __ldg(p.bias + co0 + c0 + i) : 0.f);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
             if (aux_row && co0 + c0 < p.aux_cols) {
               float av[16];
               load16_bf16(aux_row + co0 + c0, av);
@@ -196,7 +201,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         } else {
           const bool gated = p.W == 2 * p.Cout;
-          for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+          for (int c0 = half * 16; c0 < p.Cout; c0 += 32) {
             uint32_t rp[16], rq[16];
             tmem_ld_32x32b_x16(t_addr + c0, rp);
             if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + c0, rq);
@@ -204,8 +209,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             float zp[16], zq[16], res[16], h[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              zp[i] = __uint_as_float(rp[i]) + (p.bias ? __ldg(p.bias + c0 + i) : 0.f);
-              zq[i] = gated ? __uint_as_float(rq[i]) + (p.bias ? __ldg(p.bias + p.Cout + c0 + i) : 0.f) : 0.f;
+              zp[i] = __uint_as_float(rp[i]) + bias_s[c0 + i];
+              zq[i] = gated ? __uint_as_float(rq[i]) + bias_s[p.Cout + c0 + i] : 0.f;
               res[i] = 0.f;
             }
             if (aux_row && c0 < p.aux_cols) {
@@ -339,10 +344,10 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   dim3 grid(gx, pl.nCoT);
   if (q.epi == EPI_GATE) {
     STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH(umma_tap_kernel<EPI_GATE>, grid, kTapThreads, pl.smem, stream, tmX, tmW, p);
+    STGCN_LAUNCH(umma_tap_kernel<EPI_GATE>, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
   } else {
     STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH(umma_tap_kernel<EPI_LINEAR>, grid, kTapThreads, pl.smem, stream, tmX, tmW, p);
+    STGCN_LAUNCH(umma_tap_kernel<EPI_LINEAR>, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
   }
 }
 
