@@ -303,7 +303,7 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
     t.in = stack + plane; t.wt = p.w; t.ntaps = 1; t.map = RowMap{d.T, d.T, d.N, 0, 0};
   }
   launch_tapgemm(t, c.stream);
-  STGCN_LAUNCH(add_relu_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, (const T*)y, (const T*)(d.residual ? x0 : nullptr), y, (long long)plane, d.relu);
+  STGCN_LAUNCH(add_relu_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, (const T*)y, (const T*)(d.residual ? x0 : nullptr), y, (long long)plane, d.relu);
 }
 
 template <class T>
@@ -323,7 +323,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
   simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
   if (c.dry()) return;
-  STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
+  STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
   auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, mbf, c.stream);
   TapArgs<T> t{};
@@ -347,13 +347,13 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
     for (int k = d.Ks - 1; k >= 2; --k) {
       gso(dst + (size_t)k * plane, dst + (size_t)(k - 1) * plane, dst + (size_t)(k - 1) * plane, 2.f, 1.f);
-      STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, -1.f, (const T*)(dst + (size_t)k * plane),
+      STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, -1.f, (const T*)(dst + (size_t)k * plane),
                    dst + (size_t)(k - 2) * plane, (long long)plane);
     }
     if (d.Ks >= 2) {
       gso(dst + plane, dst, dst, 1.f, 1.f);
     }
-    if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(plane, 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
+    if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
   } else {
     launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
     t.wt = wT; t.out = dst + plane;
@@ -403,8 +403,12 @@ inline void lnorm_fwd(const stgcn_lnorm_desc& d, const T* x, const float* w, con
   if (dry) return;
   long long G = (long long)d.B * d.T;
   if (G == 0) return;
-  STGCN_LAUNCH(ln_fwd_kernel<T>, (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, d.N * d.C, d.eps, d.training,
-               d.p_drop, seed);
+  const int M = d.N * d.C;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (M % 8 == 0 && al16(x) && al16(y) && al16(w) && al16(b))
+    STGCN_LAUNCH((ln_fwd_kernel<T, 8>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
+  else
+    STGCN_LAUNCH((ln_fwd_kernel<T, 1>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
 }
 template <class T>
 inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats, const T* dy, const float* w,
@@ -416,14 +420,20 @@ inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats,
   if (dw) zero(dw, M, s);
   if (db) zero(db, M, s);
   if (G == 0) return;
-  if (dx) STGCN_LAUNCH(ln_bwd_kernel<T>, (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool vec = M % 8 == 0 && al16(x) && al16(dy) && al16(w) && (!dx || al16(dx));
+  if (dx) {
+    if (vec) STGCN_LAUNCH((ln_bwd_kernel<T, 8>), (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
+    else     STGCN_LAUNCH((ln_bwd_kernel<T, 1>), (unsigned)G, 512, 0, s, x, dy, w, stats, stats + G, dx, M, d.training, d.p_drop, seed);
+  }
   if (dw || db) {
-    int xb = ceil_div(M, 256);
-    int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 8) / xb));
+    const int per = vec ? 8 : 1;
+    int xb = ceil_div(M, 128 * per);
+    int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 16) / xb));
     int gpc = ceil_div(G, ychunks);
     ychunks = ceil_div(G, gpc);
-    STGCN_LAUNCH(ln_param_grad_kernel<T>, dim3(xb, ychunks), 256, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc,
-                 d.training, d.p_drop, seed);
+    if (vec) STGCN_LAUNCH((ln_param_grad_kernel<T, 8>), dim3(xb, ychunks), 128, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc, d.training, d.p_drop, seed);
+    else     STGCN_LAUNCH((ln_param_grad_kernel<T, 1>), dim3(xb, ychunks), 128, 0, s, x, dy, stats, stats + G, dw, db, M, G, gpc, d.training, d.p_drop, seed);
   }
 }
 

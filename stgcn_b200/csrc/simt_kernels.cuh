@@ -28,6 +28,33 @@ __device__ __forceinline__ float ldf(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }
 __device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+// 8-element vector access (16-byte aligned for bf16, 32-byte for float)
+__device__ __forceinline__ void store8(float* p, const float* v) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8(bf16* p, const float* v) {
+  uint4 a;
+  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
+  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
+  a.x = *reinterpret_cast<uint32_t*>(&t0); a.y = *reinterpret_cast<uint32_t*>(&t1);
+  a.z = *reinterpret_cast<uint32_t*>(&t2); a.w = *reinterpret_cast<uint32_t*>(&t3);
+  *reinterpret_cast<uint4*>(p) = a;
+}
+__device__ __forceinline__ void load8(const float* p, float* v) {
+  float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void load8(const bf16* p, float* v) {
+  uint4 a = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
+    v[2 * i] = __low2float(h);
+    v[2 * i + 1] = __high2float(h);
+  }
+}
 
 // Row geometry of a tap GEMM.  Output row r = (b, t, n), t < T_out.  Tap k reads input row
 // (b, t + t_shift*k, n) of a [B, T_in, N] tensor (invalid -> contributes 0), displaced by
@@ -410,6 +437,23 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   }
 }
 
+__device__ __forceinline__ float act_fwd(int act, float u, float q) {
+  if (act == STGCN_ACT_GLU) return u * sigmoidf_(q);
+  if (act == STGCN_ACT_GTU) return tanhf(u) * sigmoidf_(q);
+  if (act == STGCN_ACT_RELU) return fmaxf(u, 0.f);
+  if (act == STGCN_ACT_SILU) return u * sigmoidf_(u);
+  return u;
+}
+// gradients of act_fwd w.r.t. (u, q) times g
+__device__ __forceinline__ void act_bwd(int act, float u, float q, float g, float& du, float& dq) {
+  dq = 0.f;
+  if (act == STGCN_ACT_GLU) { float s = sigmoidf_(q); du = g * s; dq = g * u * s * (1.f - s); }
+  else if (act == STGCN_ACT_GTU) { float s = sigmoidf_(q), th = tanhf(u); du = g * s * (1.f - th * th); dq = g * th * s * (1.f - s); }
+  else if (act == STGCN_ACT_RELU) { du = u > 0.f ? g : 0.f; }
+  else if (act == STGCN_ACT_SILU) { float s = sigmoidf_(u); du = g * (s + u * s * (1.f - s)); }
+  else { du = g; }
+}
+
 // ---- gating / activation of the temporal conv (layers.py:92-115) ---------------------------
 template <class T>
 struct GateArgs {
@@ -500,10 +544,52 @@ __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres
   stf(dx + row * Cin + j, ldf(dx + row * Cin + j) + ldf(dz + r * W + j));
 }
 
+// 8 channels per thread (requires Cout, W and Cin to be multiples of 8 when a residual is read)
+template <class T, int ACT>
+__global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
+  const int groups = a.Cout / 8;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= a.rows * groups) return;
+  const long long r = idx / groups;
+  const int j0 = (int)(idx - r * groups) * 8;
+  constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
+  float zp[8], zq[8], res[8];
+  load8(a.z + r * a.W + j0, zp);
+  if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) res[i] = 0.f;
+  if (a.explicit_res && j0 < a.Cin) {
+    long long TN_out = (long long)a.T_out * a.N;
+    long long b = r / TN_out;
+    long long rem = r - b * TN_out;
+    long long row = b * a.T_in * a.N + rem + (long long)(a.Kt - 1) * a.N;
+    load8(a.xin + row * a.Cin + j0, res);      // Cin % 8 == 0 is checked by the launcher
+  }
+  if (!bwd) {
+    float h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = act_fwd(ACT, zp[i] + res[i], gated ? zq[i] : 0.f);
+    store8(a.y + r * a.Cout + j0, h);
+  } else {
+    float g[8], du[8], dq[8];
+    load8(a.dy + r * a.Cout + j0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) act_bwd(ACT, zp[i] + res[i], gated ? zq[i] : 0.f, g[i], du[i], dq[i]);
+    store8(a.dz + r * a.W + j0, du);
+    if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
+  }
+}
+
 template <class T, int ACT>
 inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   long long n = a.rows * a.Cout;
   if (n == 0) return;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (a.Cout % 8 == 0 && a.W % 8 == 0 && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
+      al16(a.dy) && al16(a.y) && al16(a.dz)) {
+    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, 0, s, a, bwd ? 1 : 0);
+    return;
+  }
   if (bwd) STGCN_LAUNCH((gate_bwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
   else     STGCN_LAUNCH((gate_fwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
 }
@@ -537,35 +623,6 @@ struct SmallCArgs {
   int Cin, Cout, W, Kt, T_out, T_in, N, act, explicit_res, rows_per_cta;
 };
 
-__device__ __forceinline__ void store8(float* p, const float* v) {
-  reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
-  reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
-}
-__device__ __forceinline__ void store8(bf16* p, const float* v) {
-  uint4 a;
-  __nv_bfloat162 t0 = __floats2bfloat162_rn(v[0], v[1]), t1 = __floats2bfloat162_rn(v[2], v[3]);
-  __nv_bfloat162 t2 = __floats2bfloat162_rn(v[4], v[5]), t3 = __floats2bfloat162_rn(v[6], v[7]);
-  a.x = *reinterpret_cast<uint32_t*>(&t0); a.y = *reinterpret_cast<uint32_t*>(&t1);
-  a.z = *reinterpret_cast<uint32_t*>(&t2); a.w = *reinterpret_cast<uint32_t*>(&t3);
-  *reinterpret_cast<uint4*>(p) = a;
-}
-
-__device__ __forceinline__ float act_fwd(int act, float u, float q) {
-  if (act == STGCN_ACT_GLU) return u * sigmoidf_(q);
-  if (act == STGCN_ACT_GTU) return tanhf(u) * sigmoidf_(q);
-  if (act == STGCN_ACT_RELU) return fmaxf(u, 0.f);
-  if (act == STGCN_ACT_SILU) return u * sigmoidf_(u);
-  return u;
-}
-// gradients of act_fwd w.r.t. (u, q) times g
-__device__ __forceinline__ void act_bwd(int act, float u, float q, float g, float& du, float& dq) {
-  dq = 0.f;
-  if (act == STGCN_ACT_GLU) { float s = sigmoidf_(q); du = g * s; dq = g * u * s * (1.f - s); }
-  else if (act == STGCN_ACT_GTU) { float s = sigmoidf_(q), th = tanhf(u); du = g * s * (1.f - th * th); dq = g * th * s * (1.f - s); }
-  else if (act == STGCN_ACT_RELU) { du = u > 0.f ? g : 0.f; }
-  else if (act == STGCN_ACT_SILU) { float s = sigmoidf_(u); du = g * (s + u * s * (1.f - s)); }
-  else { du = g; }
-}
 
 template <class T>
 __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T> a) {
@@ -741,24 +798,55 @@ __global__ void convert_kernel(const TI* in, TO* out, long long n) {
 // y = relu?(g + a)
 template <class T>
 __global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int relu) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  float v = ldf(g + i) + (a ? ldf(a + i) : 0.f);
-  stf(y + i, relu ? fmaxf(v, 0.f) : v);
+  if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    float u[8], w[8];
+    load8(g + i, u);
+    if (a) { load8(a + i, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] += w[k]; }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) u[k] = fmaxf(u[k], 0.f); }
+    store8(y + i, u);
+  } else {
+    for (long long e = i + 8 < n ? i + 8 : n; i < e; ++i) {
+      float v = ldf(g + i) + (a ? ldf(a + i) : 0.f);
+      stf(y + i, relu ? fmaxf(v, 0.f) : v);
+    }
+  }
 }
 // dg = relu ? dy * (y > 0) : dy
 template <class T>
 __global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int relu) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  stf(dg + i, (!relu || ldf(y + i) > 0.f) ? ldf(dy + i) : 0.f);
+  if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dg)) & 15) == 0) {
+    float d[8], v[8];
+    load8(dy + i, d); load8(y + i, v);
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = v[k] > 0.f ? d[k] : 0.f; }
+    store8(dg + i, d);
+  } else {
+    for (long long e = i + 8 < n ? i + 8 : n; i < e; ++i) stf(dg + i, (!relu || ldf(y + i) > 0.f) ? ldf(dy + i) : 0.f);
+  }
 }
 // y += alpha * x
 template <class T>
 __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
-  stf(y + i, ldf(y + i) + alpha * ldf(x + i));
+  if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    float a[8], b[8];
+    load8(x + i, a); load8(y + i, b);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) b[k] += alpha * a[k];
+    store8(y + i, b);
+  } else {
+    for (long long e = i + 8 < n ? i + 8 : n; i < e; ++i) stf(y + i, ldf(y + i) + alpha * ldf(x + i));
+  }
 }
 // y = relu(x), with optional dropout; and its backward
 template <class T>
@@ -798,7 +886,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return red[0];
 }
 
-template <class T>
+// VEC = 8: 8 elements per thread per step (requires M % 8 == 0 and 16-byte aligned tensors); VEC = 1: scalar.
+template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w, const float* b, T* y,
                                                      float* mean, float* rstd, int M, float eps, int training,
                                                      float p, uint64_t seed) {
@@ -806,23 +895,45 @@ __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w,
   long long g = blockIdx.x;
   const T* xp = x + g * M;
   float s = 0.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) s += ldf(xp + i);
+  for (int i = threadIdx.x * VEC; i < M; i += blockDim.x * VEC) {
+    if (VEC == 8) { float v[8]; load8(xp + i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k]; }
+    else s += ldf(xp + i);
+  }
   float mu = block_sum(s, red) / M;
   float q = 0.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) { float d = ldf(xp + i) - mu; q += d * d; }
+  for (int i = threadIdx.x * VEC; i < M; i += blockDim.x * VEC) {
+    if (VEC == 8) { float v[8]; load8(xp + i, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { float d = v[k] - mu; q += d * d; } }
+    else { float d = ldf(xp + i) - mu; q += d * d; }
+  }
   float var = block_sum(q, red) / M;
   float rs = rsqrtf(var + eps);
   if (threadIdx.x == 0) { mean[g] = mu; rstd[g] = rs; }
   bool drop = training && p > 0.f;
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float v = (ldf(xp + i) - mu) * rs * w[i] + b[i];
-    if (drop) v = dropout_keep(seed, (uint64_t)(g * M + i), p) ? v * keep_scale : 0.f;
-    stf(y + g * M + i, v);
+  for (int i = threadIdx.x * VEC; i < M; i += blockDim.x * VEC) {
+    if (VEC == 8) {
+      float v[8], wv[8], bv[8];
+      load8(xp + i, v); load8(w + i, wv); load8(b + i, bv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float o = (v[k] - mu) * rs * wv[k] + bv[k];
+        if (drop) o = dropout_keep(seed, (uint64_t)(g * M + i + k), p) ? o * keep_scale : 0.f;
+        v[k] = o;
+      }
+      store8(y + g * M + i, v);
+    } else {
+      float v = (ldf(xp + i) - mu) * rs * w[i] + b[i];
+      if (drop) v = dropout_keep(seed, (uint64_t)(g * M + i), p) ? v * keep_scale : 0.f;
+      stf(y + g * M + i, v);
+    }
   }
 }
 
-template <class T>
+template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
                                                      const float* rstd, T* dx, int M, int training, float p,
                                                      uint64_t seed) {
@@ -834,44 +945,70 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, co
   bool drop = training && p > 0.f;
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
   float s1 = 0.f, s2 = 0.f;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float d = ldf(dp + i);
-    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
-    float gi = d * w[i];
-    float xh = (ldf(xp + i) - mu) * rs;
-    s1 += gi; s2 += gi * xh;
+  for (int i = threadIdx.x * VEC; i < M; i += blockDim.x * VEC) {
+    float xv[VEC], dv[VEC], wv[VEC];
+    if (VEC == 8) { load8(xp + i, xv); load8(dp + i, dv); load8(w + i, wv); }
+    else { xv[0] = ldf(xp + i); dv[0] = ldf(dp + i); wv[0] = w[i]; }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float d = dv[k];
+      if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i + k), p) ? d * keep_scale : 0.f;
+      float gi = d * wv[k];
+      float xh = (xv[k] - mu) * rs;
+      s1 += gi; s2 += gi * xh;
+    }
   }
   s1 = block_sum(s1, red) / M;
   s2 = block_sum(s2, red) / M;
-  for (int i = threadIdx.x; i < M; i += blockDim.x) {
-    float d = ldf(dp + i);
-    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
-    float gi = d * w[i];
-    float xh = (ldf(xp + i) - mu) * rs;
-    stf(dx + g * M + i, rs * (gi - s1 - xh * s2));
+  for (int i = threadIdx.x * VEC; i < M; i += blockDim.x * VEC) {
+    float xv[VEC], dv[VEC], wv[VEC], o[VEC];
+    if (VEC == 8) { load8(xp + i, xv); load8(dp + i, dv); load8(w + i, wv); }
+    else { xv[0] = ldf(xp + i); dv[0] = ldf(dp + i); wv[0] = w[i]; }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float d = dv[k];
+      if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i + k), p) ? d * keep_scale : 0.f;
+      float gi = d * wv[k];
+      float xh = (xv[k] - mu) * rs;
+      o[k] = rs * (gi - s1 - xh * s2);
+    }
+    if (VEC == 8) store8(dx + g * M + i, o);
+    else stf(dx + g * M + i, o[0]);
   }
 }
 
 // dw[i] += sum_g dy'[g,i] * xhat[g,i];  db[i] += sum_g dy'[g,i]   (pre-zeroed, atomics over group chunks)
-template <class T>
+template <class T, int VEC>
 __global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean, const float* rstd, float* dw,
                                      float* db, int M, long long G, int groups_per_cta, int training, float p,
                                      uint64_t seed) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i >= M) return;
   long long g0 = (long long)blockIdx.y * groups_per_cta;
   long long g1 = min(G, g0 + groups_per_cta);
   bool drop = training && p > 0.f;
   float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
-  float aw = 0.f, ab = 0.f;
+  float aw[VEC], ab[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { aw[k] = 0.f; ab[k] = 0.f; }
   for (long long g = g0; g < g1; ++g) {
-    float d = ldf(dy + g * M + i);
-    if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i), p) ? d * keep_scale : 0.f;
-    aw += d * (ldf(x + g * M + i) - mean[g]) * rstd[g];
-    ab += d;
+    float xv[VEC], dv[VEC];
+    if (VEC == 8) { load8(x + g * M + i, xv); load8(dy + g * M + i, dv); }
+    else { xv[0] = ldf(x + g * M + i); dv[0] = ldf(dy + g * M + i); }
+    const float mu = mean[g], rs = rstd[g];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      float d = dv[k];
+      if (drop) d = dropout_keep(seed, (uint64_t)(g * M + i + k), p) ? d * keep_scale : 0.f;
+      aw[k] += d * (xv[k] - mu) * rs;
+      ab[k] += d;
+    }
   }
-  if (dw) atomicAdd(dw + i, aw);
-  if (db) atomicAdd(db + i, ab);
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) {
+    if (dw) atomicAdd(dw + i + k, aw[k]);
+    if (db) atomicAdd(db + i + k, ab[k]);
+  }
 }
 
 // loss = mean((pred-target)^2); dpred = 2 (pred-target)/n * scale

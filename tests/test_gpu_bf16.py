@@ -31,24 +31,33 @@ def _model(cfg, gso, dev):
     return cls(args, cfg["blocks"], cfg["n"]).to(dev)
 
 
-def _emulated_errors(g):
-    """Per-tensor error of the bf16-storage error model (tests/bf16_emulation.py) against the golden vectors."""
+def _emulated_errors(g, draws=6):
+    """Per-tensor error of the bf16-storage error model (tests/bf16_emulation.py): max over a few noise draws (the
+    input is perturbed by 1% so the rounding pattern is re-drawn; the fp32 oracle on the same input is the truth).
+    The distribution is heavy-tailed for tiny networks -- a single ReLU/GTU mask flip moves a small-batch gradient by
+    tens of percent -- so one draw is not a bound."""
     import bf16_emulation as E
-    params = {k: v.clone().requires_grad_(True) for k, v in g.params.items()}
-    x = g.x.clone().requires_grad_(True)
-    out = E.forward(x, params, g.gso, **g.model_cfg())
-    B = x.shape[0]
-    torch.nn.functional.mse_loss(out.reshape(B, -1), g.y).backward()
-    errs = {"out": rel_l2(out, g.out), "dx": rel_l2(x.grad, g.dx)}
-    for k, gref in g.grads.items():
-        errs["g:" + k] = rel_l2(params[k].grad, gref)
-    return errs
+    worst = {}
+    for trial in range(draws):
+        gen = torch.Generator().manual_seed(trial)
+        x0 = g.x if trial == 0 else g.x * (1 + 1e-2 * torch.randn(g.x.shape, generator=gen))
+        res = {}
+        for mode in ("ref", "emu"):
+            params = {k: v.clone().requires_grad_(True) for k, v in g.params.items()}
+            x = x0.clone().requires_grad_(True)
+            fn = O.stgcn_forward if mode == "ref" else E.forward
+            out = fn(x, params, g.gso, **g.model_cfg())
+            torch.nn.functional.mse_loss(out.reshape(x.shape[0], -1), g.y).backward()
+            res[mode] = {"out": out.detach(), "dx": x.grad, **{"g:" + k: params[k].grad for k in g.grads}}
+        for k in res["ref"]:
+            worst[k] = max(worst.get(k, 0.0), rel_l2(res["emu"][k], res["ref"][k]))
+    return worst
 
 
 @pytest.mark.parametrize("name", golden_case_names())
 def test_bf16_model_close_to_reference_golden(name, cuda_device):
     """bf16 mode vs the reference's golden vectors.  Bound: outputs 3e-2; every gradient tensor within
-    max(GRAD_TOL, 3x the bf16-storage error model) -- i.e. no worse than what storing activations in bf16 costs."""
+    max(GRAD_TOL, 2x the bf16-storage error model's worst draw) -- i.e. no worse than what storing activations in bf16 costs."""
     g = GoldenCase(name)
     dev = cuda_device
     model = _model(g.cfg, g.gso, dev)
@@ -69,7 +78,7 @@ def test_bf16_model_close_to_reference_golden(name, cuda_device):
     worst_model = max(v for k, v in model_err.items() if k != "out")
     bad = {}
     for k, v in errs.items():
-        bound = OUT_TOL if k == "out" else max(GRAD_TOL, 3.0 * model_err[k], 1.5 * worst_model)
+        bound = OUT_TOL if k == "out" else max(GRAD_TOL, 2.0 * model_err[k], 1.0 * worst_model)
         if v > bound:
             bad[k] = (round(v, 4), round(bound, 4))
     assert not bad, bad
