@@ -135,6 +135,9 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
   float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
   simt::bf16* wdbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
+  const long long sc_rpc = std::max<long long>(64, (g.rows_out + 148 * 8 - 1) / (148 * 8));
+  const int sc_ctas = g.rows_out > 0 ? ceil_div(g.rows_out, sc_rpc) : 0;
+  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows_out, Kw + 1, g.W), (size_t)sc_ctas * (Kw + 1) * g.W));
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
@@ -147,12 +150,15 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     sa.act = d.act; sa.explicit_res = (g.folded || g.linear) ? 0 : 1;
     const int threads = d.c_out >= 256 ? 256 : 256 / d.c_out * d.c_out;
     const int lanes = threads / d.c_out;
-    long long rpc = (g.rows_out + 148 * 8 - 1) / (148 * 8);
-    if (rpc < 64) rpc = 64;
-    sa.rows_per_cta = (int)rpc;
+    sa.rows_per_cta = (int)sc_rpc;
+    sa.partial = part;
     size_t smem = (size_t)lanes * 2 * (Kw + 1) * d.c_out * sizeof(float);
     STGCN_CUDA(cudaFuncSetAttribute(smallc_gate_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, ceil_div(g.rows_out, rpc), threads, smem, c.stream, sa);
+    STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, sc_ctas, threads, smem, c.stream, sa);
+    {
+      const int n = (Kw + 1) * g.W;
+      STGCN_LAUNCH(reduce_partials_kernel, ceil_div(n, 256), 256, 0, c.stream, (const float*)part, dwt, n, sc_ctas);
+    }
   } else {
     GateArgs<T> ga{};
     ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
@@ -171,7 +177,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     if (!done_w) {
       WgradArgs<T> w{};
       w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
-      w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0};
+      w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0}; w.partial = part;
       launch_wgrad(w, c.stream);
     }
     // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]
@@ -222,6 +228,24 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
                           d.c_in, d.Kt, g.T_out, d.T, d.N);
     }
   }
+}
+
+// 1-tap linear map through the tcgen05 tap kernel (bf16 path): out[(b,t,n), :Co] = in . w^T + bias (+ aux) (relu)
+// w_bf: bf16 [Kt][Co][Cin] window-ordered.  Returns false when the shape is not served (caller falls back to SIMT).
+struct UmmaLinearOpts {
+  int Kt = 1; long long in_stride_n = 0, in_stride_t = 0, in_stride_b = 0;
+  const simt::bf16* aux = nullptr; int T_aux = 1, C_aux = 0, aux_cols = 0; int relu = 0;
+};
+inline bool umma_linear(const simt::bf16* in, const simt::bf16* w_bf, const float* bias, simt::bf16* out, int B, int T_src,
+                        int T_out, int N, int Cin, int Co, const UmmaLinearOpts& o, cudaStream_t stream, bool probe_only) {
+  umma::TapProblem q{};
+  q.in = in; q.w = w_bf; q.bias = bias; q.B = B; q.N = N; q.T_src = T_src; q.T_out = T_out; q.Kt = o.Kt; q.t0 = 0;
+  q.Cin = Cin; q.Co = Co; q.epi = umma::EPI_LINEAR; q.aux = o.aux; q.aux_dt = 0; q.T_aux = o.T_aux; q.C_aux = o.C_aux;
+  q.aux_cols = o.aux_cols; q.out = out; q.ld_out = Co; q.in_stride_n = o.in_stride_n; q.in_stride_t = o.in_stride_t;
+  q.in_stride_b = o.in_stride_b; q.relu = o.relu;
+  if (B <= 0 || !umma::tap_supported(q)) return false;
+  if (!probe_only) umma::launch_tap(q, stream);
+  return true;
 }
 
 // ============================ graph convolution layer ========================================
@@ -276,10 +300,22 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   const size_t plane = (size_t)rows * C;
   float* wat = c.ws.take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
   simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
+  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
+                                              ? std::max((size_t)d.c_in * C, (size_t)(d.Ks > 1 ? d.Ks : 1) * C * C) : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
   T* x0 = stack;
-  if (d.c_in > C) {
+  bool align_done = false, mix_done = false;
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (d.c_in > C && umma_linear(x, wbf, p.align_b, x0, d.B, d.T, d.T, d.N, d.c_in, C, UmmaLinearOpts{}, c.stream, true)) {
+      STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
+      launch_gather3(p.align_w, wbf, 1, 1, C * d.c_in, 0, 0, 0, 1, 0, c.stream);            // [o][c] as is
+      umma_linear(x, wbf, p.align_b, x0, d.B, d.T, d.T, d.N, d.c_in, C, UmmaLinearOpts{}, c.stream, false);
+      align_done = true;
+    }
+  }
+  if (align_done) {
+  } else if (d.c_in > C) {
     STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
     launch_gather3(p.align_w, wat, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // wat[c][o] = align_w[o][c]
     TapArgs<T> t{};
@@ -302,8 +338,26 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
     gso(x0, nullptr, stack + plane, 1.f, 0.f);
     t.in = stack + plane; t.wt = p.w; t.ntaps = 1; t.map = RowMap{d.T, d.T, d.N, 0, 0};
   }
-  launch_tapgemm(t, c.stream);
-  STGCN_LAUNCH(add_relu_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, (const T*)y, (const T*)(d.residual ? x0 : nullptr), y, (long long)plane, d.relu);
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    // weight contraction + bias + residual + ReLU in one tcgen05 kernel: the stack planes are the "taps"
+    const int BT = d.B * d.T;
+    UmmaLinearOpts o{};
+    o.in_stride_n = C; o.in_stride_t = (long long)plane; o.in_stride_b = (long long)d.N * C;
+    o.aux = d.residual ? x0 : nullptr; o.T_aux = 1; o.C_aux = C; o.aux_cols = d.residual ? C : 0; o.relu = d.relu;
+    const bool cheb = d.gconv == STGCN_GCONV_CHEB;
+    o.Kt = cheb ? d.Ks : 1;
+    const simt::bf16* src = cheb ? stack : stack + plane;
+    if (umma_linear(src, wbf, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, true)) {
+      // W_j[o][c] = w[j][c][o]
+      launch_gather3(p.w, wbf, o.Kt, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
+      umma_linear(src, wbf, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, false);
+      mix_done = true;
+    }
+  }
+  if (!mix_done) {
+    launch_tapgemm(t, c.stream);
+    STGCN_LAUNCH(add_relu_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, (const T*)y, (const T*)(d.residual ? x0 : nullptr), y, (long long)plane, d.relu);
+  }
 }
 
 template <class T>
@@ -322,6 +376,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
   simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
+  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(rows, ntw * C + 1, C),
+                                          d.c_in > C ? wgrad_partial_elems(rows, d.c_in + 1, C) : (size_t)0));
+  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
+                                              ? std::max((size_t)d.c_in * C, (size_t)ntw * C * C) : 0);
   if (c.dry()) return;
   STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
@@ -330,15 +388,27 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
   t.map = RowMap{d.T, d.T, d.N, 0, 0};
   WgradArgs<T> w{};
-  w.dz = dg; w.dwt = dwt; w.rows = rows; w.Cin = C; w.Co = C; w.ldz = C; w.bias_row = 1;
+  w.dz = dg; w.dwt = dwt; w.rows = rows; w.Cin = C; w.Co = C; w.ldz = C; w.bias_row = 1; w.partial = part;
   zero(dwt, (size_t)(ntw * C + 1) * C, c.stream);
 
   if (d.gconv == STGCN_GCONV_CHEB) {
     // wT[k][j][i] = w[k][i][j];  d stack[k] = dG W_k^T
-    launch_gather3(p.w, wT, d.Ks, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
-    for (int k = 0; k < d.Ks; ++k) {
-      t.wt = wT + (size_t)k * C * C; t.out = dst + (size_t)k * plane;
-      launch_tapgemm(t, c.stream);
+    bool dstack_done = false;
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (umma_linear(dg, wbf, nullptr, dst, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
+        launch_gather3(p.w, wbf, 1, 1, d.Ks * C * C, 0, 0, 0, 1, 0, c.stream);      // [k][o=i][c=j] = w[k][i][j] as is
+        for (int k = 0; k < d.Ks; ++k)
+          umma_linear(dg, wbf + (size_t)k * C * C, nullptr, dst + (size_t)k * plane, d.B, d.T, d.T, d.N, C, C,
+                      UmmaLinearOpts{}, c.stream, false);
+        dstack_done = true;
+      }
+    }
+    if (!dstack_done) {
+      launch_gather3(p.w, wT, d.Ks, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
+      for (int k = 0; k < d.Ks; ++k) {
+        t.wt = wT + (size_t)k * C * C; t.out = dst + (size_t)k * plane;
+        launch_tapgemm(t, c.stream);
+      }
     }
     if (gr.w || gr.b) {
       w.in = stack; w.ntaps = d.Ks; w.map = RowMap{d.T, d.T, d.N, 0, rows};
@@ -355,9 +425,19 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     }
     if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
   } else {
-    launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
-    t.wt = wT; t.out = dst + plane;
-    launch_tapgemm(t, c.stream);
+    bool dx1_done = false;
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
+        launch_gather3(p.w, wbf, 1, 1, C * C, 0, 0, 0, 1, 0, c.stream);             // [o=i][c=j] = w[i][j] as is
+        umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, false);
+        dx1_done = true;
+      }
+    }
+    if (!dx1_done) {
+      launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
+      t.wt = wT; t.out = dst + plane;
+      launch_tapgemm(t, c.stream);
+    }
     if (gr.w || gr.b) {
       w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
       launch_wgrad(w, c.stream);
@@ -373,10 +453,17 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
       WgradArgs<T> wa{};
       wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
-      wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0};
+      wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
       launch_wgrad(wa, c.stream);
       if (gr.align_w) launch_gather3(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C, 0, c.stream);
       if (gr.align_b) launch_gather3(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1, 0, c.stream);
+    }
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (dx && umma_linear(dst, wbf, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, true)) {
+        launch_gather3(p.align_w, wbf, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // [o=i][c] = align_w[c][i]
+        umma_linear(dst, wbf, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, false);
+        dx = nullptr;
+      }
     }
     if (dx) {
       TapArgs<T> ta{};
@@ -542,6 +629,7 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
   ScopedMark sm(c.ws);
   float* w1t = c.ws.take<float>((size_t)d.c0 * d.c1);
   float* w2t = c.ws.take<float>((size_t)d.c1 * d.c_end);
+  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.fc1_w && p.fc2_w, STGCN_E_INVALID, "outblock: missing fc weights");
   launch_gather3(p.fc1_w, w1t, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);      // w1t[c][o] = fc1_w[o][c]
@@ -549,7 +637,15 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
   TapArgs<T> t{};
   t.in = s.l; t.wt = w1t; t.bias = p.fc1_b; t.out = s.f1; t.rows = g.rows1; t.Cin = d.c0; t.Co = d.c1; t.ntaps = 1;
   t.ldo = d.c1; t.map = RowMap{g.T1, g.T1, d.N, 0, 0};
-  launch_tapgemm(t, c.stream);
+  bool fc1_done = false;
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, true)) {
+      launch_gather3(p.fc1_w, wbf, 1, 1, d.c1 * d.c0, 0, 0, 0, 1, 0, c.stream);      // [o][c] as is
+      umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, false);
+      fc1_done = true;
+    }
+  }
+  if (!fc1_done) launch_tapgemm(t, c.stream);
   long long n1 = g.rows1 * d.c1;
   if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
   TapArgs<T, float> t2{};
@@ -572,6 +668,9 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   T* dyT = c.ws.take<T>(sizeof(T) == sizeof(float) ? 0 : (size_t)g.rows1 * d.c_end);
   float* dw2 = c.ws.take<float>((size_t)(d.c1 + 1) * d.c_end);
   float* dw1 = c.ws.take<float>((size_t)(d.c0 + 1) * d.c1);
+  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
+                                          wgrad_partial_elems(g.rows1, d.c0 + 1, d.c1)));
+  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
   if (!c.dry()) {
     Tag t_fc("out.fc.bwd");
     RowMap rm{g.T1, g.T1, d.N, 0, 0};
@@ -594,7 +693,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
       WgradArgs<T> w{};
       w.in = s.r; w.dz = dy_t; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
-      w.bias_row = 1; w.map = rm;
+      w.bias_row = 1; w.map = rm; w.partial = part;
       launch_wgrad(w, c.stream);
       if (gr.fc2_w) launch_gather3(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end, 0, c.stream);
       if (gr.fc2_b) launch_gather3(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1, 0, c.stream);
@@ -602,8 +701,18 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     long long n1 = g.rows1 * d.c1;
     if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, (const T*)s.f1, df1, n1, d.training, d.p_drop, seed);
     // fc1
-    t.in = df1; t.wt = p.fc1_w; t.out = dl; t.Cin = d.c1; t.Co = d.c0; t.ldo = d.c0;
-    launch_tapgemm(t, c.stream);
+    bool dl_done = false;
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (umma_linear(df1, wbf, nullptr, dl, d.B, g.T1, g.T1, d.N, d.c1, d.c0, UmmaLinearOpts{}, c.stream, true)) {
+        launch_gather3(p.fc1_w, wbf, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);     // [o=c0 idx][c=c1 idx] = fc1_w[c][o]
+        umma_linear(df1, wbf, nullptr, dl, d.B, g.T1, g.T1, d.N, d.c1, d.c0, UmmaLinearOpts{}, c.stream, false);
+        dl_done = true;
+      }
+    }
+    if (!dl_done) {
+      t.in = df1; t.wt = p.fc1_w; t.out = dl; t.Cin = d.c1; t.Co = d.c0; t.ldo = d.c0;
+      launch_tapgemm(t, c.stream);
+    }
     if (gr.fc1_w || gr.fc1_b) {
       zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.stream);
       bool done_w = false;
@@ -616,7 +725,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       if (!done_w) {
         WgradArgs<T> w{};
         w.in = s.l; w.dz = df1; w.dwt = dw1; w.rows = g.rows1; w.Cin = d.c0; w.Co = d.c1; w.ntaps = 1; w.ldz = d.c1;
-        w.bias_row = 1; w.map = rm;
+        w.bias_row = 1; w.map = rm; w.partial = part;
         launch_wgrad(w, c.stream);
       }
       if (gr.fc1_w) launch_gather3(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1, 0, c.stream);

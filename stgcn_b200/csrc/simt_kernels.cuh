@@ -304,6 +304,8 @@ struct WgradArgs {
   int bias_row;        // 1: extra last row = column sums of dz (bias gradient)
   int rows_per_cta;
   RowMap map;
+  float* partial;      // optional [gridDim.z][Mtot*Co] scratch: per-CTA partial sums (two-stage reduction) instead of
+                       // same-address atomics from ~1000 CTAs, which serialise in L2
 };
 
 template <class T, int BM, int BN, int TM, int TN>
@@ -405,35 +407,59 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) {
       int o = col0 + tx * TN + j;
-      if (o < a.Co) atomicAdd(a.dwt + (long long)mm * a.Co + o, acc[i][j]);
+      if (o >= a.Co) continue;
+      if (a.partial) a.partial[((long long)blockIdx.z * Mtot + mm) * a.Co + o] = acc[i][j];
+      else atomicAdd(a.dwt + (long long)mm * a.Co + o, acc[i][j]);
     }
   }
+}
+
+// out[e] += sum_c partial[c][e]
+__global__ void reduce_partials_kernel(const float* partial, float* out, int n, int chunks) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float s = 0.f;
+  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * n + e];
+  out[e] += s;
+}
+
+struct WgradPlanSimt { int mode, tiles, chunks; long long rpc; };
+inline WgradPlanSimt plan_wgrad_simt(long long rows, int Mtot, int Co) {
+  WgradPlanSimt pl;
+  if (Co <= 16) { pl.mode = Mtot <= 64 ? 0 : 1; pl.tiles = ceil_div(Mtot, pl.mode == 0 ? 64 : 128); }
+  else if (Mtot <= 16) { pl.mode = 2; pl.tiles = ceil_div(Co, 64); }
+  else { pl.mode = 3; pl.tiles = ceil_div(Mtot, 64) * ceil_div(Co, 64); }
+  // aim for ~8 CTAs per SM in total, at least 256 rows per CTA
+  long long want = (148 * 8 + pl.tiles - 1) / pl.tiles;
+  long long rpc = (rows + want - 1) / want;
+  if (rpc < 256) rpc = 256;
+  pl.rpc = (rpc + BK - 1) / BK * BK;
+  pl.chunks = rows > 0 ? ceil_div(rows, pl.rpc) : 0;
+  return pl;
+}
+inline size_t wgrad_partial_elems(long long rows, int Mtot, int Co) {
+  return (size_t)plan_wgrad_simt(rows, Mtot, Co).chunks * Mtot * Co;
 }
 
 template <class T>
 inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
   const int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
-  // tile shape by output shape: skinny in Co (<=16), skinny in M (<=16, e.g. the first layer's Cin = 1), or square
-  int mode, tiles;
-  if (a.Co <= 16) { mode = Mtot <= 64 ? 0 : 1; tiles = ceil_div(Mtot, mode == 0 ? 64 : 128); }
-  else if (Mtot <= 16) { mode = 2; tiles = ceil_div(a.Co, 64); }
-  else { mode = 3; tiles = ceil_div(Mtot, 64) * ceil_div(a.Co, 64); }
-  // aim for ~8 CTAs per SM in total, at least 256 rows per CTA
-  long long want = (148 * 8 + tiles - 1) / tiles;
-  long long rpc = (a.rows + want - 1) / want;
-  if (rpc < 256) rpc = 256;
-  rpc = (rpc + BK - 1) / BK * BK;
-  a.rows_per_cta = (int)rpc;
-  const int chunks = ceil_div(a.rows, rpc);
-  if (mode == 0) {
+  const WgradPlanSimt pl = plan_wgrad_simt(a.rows, Mtot, a.Co);
+  a.rows_per_cta = (int)pl.rpc;
+  const int chunks = pl.chunks;
+  if (pl.mode == 0) {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 16, 1, 4>), dim3(ceil_div(Mtot, 64), 1, chunks), NT, 0, s, a);
-  } else if (mode == 1) {
+  } else if (pl.mode == 1) {
     STGCN_LAUNCH((wgrad_kernel<T, 128, 16, 2, 4>), dim3(ceil_div(Mtot, 128), 1, chunks), NT, 0, s, a);
-  } else if (mode == 2) {
+  } else if (pl.mode == 2) {
     STGCN_LAUNCH((wgrad_kernel<T, 16, 64, 1, 4>), dim3(1, ceil_div(a.Co, 64), chunks), NT, 0, s, a);
   } else {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 64, 4, 4>), dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks), NT, 0, s, a);
+  }
+  if (a.partial) {
+    const int n = Mtot * a.Co;
+    STGCN_LAUNCH(reduce_partials_kernel, ceil_div(n, 256), 256, 0, s, (const float*)a.partial, a.dwt, n, chunks);
   }
 }
 
@@ -619,6 +645,7 @@ struct SmallCArgs {
   const T* dh;         // bwd: [rows, Cout]
   T* dz;               // bwd (optional): [rows, W]
   float* dwt;          // bwd: [(Kt*Cin + 1)][W], pre-zeroed
+  float* partial;      // bwd, optional: [gridDim.x][(Kt*Cin + 1)*W] per-CTA partial sums (reduced by reduce_partials_kernel)
   long long rows;
   int Cin, Cout, W, Kt, T_out, T_in, N, act, explicit_res, rows_per_cta;
 };
@@ -732,7 +759,9 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
     float v = 0.f;
     for (int l = 0; l < lanes; ++l) v += red[(l * 2 + half) * stride + rest];
     const int kk = rest / a.Cout, jj = rest - kk * a.Cout;
-    atomicAdd(a.dwt + (long long)kk * a.W + half * a.Cout + jj, v);
+    const long long off = (long long)kk * a.W + half * a.Cout + jj;
+    if (a.partial) a.partial[(long long)blockIdx.x * (K + 1) * a.W + off] = v;
+    else atomicAdd(a.dwt + off, v);
   }
 }
 
@@ -743,7 +772,8 @@ inline bool smallc_supported(int Cin, int Cout, int W, int Kt) {
 
 // ---- small elementwise / layout kernels ----------------------------------------------------
 // out[i0][i1][i2] (contiguous) (+)= in[off + i0*s0 + i1*s1 + i2*s2]
-__global__ void gather3_kernel(const float* in, float* out, int d0, int d1, int d2, long long off,
+template <class TO>
+__global__ void gather3_kernel(const float* in, TO* out, int d0, int d1, int d2, long long off,
                                long long s0, long long s1, long long s2, int accumulate) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (long long)d0 * d1 * d2;
@@ -753,13 +783,15 @@ __global__ void gather3_kernel(const float* in, float* out, int d0, int d1, int 
   int i1 = (int)(q % d1);
   int i0 = (int)(q / d1);
   float v = in[off + i0 * s0 + i1 * s1 + i2 * s2];
-  if (accumulate) out[idx] += v; else out[idx] = v;
+  if (accumulate) v += ldf(out + idx);
+  stf(out + idx, v);
 }
-inline void launch_gather3(const float* in, float* out, int d0, int d1, int d2, long long off, long long s0,
+template <class TO>
+inline void launch_gather3(const float* in, TO* out, int d0, int d1, int d2, long long off, long long s0,
                            long long s1, long long s2, int accumulate, cudaStream_t s) {
   long long tot = (long long)d0 * d1 * d2;
   if (tot == 0) return;
-  STGCN_LAUNCH(gather3_kernel, ceil_div(tot, 256), 256, 0, s, in, out, d0, d1, d2, off, s0, s1, s2, accumulate);
+  STGCN_LAUNCH(gather3_kernel<TO>, ceil_div(tot, 256), 256, 0, s, in, out, d0, d1, d2, off, s0, s1, s2, accumulate);
 }
 
 // out[i*ldo + j] += in[i*si + j*sj]   (strided block accumulate; used to fold 1x1 align weights)

@@ -46,6 +46,7 @@ struct TapParams {
   int ld_out, co_valid;
   bf16* out_z;                // gate: z [rows_out, W]
   int n_items, n_node_tiles;
+  int relu;                   // linear epilogue: clamp at 0 after bias/aux
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -197,6 +198,10 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               for (int i = 0; i < 16; ++i)
                 if (co0 + c0 + i < p.aux_cols) v[i] += av[i];
             }
+            if (p.relu) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
             if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
           }
         } else {
@@ -264,6 +269,10 @@ struct TapProblem {
   const bf16* aux; int aux_dt, T_aux, C_aux, aux_cols;
   bf16* out; int ld_out;
   bf16* out_z;
+  // optional element strides of `in` for the vertex / time / batch axes (0 = dense [B,T_src,N,Cin]); lets a stack of
+  // planes [Kt][B*T][N][C] be read with the plane index as the "time" axis
+  long long in_stride_n, in_stride_t, in_stride_b;
+  int relu;
 };
 
 constexpr size_t kSmemBudget = 225 * 1024;
@@ -323,6 +332,9 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
                                : (pl.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   uint64_t xd[4] = {(uint64_t)q.Cin, (uint64_t)q.N, (uint64_t)q.T_src, (uint64_t)q.B};
   uint64_t xs[3] = {(uint64_t)q.Cin * 2, (uint64_t)q.N * q.Cin * 2, (uint64_t)q.T_src * q.N * q.Cin * 2};
+  if (q.in_stride_n) xs[0] = (uint64_t)q.in_stride_n * 2;
+  if (q.in_stride_t) xs[1] = (uint64_t)q.in_stride_t * 2;
+  if (q.in_stride_b) xs[2] = (uint64_t)q.in_stride_b * 2;
   uint32_t xb[4] = {(uint32_t)pl.KB, 128, 1, 1};
   CUtensorMap tmX = make_tmap_bf16(q.in, 4, xd, xs, xb, tsw);
   uint64_t wd[3] = {(uint64_t)q.Cin, (uint64_t)q.Co, (uint64_t)q.Kt};
@@ -336,7 +348,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.tile_bytes = pl.tile_bytes; p.w_bytes = pl.w_bytes;
   p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
   p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
-  p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z;
+  p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
   p.n_node_tiles = (q.N + 127) / 128;
   p.n_items = q.B * p.n_node_tiles;
   int gx = p.n_items < sm_count() / pl.nCoT ? p.n_items : sm_count() / pl.nCoT;
