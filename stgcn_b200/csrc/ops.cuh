@@ -46,6 +46,7 @@ inline TconvGeom tconv_geom(const stgcn_tconv_desc& d) {
   STGCN_CHECK(d.act >= STGCN_ACT_GLU && d.act <= STGCN_ACT_LINEAR, STGCN_E_UNSUPPORTED,
               "ERROR: The activation function is not implemented.");
   STGCN_CHECK(d.T >= d.Kt, STGCN_E_INVALID, "Kernel size can't be greater than actual input size (T < Kt)");
+  STGCN_CHECK((long long)d.B * d.T * d.N < (1LL << 31), STGCN_E_UNSUPPORTED, "more than 2^31 rows per tensor");
   TconvGeom g;
   g.T_out = d.T - d.Kt + 1;
   g.rows_in = (long long)d.B * d.T * d.N;
@@ -280,6 +281,7 @@ inline GsoRunner<T> make_gso_runner(const float* M, int trans, int N, int C, lon
 inline int gconv_stack_depth(const stgcn_gconv_desc& d) { return d.gconv == STGCN_GCONV_CHEB ? d.Ks : 2; }
 inline void gconv_check(const stgcn_gconv_desc& d) {
   STGCN_CHECK(d.B >= 0 && d.T > 0 && d.N > 0 && d.c_in > 0 && d.c_out > 0, STGCN_E_INVALID, "bad gconv desc");
+  STGCN_CHECK((long long)d.B * d.T * d.N < (1LL << 31), STGCN_E_UNSUPPORTED, "more than 2^31 rows per tensor");
   STGCN_CHECK(d.gconv == STGCN_GCONV_CHEB || d.gconv == STGCN_GCONV_GCN, STGCN_E_UNSUPPORTED, "unknown graph_conv_type");
   if (d.gconv == STGCN_GCONV_CHEB)
     STGCN_CHECK(d.Ks >= 1, STGCN_E_INVALID,

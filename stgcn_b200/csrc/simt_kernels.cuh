@@ -56,6 +56,16 @@ __device__ __forceinline__ void load8(const bf16* p, float* v) {
   }
 }
 
+// (b, rem) = divmod(r, TN_out), t = rem / N with 32-bit arithmetic (64-bit integer division costs ~100 instructions on
+// the GPU and dominated the elementwise kernels); the host guarantees rows < 2^31.
+__device__ __forceinline__ void row_decode(long long r, int TN_out, int N, long long TN_in, long long& base, int& t) {
+  const unsigned ru = (unsigned)r;
+  const unsigned b = ru / (unsigned)TN_out;
+  const unsigned rem = ru - b * (unsigned)TN_out;
+  t = (int)(rem / (unsigned)N);
+  base = (long long)b * TN_in + rem;
+}
+
 // Row geometry of a tap GEMM.  Output row r = (b, t, n), t < T_out.  Tap k reads input row
 // (b, t + t_shift*k, n) of a [B, T_in, N] tensor (invalid -> contributes 0), displaced by
 // k * tap_row_stride rows (stacked operands).
@@ -104,10 +114,7 @@ __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs<TI, TO> a) {
     int m = e / BK;
     long long r = row0 + m;
     if (r < a.rows) {
-      long long b = r / TN_out;
-      long long rem = r - b * TN_out;
-      a_t[j] = (int)(rem / a.map.N);
-      a_base[j] = b * TN_in + rem;
+      row_decode(r, (int)TN_out, a.map.N, TN_in, a_base[j], a_t[j]);
     } else {
       a_t[j] = -1000000;
       a_base[j] = 0;
@@ -349,10 +356,10 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
     if (tid < BK) {      // one row decode per K row (not per element): the divisions dominated this kernel
       long long r = k0 + tid;
       if (r < r_end) {
-        long long b = r / TN_out;
-        long long rem = r - b * TN_out;
-        row_t[tid] = (int)(rem / a.map.N);
-        row_base[tid] = b * TN_in + rem;
+        long long base; int t;
+        row_decode(r, (int)TN_out, a.map.N, TN_in, base, t);
+        row_t[tid] = t;
+        row_base[tid] = base;
       } else {
         row_t[tid] = 0;
         row_base[tid] = -1;
@@ -497,18 +504,16 @@ struct GateArgs {
 template <class T>
 __device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r, int j) {
   if (!a.explicit_res || j >= a.Cin) return 0.f;
-  long long TN_out = (long long)a.T_out * a.N;
-  long long b = r / TN_out;
-  long long rem = r - b * TN_out;
-  long long row = b * a.T_in * a.N + rem + (long long)(a.Kt - 1) * a.N;
-  return ldf(a.xin + row * a.Cin + j);
+  long long base; int t;
+  row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, base, t);
+  return ldf(a.xin + (base + (long long)(a.Kt - 1) * a.N) * a.Cin + j);
 }
 
 template <class T, int ACT>
 __global__ void gate_fwd_kernel(GateArgs<T> a) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
-  long long r = idx / a.Cout;
+  long long r = (long long)((unsigned long long)idx / (unsigned)a.Cout);
   int j = (int)(idx - r * a.Cout);
   float res = gate_residual(a, r, j);
   float p = ldf(a.z + r * a.W + j) + res;
@@ -563,10 +568,9 @@ __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres
   if (idx >= rows * Cres) return;
   long long r = idx / Cres;
   int j = (int)(idx - r * Cres);
-  long long TN_out = (long long)T_out * N;
-  long long b = r / TN_out;
-  long long rem = r - b * TN_out;
-  long long row = b * T_in * N + rem + (long long)(Kt - 1) * N;
+  long long base; int t;
+  row_decode(r, T_out * N, N, (long long)T_in * N, base, t);
+  long long row = base + (long long)(Kt - 1) * N;
   stf(dx + row * Cin + j, ldf(dx + row * Cin + j) + ldf(dz + r * W + j));
 }
 
@@ -576,7 +580,7 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
   const int groups = a.Cout / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * groups) return;
-  const long long r = idx / groups;
+  const long long r = (long long)((unsigned)idx / (unsigned)groups);    // rows * groups < 2^31 (launcher)
   const int j0 = (int)(idx - r * groups) * 8;
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   float zp[8], zq[8], res[8];
@@ -585,11 +589,9 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) res[i] = 0.f;
   if (a.explicit_res && j0 < a.Cin) {
-    long long TN_out = (long long)a.T_out * a.N;
-    long long b = r / TN_out;
-    long long rem = r - b * TN_out;
-    long long row = b * a.T_in * a.N + rem + (long long)(a.Kt - 1) * a.N;
-    load8(a.xin + row * a.Cin + j0, res);      // Cin % 8 == 0 is checked by the launcher
+    long long base; int t;
+    row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, base, t);
+    load8(a.xin + (base + (long long)(a.Kt - 1) * a.N) * a.Cin + j0, res);      // Cin % 8 == 0 is checked by the launcher
   }
   if (!bwd) {
     float h[8];
@@ -611,7 +613,7 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   long long n = a.rows * a.Cout;
   if (n == 0) return;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (a.Cout % 8 == 0 && a.W % 8 == 0 && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
+  if (a.Cout % 8 == 0 && a.W % 8 == 0 && n / 8 < (1LL << 31) && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
       al16(a.dy) && al16(a.y) && al16(a.dz)) {
     STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, 0, s, a, bwd ? 1 : 0);
     return;
@@ -665,12 +667,10 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
   const long long total = a.rows * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / groups;
+    const long long r = (long long)((unsigned long long)idx / (unsigned)groups);
     const int j0 = (int)(idx - r * groups) * 8;
-    const long long TN_out = (long long)a.T_out * a.N;
-    const long long b = r / TN_out;
-    const long long rem = r - b * TN_out;
-    const long long in0 = b * a.T_in * a.N + rem;
+    long long in0; int t_unused;
+    row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
     float zp[8], zq[8], hv[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { zp[i] = bs[j0 + i]; zq[i] = gated ? bs[a.Cout + j0 + i] : 0.f; }
@@ -712,12 +712,10 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
   for (int i = 0; i < 17; ++i) { accp[i] = 0.f; accq[i] = 0.f; }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   const long long r1 = min(a.rows, r0 + a.rows_per_cta);
-  const long long TN_out = (long long)a.T_out * a.N;
   if (rl < lanes) {
     for (long long r = r0 + rl; r < r1; r += lanes) {
-      const long long b = r / TN_out;
-      const long long rem = r - b * TN_out;
-      const long long in0 = b * a.T_in * a.N + rem;
+      long long in0; int t_unused;
+      row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
       const float res = (a.explicit_res && j < a.Cin) ? ldf(a.x + (in0 + (long long)(a.Kt - 1) * a.N) * a.Cin + j) : 0.f;
       const float u = ldf(a.z + r * a.W + j) + res;
       const float q = gated ? ldf(a.z + r * a.W + a.Cout + j) : 0.f;

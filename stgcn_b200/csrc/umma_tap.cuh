@@ -105,8 +105,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (lane == 0) {
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmW);
-      mbar_arrive_expect_tx(&wfull, p.w_bytes);
       const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2;
+      mbar_arrive_expect_tx(&wfull, (uint32_t)p.Kt * p.nKB * wblk);   // exact bytes (w_bytes is rounded up to 1 KB)
       for (int j = 0; j < p.Kt; ++j)
         for (int kb = 0; kb < p.nKB; ++kb) tma_load_3d(w_s + (size_t)(j * p.nKB + kb) * wblk, &tmW, &wfull, kb * p.KB, co0, j);
       uint32_t g = 0;
