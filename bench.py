@@ -214,6 +214,7 @@ def main():
                     help="dropout p for BOTH arms (0 = the stricter CPU comparison, BASELINE.md §2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -288,7 +289,7 @@ def main():
     loss_buf = torch.zeros(1, device=dev)
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(x, y):
+    def eager_step(x, y):
         model.zero_grad(set_to_none=True)
         pred = model(x).reshape(B, -1)                      # (B,1,1,N) view -> (B,N), main.py:166
         dpred = torch.empty_like(pred)
@@ -296,6 +297,24 @@ def main():
                                       dpred.data_ptr(), torch.cuda.current_stream().cuda_stream))
         pred.backward(dpred)
         reducer()
+
+    # The public API for a launch-free step: the whole forward + loss + backward captured once in a CUDA graph
+    # (stgcn_b200.graph.GraphedStep); the gradient all-reduce (N > 1) is issued right after the replay.
+    graphed = None
+    launches_per_step = None
+    if not a.no_graph:
+        from stgcn_b200.graph import GraphedStep
+        n_before = L.launch_count()
+        graphed = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=3)
+        launches_per_step = (L.launch_count() - n_before) // 4       # 3 warm-up bodies + 1 capture
+        loss_buf = graphed.loss
+
+    def step(x, y):
+        if graphed is None:
+            eager_step(x, y)
+        else:
+            graphed(x, y)                                   # device-to-device copy into the static buffers + replay
+            reducer()
 
     def sync_all():
         if world > 1:
@@ -322,16 +341,20 @@ def main():
         sampler.start()
     n0 = L.launch_count()
     ms_total = timed(lambda i: step(xs[i % POOL], ys[i % POOL]), steps)
-    launches = L.launch_count() - n0
+    launches = (L.launch_count() - n0) if graphed is None else launches_per_step * steps
     value = B * world * steps / (ms_total / 1e3)
 
     # e2e: host (pinned) buffers in, loss out, copies inside the timed region, through the public module API
     x_dev, y_dev = torch.empty_like(xs[0]), torch.empty_like(ys[0])
 
     def e2e_step(i):
-        x_dev.copy_(xs_host[i % POOL], non_blocking=True)
-        y_dev.copy_(ys_host[i % POOL], non_blocking=True)
-        step(x_dev, y_dev)
+        if graphed is None:
+            x_dev.copy_(xs_host[i % POOL], non_blocking=True)
+            y_dev.copy_(ys_host[i % POOL], non_blocking=True)
+            eager_step(x_dev, y_dev)
+        else:
+            graphed(xs_host[i % POOL], ys_host[i % POOL])   # pinned host -> static device buffers, then replay
+            reducer()
         loss_host.copy_(loss_buf, non_blocking=True)
 
     for i in range(2):
@@ -353,7 +376,7 @@ def main():
         psteps = 3
         L.profile_begin()
         for i in range(psteps):
-            step(xs[i % POOL], ys[i % POOL])
+            eager_step(xs[i % POOL], ys[i % POOL])        # eager: the event profiler brackets individual launches
         prof = L.profile_end()
         tot_ms = sum(v[1] for v in prof.values())
         rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
@@ -391,7 +414,7 @@ def main():
                 "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
                 "config": {**cfg_common, "precision": a.precision,
                            "l2": f"{POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
-                           "parallelism": f"dp{world}"},
+                           "parallelism": f"dp{world}", "cuda_graph": graphed is not None},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,

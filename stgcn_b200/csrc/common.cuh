@@ -75,12 +75,15 @@ inline void prof_end(const char* kernel, cudaEvent_t a, cudaStream_t s) {
 
 // Every kernel launch goes through this: counts it and checks the launch status.
 #define STGCN_LAUNCH(kernel, grid, block, smem, stream, ...)               \
+  STGCN_LAUNCH_NAMED(#kernel, kernel, grid, block, smem, stream, __VA_ARGS__)
+
+#define STGCN_LAUNCH_NAMED(name, kernel, grid, block, smem, stream, ...)   \
   do {                                                                     \
     bool _prof = ::stgcn::g_prof.on.load(std::memory_order_relaxed);       \
     cudaEvent_t _ea = nullptr;                                             \
     if (_prof) _ea = ::stgcn::prof_begin(stream);                          \
     kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);            \
-    if (_prof) ::stgcn::prof_end(#kernel, _ea, stream);                    \
+    if (_prof) ::stgcn::prof_end(name, _ea, stream);                       \
     ::stgcn::g_launches.fetch_add(1, std::memory_order_relaxed);           \
     STGCN_CUDA(cudaPeekAtLastError());                                     \
   } while (0)

@@ -153,13 +153,15 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     const int lanes = threads / d.c_out;
     sa.rows_per_cta = (int)sc_rpc;
     sa.partial = part;
-    size_t smem = (size_t)lanes * 2 * (Kw + 1) * d.c_out * sizeof(float);
-    STGCN_CUDA(cudaFuncSetAttribute(smallc_gate_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, sc_ctas, threads, smem, c.stream, sa);
-    {
-      const int n = (Kw + 1) * g.W;
-      STGCN_LAUNCH(reduce_partials_kernel, ceil_div(n, 256), 256, 0, c.stream, (const float*)part, dwt, n, sc_ctas);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved) && al16(dy) && al16(sa.dz)) {
+      launch_smallc1_gate_wgrad(sa, sc_ctas, c.stream);
+    } else {
+      size_t smem = (size_t)lanes * 2 * (Kw + 1) * d.c_out * sizeof(float);
+      STGCN_CUDA(cudaFuncSetAttribute(smallc_gate_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, sc_ctas, threads, smem, c.stream, sa);
     }
+    launch_reduce_partials(part, dwt, (Kw + 1) * g.W, sc_ctas, c.stream);
   } else {
     GateArgs<T> ga{};
     ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;

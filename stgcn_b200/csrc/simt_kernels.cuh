@@ -421,18 +421,111 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
   }
 }
 
-// out[e] += sum_c partial[c][e]
+// out[e] += sum_c partial[c][e]: one warp per 8 elements x 4 lanes-groups; lanes stride over the chunks, shuffle-reduce
 __global__ void reduce_partials_kernel(const float* partial, float* out, int n, int chunks) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int e = blockIdx.x * (blockDim.x >> 5) + warp;
   if (e >= n) return;
   float s = 0.f;
-  for (int c = 0; c < chunks; ++c) s += partial[(long long)c * n + e];
-  out[e] += s;
+  for (int c = lane; c < chunks; c += 32) s += partial[(long long)c * n + e];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[e] += s;
+}
+inline void launch_reduce_partials(const float* partial, float* out, int n, int chunks, cudaStream_t s) {
+  if (n == 0 || chunks == 0) return;
+  STGCN_LAUNCH(reduce_partials_kernel, ceil_div(n, 8), 256, 0, s, partial, out, n, chunks);
+}
+
+// ---- skinny weight gradient (Co <= 16: align convs, Chebyshev mix, fc2) -------------------------------------------
+// dwt[(tap,c) | bias][o] = sum_r in[row(r,tap), c] * dz[r, o].  The output is tiny (<= 1k elements) and the work is
+// streaming rows, so: one CTA per row range, a 32-row tile of both operands staged in shared memory with coalesced
+// loads, thread (m, o-quad) accumulates 4 outputs in registers (2 LDS + 4 FMA per row), per-CTA partials are written
+// out and reduced by reduce_partials_kernel (no same-address atomics).
+constexpr int kSkR = 32;
+template <class T>
+__global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
+  extern __shared__ float sk[];
+  const int Kw = a.ntaps * a.Cin;
+  const int Mtot = Kw + (a.bias_row ? 1 : 0);
+  const int OG = (a.Co + 3) / 4;
+  float* As = sk;                              // [kSkR][Mtot]
+  float* Bs = sk + kSkR * Mtot;                // [kSkR][16]
+  long long* rbase = reinterpret_cast<long long*>(Bs + kSkR * 16);   // [kSkR]
+  int* rt = reinterpret_cast<int*>(rbase + kSkR);                    // [kSkR]
+  short* tap_of = reinterpret_cast<short*>(rt + kSkR);               // [Kw]
+  short* c_of = tap_of + Kw;                                         // [Kw]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < Kw; i += blockDim.x) { tap_of[i] = (short)(i / a.Cin); c_of[i] = (short)(i % a.Cin); }
+  const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
+  const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
+  const long long TN_in = (long long)a.map.T_in * a.map.N;
+  const int TN_out = a.map.T_out * a.map.N;
+  const long long tap_step = (long long)a.map.t_shift * a.map.N + a.map.tap_row_stride;
+  const int m = tid / OG, og = tid % OG;
+  const bool active = m < Mtot;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long k0 = r_begin; k0 < r_end; k0 += kSkR) {
+    __syncthreads();
+    if (tid < kSkR) {
+      long long r = k0 + tid;
+      if (r < r_end) { row_decode(r, TN_out, a.map.N, TN_in, rbase[tid], rt[tid]); }
+      else { rbase[tid] = -1; rt[tid] = 0; }
+    }
+    __syncthreads();
+    for (int e = tid; e < kSkR * Mtot; e += blockDim.x) {
+      const int r = e / Mtot, mm = e - r * Mtot;
+      float v = 0.f;
+      const long long rb = rbase[r];
+      if (rb >= 0) {
+        if (mm == Kw) v = 1.f;
+        else {
+          const int tap = tap_of[mm];
+          const int ti = rt[r] + a.map.t_shift * tap;
+          if (ti >= 0 && ti < a.map.T_in) v = ldf(a.in + (rb + tap * tap_step) * a.Cin + c_of[mm]);
+        }
+      }
+      As[e] = v;
+    }
+    for (int e = tid; e < kSkR * 16; e += blockDim.x) {
+      const int r = e >> 4, o = e & 15;
+      const long long rr = k0 + r;
+      Bs[e] = (rr < r_end && o < a.Co) ? ldf(a.dz + rr * a.ldz + o) : 0.f;
+    }
+    __syncthreads();
+    if (active) {
+#pragma unroll 8
+      for (int r = 0; r < kSkR; ++r) {
+        const float av = As[r * Mtot + m];
+        const float4 bv = *reinterpret_cast<const float4*>(Bs + r * 16 + og * 4);
+        acc[0] = fmaf(av, bv.x, acc[0]); acc[1] = fmaf(av, bv.y, acc[1]);
+        acc[2] = fmaf(av, bv.z, acc[2]); acc[3] = fmaf(av, bv.w, acc[3]);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int o = og * 4 + i;
+      if (o < a.Co) a.partial[((long long)blockIdx.x * Mtot + m) * a.Co + o] = acc[i];
+    }
+  }
+}
+inline size_t wgrad_skinny_smem(int Mtot, int Kw) {
+  return (size_t)kSkR * Mtot * 4 + kSkR * 16 * 4 + kSkR * 8 + kSkR * 4 + (size_t)Kw * 4 + 16;
 }
 
 struct WgradPlanSimt { int mode, tiles, chunks; long long rpc; };
 inline WgradPlanSimt plan_wgrad_simt(long long rows, int Mtot, int Co) {
   WgradPlanSimt pl;
+  if (Co <= 16 && Mtot * ((Co + 3) / 4) <= 320) {     // skinny kernel: one CTA per row range, ~6 CTAs per SM
+    pl.mode = 4; pl.tiles = 1;
+    long long rpc = (rows + 148 * 6 - 1) / (148 * 6);
+    if (rpc < 4 * kSkR) rpc = 4 * kSkR;
+    pl.rpc = (rpc + kSkR - 1) / kSkR * kSkR;
+    pl.chunks = rows > 0 ? ceil_div(rows, pl.rpc) : 0;
+    return pl;
+  }
   if (Co <= 16) { pl.mode = Mtot <= 64 ? 0 : 1; pl.tiles = ceil_div(Mtot, pl.mode == 0 ? 64 : 128); }
   else if (Mtot <= 16) { pl.mode = 2; pl.tiles = ceil_div(Co, 64); }
   else { pl.mode = 3; pl.tiles = ceil_div(Mtot, 64) * ceil_div(Co, 64); }
@@ -455,7 +548,10 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   const WgradPlanSimt pl = plan_wgrad_simt(a.rows, Mtot, a.Co);
   a.rows_per_cta = (int)pl.rpc;
   const int chunks = pl.chunks;
-  if (pl.mode == 0) {
+  if (pl.mode == 4 && a.partial) {
+    const size_t smem = wgrad_skinny_smem(Mtot, a.ntaps * a.Cin);
+    STGCN_LAUNCH(wgrad_skinny_kernel<T>, chunks, 320, smem, s, a);
+  } else if (pl.mode == 4 || pl.mode == 0) {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 16, 1, 4>), dim3(ceil_div(Mtot, 64), 1, chunks), NT, 0, s, a);
   } else if (pl.mode == 1) {
     STGCN_LAUNCH((wgrad_kernel<T, 128, 16, 2, 4>), dim3(ceil_div(Mtot, 128), 1, chunks), NT, 0, s, a);
@@ -464,10 +560,7 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   } else {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 64, 4, 4>), dim3(ceil_div(Mtot, 64), ceil_div(a.Co, 64), chunks), NT, 0, s, a);
   }
-  if (a.partial) {
-    const int n = Mtot * a.Co;
-    STGCN_LAUNCH(reduce_partials_kernel, ceil_div(n, 256), 256, 0, s, (const float*)a.partial, a.dwt, n, chunks);
-  }
+  if (a.partial) launch_reduce_partials(a.partial, a.dwt, Mtot * a.Co, chunks, s);
 }
 
 __device__ __forceinline__ float act_fwd(int act, float u, float q) {
@@ -761,6 +854,88 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
     if (a.partial) a.partial[(long long)blockIdx.x * (K + 1) * a.W + off] = v;
     else atomicAdd(a.dwt + off, v);
   }
+}
+
+// Cin == 1 specialisation of the above (the model input): 8 channels per thread with 16-byte loads, K = Kt taps known
+// at compile time, shuffle + shared-memory reduction, per-CTA partials.
+template <class T, int K>
+__global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
+  __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
+  const bool gated = a.W == 2 * a.Cout;
+  const int G = a.Cout / 8;                         // channel groups (power of two <= 32 checked by the launcher)
+  const int g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;
+  const int j0 = g * 8;
+  float accp[K + 1][8], accq[K + 1][8];
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { accp[k][i] = 0.f; accq[k][i] = 0.f; }
+  const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
+  const long long r1 = min(a.rows, r0 + a.rows_per_cta);
+  for (long long r = r0 + rl; r < r1; r += lanes) {
+    long long in0; int t_unused;
+    row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = ldf(a.x + in0 + (long long)k * a.N);
+    float zp[8], zq[8], dh[8], du[8], dq[8];
+    load8(a.z + r * a.W + j0, zp);
+    if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+    load8(a.dh + r * a.Cout + j0, dh);
+    if (a.explicit_res && j0 == 0) zp[0] += xv[K - 1];        // residual = zero-padded input: channel 0 only
+#pragma unroll
+    for (int i = 0; i < 8; ++i) act_bwd(a.act, zp[i], gated ? zq[i] : 0.f, dh[i], du[i], dq[i]);
+    if (a.dz) {
+      store8(a.dz + r * a.W + j0, du);
+      if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { accp[k][i] = fmaf(xv[k], du[i], accp[k][i]); accq[k][i] = fmaf(xv[k], dq[i], accq[k][i]); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { accp[K][i] += du[i]; accq[K][i] += dq[i]; }
+  }
+  // reduce over the rows held by one warp (lanes with equal g), then over warps through shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k <= K; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float vp = accp[k][i], vq = accq[k][i];
+      for (int o = G; o < 32; o <<= 1) { vp += __shfl_xor_sync(0xffffffffu, vp, o); vq += __shfl_xor_sync(0xffffffffu, vq, o); }
+      accp[k][i] = vp; accq[k][i] = vq;
+    }
+  const int Cp = a.Cout;                            // <= 64 here
+  if (lane < G) {
+#pragma unroll
+    for (int k = 0; k <= K; ++k)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        red[warp][(0 * (K + 1) + k) * 64 + j0 + i] = accp[k][i];
+        red[warp][(1 * (K + 1) + k) * 64 + j0 + i] = accq[k][i];
+      }
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  for (int e = threadIdx.x; e < 2 * (K + 1) * Cp; e += blockDim.x) {
+    const int half = e / ((K + 1) * Cp), rest = e - half * (K + 1) * Cp;
+    if (half == 1 && !gated) continue;
+    const int k = rest / Cp, j = rest - k * Cp;
+    float v = 0.f;
+    for (int w = 0; w < nw; ++w) v += red[w][(half * (K + 1) + k) * 64 + j];
+    a.partial[(long long)blockIdx.x * (K + 1) * a.W + (long long)k * a.W + half * a.Cout + j] = v;
+  }
+}
+template <class T>
+inline bool smallc1_supported(int Cin, int Cout, int Kt) {
+  return Cin == 1 && Kt >= 2 && Kt <= 4 && (Cout == 8 || Cout == 16 || Cout == 32 || Cout == 64);
+}
+template <class T>
+inline void launch_smallc1_gate_wgrad(const SmallCArgs<T>& a, int ctas, cudaStream_t s) {
+  if (a.Kt == 2) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 2>), ctas, 256, 0, s, a);
+  else if (a.Kt == 3) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3>), ctas, 256, 0, s, a);
+  else STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 4>), ctas, 256, 0, s, a);
 }
 
 template <class T>

@@ -64,14 +64,35 @@ __device__ __forceinline__ void load16_bf16(const bf16* src, float* v) {
   uint4 a = reinterpret_cast<const uint4*>(src)[0], b = reinterpret_cast<const uint4*>(src)[1];
   const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[i]);
-    v[2 * i] = __low2float(h);
-    v[2 * i + 1] = __high2float(h);
+  for (int i = 0; i < 8; ++i) {          // bf16 -> fp32 is a 16-bit shift
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+// epilogue math: MUFU-based (ex2 / rcp / tanh.approx), accurate far beyond the bf16 the results are stored in
+__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float epi_act(float u, float q) {
+  if (ACT == STGCN_ACT_GLU) return u * fast_sigmoid(q);
+  if (ACT == STGCN_ACT_GTU) return fast_tanh(u) * fast_sigmoid(q);
+  if (ACT == STGCN_ACT_RELU) return fmaxf(u, 0.f);
+  if (ACT == STGCN_ACT_SILU) return u * fast_sigmoid(u);
+  return u;
+}
+__device__ __forceinline__ void add_bias16(float* v, const float* bias_smem) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 b = reinterpret_cast<const float4*>(bias_smem)[i];
+    v[4 * i] += b.x; v[4 * i + 1] += b.y; v[4 * i + 2] += b.z; v[4 * i + 3] += b.w;
   }
 }
 
-template <int EPI>
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TapParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -80,7 +101,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* ring = smem + p.w_bytes;       // w_bytes is a multiple of 1024
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[2], tempty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float bias_s[256];
+  __shared__ __align__(16) float bias_s[256];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.CoT;
@@ -187,16 +208,17 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int c0 = half * 16; c0 < p.CoT; c0 += 32) {
             uint32_t r[16];
             tmem_ld_32x32b_x16(t_addr + c0, r);
+            float av[16];
+            const bool has_aux = aux_row != nullptr && co0 + c0 < p.aux_cols;     // aux_cols is a multiple of 16 here
+            if (has_aux) load16_bf16(aux_row + co0 + c0, av);
             tmem_ld_wait();
             float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bias_s[c0 + i];
-            if (aux_row && co0 + c0 < p.aux_cols) {
-              float av[16];
-              load16_bf16(aux_row + co0 + c0, av);
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            add_bias16(v, bias_s + c0);
+            if (has_aux) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i)
-                if (co0 + c0 + i < p.aux_cols) v[i] += av[i];
+              for (int i = 0; i < 16; ++i) v[i] += av[i];
             }
             if (p.relu) {
 #pragma unroll
@@ -205,40 +227,22 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
           }
         } else {
-          const bool gated = p.W == 2 * p.Cout;
+          constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
           for (int c0 = half * 16; c0 < p.Cout; c0 += 32) {
             uint32_t rp[16], rq[16];
             tmem_ld_32x32b_x16(t_addr + c0, rp);
             if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + c0, rq);
+            float res[16];
+            const bool has_res = aux_row != nullptr && c0 < p.aux_cols;           // aux_cols, C_aux multiples of 16 here
+            if (has_res) load16_bf16(aux_row + c0, res);
             tmem_ld_wait();
-            float zp[16], zq[16], res[16], h[16];
+            float zp[16], zq[16], h[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              zp[i] = __uint_as_float(rp[i]) + bias_s[c0 + i];
-              zq[i] = gated ? __uint_as_float(rq[i]) + bias_s[p.Cout + c0 + i] : 0.f;
-              res[i] = 0.f;
-            }
-            if (aux_row && c0 < p.aux_cols) {
-              if (c0 + 16 <= p.C_aux) {
-                load16_bf16(aux_row + c0, res);
+            for (int i = 0; i < 16; ++i) { zp[i] = __uint_as_float(rp[i]); zq[i] = gated ? __uint_as_float(rq[i]) : 0.f; }
+            add_bias16(zp, bias_s + c0);
+            if (gated) add_bias16(zq, bias_s + p.Cout + c0);
 #pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (c0 + i >= p.aux_cols) res[i] = 0.f;
-              } else {
-                for (int i = 0; i < 16; ++i) res[i] = (c0 + i < p.aux_cols) ? __bfloat162float(aux_row[c0 + i]) : 0.f;
-              }
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const float u = zp[i] + res[i];
-              float o;
-              if (p.act == STGCN_ACT_GLU) o = u * sigmoidf_(zq[i]);
-              else if (p.act == STGCN_ACT_GTU) o = tanhf(u) * sigmoidf_(zq[i]);
-              else if (p.act == STGCN_ACT_RELU) o = fmaxf(u, 0.f);
-              else if (p.act == STGCN_ACT_SILU) o = u * sigmoidf_(u);
-              else o = u;
-              h[i] = o;
-            }
+            for (int i = 0; i < 16; ++i) h[i] = epi_act<ACT>(has_res ? zp[i] + res[i] : zp[i], zq[i]);
             if (valid) {
               store16_bf16(p.out_z + orow * p.W + c0, zp);
               if (gated) store16_bf16(p.out_z + orow * p.W + p.Cout + c0, zq);
@@ -311,6 +315,7 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate) {
 
 inline bool tap_supported(const TapProblem& q) {
   if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
+  if (q.aux && (q.aux_cols % 16 != 0 || q.C_aux % 16 != 0)) return false;      // vector residual loads
   if (q.T_out < 1 || q.T_src < 1 || q.N < 1 || q.B < 1) return false;
   return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE).ok;
 }
@@ -354,12 +359,21 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   int gx = p.n_items < sm_count() / pl.nCoT ? p.n_items : sm_count() / pl.nCoT;
   if (gx < 1) gx = 1;
   dim3 grid(gx, pl.nCoT);
+  const char* kname = q.epi == EPI_GATE ? "umma_tap_kernel<EPI_GATE>" : "umma_tap_kernel<EPI_LINEAR>";
+  auto go = [&](auto kern) {
+    STGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    STGCN_LAUNCH_NAMED(kname, kern, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
+  };
   if (q.epi == EPI_GATE) {
-    STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH(umma_tap_kernel<EPI_GATE>, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
+    switch (q.act) {
+      case STGCN_ACT_GLU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_GLU>); break;
+      case STGCN_ACT_GTU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_GTU>); break;
+      case STGCN_ACT_RELU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_RELU>); break;
+      case STGCN_ACT_SILU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_SILU>); break;
+      default: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_LINEAR>); break;
+    }
   } else {
-    STGCN_CUDA(cudaFuncSetAttribute(umma_tap_kernel<EPI_LINEAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH(umma_tap_kernel<EPI_LINEAR>, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
+    go(umma_tap_kernel<EPI_LINEAR, STGCN_ACT_LINEAR>);
   }
 }
 
