@@ -443,20 +443,22 @@ inline void launch_reduce_partials(const float* partial, float* out, int n, int 
 // loads, thread (m, o-quad) accumulates 4 outputs in registers (2 LDS + 4 FMA per row), per-CTA partials are written
 // out and reduced by reduce_partials_kernel (no same-address atomics).
 constexpr int kSkR = 32;
-template <class T>
+template <class T, bool VEC>
 __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
-  extern __shared__ float sk[];
+  extern __shared__ __align__(16) float sk[];
   const int Kw = a.ntaps * a.Cin;
   const int Mtot = Kw + (a.bias_row ? 1 : 0);
+  const int Mp = (Mtot + 3) & ~3;              // row pitch of the A tile (16-byte aligned rows)
   const int OG = (a.Co + 3) / 4;
-  float* As = sk;                              // [kSkR][Mtot]
-  float* Bs = sk + kSkR * Mtot;                // [kSkR][16]
+  float* As = sk;                              // [kSkR][Mp]
+  float* Bs = sk + kSkR * Mp;                  // [kSkR][16]
   long long* rbase = reinterpret_cast<long long*>(Bs + kSkR * 16);   // [kSkR]
   int* rt = reinterpret_cast<int*>(rbase + kSkR);                    // [kSkR]
   short* tap_of = reinterpret_cast<short*>(rt + kSkR);               // [Kw]
   short* c_of = tap_of + Kw;                                         // [Kw]
   const int tid = threadIdx.x;
   for (int i = tid; i < Kw; i += blockDim.x) { tap_of[i] = (short)(i / a.Cin); c_of[i] = (short)(i % a.Cin); }
+  if (a.bias_row) for (int r = tid; r < kSkR; r += blockDim.x) As[r * Mp + Kw] = 1.f;   // bias column: constant ones
   const long long r_begin = (long long)blockIdx.x * a.rows_per_cta;
   const long long r_end = min(a.rows, r_begin + a.rows_per_cta);
   const long long TN_in = (long long)a.map.T_in * a.map.N;
@@ -464,6 +466,7 @@ __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
   const long long tap_step = (long long)a.map.t_shift * a.map.N + a.map.tap_row_stride;
   const int m = tid / OG, og = tid % OG;
   const bool active = m < Mtot;
+  const int kw8 = Kw >> 3;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (long long k0 = r_begin; k0 < r_end; k0 += kSkR) {
     __syncthreads();
@@ -473,30 +476,57 @@ __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
       else { rbase[tid] = -1; rt[tid] = 0; }
     }
     __syncthreads();
-    for (int e = tid; e < kSkR * Mtot; e += blockDim.x) {
-      const int r = e / Mtot, mm = e - r * Mtot;
-      float v = 0.f;
-      const long long rb = rbase[r];
-      if (rb >= 0) {
-        if (mm == Kw) v = 1.f;
-        else {
+    if (VEC) {
+      // 8 channels (16 bytes of bf16) per load: Cin % 8 == 0, so a vector never straddles a tap
+      for (int v = tid; v < kSkR * kw8; v += blockDim.x) {
+        const int r = v / kw8, m8 = (v - r * kw8) << 3;
+        float x8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x8[i] = 0.f;
+        const long long rb = rbase[r];
+        if (rb >= 0) {
+          const int tap = tap_of[m8];
+          const int ti = rt[r] + a.map.t_shift * tap;
+          if (ti >= 0 && ti < a.map.T_in) load8(a.in + (rb + tap * tap_step) * a.Cin + c_of[m8], x8);
+        }
+        float4* dst = reinterpret_cast<float4*>(As + r * Mp + m8);
+        dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
+        dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+      }
+      for (int v = tid; v < kSkR * 2; v += blockDim.x) {      // Co == 16 here: two vectors per row
+        const int r = v >> 1, o8 = (v & 1) << 3;
+        const long long rr = k0 + r;
+        float x8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x8[i] = 0.f;
+        if (rr < r_end) load8(a.dz + rr * a.ldz + o8, x8);
+        float4* dst = reinterpret_cast<float4*>(Bs + r * 16 + o8);
+        dst[0] = make_float4(x8[0], x8[1], x8[2], x8[3]);
+        dst[1] = make_float4(x8[4], x8[5], x8[6], x8[7]);
+      }
+    } else {
+      for (int e = tid; e < kSkR * Kw; e += blockDim.x) {
+        const int r = e / Kw, mm = e - r * Kw;
+        float v = 0.f;
+        const long long rb = rbase[r];
+        if (rb >= 0) {
           const int tap = tap_of[mm];
           const int ti = rt[r] + a.map.t_shift * tap;
           if (ti >= 0 && ti < a.map.T_in) v = ldf(a.in + (rb + tap * tap_step) * a.Cin + c_of[mm]);
         }
+        As[r * Mp + mm] = v;
       }
-      As[e] = v;
-    }
-    for (int e = tid; e < kSkR * 16; e += blockDim.x) {
-      const int r = e >> 4, o = e & 15;
-      const long long rr = k0 + r;
-      Bs[e] = (rr < r_end && o < a.Co) ? ldf(a.dz + rr * a.ldz + o) : 0.f;
+      for (int e = tid; e < kSkR * 16; e += blockDim.x) {
+        const int r = e >> 4, o = e & 15;
+        const long long rr = k0 + r;
+        Bs[e] = (rr < r_end && o < a.Co) ? ldf(a.dz + rr * a.ldz + o) : 0.f;
+      }
     }
     __syncthreads();
     if (active) {
 #pragma unroll 8
       for (int r = 0; r < kSkR; ++r) {
-        const float av = As[r * Mtot + m];
+        const float av = As[r * Mp + m];
         const float4 bv = *reinterpret_cast<const float4*>(Bs + r * 16 + og * 4);
         acc[0] = fmaf(av, bv.x, acc[0]); acc[1] = fmaf(av, bv.y, acc[1]);
         acc[2] = fmaf(av, bv.z, acc[2]); acc[3] = fmaf(av, bv.w, acc[3]);
@@ -512,7 +542,7 @@ __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
   }
 }
 inline size_t wgrad_skinny_smem(int Mtot, int Kw) {
-  return (size_t)kSkR * Mtot * 4 + kSkR * 16 * 4 + kSkR * 8 + kSkR * 4 + (size_t)Kw * 4 + 16;
+  return (size_t)kSkR * ((Mtot + 3) & ~3) * 4 + kSkR * 16 * 4 + kSkR * 8 + kSkR * 4 + (size_t)Kw * 4 + 16;
 }
 
 struct WgradPlanSimt { int mode, tiles, chunks; long long rpc; };
@@ -550,7 +580,11 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   const int chunks = pl.chunks;
   if (pl.mode == 4 && a.partial) {
     const size_t smem = wgrad_skinny_smem(Mtot, a.ntaps * a.Cin);
-    STGCN_LAUNCH(wgrad_skinny_kernel<T>, chunks, 320, smem, s, a);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec = a.Cin % 8 == 0 && a.Co == 16 && a.ldz % 8 == 0 && al16(a.in) && al16(a.dz) &&
+                     (a.map.tap_row_stride * a.Cin) % 8 == 0;
+    if (vec) STGCN_LAUNCH((wgrad_skinny_kernel<T, true>), chunks, 320, smem, s, a);
+    else     STGCN_LAUNCH((wgrad_skinny_kernel<T, false>), chunks, 320, smem, s, a);
   } else if (pl.mode == 4 || pl.mode == 0) {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 16, 1, 4>), dim3(ceil_div(Mtot, 64), 1, chunks), NT, 0, s, a);
   } else if (pl.mode == 1) {
