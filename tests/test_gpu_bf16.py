@@ -110,7 +110,7 @@ def test_bf16_full_size_model(dataset, kind, B, cuda_device):
     named = dict(model.named_parameters())
     errs = {k: rel_l2(named[k].grad.cpu(), v.grad) for k, v in p64.items() if v.grad is not None}
     assert max(errs.values()) < 1.5 * GRAD_TOL, max(errs.items(), key=lambda kv: kv[1])   # small B: bias sums are noisy
-    assert sorted(errs.values())[len(errs) // 2] < 6e-2
+    assert sorted(errs.values())[len(errs) // 2] < 8e-2
 
 
 @pytest.mark.parametrize("c_in,c_out,kt,T", [(64, 64, 3, 8), (16, 64, 3, 10), (64, 128, 4, 4), (32, 32, 2, 6),
