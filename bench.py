@@ -209,7 +209,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pemsd7m", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's BASELINE batch)")
-    ap.add_argument("--precision", default=os.environ.get("STGCN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("STGCN_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = BASELINE.json configs[1] (tcgen05 path); fp32 = the 1e-3 parity path")
     ap.add_argument("--droprate", type=float, default=0.0,
                     help="dropout p for BOTH arms (0 = the stricter CPU comparison, BASELINE.md §2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -382,17 +383,25 @@ def main():
         rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
         top = [{"key": k, "launches_per_step": v[0] / psteps, "ms_per_step": v[1] / psteps,
                 "share": v[1] / tot_ms} for k, v in rows[:60]]
-        # dominant kernel: algorithmic FLOPs of the stage it implements / its measured time
-        k0, (c0, ms0) = rows[0]
-        stage_flops = _stage_flops_for_key(k0, stages, B)
-        per_launch_ms = ms0 / c0
-        launches_per_step = c0 / psteps
-        if stage_flops:
-            ach = stage_flops / launches_per_step / (per_launch_ms * 1e-3) / 1e12
-            peak = peaks["bf16_tflops_sustained"]
-            roofline = {"kernel": k0, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                        "frac": ach / peak, "traffic": None, "peak_source": peaks["source"] + " (sustained)",
-                        "avg_launch_ms": per_launch_ms, "share_of_step": ms0 / tot_ms}
+        # dominant kernel: algorithmic FLOPs / bytes of the stage it implements over its measured time, against the
+        # roof that bounds it (ridge = peak FLOP/s / peak B/s)
+        esize = 4 if a.precision == "fp32" else 2
+        ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
+        for k0, (c0, ms0) in rows:
+            work = _kernel_work(k0, n, B, kind, ks, esize)
+            if not work:
+                continue
+            fl, by = work
+            t_s = ms0 / psteps * 1e-3
+            if by > 0 and fl / by < ridge:
+                ach, peak, bound, unit = by / t_s / 1e9, peaks["hbm_gbs"], "hbm", "GB/s"
+            else:
+                ach, peak, bound, unit = fl / t_s / 1e12, peaks["bf16_tflops_sustained"], "tensor", "TFLOP/s"
+            roofline = {"kernel": k0, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                        "traffic": None, "peak_source": peaks["source"], "alg_flops_per_step": fl,
+                        "alg_bytes_per_step": by, "launches_per_step": c0 / psteps,
+                        "avg_launch_ms": ms0 / c0, "share_of_step": ms0 / tot_ms}
+            break
     step_tflops = tot_f * value / world / 1e12          # per GPU
     roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
@@ -425,27 +434,63 @@ def main():
         dist.destroy_process_group()
 
 
-def _stage_flops_for_key(key, stages, B):
-    """FLOPs per step (all launches under this op tag) for a '<stage>.<op>.<dir>:kernel' profile key; used only to
-    convert the dominant kernel's measured time into achieved TFLOP/s."""
-    tagk = key.split(":")[0].split(".")
-    if len(tagk) < 3 or tagk[0] not in stages:
+def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
+    """Algorithmic (FLOPs, HBM bytes) per step of all launches under one '<stage>.<op>.<dir>:<kernel>' profile key:
+    the closed-form GEMM term of the stage the kernel implements and the tensors it must read/write
+    once (esize = bytes per activation element).  Returns None for kernels that are not modelled."""
+    tag, kern = key.split(":", 1)
+    parts = tag.split(".")
+    if len(parts) < 3:
         return None
-    st, op, direction = tagk[0], tagk[1], tagk[2]
-    s = stages[st]
-    kern = key.split(":")[1]
+    st, op, direction = parts[0], parts[1], parts[2]
+    T = n_his
+    dims = {}
+    n_st = len(blocks) - 3
+    for l in range(n_st):
+        c0 = blocks[l][-1]
+        c1, c2, c3 = blocks[l + 1]
+        dims[f"st{l}"] = dict(c0=c0, c1=c1, c2=c2, c3=c3, T0=T, T1=T - kt + 1, T2=T - 2 * (kt - 1), kt=kt)
+        T -= 2 * (kt - 1)
+    if T > 1:
+        dims["out"] = dict(c0=blocks[-3][-1], c1=blocks[-2][0], c2=blocks[-2][1], c3=blocks[-1][0], T0=T, T1=1, T2=1, kt=T)
+    if st not in dims:
+        return None
+    d = dims[st]
+    rows = lambda t: B * t * n
+    e = esize
     if op in ("tc1", "tc2"):
-        total = s[op]                      # fwd+bwd of this conv
-        first = st == "st0" and op == "tc1"
-        parts = 2 if first else 3
-        if "tapgemm" in kern or "umma" in kern:
-            return total / parts * B       # one GEMM-equivalent (fwd, or dgrad in bwd)
+        cin, cout = (d["c0"], d["c1"]) if op == "tc1" else (d["c2"], d["c3"])
+        tin, tout = (d["T0"], d["T1"]) if op == "tc1" else (d["T1"], d["T2"])
+        W = 2 * cout
+        gemm = 2.0 * W * cin * d["kt"] * rows(tout)
+        if "umma_tap" in kern or "tapgemm" in kern:
+            if direction == "fwd":
+                return gemm, (rows(tin) * cin + rows(tout) * (W + cout)) * e
+            return gemm, (rows(tout) * W + rows(tin) * cin) * e                      # data gradient
+        if "wgrad" in kern and "smallc" not in kern:
+            return gemm, (rows(tin) * cin + rows(tout) * W) * e
+        if "smallc_conv" in kern:
+            return gemm, (rows(tin) * cin + rows(tout) * (W + cout)) * e
+        if "smallc" in kern:                                                         # gate bwd + wgrad fused
+            return gemm, (rows(tin) * cin + rows(tout) * (W + cout)) * e
+        if "gate" in kern:
+            return 0.0, (rows(tout) * (W + cout + W)) * e
+    if op == "gc":
+        c1, c2, t1 = d["c1"], d["c2"], d["T1"]
+        nk = (ks - 1) if kind == "cheb_graph_conv" else 1
+        kmix = ks if kind == "cheb_graph_conv" else 1
+        if "gso" in kern:
+            return nk * 2.0 * n * n * c2 * rows(t1) / n, nk * 3 * rows(t1) * c2 * e
         if "wgrad" in kern:
-            return total / parts * B
-    if op == "gc" and "gso" in kern:
-        return s["gso"] / 2 * B
+            return 2.0 * rows(t1) * c2 * (c1 + kmix * c2), rows(t1) * (c1 + c2 + kmix * c2 + c2) * e
+        if "umma_tap" in kern or "tapgemm" in kern:
+            fl = 2.0 * rows(t1) * c2 * (c1 + kmix * c2)
+            return fl, rows(t1) * (c1 + c2 + kmix * c2 + c2) * e
     if op == "fc":
-        return s["fc"] / 3 * B
+        return 2.0 * rows(1) * d["c1"] * d["c2"], rows(1) * (d["c1"] + d["c2"]) * e
+    if op == "ln":
+        c, t = (d["c3"], d["T2"]) if st != "out" else (d["c1"], 1)
+        return 0.0, 2 * rows(t) * c * e
     return None
 
 
