@@ -47,6 +47,8 @@ struct TapParams {
   bf16* out_z;                // gate: z [rows_out, W]
   int n_items, n_node_tiles;
   int relu;                   // linear epilogue: clamp at 0 after bias/aux
+  int NB, nb_shift;           // TMEM accumulator ring depth (power of two) and its log2
+  int split_tiles;            // 1: the two epilogue warp groups take alternate tiles (narrow outputs); 0: alternate column chunks
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -99,7 +101,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
   uint8_t* ring = smem + p.w_bytes;       // w_bytes is a multiple of 1024
-  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[2], tempty[2];
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[8], tempty[8];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
 
@@ -107,12 +109,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int co0 = blockIdx.y * p.CoT;
   for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
   uint32_t ncols = 32;
-  while ((int)ncols < 2 * p.CoT) ncols <<= 1;
+  while ((int)ncols < p.NB * p.CoT) ncols <<= 1;
+  const int epi_arrivals = p.split_tiles ? kTapEpiWarps / 2 : kTapEpiWarps;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&wfull, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kTapEpiWarps); }
+    for (int i = 0; i < p.NB; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_arrivals); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
@@ -153,7 +156,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t g_base = 0, acc_cnt = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
-          const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
+          const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
           mbar_wait(&tempty[ab], aph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ab * p.CoT;
@@ -195,22 +198,37 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int n = n0 + row;
       const bool valid = n < p.N;
       for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
-        const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
-        mbar_wait(&tfull[ab], aph);
-        tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
+        if (p.split_tiles && (int)(acc_cnt & 1) != half) continue;      // narrow outputs: warp groups alternate tiles
+        const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
         const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
         const int t_aux = t_o + p.aux_dt;
         const bool aux_ok = p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
         const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
+        const int cfirst = p.split_tiles ? 0 : half * 16;
+        const int cstep = p.split_tiles ? 16 : 32;
+        // first chunk's residual / aux values: independent of the MMA, so fetch them before waiting for it
+        float aux0[16];
+        const int aux_c0 = (EPI == EPI_LINEAR ? co0 : 0) + cfirst;
+        const bool pre_aux = aux_row != nullptr && aux_c0 < p.aux_cols;
+        if (pre_aux) load16_bf16(aux_row + aux_c0, aux0);
+        mbar_wait(&tfull[ab], aph);
+        tc_fence_after();
+        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
 
         if (EPI == EPI_LINEAR) {
-          for (int c0 = half * 16; c0 < p.CoT; c0 += 32) {
+          for (int c0 = cfirst; c0 < p.CoT; c0 += cstep) {
             uint32_t r[16];
             tmem_ld_32x32b_x16(t_addr + c0, r);
             float av[16];
             const bool has_aux = aux_row != nullptr && co0 + c0 < p.aux_cols;     // aux_cols is a multiple of 16 here
-            if (has_aux) load16_bf16(aux_row + co0 + c0, av);
+            if (has_aux) {
+              if (c0 == cfirst) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) av[i] = aux0[i];
+              } else {
+                load16_bf16(aux_row + co0 + c0, av);
+              }
+            }
             tmem_ld_wait();
             float v[16];
 #pragma unroll
@@ -228,13 +246,20 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         } else {
           constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
-          for (int c0 = half * 16; c0 < p.Cout; c0 += 32) {
+          for (int c0 = cfirst; c0 < p.Cout; c0 += cstep) {
             uint32_t rp[16], rq[16];
             tmem_ld_32x32b_x16(t_addr + c0, rp);
             if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + c0, rq);
             float res[16];
             const bool has_res = aux_row != nullptr && c0 < p.aux_cols;           // aux_cols, C_aux multiples of 16 here
-            if (has_res) load16_bf16(aux_row + c0, res);
+            if (has_res) {
+              if (c0 == cfirst) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) res[i] = aux0[i];
+              } else {
+                load16_bf16(aux_row + c0, res);
+              }
+            }
             tmem_ld_wait();
             float zp[16], zq[16], h[16];
 #pragma unroll
@@ -354,6 +379,13 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
   p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
+  {   // accumulator ring: as many [128 x CoT] fp32 buffers as TMEM's 512 columns allow (max 8)
+    int nb = 512 / pl.CoT;
+    nb = nb >= 8 ? 8 : (nb >= 4 ? 4 : 2);
+    p.NB = nb; p.nb_shift = nb == 8 ? 3 : (nb == 4 ? 2 : 1);
+    const int width = q.epi == EPI_GATE ? q.Cout : pl.CoT;
+    p.split_tiles = width < 32 ? 1 : 0;
+  }
   p.n_node_tiles = (q.N + 127) / 128;
   p.n_items = q.B * p.n_node_tiles;
   int gx = p.n_items < sm_count() / pl.nCoT ? p.n_items : sm_count() / pl.nCoT;
