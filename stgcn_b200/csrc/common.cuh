@@ -126,7 +126,8 @@ struct Arena {
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers ----------------------------------------------------------------------
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
+// MUFU ex2 + approximate divide (2 ulp): ~6 instructions instead of ~20 for the IEEE divide
+__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
 
 // Counter-based dropout keep-mask: splitmix64 finaliser over (seed, element index).
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {

@@ -79,16 +79,20 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
     q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
     q.out = y; q.ld_out = d.c_out; q.out_z = z_saved;
     if (d.B > 0 && umma::tap_supported(q)) {
-      // window-ordered K-major weights: wt[(j*W + o)*c_in + c] = conv_w[o][c][j] (+ align fold on tap Kt-1)
-      launch_gather3(p.conv_w, wt, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
-      launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
-      if (g.folded) {
+      // window-ordered K-major weights: w[(j*W + o)*c_in + c] = conv_w[o][c][j] (+ align fold on tap Kt-1)
+      if (!g.folded) {
+        GatherBatch gb(c.stream);
+        gb.add(p.conv_w, wbf, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt);
+        gb.add(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1);
+      } else {
         STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "tconv: c_in > c_out needs align conv parameters");
+        launch_gather3(p.conv_w, wt, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
+        launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
         launch_gather3(p.align_w, wt + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
         launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
+        long long nw = (long long)d.Kt * g.W * d.c_in;
+        STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wt, wbf, nw);
       }
-      long long nw = (long long)d.Kt * g.W * d.c_in;
-      STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wt, wbf, nw);
       umma::launch_tap(q, c.stream);
       return;
     }
@@ -109,6 +113,11 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
     sa.x = x; sa.wt = wt; sa.bias = bias; sa.z = z_saved; sa.h = y; sa.rows = g.rows_out; sa.Cin = d.c_in;
     sa.Cout = d.c_out; sa.W = g.W; sa.Kt = d.Kt; sa.T_out = g.T_out; sa.T_in = d.T; sa.N = d.N; sa.act = d.act;
     sa.explicit_res = (g.folded || g.linear) ? 0 : 1;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    if (smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved) && al16(y)) {
+      launch_smallc1_conv_gate_fwd(sa, c.stream);
+      return;
+    }
     size_t smem = (size_t)(d.Kt * d.c_in + 1) * g.W * sizeof(float);
     long long total = g.rows_out * (d.c_out / 8);
     int blocks = (int)std::min<long long>(ceil_div(total, 256), 148 * 16);
@@ -184,13 +193,14 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
       launch_wgrad(w, c.stream);
     }
     // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]
-    if (gr.conv_w) launch_gather3(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W, 0, c.stream);
-    if (gr.conv_b) launch_gather3(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
+    GatherBatch gb(c.stream);
+    if (gr.conv_w) gb.add(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W);
+    if (gr.conv_b) gb.add(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1);
     if (g.folded) {
-      if (gr.align_w)
-        launch_gather3(dwt, gr.align_w, 1, d.c_out, d.c_in, (long long)(d.Kt - 1) * d.c_in * g.W, 0, 1, g.W, 0, c.stream);
-      if (gr.align_b) launch_gather3(dwt, gr.align_b, 1, 1, d.c_out, (long long)Kw * g.W, 0, 0, 1, 0, c.stream);
+      if (gr.align_w) gb.add(dwt, gr.align_w, 1, d.c_out, d.c_in, (long long)(d.Kt - 1) * d.c_in * g.W, 0, 1, g.W);
+      if (gr.align_b) gb.add(dwt, gr.align_b, 1, 1, d.c_out, (long long)Kw * g.W, 0, 0, 1);
     }
+    gb.flush();
   }
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (dx) {
@@ -203,12 +213,16 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
       q.out = dx; q.ld_out = d.c_in; q.out_z = nullptr;
       if (d.B > 0 && umma::tap_supported(q)) {
         // window-ordered weights of the transposed conv: wd[(j*c_in + c)*W + o] = conv_w[o][c][Kt-1-j]
-        launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
-        if (g.folded)   // align conv acts at tap Kt-1, i.e. window position j = 0
+        if (!g.folded) {
+          launch_gather3(p.conv_w, wdbf, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
+        } else {
+          launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
+          // align conv acts at tap Kt-1, i.e. window position j = 0
           STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, c.stream, wd, g.W,
                        p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
-        long long nw = (long long)d.Kt * g.W * d.c_in;
-        STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wd, wdbf, nw);
+          long long nw = (long long)d.Kt * g.W * d.c_in;
+          STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wd, wdbf, nw);
+        }
         umma::launch_tap(q, c.stream);
         dx = nullptr;   // done
       }
@@ -448,8 +462,11 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     }
     gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
   }
-  if (gr.w) launch_gather3(dwt, gr.w, 1, 1, ntw * C * C, 0, 0, 0, 1, 0, c.stream);
-  if (gr.b) launch_gather3(dwt, gr.b, 1, 1, C, (long long)ntw * C * C, 0, 0, 1, 0, c.stream);
+  {
+    GatherBatch gb(c.stream);
+    if (gr.w) gb.add(dwt, gr.w, 1, 1, ntw * C * C, 0, 0, 0, 1);
+    if (gr.b) gb.add(dwt, gr.b, 1, 1, C, (long long)ntw * C * C, 0, 0, 1);
+  }
 
   // dst[0] now holds the gradient w.r.t. the aligned input
   if (d.c_in > C) {
@@ -459,8 +476,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
       wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
       launch_wgrad(wa, c.stream);
-      if (gr.align_w) launch_gather3(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C, 0, c.stream);
-      if (gr.align_b) launch_gather3(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1, 0, c.stream);
+      GatherBatch gb(c.stream);
+      if (gr.align_w) gb.add(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C);
+      if (gr.align_b) gb.add(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1);
+      gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
       if (dx && umma_linear(dst, wbf, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, true)) {
@@ -699,8 +718,10 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       w.in = s.r; w.dz = dy_t; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
       w.bias_row = 1; w.map = rm; w.partial = part;
       launch_wgrad(w, c.stream);
-      if (gr.fc2_w) launch_gather3(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end, 0, c.stream);
-      if (gr.fc2_b) launch_gather3(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1, 0, c.stream);
+      GatherBatch gb(c.stream);
+      if (gr.fc2_w) gb.add(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end);
+      if (gr.fc2_b) gb.add(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1);
+      gb.flush();
     }
     long long n1 = g.rows1 * d.c1;
     if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, (const T*)s.f1, df1, n1, d.training, d.p_drop, seed);
@@ -732,8 +753,10 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
         w.bias_row = 1; w.map = rm; w.partial = part;
         launch_wgrad(w, c.stream);
       }
-      if (gr.fc1_w) launch_gather3(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1, 0, c.stream);
-      if (gr.fc1_b) launch_gather3(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1, 0, c.stream);
+      GatherBatch gb(c.stream);
+      if (gr.fc1_w) gb.add(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1);
+      if (gr.fc1_b) gb.add(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1);
+      gb.flush();
     }
   }
   { Tag t("out.ln.bwd"); lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }

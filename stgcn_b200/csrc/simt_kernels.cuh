@@ -14,6 +14,9 @@
 //   * weight gradients = GEMMs whose contraction axis is the row axis, split over CTAs and
 //     reduced with fp32 atomics.
 #pragma once
+#include <type_traits>
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace stgcn {
@@ -442,7 +445,7 @@ inline void launch_reduce_partials(const float* partial, float* out, int n, int 
 // streaming rows, so: one CTA per row range, a 32-row tile of both operands staged in shared memory with coalesced
 // loads, thread (m, o-quad) accumulates 4 outputs in registers (2 LDS + 4 FMA per row), per-CTA partials are written
 // out and reduced by reduce_partials_kernel (no same-address atomics).
-constexpr int kSkR = 32;
+constexpr int kSkR = 128;     // rows per tile: the three block barriers per tile were the bottleneck at 32
 template <class T, bool VEC>
 __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
   extern __shared__ __align__(16) float sk[];
@@ -548,7 +551,7 @@ inline size_t wgrad_skinny_smem(int Mtot, int Kw) {
 struct WgradPlanSimt { int mode, tiles, chunks; long long rpc; };
 inline WgradPlanSimt plan_wgrad_simt(long long rows, int Mtot, int Co) {
   WgradPlanSimt pl;
-  if (Co <= 16 && Mtot * ((Co + 3) / 4) <= 320) {     // skinny kernel: one CTA per row range, ~6 CTAs per SM
+  if (Co <= 16 && Mtot * ((Co + 3) / 4) <= 320 && wgrad_skinny_smem(Mtot, Mtot) <= 160 * 1024) {     // skinny kernel: one CTA per row range, ~6 CTAs per SM
     pl.mode = 4; pl.tiles = 1;
     long long rpc = (rows + 148 * 6 - 1) / (148 * 6);
     if (rpc < 4 * kSkR) rpc = 4 * kSkR;
@@ -583,8 +586,13 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool vec = a.Cin % 8 == 0 && a.Co == 16 && a.ldz % 8 == 0 && al16(a.in) && al16(a.dz) &&
                      (a.map.tap_row_stride * a.Cin) % 8 == 0;
-    if (vec) STGCN_LAUNCH((wgrad_skinny_kernel<T, true>), chunks, 320, smem, s, a);
-    else     STGCN_LAUNCH((wgrad_skinny_kernel<T, false>), chunks, 320, smem, s, a);
+    if (vec) {
+      STGCN_CUDA(cudaFuncSetAttribute(wgrad_skinny_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      STGCN_LAUNCH((wgrad_skinny_kernel<T, true>), chunks, 320, smem, s, a);
+    } else {
+      STGCN_CUDA(cudaFuncSetAttribute(wgrad_skinny_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      STGCN_LAUNCH((wgrad_skinny_kernel<T, false>), chunks, 320, smem, s, a);
+    }
   } else if (pl.mode == 4 || pl.mode == 0) {
     STGCN_LAUNCH((wgrad_kernel<T, 64, 16, 1, 4>), dim3(ceil_div(Mtot, 64), 1, chunks), NT, 0, s, a);
   } else if (pl.mode == 1) {
@@ -824,6 +832,59 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
   }
 }
 
+// Cin == 1 specialisation: the K = Kt weights of this thread's 8 (+8 gate) channels live in registers; each thread
+// walks rows with a grid stride (its channel group never changes), so the loop body is K loads of x, K*16 FMAs, the
+// gate, and three 16-byte stores.
+template <class T, int K>
+__global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
+  const int groups = a.Cout / 8;
+  const bool gated = a.W == 2 * a.Cout;
+  const int j0 = (threadIdx.x % groups) * 8;
+  const int rl = threadIdx.x / groups, lanes = blockDim.x / groups;
+  float wp[K][8], wq[K][8], bp[8], bq[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    bp[i] = a.bias[j0 + i];
+    bq[i] = gated ? a.bias[a.Cout + j0 + i] : 0.f;
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      wp[k][i] = a.wt[k * a.W + j0 + i];
+      wq[k][i] = gated ? a.wt[k * a.W + a.Cout + j0 + i] : 0.f;
+    }
+  }
+  for (long long r = (long long)blockIdx.x * lanes + rl; r < a.rows; r += (long long)gridDim.x * lanes) {
+    long long in0; int t_unused;
+    row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
+    float xv[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xv[k] = ldf(a.x + in0 + (long long)k * a.N);
+    float zp[8], zq[8], hv[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float p = bp[i], q = bq[i];
+#pragma unroll
+      for (int k = 0; k < K; ++k) { p = fmaf(xv[k], wp[k][i], p); q = fmaf(xv[k], wq[k][i], q); }
+      zp[i] = p; zq[i] = q;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float res = (a.explicit_res && j0 + i == 0) ? xv[K - 1] : 0.f;
+      hv[i] = act_fwd(a.act, zp[i] + res, zq[i]);
+    }
+    store8(a.z + r * a.W + j0, zp);
+    if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
+    store8(a.h + r * a.Cout + j0, hv);
+  }
+}
+template <class T>
+inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s) {
+  const int lanes = 256 / (a.Cout / 8);
+  const int blocks = (int)std::min<long long>(ceil_div(a.rows, lanes), 148 * 8);
+  if (a.Kt == 2) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 2>), blocks, 256, 0, s, a);
+  else if (a.Kt == 3) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 3>), blocks, 256, 0, s, a);
+  else STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 4>), blocks, 256, 0, s, a);
+}
+
 // Fused gate-backward + weight gradient for the same layer: per CTA a row range, thread = (channel j, row lane);
 // dW[(k,c)][o] and db[o] accumulate in registers, are reduced across the row lanes in shared memory and added to the
 // global buffer with one atomic per element per CTA.  Optionally also materialises dz (when dx is needed).
@@ -1000,6 +1061,47 @@ inline void launch_gather3(const float* in, TO* out, int d0, int d1, int d2, lon
   if (tot == 0) return;
   STGCN_LAUNCH(gather3_kernel<TO>, ceil_div(tot, 256), 256, 0, s, in, out, d0, d1, d2, off, s0, s1, s2, accumulate);
 }
+
+// Several independent gather3 jobs in ONE launch (the per-call weight re-layouts and gradient scatters are a dozen
+// tiny tensors; one launch each was ~8% of the bf16 step).  Jobs must not depend on each other.
+struct GatherJob {
+  const float* in; void* out; int out_bf16;
+  int d0, d1, d2; long long off, s0, s1, s2;
+};
+constexpr int kMaxGatherJobs = 8;
+struct GatherJobs { GatherJob j[kMaxGatherJobs]; int n; };
+__global__ void gather3_multi_kernel(GatherJobs jobs) {
+  const GatherJob& g = jobs.j[blockIdx.y];
+  const long long tot = (long long)g.d0 * g.d1 * g.d2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
+    int i2 = (int)(idx % g.d2);
+    long long q = idx / g.d2;
+    int i1 = (int)(q % g.d1);
+    int i0 = (int)(q / g.d1);
+    float v = g.in[g.off + i0 * g.s0 + i1 * g.s1 + i2 * g.s2];
+    if (g.out_bf16) reinterpret_cast<bf16*>(g.out)[idx] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(g.out)[idx] = v;
+  }
+}
+struct GatherBatch {
+  GatherJobs jobs; cudaStream_t stream;
+  explicit GatherBatch(cudaStream_t s) : stream(s) { jobs.n = 0; }
+  template <class TO>
+  void add(const float* in, TO* out, int d0, int d1, int d2, long long off, long long s0, long long s1, long long s2) {
+    if ((long long)d0 * d1 * d2 == 0) return;
+    if (jobs.n == kMaxGatherJobs) flush();
+    jobs.j[jobs.n++] = GatherJob{in, (void*)out, std::is_same<TO, bf16>::value ? 1 : 0, d0, d1, d2, off, s0, s1, s2};
+  }
+  void flush() {
+    if (jobs.n == 0) return;
+    long long mx = 0;
+    for (int i = 0; i < jobs.n; ++i) mx = std::max(mx, (long long)jobs.j[i].d0 * jobs.j[i].d1 * jobs.j[i].d2);
+    int gx = (int)std::min<long long>(ceil_div(mx, 256), 64);
+    STGCN_LAUNCH(gather3_multi_kernel, dim3(gx, jobs.n), 256, 0, stream, jobs);
+    jobs.n = 0;
+  }
+  ~GatherBatch() noexcept(false) { flush(); }
+};
 
 // out[i*ldo + j] += in[i*si + j*sj]   (strided block accumulate; used to fold 1x1 align weights)
 __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, int d1, long long si, long long sj) {
