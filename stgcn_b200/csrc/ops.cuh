@@ -429,8 +429,17 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       }
     }
     if (gr.w || gr.b) {
-      w.in = stack; w.ntaps = d.Ks; w.map = RowMap{d.T, d.T, d.N, 0, rows};
-      launch_wgrad(w, c.stream);
+      bool done_w = false;
+      if constexpr (std::is_same<T, simt::bf16>::value) {
+        if (umma::wgrad_supported(C, C, d.Ks, d.T, d.B, true)) {    // stack planes as taps, dG zero-padded to M = 128
+          umma::launch_wgrad_umma(stack, dg, dwt, d.B, d.N, d.T, d.Ks, C, C, 1, c.stream, true);
+          done_w = true;
+        }
+      }
+      if (!done_w) {
+        w.in = stack; w.ntaps = d.Ks; w.map = RowMap{d.T, d.T, d.N, 0, rows};
+        launch_wgrad(w, c.stream);
+      }
     }
     // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
     for (int k = d.Ks - 1; k >= 2; --k) {
@@ -457,8 +466,17 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       launch_tapgemm(t, c.stream);
     }
     if (gr.w || gr.b) {
-      w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
-      launch_wgrad(w, c.stream);
+      bool done_w = false;
+      if constexpr (std::is_same<T, simt::bf16>::value) {
+        if (umma::wgrad_supported(C, C, 1, d.T, d.B)) {
+          umma::launch_wgrad_umma(stack + plane, dg, dwt, d.B, d.N, d.T, 1, C, C, 1, c.stream);
+          done_w = true;
+        }
+      }
+      if (!done_w) {
+        w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
+        launch_wgrad(w, c.stream);
+      }
     }
     gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
   }
@@ -472,10 +490,19 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   if (d.c_in > C) {
     if (gr.align_w || gr.align_b) {
       zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
-      WgradArgs<T> wa{};
-      wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
-      wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
-      launch_wgrad(wa, c.stream);
+      bool done_wa = false;
+      if constexpr (std::is_same<T, simt::bf16>::value) {
+        if (umma::wgrad_supported(d.c_in, C, 1, d.T, d.B)) {
+          umma::launch_wgrad_umma(x, dst, dwa, d.B, d.N, d.T, 1, d.c_in, C, 1, c.stream);
+          done_wa = true;
+        }
+      }
+      if (!done_wa) {
+        WgradArgs<T> wa{};
+        wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
+        wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
+        launch_wgrad(wa, c.stream);
+      }
       GatherBatch gb(c.stream);
       if (gr.align_w) gb.add(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C);
       if (gr.align_b) gb.add(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1);

@@ -24,6 +24,12 @@ struct WgradParams {
   uint32_t x_bytes, z_bytes, b_swz, b_sbo, b_kadv;
   float* dwt;
   int want_bias;
+  // A operand (dZ) geometry: `a_real` chunks of `a_cw` channels are loaded by TMA; when they cover fewer than the 128
+  // M rows of the MMA the remaining chunk slots of the stage stay zero (narrow dZ, e.g. 16 channels)
+  int a_cw, a_real;
+  uint32_t a_swz, a_lbo, a_sbo, a_kadv, a_chunk_bytes;
+  // plane mode: tap j reads batch coordinate b + j*plane_b at the SAME time step (stacked operands) instead of time t+j
+  int plane_mode, plane_b;
 };
 
 __global__ void __launch_bounds__(kTapThreads, 1)
@@ -43,6 +49,11 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   while ((int)ncols < ncol_used) ncols <<= 1;
 
   for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(1.f);
+  if (p.a_real * p.a_cw < 128) {         // narrow dZ: the unloaded chunk slots must read as zeros
+    uint4* zr = reinterpret_cast<uint4*>(smem + 2048);
+    const int n16 = (int)((size_t)p.Sz * p.z_bytes / 16);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) zr[i] = make_uint4(0, 0, 0, 0);
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.Sx; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
     for (int s = 0; s < p.Sz; ++s) { mbar_init(&zfull[s], 1); mbar_init(&zempty[s], 1); }
@@ -63,25 +74,35 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       tma_prefetch_desc(&tmZ);
       tma_prefetch_desc(&tmX);
       uint32_t gx = 0, gz = 0;
+      const uint32_t z_tx = (uint32_t)p.a_real * p.a_chunk_bytes;
+      auto load_x = [&](int ti, int bi, int n0) {
+        const uint32_t s = gx % p.Sx, ph = (gx / p.Sx) & 1;
+        mbar_wait(&xempty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&xfull[s], p.x_bytes);
+        uint8_t* dst = xring + (size_t)s * p.x_bytes;
+        for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * 64 * xcw * 2, &tmX, &xfull[s], c * xcw, n0, ti, bi);
+        ++gx;
+      };
+      auto load_z = [&](int t_o, int b, int n0) {
+        const uint32_t s = gz % p.Sz, ph = (gz / p.Sz) & 1;
+        mbar_wait(&zempty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&zfull[s], z_tx);
+        uint8_t* dst = zring + (size_t)s * p.z_bytes;
+        for (int c = 0; c < p.a_real; ++c) tma_load_4d(dst + (size_t)c * p.a_chunk_bytes, &tmZ, &zfull[s], o0 + c * p.a_cw, n0, t_o, b);
+        ++gz;
+      };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int b = item / p.n_chunks, n0 = (item % p.n_chunks) * 64;
-        for (int ti = 0; ti < p.T_in; ++ti) {
-          {
-            const uint32_t s = gx % p.Sx, ph = (gx / p.Sx) & 1;
-            mbar_wait(&xempty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&xfull[s], p.x_bytes);
-            uint8_t* dst = xring + (size_t)s * p.x_bytes;
-            for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * 64 * xcw * 2, &tmX, &xfull[s], c * 64, n0, ti, b);
-            ++gx;
+        if (p.plane_mode) {
+          for (int t_o = 0; t_o < p.T_out; ++t_o) {
+            for (int j = 0; j < p.Kt; ++j) load_x(t_o, b + j * p.plane_b, n0);
+            load_z(t_o, b, n0);
           }
-          const int t_o = ti - (p.Kt - 1);
-          if (t_o >= 0 && t_o < p.T_out) {
-            const uint32_t s = gz % p.Sz, ph = (gz / p.Sz) & 1;
-            mbar_wait(&zempty[s], ph ^ 1);
-            mbar_arrive_expect_tx(&zfull[s], p.z_bytes);
-            uint8_t* dst = zring + (size_t)s * p.z_bytes;
-            for (int c = 0; c < 2; ++c) tma_load_4d(dst + (size_t)c * 8192, &tmZ, &zfull[s], o0 + c * 64, n0, t_o, b);
-            ++gz;
+        } else {
+          for (int ti = 0; ti < p.T_in; ++ti) {
+            load_x(ti, b, n0);
+            const int t_o = ti - (p.Kt - 1);
+            if (t_o >= 0 && t_o < p.T_out) load_z(t_o, b, n0);
           }
         }
       }
@@ -99,14 +120,14 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
           tc_fence_after();
           const uint32_t a_base = smem_u32(zring + (size_t)sz * p.z_bytes);
           for (int j = 0; j < p.Kt; ++j) {
-            const uint32_t gx = gx_base + t_o + j, sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
+            const uint32_t gx = gx_base + (p.plane_mode ? t_o * p.Kt + j : t_o + j), sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
             mbar_wait(&xfull[sx], phx);
             tc_fence_after();
             const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
             const uint32_t acc = (started >> j) & 1;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024, SWZ_128B);
+              const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
               const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, 64u * xcw * 2, p.b_sbo, p.b_swz);
               mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, acc | (k != 0));
             }
@@ -116,18 +137,22 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
             const uint32_t acc = (started >> 31) & 1;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t da = make_smem_desc(a_base + k * 2048, 8192, 1024, SWZ_128B);
+              const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
               const uint64_t db = make_smem_desc(ones_a + k * 512, 2048, 256, SWZ_32B);
               mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, acc | (k != 0));
             }
             started |= 1u << 31;
           }
           mma_commit(&zempty[sz]);
-          mma_commit(&xempty[(gx_base + t_o) % p.Sx]);
-          if (t_o == p.T_out - 1)
-            for (int ti = p.T_out; ti < p.T_in; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
+          if (p.plane_mode) {
+            for (int j = 0; j < p.Kt; ++j) mma_commit(&xempty[(gx_base + t_o * p.Kt + j) % p.Sx]);
+          } else {
+            mma_commit(&xempty[(gx_base + t_o) % p.Sx]);
+            if (t_o == p.T_out - 1)
+              for (int ti = p.T_out; ti < p.T_in; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
+          }
         }
-        gx_base += p.T_in;
+        gx_base += p.plane_mode ? p.T_out * p.Kt : p.T_in;
       }
       mma_commit(&done);
     }
@@ -164,18 +189,24 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
-struct WgradPlan { bool ok; int Sx, Sz, nMT; uint32_t x_bytes, z_bytes; size_t smem; };
+struct WgradPlan { bool ok; int Sx, Sz, nMT, a_cw, a_real; uint32_t x_bytes, z_bytes; size_t smem; };
 
-inline WgradPlan plan_wgrad(int Cin, int W, int Kt, int T_in) {
+// W: channels of dz (128-multiples: full tiles; 16/32/64: one narrow, zero-padded tile)
+inline WgradPlan plan_wgrad(int Cin, int W, int Kt, int T_in, bool plane_mode) {
   WgradPlan pl{};
   pl.ok = false;
-  if (W % 128 || W < 128) return pl;
+  if (W >= 128) {
+    if (W % 128) return pl;
+    pl.a_cw = 64; pl.a_real = 2; pl.nMT = W / 128;
+  } else {
+    if (W != 16 && W != 32 && W != 64) return pl;
+    pl.a_cw = W; pl.a_real = 1; pl.nMT = 1;
+  }
   if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
   if (Kt * Cin + 16 > 512 || Kt > 30) return pl;
   pl.x_bytes = 64u * Cin * 2;
   pl.z_bytes = 16384;
-  pl.nMT = W / 128;
-  int live = Kt < T_in ? Kt : T_in;
+  int live = plane_mode ? Kt : (Kt < T_in ? Kt : T_in);
   pl.Sx = live + 3 > kMaxStages ? kMaxStages : live + 3;
   if (pl.Sx < live) return pl;
   pl.Sz = 3;
@@ -184,20 +215,27 @@ inline WgradPlan plan_wgrad(int Cin, int W, int Kt, int T_in) {
   pl.ok = true;
   return pl;
 }
-inline bool wgrad_supported(int Cin, int W, int Kt, int T_in, int B) { return B > 0 && plan_wgrad(Cin, W, Kt, T_in).ok; }
+inline bool wgrad_supported(int Cin, int W, int Kt, int T_in, int B, bool plane_mode = false) {
+  return B > 0 && plan_wgrad(Cin, W, Kt, T_in, plane_mode).ok;
+}
 
-// x: [B, T_in, N, Cin], dz: [B, T_out, N, W] (T_out = T_in - Kt + 1); dwt: fp32 [(Kt*Cin + 1), W], pre-zeroed
+// Time mode : x [B, T_in, N, Cin], dz [B, T_out, N, W], T_out = T_in - Kt + 1; tap j pairs dz(t) with x(t + j).
+// Plane mode: x [Kt*B, T, N, Cin] (Kt stacked planes), dz [B, T, N, W]; tap j pairs dz(b, t) with x(b + j*B, t).
+// dwt: fp32 [(Kt*Cin + 1), W], pre-zeroed.
 inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, int N, int T_in, int Kt, int Cin, int W,
-                              int want_bias, cudaStream_t stream) {
-  WgradPlan pl = plan_wgrad(Cin, W, Kt, T_in);
+                              int want_bias, cudaStream_t stream, bool plane_mode = false) {
+  WgradPlan pl = plan_wgrad(Cin, W, Kt, T_in, plane_mode);
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma wgrad: unsupported shape");
-  const int T_out = T_in - Kt + 1;
+  const int T_out = plane_mode ? T_in : T_in - Kt + 1;
   uint64_t zd[4] = {(uint64_t)W, (uint64_t)N, (uint64_t)T_out, (uint64_t)B};
   uint64_t zs[3] = {(uint64_t)W * 2, (uint64_t)N * W * 2, (uint64_t)T_out * N * W * 2};
-  uint32_t zb[4] = {64, 64, 1, 1};
-  CUtensorMap tmZ = make_tmap_bf16(dz, 4, zd, zs, zb, CU_TENSOR_MAP_SWIZZLE_128B);
+  uint32_t zb[4] = {(uint32_t)pl.a_cw, 64, 1, 1};
+  const CUtensorMapSwizzle zsw = pl.a_cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                               : (pl.a_cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUtensorMap tmZ = make_tmap_bf16(dz, 4, zd, zs, zb, zsw);
   const int xcw = Cin > 64 ? 64 : Cin;
-  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)T_in, (uint64_t)B};
+  const int xB = plane_mode ? Kt * B : B;
+  uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)T_in, (uint64_t)xB};
   uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2, (uint64_t)T_in * N * Cin * 2};
   uint32_t xb[4] = {(uint32_t)xcw, 64, 1, 1};
   const CUtensorMapSwizzle sw = xcw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (xcw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -208,6 +246,11 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
   p.x_bytes = pl.x_bytes; p.z_bytes = pl.z_bytes;
   p.b_swz = xcw == 64 ? SWZ_128B : (xcw == 32 ? SWZ_64B : SWZ_32B);
   p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
+  p.a_cw = pl.a_cw; p.a_real = pl.a_real;
+  p.a_swz = pl.a_cw == 64 ? SWZ_128B : (pl.a_cw == 32 ? SWZ_64B : SWZ_32B);
+  p.a_chunk_bytes = 64u * pl.a_cw * 2;          // one chunk: 64 K-rows x a_cw channels
+  p.a_lbo = p.a_chunk_bytes; p.a_sbo = 8u * pl.a_cw * 2; p.a_kadv = 16u * pl.a_cw * 2;
+  p.plane_mode = plane_mode ? 1 : 0; p.plane_b = B;
   p.dwt = dwt; p.want_bias = want_bias;
   int per = sm_count() / pl.nMT;
   int gx = p.n_items < per ? p.n_items : per;
