@@ -203,6 +203,10 @@ int stgcn_outblock_bwd(const stgcn_outblock_desc*, const void* x, const void* sa
 int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M, int N, int K,
                         uint32_t lbo_a, uint32_t sbo_a, uint32_t lbo_b, uint32_t sbo_b, void* stream);
 
+/* Diagnostics: while a device buffer of 16 uint64 is registered (NULL to stop), every umma_tap launch has CTA (0,0)
+ * write %globaltimer stamps of its pipeline milestones into it (see csrc/umma_tap.cuh STGCN_STAMP).          */
+int stgcn_debug_timeline(unsigned long long* device_buf16);
+
 /* ---- training-step helpers (main.py:166-168) ------------------------------------------ */
 /* loss = mean((pred - target)^2) over n elements, written to *loss (device, fp32);
  * dpred = 2 (pred - target) / n * loss_scale.  Replaces nn.MSELoss fwd+bwd (main.py:136,167-168). */

@@ -1,0 +1,23 @@
+import sys; sys.path.insert(0,'/root/repo')
+import torch, stgcn_b200
+from stgcn_b200 import layers, _lib as L
+stgcn_b200.set_precision("bf16")
+dev=torch.device('cuda')
+buf=torch.zeros(16,dtype=torch.int64,device=dev)
+def run(name, fn):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    L.check(L.lib().stgcn_debug_timeline(buf.data_ptr()))
+    buf.zero_(); fn(); torch.cuda.synchronize()
+    L.check(L.lib().stgcn_debug_timeline(None))
+    t=buf.cpu().tolist(); t0=t[0]
+    lab=['start','setup done','weights ready(mma)','tile0 full(mma)','tile0 tfull(epi)','tile0 stored','epi done','end','tile8 full(mma)','tile8 tfull(epi)','tile16 tfull(epi)']
+    print(name, {lab[i]: (t[i]-t0)/1e3 if t[i] else None for i in range(11)})
+B,N=256,228
+for (cin,cout,T) in [(16,64,10),(64,64,8)]:
+    lay=layers.TemporalConvLayer(3,cin,cout,N,'glu').to(dev)
+    x=torch.randn(B,cin,T,N,device=dev)
+    run(f"tconv {cin}->{cout} T={T}", lambda: lay(x))
+gl=layers.GraphConvLayer('cheb_graph_conv',64,16,3,torch.eye(N,device=dev),True).to(dev)
+x=torch.randn(B,64,10,N,device=dev)
+run("gconv (last tap launch = mix)", lambda: gl(x))

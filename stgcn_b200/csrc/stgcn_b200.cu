@@ -257,6 +257,10 @@ int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M,
   });
 }
 
+int stgcn_debug_timeline(unsigned long long* device_buf16) {
+  return guarded([&] { umma::g_tap_dbg = device_buf16; });
+}
+
 // ---------------------------------------------------------------- loss
 int stgcn_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float loss_scale, float* loss, float* dpred,
                       void* stream) {

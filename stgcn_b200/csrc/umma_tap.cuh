@@ -49,6 +49,7 @@ struct TapParams {
   int relu;                   // linear epilogue: clamp at 0 after bias/aux
   int NB, nb_shift;           // TMEM accumulator ring depth (power of two) and its log2
   int split_tiles;            // 1: the two epilogue warp groups take alternate tiles (narrow outputs); 0: alternate column chunks
+  unsigned long long* dbg;    // optional [16] timeline stamps (globaltimer ns) written by CTA (0,0); diagnostics only
 };
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
@@ -94,6 +95,13 @@ __device__ __forceinline__ void add_bias16(float* v, const float* bias_smem) {
   }
 }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define STGCN_STAMP(i) do { if (dbg_on) p.dbg[i] = gtime(); } while (0)
+
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TapParams p) {
@@ -107,6 +115,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.CoT;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  if (threadIdx.x == 0) STGCN_STAMP(0);
   for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
   uint32_t ncols = 32;
   while ((int)ncols < p.NB * p.CoT) ncols <<= 1;
@@ -123,6 +133,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
+  if (threadIdx.x == 0) STGCN_STAMP(1);
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
@@ -153,6 +164,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2, ablk = 128u * p.KB * 2;
       const int nk16 = p.KB / 16;
       mbar_wait(&wfull, 0);
+      STGCN_STAMP(2);
       uint32_t g_base = 0, acc_cnt = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
@@ -166,6 +178,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (ti < 0 || ti >= p.T_src) continue;
             const uint32_t g = g_base + ti, s = g % p.S, ph = (g / p.S) & 1;
             mbar_wait(&full[s], ph);
+            if (acc_cnt == 0) STGCN_STAMP(3);
+            if (acc_cnt == 8) STGCN_STAMP(8);
             tc_fence_after();
             const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes);
             const uint32_t b_base = smem_u32(w_s + (size_t)j * p.nKB * wblk);
@@ -212,6 +226,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const bool pre_aux = aux_row != nullptr && aux_c0 < p.aux_cols;
         if (pre_aux) load16_bf16(aux_row + aux_c0, aux0);
         mbar_wait(&tfull[ab], aph);
+        if (warp == 2 && acc_cnt == 0) STGCN_STAMP(4);
+        if (warp == 2 && acc_cnt == 8) STGCN_STAMP(9);
+        if (warp == 2 && acc_cnt == 16) STGCN_STAMP(10);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
 
@@ -278,17 +295,23 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
+        if (warp == 2 && acc_cnt == 0) STGCN_STAMP(5);
       }
     }
+    if (warp == 2) STGCN_STAMP(6);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (threadIdx.x == 32) STGCN_STAMP(7);
 }
 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// diagnostics: when set (stgcn_debug_timeline), the next tap launches write their CTA-0 timeline here
+inline unsigned long long* g_tap_dbg = nullptr;
+
 struct TapProblem {
   const bf16* in;          // [B, T_src, N, Cin]
   const bf16* w;           // [Kt][Co][Cin] bf16, already in window order (W_j)
@@ -379,6 +402,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
   p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
+  p.dbg = g_tap_dbg;
   {   // accumulator ring: as many [128 x CoT] fp32 buffers as TMEM's 512 columns allow (max 8)
     int nb = 512 / pl.CoT;
     nb = nb >= 8 ? 8 : (nb >= 4 ? 4 : 2);
