@@ -49,6 +49,11 @@ struct TapParams {
   int relu;                   // linear epilogue: clamp at 0 after bias/aux
   int NB, nb_shift;           // TMEM accumulator ring depth (power of two) and its log2
   int split_tiles;            // 1: the two epilogue warp groups take alternate tiles (narrow outputs); 0: alternate column chunks
+  // output staging: tiles are assembled in 128B-swizzled shared memory and written with TMA bulk tensor stores
+  // (per-thread 32-byte stores to 128 different rows cost ~32 LSU wavefronts per instruction and made the epilogue
+  // the bottleneck: 3.6 us per 128x128 tile, profiles/r01_bf16_summary.md)
+  int store_tma, nbuf, nZ, nO;
+  uint32_t stage_off, stage_bytes;
   unsigned long long* dbg;    // optional [16] timeline stamps (globaltimer ns) written by CTA (0,0); diagnostics only
 };
 
@@ -102,9 +107,21 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define STGCN_STAMP(i) do { if (dbg_on) p.dbg[i] = gtime(); } while (0)
 
+// 16 bf16 (32 bytes) of row `row` at column c (multiple of 16, < 64) of a [128 rows x 128 B] 128B-swizzled sub-tile
+__device__ __forceinline__ void stage_store16(uint8_t* sub, int row, int c, const float* v) {
+  uint4 a, b;
+  a.x = pack_bf16x2(v[0], v[1]);  a.y = pack_bf16x2(v[2], v[3]);  a.z = pack_bf16x2(v[4], v[5]);  a.w = pack_bf16x2(v[6], v[7]);
+  b.x = pack_bf16x2(v[8], v[9]);  b.y = pack_bf16x2(v[10], v[11]); b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+  const int cc = c >> 3, sw = row & 7;
+  uint8_t* r = sub + row * 128;
+  *reinterpret_cast<uint4*>(r + ((cc ^ sw) << 4)) = a;
+  *reinterpret_cast<uint4*>(r + (((cc + 1) ^ sw) << 4)) = b;
+}
+
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
-umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW, TapParams p) {
+umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmZ, TapParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
@@ -225,6 +242,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int aux_c0 = (EPI == EPI_LINEAR ? co0 : 0) + cfirst;
         const bool pre_aux = aux_row != nullptr && aux_c0 < p.aux_cols;
         if (pre_aux) load16_bf16(aux_row + aux_c0, aux0);
+        uint8_t* stg = nullptr;
+        if (p.store_tma) {
+          // the staging buffer used nbuf tiles ago must have been read out by its TMA store
+          if (threadIdx.x == 64) { if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+          named_bar_sync(1, 32 * kTapEpiWarps);
+          stg = smem + p.stage_off + (size_t)(acc_cnt % p.nbuf) * p.stage_bytes;
+        }
         mbar_wait(&tfull[ab], aph);
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(4);
         if (warp == 2 && acc_cnt == 8) STGCN_STAMP(9);
@@ -259,7 +283,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #pragma unroll
               for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
             }
-            if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
+            if (stg) stage_store16(stg + (size_t)(c0 >> 6) * 16384, row, c0 & 63, v);
+            else if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
           }
         } else {
           constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
@@ -285,7 +310,11 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (gated) add_bias16(zq, bias_s + p.Cout + c0);
 #pragma unroll
             for (int i = 0; i < 16; ++i) h[i] = epi_act<ACT>(has_res ? zp[i] + res[i] : zp[i], zq[i]);
-            if (valid) {
+            if (stg) {
+              stage_store16(stg + (size_t)(c0 >> 6) * 16384, row, c0 & 63, zp);
+              if (gated) stage_store16(stg + (size_t)((p.Cout + c0) >> 6) * 16384, row, c0 & 63, zq);
+              stage_store16(stg + (size_t)(p.nZ + (c0 >> 6)) * 16384, row, c0 & 63, h);
+            } else if (valid) {
               store16_bf16(p.out_z + orow * p.W + c0, zp);
               if (gated) store16_bf16(p.out_z + orow * p.W + p.Cout + c0, zq);
               store16_bf16(p.out + orow * p.Cout + c0, h);
@@ -295,9 +324,19 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
+        if (stg) {
+          fence_proxy_async();                       // staged tile -> visible to the TMA (async proxy)
+          named_bar_sync(2, 32 * kTapEpiWarps);
+          if (threadIdx.x == 64) {
+            for (int z = 0; z < p.nZ; ++z) tma_store_4d(&tmZ, stg + (size_t)z * 16384, z * 64, n0, t_o, b);
+            for (int o = 0; o < p.nO; ++o) tma_store_4d(&tmO, stg + (size_t)(p.nZ + o) * 16384, co0 + o * 64, n0, t_o, b);
+            tma_store_commit();
+          }
+        }
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(5);
       }
     }
+    if (p.store_tma && threadIdx.x == 64) tma_store_wait_all<0>();
     if (warp == 2) STGCN_STAMP(6);
   }
   tc_fence_before();
@@ -329,9 +368,13 @@ struct TapProblem {
 
 constexpr size_t kSmemBudget = 225 * 1024;
 
-struct TapPlan { bool ok; int KB, nKB, CoT, nCoT, S; uint32_t swz, sbo, tile_bytes, w_bytes; size_t smem; };
+struct TapPlan {
+  bool ok; int KB, nKB, CoT, nCoT, S; uint32_t swz, sbo, tile_bytes, w_bytes; size_t smem;
+  int store_tma, nbuf, nZ, nO; uint32_t stage_off, stage_bytes;
+};
 
-inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate) {
+// gate: the epilogue needs the whole pre-activation width W = Co in one CTA; Cout = its output channels.
+inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout = 0) {
   TapPlan pl{};
   pl.ok = false;
   if (Cin % 16 || Co % 16 || Cin < 16 || Co < 16) return pl;
@@ -343,18 +386,29 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate) {
   pl.sbo = 8u * pl.KB * 2;
   pl.tile_bytes = 128u * Cin * 2;
   const int live = Kt < T_src ? Kt : T_src;
-  // N tile: the gate epilogue needs the whole width in one CTA; otherwise halve until the weights + ring fit
   for (int CoT = Co > 256 ? 256 : Co; CoT >= 16; CoT /= 2) {
     if (Co % CoT || CoT % 16) { if (gate) break; continue; }
     if (gate && CoT != Co) break;
     size_t wb = (size_t)Kt * CoT * Cin * 2;
     wb = (wb + 1023) & ~size_t(1023);
     if (wb + (size_t)live * pl.tile_bytes > kSmemBudget) continue;
-    int S = (int)((kSmemBudget - wb) / pl.tile_bytes);
+    // output staging for TMA stores (64-column sub-tiles of 16 KB); two buffers if they fit next to >= live+1 stages
+    int nZ = 0, nO = 0;
+    const bool stageable = gate ? (Co % 64 == 0 && Cout % 64 == 0) : (CoT % 64 == 0);
+    if (stageable) { nZ = gate ? Co / 64 : 0; nO = gate ? Cout / 64 : CoT / 64; }
+    const size_t per_buf = (size_t)(nZ + nO) * 16384;
+    int nbuf = 0;
+    for (int cand = 2; cand >= 1 && stageable; --cand)
+      if (wb + cand * per_buf + (size_t)(live + 1) * pl.tile_bytes <= kSmemBudget) { nbuf = cand; break; }
+    const size_t stage_total = (size_t)nbuf * per_buf;
+    int S = (int)((kSmemBudget - wb - stage_total) / pl.tile_bytes);
     if (S > kMaxStages) S = kMaxStages;
     if (S < live) continue;
     pl.CoT = CoT; pl.nCoT = Co / CoT; pl.S = S; pl.w_bytes = (uint32_t)wb;
-    pl.smem = wb + (size_t)S * pl.tile_bytes + 1024;
+    pl.store_tma = nbuf > 0; pl.nbuf = nbuf; pl.nZ = nZ; pl.nO = nO;
+    pl.stage_off = (uint32_t)(wb + (size_t)S * pl.tile_bytes);
+    pl.stage_bytes = (uint32_t)per_buf;
+    pl.smem = wb + (size_t)S * pl.tile_bytes + stage_total + 1024;
     pl.ok = true;
     return pl;
   }
@@ -365,7 +419,7 @@ inline bool tap_supported(const TapProblem& q) {
   if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
   if (q.aux && (q.aux_cols % 16 != 0 || q.C_aux % 16 != 0)) return false;      // vector residual loads
   if (q.T_out < 1 || q.T_src < 1 || q.N < 1 || q.B < 1) return false;
-  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE).ok;
+  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout).ok;
 }
 
 inline int sm_count() {
@@ -379,7 +433,7 @@ inline int sm_count() {
 }
 
 inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
-  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE);
+  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout);
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma tap GEMM: unsupported shape");
   const CUtensorMapSwizzle tsw = pl.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : (pl.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -395,7 +449,23 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   uint32_t wb[3] = {(uint32_t)pl.KB, (uint32_t)pl.CoT, 1};
   CUtensorMap tmW = make_tmap_bf16(q.w, 3, wd, wsd, wb, tsw);
 
+  // output tensor maps (TMA store path): [channels, N, T_out, B], 64-channel x 128-vertex boxes, 128B swizzle
+  CUtensorMap tmO = tmX, tmZ = tmX;
+  if (pl.store_tma) {
+    const int Cmain = q.epi == EPI_GATE ? q.Cout : q.ld_out;
+    uint64_t od[4] = {(uint64_t)Cmain, (uint64_t)q.N, (uint64_t)q.T_out, (uint64_t)q.B};
+    uint64_t os[3] = {(uint64_t)Cmain * 2, (uint64_t)q.N * Cmain * 2, (uint64_t)q.T_out * q.N * Cmain * 2};
+    uint32_t ob[4] = {64, 128, 1, 1};
+    tmO = make_tmap_bf16(q.out, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (q.epi == EPI_GATE) {
+      uint64_t zd[4] = {(uint64_t)q.Co, (uint64_t)q.N, (uint64_t)q.T_out, (uint64_t)q.B};
+      uint64_t zs[3] = {(uint64_t)q.Co * 2, (uint64_t)q.N * q.Co * 2, (uint64_t)q.T_out * q.N * q.Co * 2};
+      tmZ = make_tmap_bf16(q.out_z, 4, zd, zs, ob, CU_TENSOR_MAP_SWIZZLE_128B);
+    }
+  }
   TapParams p{};
+  p.store_tma = pl.store_tma; p.nbuf = pl.nbuf; p.nZ = pl.nZ; p.nO = pl.nO; p.stage_off = pl.stage_off;
+  p.stage_bytes = pl.stage_bytes;
   p.B = q.B; p.N = q.N; p.T_src = q.T_src; p.T_out = q.T_out; p.Kt = q.Kt; p.t0 = q.t0;
   p.Cin = q.Cin; p.KB = pl.KB; p.nKB = pl.nKB; p.CoT = pl.CoT; p.S = pl.S; p.swz = pl.swz; p.sbo = pl.sbo;
   p.tile_bytes = pl.tile_bytes; p.w_bytes = pl.w_bytes;
@@ -409,6 +479,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     p.NB = nb; p.nb_shift = nb == 8 ? 3 : (nb == 4 ? 2 : 1);
     const int width = q.epi == EPI_GATE ? q.Cout : pl.CoT;
     p.split_tiles = width < 32 ? 1 : 0;
+    if (p.split_tiles) p.store_tma = 0;
   }
   p.n_node_tiles = (q.N + 127) / 128;
   p.n_items = q.B * p.n_node_tiles;
@@ -418,7 +489,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   const char* kname = q.epi == EPI_GATE ? "umma_tap_kernel<EPI_GATE>" : "umma_tap_kernel<EPI_LINEAR>";
   auto go = [&](auto kern) {
     STGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH_NAMED(kname, kern, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, p);
+    STGCN_LAUNCH_NAMED(kname, kern, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, tmO, tmZ, p);
   };
   if (q.epi == EPI_GATE) {
     switch (q.act) {
