@@ -13,6 +13,8 @@ def run(name, fn):
     t=buf.cpu().tolist(); t0=t[0]
     lab=['start','setup done','weights ready(mma)','tile0 full(mma)','tile0 tfull(epi)','tile0 stored','epi done','end','tile8 full(mma)','tile8 tfull(epi)','tile16 tfull(epi)']
     print(name, {lab[i]: (t[i]-t0)/1e3 if t[i] else None for i in range(11)})
+    lab2={9:'tile8 tfull',11:'t8 chunk0 start',12:'t8 chunk0 tmem loaded',13:'t8 chunk0 math done',14:'t8 all chunks done',15:'t8 released+store issued'}
+    print('   tile 8 detail (us):', {v: (t[k]-t0)/1e3 if t[k] else None for k,v in lab2.items()})
 B,N=256,228
 for (cin,cout,T) in [(16,64,10),(64,64,8)]:
     lay=layers.TemporalConvLayer(3,cin,cout,N,'glu').to(dev)

@@ -170,6 +170,11 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
 // TMEM -> registers.  Warp w of a warpgroup may only touch lanes [32*(w%4), 32*(w%4)+32).
 // taddr = (lane << 16) | column.  32x32b.xN: each thread gets N consecutive 32-bit columns of its lane.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"

@@ -107,6 +107,24 @@ __device__ __forceinline__ unsigned long long gtime() {
 }
 #define STGCN_STAMP(i) do { if (dbg_on) p.dbg[i] = gtime(); } while (0)
 
+__device__ __forceinline__ uint4 pack8_bf16(const float* v) {
+  uint4 a;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]); a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  return a;
+}
+__device__ __forceinline__ void unpack8_bf16(const uint4& a, float* v) {
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+// 8 bf16 (16 bytes) of row `row` at column c (multiple of 8, < 64) of a [128 rows x 128 B] 128B-swizzled sub-tile
+__device__ __forceinline__ void stage_store8(uint8_t* sub, int row, int c, const uint4& v) {
+  *reinterpret_cast<uint4*>(sub + row * 128 + (((c >> 3) ^ (row & 7)) << 4)) = v;
+}
+__device__ __forceinline__ void add_bias8(float* v, const float* bias_smem) {
+  const float4 b0 = reinterpret_cast<const float4*>(bias_smem)[0], b1 = reinterpret_cast<const float4*>(bias_smem)[1];
+  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
 // 16 bf16 (32 bytes) of row `row` at column c (multiple of 16, < 64) of a [128 rows x 128 B] 128B-swizzled sub-tile
 __device__ __forceinline__ void stage_store16(uint8_t* sub, int row, int c, const float* v) {
   uint4 a, b;
@@ -237,11 +255,14 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
         const int cfirst = p.split_tiles ? 0 : half * 16;
         const int cstep = p.split_tiles ? 16 : 32;
-        // first chunk's residual / aux values: independent of the MMA, so fetch them before waiting for it
-        float aux0[16];
-        const int aux_c0 = (EPI == EPI_LINEAR ? co0 : 0) + cfirst;
-        const bool pre_aux = aux_row != nullptr && aux_c0 < p.aux_cols;
-        if (pre_aux) load16_bf16(aux_row + aux_c0, aux0);
+        // Columns are processed in 8-wide groups by a ROLLED loop: the fully unrolled 16-wide version was ~60 KB of
+        // SASS and thrashed the instruction caches (144 cycles per element, profiles/r01_bf16_summary.md).  The
+        // residual / aux operand of the next group is fetched one iteration ahead.
+        const int cbase = EPI == EPI_LINEAR ? co0 : 0;              // column offset of aux / output tensors
+        const int width = EPI == EPI_LINEAR ? p.CoT : p.Cout;
+        const int n_aux = aux_row ? p.aux_cols - cbase : 0;         // aux covers local columns [0, n_aux)
+        uint4 rnext = make_uint4(0, 0, 0, 0);
+        if (cfirst < n_aux) rnext = *reinterpret_cast<const uint4*>(aux_row + cbase + cfirst);
         uint8_t* stg = nullptr;
         if (p.store_tma) {
           // the staging buffer used nbuf tiles ago must have been read out by its TMA store
@@ -255,72 +276,58 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (warp == 2 && acc_cnt == 16) STGCN_STAMP(10);
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
-
-        if (EPI == EPI_LINEAR) {
-          for (int c0 = cfirst; c0 < p.CoT; c0 += cstep) {
-            uint32_t r[16];
-            tmem_ld_32x32b_x16(t_addr + c0, r);
-            float av[16];
-            const bool has_aux = aux_row != nullptr && co0 + c0 < p.aux_cols;     // aux_cols is a multiple of 16 here
+        constexpr bool gated = EPI == EPI_GATE && (ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU);
+        const int n_grp = ((width - cfirst + cstep - 1) / cstep) * 2;      // 8-column groups this warp handles
+#pragma unroll 1
+        for (int gi = 0; gi < n_grp; ++gi) {
+          const int cc = cfirst + (gi >> 1) * cstep + (gi & 1) * 8;       // local column of this group
+          if (cc >= width) break;
+          uint32_t rp[8], rq[8];
+          tmem_ld_32x32b_x8(t_addr + cc, rp);
+          if (gated) tmem_ld_32x32b_x8(t_addr + p.Cout + cc, rq);
+          const uint4 rcur = rnext;
+          const bool has_aux = cc < n_aux;
+          {   // prefetch the next group's aux
+            const int gn = gi + 1;
+            const int cn = cfirst + (gn >> 1) * cstep + (gn & 1) * 8;
+            if (gn < n_grp && cn < n_aux) rnext = *reinterpret_cast<const uint4*>(aux_row + cbase + cn);
+          }
+          tmem_ld_wait();
+          float zp[8], zq[8], av[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { zp[i] = __uint_as_float(rp[i]); zq[i] = gated ? __uint_as_float(rq[i]) : 0.f; }
+          add_bias8(zp, bias_s + cc);
+          if (gated) add_bias8(zq, bias_s + p.Cout + cc);
+          if (has_aux) unpack8_bf16(rcur, av);
+          if (EPI == EPI_LINEAR) {
             if (has_aux) {
-              if (c0 == cfirst) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) av[i] = aux0[i];
-              } else {
-                load16_bf16(aux_row + co0 + c0, av);
-              }
-            }
-            tmem_ld_wait();
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            add_bias16(v, bias_s + c0);
-            if (has_aux) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += av[i];
+              for (int i = 0; i < 8; ++i) zp[i] += av[i];
             }
             if (p.relu) {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+              for (int i = 0; i < 8; ++i) zp[i] = fmaxf(zp[i], 0.f);
             }
-            if (stg) stage_store16(stg + (size_t)(c0 >> 6) * 16384, row, c0 & 63, v);
-            else if (valid && co0 + c0 < p.co_valid) store16_bf16(p.out + orow * p.ld_out + co0 + c0, v);
-          }
-        } else {
-          constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
-          for (int c0 = cfirst; c0 < p.Cout; c0 += cstep) {
-            uint32_t rp[16], rq[16];
-            tmem_ld_32x32b_x16(t_addr + c0, rp);
-            if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + c0, rq);
-            float res[16];
-            const bool has_res = aux_row != nullptr && c0 < p.aux_cols;           // aux_cols, C_aux multiples of 16 here
-            if (has_res) {
-              if (c0 == cfirst) {
+            const uint4 o = pack8_bf16(zp);
+            if (stg) stage_store8(stg + (size_t)(cc >> 6) * 16384, row, cc & 63, o);
+            else if (valid && co0 + cc < p.co_valid) *reinterpret_cast<uint4*>(p.out + orow * p.ld_out + co0 + cc) = o;
+          } else {
+            float h[8];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) res[i] = aux0[i];
-              } else {
-                load16_bf16(aux_row + c0, res);
-              }
-            }
-            tmem_ld_wait();
-            float zp[16], zq[16], h[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { zp[i] = __uint_as_float(rp[i]); zq[i] = gated ? __uint_as_float(rq[i]) : 0.f; }
-            add_bias16(zp, bias_s + c0);
-            if (gated) add_bias16(zq, bias_s + p.Cout + c0);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) h[i] = epi_act<ACT>(has_res ? zp[i] + res[i] : zp[i], zq[i]);
+            for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>(has_aux ? zp[i] + av[i] : zp[i], zq[i]);
+            const uint4 op = pack8_bf16(zp), oh = pack8_bf16(h);
             if (stg) {
-              stage_store16(stg + (size_t)(c0 >> 6) * 16384, row, c0 & 63, zp);
-              if (gated) stage_store16(stg + (size_t)((p.Cout + c0) >> 6) * 16384, row, c0 & 63, zq);
-              stage_store16(stg + (size_t)(p.nZ + (c0 >> 6)) * 16384, row, c0 & 63, h);
+              stage_store8(stg + (size_t)(cc >> 6) * 16384, row, cc & 63, op);
+              if (gated) stage_store8(stg + (size_t)((p.Cout + cc) >> 6) * 16384, row, cc & 63, pack8_bf16(zq));
+              stage_store8(stg + (size_t)(p.nZ + (cc >> 6)) * 16384, row, cc & 63, oh);
             } else if (valid) {
-              store16_bf16(p.out_z + orow * p.W + c0, zp);
-              if (gated) store16_bf16(p.out_z + orow * p.W + p.Cout + c0, zq);
-              store16_bf16(p.out + orow * p.Cout + c0, h);
+              *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = op;
+              if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
+              *reinterpret_cast<uint4*>(p.out + orow * p.Cout + cc) = oh;
             }
           }
         }
+        if (warp == 2 && acc_cnt == 8) STGCN_STAMP(14);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -334,6 +341,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         }
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(5);
+        if (warp == 2 && acc_cnt == 8) STGCN_STAMP(15);
       }
     }
     if (p.store_tma && threadIdx.x == 64) tma_store_wait_all<0>();
