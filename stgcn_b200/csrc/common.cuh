@@ -126,8 +126,11 @@ struct Arena {
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers ----------------------------------------------------------------------
-// MUFU ex2 + approximate divide (2 ulp): ~6 instructions instead of ~20 for the IEEE divide
-__device__ __forceinline__ float sigmoidf_(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
+// Branch-free MUFU math.  (__frcp_rn / IEEE division put a slow-path CALL inside BSSY/BSYNC regions around every
+// element, which stops the compiler from interleaving elements: a serialized ~150-cycle chain per sigmoid.)
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoidf_(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
 
 // Counter-based dropout keep-mask: splitmix64 finaliser over (seed, element index).
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {

@@ -78,7 +78,7 @@ __device__ __forceinline__ void load16_bf16(const bf16* src, float* v) {
   }
 }
 // epilogue math: MUFU-based (ex2 / rcp / tanh.approx), accurate far beyond the bf16 the results are stored in
-__device__ __forceinline__ float fast_sigmoid(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float fast_sigmoid(float x) { return sigmoidf_(x); }   // branch-free ex2/rcp.approx
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
