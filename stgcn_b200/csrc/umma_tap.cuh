@@ -28,7 +28,8 @@ namespace umma {
 
 using simt::bf16;
 enum { EPI_LINEAR = 0, EPI_GATE = 1 };
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 12;
+constexpr int kCpDepth = 6;            // cp.async producer: slices published this many groups late (copies in flight)
 constexpr int kTapThreads = 192;       // gso / wgrad kernels: 4 epilogue warps
 constexpr int kTapEpiWarps = 8;        // tap kernel: two epilogue warps per TMEM lane quarter (column halves)
 constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps;
@@ -54,6 +55,11 @@ struct TapParams {
   // the bottleneck: 3.6 us per 128x128 tile, profiles/r01_bf16_summary.md)
   int store_tma, nbuf, nZ, nO;
   uint32_t stage_off, stage_bytes;
+  // narrow inputs (Cin == 16: 32-byte rows): TMA issues one request per 32-byte row and cannot keep the MMA fed
+  // (1.8 us per 3-slice tile measured); a producer WARP copies with cp.async instead (16 B per lane, swizzle applied on
+  // the shared-memory address, zero fill past N)
+  int narrow_cp;
+  const bf16* in_ptr; long long sn, st, sb;   // element strides of `in` (vertex, time, batch)
   unsigned long long* dbg;    // optional [16] timeline stamps (globaltimer ns) written by CTA (0,0); diagnostics only
 };
 
@@ -171,7 +177,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (threadIdx.x == 0) STGCN_STAMP(1);
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
+    // =========================== producer ================================
     if (lane == 0) {
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmW);
@@ -179,18 +185,56 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       mbar_arrive_expect_tx(&wfull, (uint32_t)p.Kt * p.nKB * wblk);   // exact bytes (w_bytes is rounded up to 1 KB)
       for (int j = 0; j < p.Kt; ++j)
         for (int kb = 0; kb < p.nKB; ++kb) tma_load_3d(w_s + (size_t)(j * p.nKB + kb) * wblk, &tmW, &wfull, kb * p.KB, co0, j);
-      uint32_t g = 0;
-      const uint32_t ablk = 128u * p.KB * 2;
+    }
+    if (!p.narrow_cp) {
+      if (lane == 0) {
+        uint32_t g = 0;
+        const uint32_t ablk = 128u * p.KB * 2;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+          const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
+          for (int ti = 0; ti < p.T_src; ++ti, ++g) {
+            const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], p.tile_bytes);
+            uint8_t* dst = ring + (size_t)s * p.tile_bytes;
+            for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
+          }
+        }
+      }
+    } else {
+      // cp.async producer warp: slice = 128 rows x 32 B = 256 16-byte chunks, 8 per lane; chunk (row, h) lands at
+      // row*32 + ((h ^ ((row >> 2) & 1)) << 4)  (the 32B-swizzle pattern of the UMMA descriptor).  Slices are published
+      // D groups late so that D copies stay in flight per lane.
+      constexpr int D = kCpDepth;
+      uint32_t g = 0, pub = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
         for (int ti = 0; ti < p.T_src; ++ti, ++g) {
           const uint32_t s = g % p.S, ph = (g / p.S) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], p.tile_bytes);
           uint8_t* dst = ring + (size_t)s * p.tile_bytes;
-          for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
+          const bf16* src0 = p.in_ptr + (long long)b * p.sb + (long long)ti * p.st;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int q = lane + 32 * i, row = q >> 1, h = q & 1;
+            const bool ok = n0 + row < p.N;
+            const bf16* src = src0 + (long long)(ok ? n0 + row : 0) * p.sn + h * 8;
+            cp_async16(dst + row * 32 + ((h ^ ((row >> 2) & 1)) << 4), src, ok ? 16u : 0u);
+          }
+          cp_async_commit();
+          if (g - pub >= (uint32_t)D) {          // the oldest unpublished slice has landed for every lane after this
+            cp_async_wait<D>();
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[pub % p.S]);
+            ++pub;
+          }
         }
       }
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) for (; pub < g; ++pub) mbar_arrive(&full[pub % p.S]);
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
@@ -481,6 +525,12 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
   p.dbg = g_tap_dbg;
+  // a stage is recycled only after a window of Kt published slices was consumed: S >= depth + Kt + 1 or it deadlocks
+  p.narrow_cp = (pl.KB == 16 && pl.nKB == 1 && pl.S >= kCpDepth + q.Kt + 1) ? 1 : 0;
+  p.in_ptr = q.in;
+  p.sn = q.in_stride_n ? q.in_stride_n : q.Cin;
+  p.st = q.in_stride_t ? q.in_stride_t : (long long)q.N * q.Cin;
+  p.sb = q.in_stride_b ? q.in_stride_b : (long long)q.T_src * q.N * q.Cin;
   {   // accumulator ring: as many [128 x CoT] fp32 buffers as TMEM's 512 columns allow (max 8)
     int nb = 512 / pl.CoT;
     nb = nb >= 8 ? 8 : (nb >= 4 ? 4 : 2);
