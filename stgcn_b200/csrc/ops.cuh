@@ -431,7 +431,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     if (gr.w || gr.b) {
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
-        if (umma::wgrad_supported(C, C, d.Ks, d.T, d.B, true)) {    // stack planes as taps, dG zero-padded to M = 128
+        if (umma::wgrad_flat_supported(C, C, d.Ks, rows)) {          // stack planes as taps over flat 256-row tiles
+          umma::launch_wgrad_flat(stack, dg, dwt, rows, rows, d.Ks, C, C, 1, c.stream);
+          done_w = true;
+        } else if (umma::wgrad_supported(C, C, d.Ks, d.T, d.B, true)) {
           umma::launch_wgrad_umma(stack, dg, dwt, d.B, d.N, d.T, d.Ks, C, C, 1, c.stream, true);
           done_w = true;
         }
@@ -468,7 +471,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     if (gr.w || gr.b) {
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
-        if (umma::wgrad_supported(C, C, 1, d.T, d.B)) {
+        if (umma::wgrad_flat_supported(C, C, 1, rows)) {
+          umma::launch_wgrad_flat(stack + plane, dg, dwt, rows, 0, 1, C, C, 1, c.stream);
+          done_w = true;
+        } else if (umma::wgrad_supported(C, C, 1, d.T, d.B)) {
           umma::launch_wgrad_umma(stack + plane, dg, dwt, d.B, d.N, d.T, 1, C, C, 1, c.stream);
           done_w = true;
         }
@@ -492,7 +498,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
       bool done_wa = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
-        if (umma::wgrad_supported(d.c_in, C, 1, d.T, d.B)) {
+        if (umma::wgrad_flat_supported(d.c_in, C, 1, rows)) {
+          umma::launch_wgrad_flat(x, dst, dwa, rows, 0, 1, d.c_in, C, 1, c.stream);
+          done_wa = true;
+        } else if (umma::wgrad_supported(d.c_in, C, 1, d.T, d.B)) {
           umma::launch_wgrad_umma(x, dst, dwa, d.B, d.N, d.T, 1, d.c_in, C, 1, c.stream);
           done_wa = true;
         }

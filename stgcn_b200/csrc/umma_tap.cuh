@@ -194,10 +194,15 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
           for (int ti = 0; ti < p.T_src; ++ti, ++g) {
             const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+            if (g == 24) STGCN_STAMP(25);
             mbar_wait(&empty[s], ph ^ 1);
+            if (g == 24) STGCN_STAMP(26);
             mbar_arrive_expect_tx(&full[s], p.tile_bytes);
             uint8_t* dst = ring + (size_t)s * p.tile_bytes;
             for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
+            if (g == 24) STGCN_STAMP(27);
+            if (g == 25) STGCN_STAMP(28);
+            if (g == 32) STGCN_STAMP(29);
           }
         }
       }
@@ -211,7 +216,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
         for (int ti = 0; ti < p.T_src; ++ti, ++g) {
           const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          if (g == 24) STGCN_STAMP(25);
           mbar_wait(&empty[s], ph ^ 1);
+          if (g == 24) STGCN_STAMP(26);
           uint8_t* dst = ring + (size_t)s * p.tile_bytes;
           const bf16* src0 = p.in_ptr + (long long)b * p.sb + (long long)ti * p.st;
 #pragma unroll
@@ -222,6 +229,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             cp_async16(dst + row * 32 + ((h ^ ((row >> 2) & 1)) << 4), src, ok ? 16u : 0u);
           }
           cp_async_commit();
+          if (g == 24) STGCN_STAMP(27);
           if (g - pub >= (uint32_t)D) {          // the oldest unpublished slice has landed for every lane after this
             cp_async_wait<D>();
             fence_proxy_async();
@@ -229,6 +237,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (lane == 0) mbar_arrive(&full[pub % p.S]);
             ++pub;
           }
+          if (g == 24) STGCN_STAMP(28);
+          if (g == 32) STGCN_STAMP(29);
         }
       }
       cp_async_wait<0>();
@@ -248,7 +258,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
           const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
+          if (acc_cnt == 8) STGCN_STAMP(16);
           mbar_wait(&tempty[ab], aph ^ 1);
+          if (acc_cnt == 8) STGCN_STAMP(17);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ab * p.CoT;
           uint32_t accumulate = 0;
@@ -259,6 +271,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&full[s], ph);
             if (acc_cnt == 0) STGCN_STAMP(3);
             if (acc_cnt == 8) STGCN_STAMP(8);
+            if (acc_cnt == 8) STGCN_STAMP(18 + j);
             tc_fence_after();
             const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes);
             const uint32_t b_base = smem_u32(w_s + (size_t)j * p.nKB * wblk);
@@ -270,12 +283,15 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 accumulate = 1;
               }
           }
+          if (acc_cnt == 8) STGCN_STAMP(22);
           mma_commit(&tfull[ab]);
+          if (acc_cnt == 8) STGCN_STAMP(23);
           // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
           const int t_rel = t_o + p.t0;
           if (t_rel >= 0 && t_rel < p.T_src) mma_commit(&empty[(g_base + t_rel) % p.S]);
           if (t_o == p.T_out - 1)
             for (int ti = (t_rel + 1 > 0 ? t_rel + 1 : 0); ti < p.T_src; ++ti) mma_commit(&empty[(g_base + ti) % p.S]);
+          if (acc_cnt == 8) STGCN_STAMP(24);
         }
         g_base += p.T_src;
       }

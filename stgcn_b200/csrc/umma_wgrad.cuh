@@ -189,6 +189,174 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Flat-row variant for weight gradients WITHOUT a time shift (1x1 align conv, Chebyshev / GCN weight contraction):
+//   dW_j[o, c] = sum_r dZ[r, o] * X_j[r, c],   r over all B*T*N rows, X_j = plane j of a stack (or the input itself).
+// The rows are one flat axis, so a pipeline stage is 256 consecutive rows of dZ and of every plane (2-D TMA boxes):
+// 4x fewer, 4x larger steps than the (sample, 64-vertex) items above, whose ~1.6 us per-step latency dominated.
+// dZ is narrow here (W = 16/32/64 channels): the MMA's M = 128 rows are filled by aliasing the single W-wide chunk
+// (descriptor leading-dim offset 0); accumulator lanes >= W hold duplicates and are never read.
+// ------------------------------------------------------------------------------------------------
+struct WgradFlatParams {
+  long long rows, plane_rows;
+  int Kt, Cin, W, S, n_tiles;
+  uint32_t z_bytes, x_bytes, stage_bytes, a_swz, a_sbo, a_kadv, b_swz, b_sbo, b_kadv;
+  float* dwt;
+  int want_bias;
+};
+constexpr int kFlatRows = 256;
+
+__global__ void __launch_bounds__(kTapThreads, 1)
+umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradFlatParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem;                       // [64 rows][16] bf16 1.0
+  uint8_t* ring = smem + 2048;                // S x { dZ [256][W*2 B] , Kt x X [256][Cin*2 B] }
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t ncols = 32;
+  while ((int)ncols < p.Kt * p.Cin + 16) ncols <<= 1;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) reinterpret_cast<__nv_bfloat16*>(ones)[i] = __float2bfloat16_rn(1.f);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int nxc = p.Cin > 64 ? p.Cin / 64 : 1, xcw = p.Cin > 64 ? 64 : p.Cin;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmZ);
+      tma_prefetch_desc(&tmX);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
+        const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        const int r0 = tile * kFlatRows;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&full[s], p.stage_bytes);
+        uint8_t* dst = ring + (size_t)s * p.stage_bytes;
+        tma_load_2d(dst, &tmZ, &full[s], 0, r0);
+        for (int j = 0; j < p.Kt; ++j)
+          for (int c = 0; c < nxc; ++c)
+            tma_load_2d(dst + p.z_bytes + (size_t)j * p.x_bytes + (size_t)c * kFlatRows * xcw * 2, &tmX, &full[s], c * xcw,
+                        (int)(r0 + j * p.plane_rows));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, p.Cin, 1, 1), idesc_b = make_idesc_bf16(128, 16, 1, 1);
+      const uint32_t ones_a = smem_u32(ones);
+      uint32_t g = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
+        const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(ring + (size_t)s * p.stage_bytes);
+        for (int j = 0; j < p.Kt; ++j) {
+          const uint32_t b_base = a_base + p.z_bytes + j * p.x_bytes;
+          for (int k = 0; k < kFlatRows / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, 0, p.a_sbo, p.a_swz);      // LBO 0: chunk aliased
+            const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, (uint32_t)kFlatRows * xcw * 2, p.b_sbo, p.b_swz);
+            mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, (g | (uint32_t)k) != 0);
+          }
+        }
+        if (p.want_bias)
+          for (int k = 0; k < kFlatRows / 16; ++k) {
+            const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, 0, p.a_sbo, p.a_swz);
+            const uint64_t db = make_smem_desc(ones_a + (k & 3) * 512, 2048, 256, SWZ_32B);
+            mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, (g | (uint32_t)k) != 0);
+          }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(&done);
+    }
+  } else {
+    const int q = warp & 3;
+    const int o = q * 32 + lane;
+    if (blockIdx.x < p.n_tiles) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < p.Kt * p.Cin; c0 += 8) {
+        uint32_t r[8];
+        tmem_ld_32x32b_x8(t_addr + c0, r);
+        tmem_ld_wait();
+        if (o < p.W) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(p.dwt + (size_t)(c0 + i) * p.W + o, __uint_as_float(r[i]));
+        }
+      }
+      if (p.want_bias) {
+        uint32_t r[8];
+        tmem_ld_32x32b_x8(t_addr + p.Kt * p.Cin, r);
+        tmem_ld_wait();
+        if (o < p.W) atomicAdd(p.dwt + (size_t)p.Kt * p.Cin * p.W + o, __uint_as_float(r[0]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
+struct WgradFlatPlan { bool ok; int S; uint32_t z_bytes, x_bytes, stage_bytes; size_t smem; };
+inline WgradFlatPlan plan_wgrad_flat(int Cin, int W, int Kt) {
+  WgradFlatPlan pl{};
+  pl.ok = false;
+  if (W != 16 && W != 32 && W != 64) return pl;
+  if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
+  if (Kt < 1 || Kt * Cin + 16 > 512) return pl;
+  pl.z_bytes = (uint32_t)kFlatRows * W * 2;
+  pl.x_bytes = (uint32_t)kFlatRows * Cin * 2;
+  pl.stage_bytes = pl.z_bytes + (uint32_t)Kt * pl.x_bytes;
+  int S = (int)((kSmemBudget - 2048) / pl.stage_bytes);
+  if (S > 6) S = 6;
+  if (S < 2) return pl;
+  pl.S = S;
+  pl.smem = 2048 + (size_t)S * pl.stage_bytes + 1024;
+  pl.ok = true;
+  return pl;
+}
+inline bool wgrad_flat_supported(int Cin, int W, int Kt, long long rows) {
+  return rows > 0 && rows * (long long)(Kt > 1 ? Kt : 1) < (1LL << 31) && plan_wgrad_flat(Cin, W, Kt).ok;
+}
+// x: Kt planes of [rows, Cin] (plane stride = plane_rows rows); dz: [rows, W]; dwt: fp32 [(Kt*Cin + 1), W], pre-zeroed
+inline void launch_wgrad_flat(const bf16* x, const bf16* dz, float* dwt, long long rows, long long plane_rows, int Kt,
+                              int Cin, int W, int want_bias, cudaStream_t stream) {
+  WgradFlatPlan pl = plan_wgrad_flat(Cin, W, Kt);
+  STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma flat wgrad: unsupported shape");
+  auto swz_of = [](int cw) { return cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B); };
+  auto dsw_of = [](int cw) { return cw == 64 ? SWZ_128B : (cw == 32 ? SWZ_64B : SWZ_32B); };
+  uint64_t zd[2] = {(uint64_t)W, (uint64_t)rows};
+  uint64_t zs[1] = {(uint64_t)W * 2};
+  uint32_t zb[2] = {(uint32_t)W, (uint32_t)kFlatRows};
+  CUtensorMap tmZ = make_tmap_bf16(dz, 2, zd, zs, zb, swz_of(W));
+  const int xcw = Cin > 64 ? 64 : Cin;
+  const long long xrows = plane_rows * (Kt - 1) + rows;
+  uint64_t xd[2] = {(uint64_t)Cin, (uint64_t)xrows};
+  uint64_t xs[1] = {(uint64_t)Cin * 2};
+  uint32_t xb[2] = {(uint32_t)xcw, (uint32_t)kFlatRows};
+  CUtensorMap tmX = make_tmap_bf16(x, 2, xd, xs, xb, swz_of(xcw));
+  WgradFlatParams p{};
+  p.rows = rows; p.plane_rows = plane_rows; p.Kt = Kt; p.Cin = Cin; p.W = W; p.S = pl.S;
+  p.n_tiles = (int)((rows + kFlatRows - 1) / kFlatRows);
+  p.z_bytes = pl.z_bytes; p.x_bytes = pl.x_bytes; p.stage_bytes = pl.stage_bytes;
+  p.a_swz = dsw_of(W); p.a_sbo = 8u * W * 2; p.a_kadv = 16u * W * 2;
+  p.b_swz = dsw_of(xcw); p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
+  p.dwt = dwt; p.want_bias = want_bias;
+  int gx = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  STGCN_CUDA(cudaFuncSetAttribute(umma_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+  STGCN_LAUNCH(umma_wgrad_flat_kernel, gx, kTapThreads, pl.smem, stream, tmZ, tmX, p);
+}
+
 struct WgradPlan { bool ok; int Sx, Sz, nMT, a_cw, a_real; uint32_t x_bytes, z_bytes; size_t smem; };
 
 // W: channels of dz (128-multiples: full tiles; 16/32/64: one narrow, zero-padded tile)
