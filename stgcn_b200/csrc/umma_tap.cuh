@@ -32,7 +32,8 @@ constexpr int kMaxStages = 12;
 constexpr int kCpDepth = 6;            // cp.async producer: slices published this many groups late (copies in flight)
 constexpr int kTapThreads = 192;       // gso / wgrad kernels: 4 epilogue warps
 constexpr int kTapEpiWarps = 8;        // tap kernel: two epilogue warps per TMEM lane quarter (column halves)
-constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps;
+constexpr int kTapProducers = 4;        // cp.async producer warps for narrow inputs: warp 0 and warps 10..12
+constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps + 32 * (kTapProducers - 1);
 
 struct TapParams {
   int B, N, T_src, T_out, Kt, t0;
@@ -176,9 +177,11 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) STGCN_STAMP(1);
 
-  if (warp == 0) {
+  const bool is_producer = warp == 0 || warp >= 2 + kTapEpiWarps;
+  const int prod_idx = warp == 0 ? 0 : warp - (2 + kTapEpiWarps) + 1;
+  if (is_producer) {
     // =========================== producer ================================
-    if (lane == 0) {
+    if (warp == 0 && lane == 0) {
       tma_prefetch_desc(&tmX);
       tma_prefetch_desc(&tmW);
       const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2;
@@ -187,7 +190,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int kb = 0; kb < p.nKB; ++kb) tma_load_3d(w_s + (size_t)(j * p.nKB + kb) * wblk, &tmW, &wfull, kb * p.KB, co0, j);
     }
     if (!p.narrow_cp) {
-      if (lane == 0) {
+      if (warp == 0 && lane == 0) {
         uint32_t g = 0;
         const uint32_t ablk = 128u * p.KB * 2;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -207,14 +210,16 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
       }
     } else {
-      // cp.async producer warp: slice = 128 rows x 32 B = 256 16-byte chunks, 8 per lane; chunk (row, h) lands at
-      // row*32 + ((h ^ ((row >> 2) & 1)) << 4)  (the 32B-swizzle pattern of the UMMA descriptor).  Slices are published
-      // D groups late so that D copies stay in flight per lane.
-      constexpr int D = kCpDepth;
-      uint32_t g = 0, pub = 0;
+      // cp.async producer warps: slice = 128 rows x 32 B = 256 16-byte chunks, 8 per lane; chunk (row, h) lands at
+      // row*32 + ((h ^ ((row >> 2) & 1)) << 4)  (the 32B-swizzle pattern of the UMMA descriptor).  The kTapProducers
+      // warps take alternate slices (one warp's per-slice bookkeeping latency, ~0.4 us, was the limiter); each
+      // publishes a slice when it has issued its next one, so one copy group per warp is always in flight.
+      uint32_t g = 0;
+      int pending = -1;                                  // this warp's issued-but-unpublished slice (stage index)
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
         for (int ti = 0; ti < p.T_src; ++ti, ++g) {
+          if ((int)(g % kTapProducers) != prod_idx) continue;
           const uint32_t s = g % p.S, ph = (g / p.S) & 1;
           if (g == 24) STGCN_STAMP(25);
           mbar_wait(&empty[s], ph ^ 1);
@@ -230,21 +235,23 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           cp_async_commit();
           if (g == 24) STGCN_STAMP(27);
-          if (g - pub >= (uint32_t)D) {          // the oldest unpublished slice has landed for every lane after this
-            cp_async_wait<D>();
+          if (pending >= 0) {                            // the previous slice of this warp has landed after this wait
+            cp_async_wait<1>();
             fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[pub % p.S]);
-            ++pub;
+            if (lane == 0) mbar_arrive(&full[pending]);
           }
+          pending = (int)s;
           if (g == 24) STGCN_STAMP(28);
           if (g == 32) STGCN_STAMP(29);
         }
       }
-      cp_async_wait<0>();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) for (; pub < g; ++pub) mbar_arrive(&full[pub % p.S]);
+      if (pending >= 0) {
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&full[pending]);
+      }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
@@ -542,7 +549,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
   p.dbg = g_tap_dbg;
   // a stage is recycled only after a window of Kt published slices was consumed: S >= depth + Kt + 1 or it deadlocks
-  p.narrow_cp = (pl.KB == 16 && pl.nKB == 1 && pl.S >= kCpDepth + q.Kt + 1) ? 1 : 0;
+  p.narrow_cp = (pl.KB == 16 && pl.nKB == 1 && pl.S >= kTapProducers + q.Kt + 2) ? 1 : 0;
   p.in_ptr = q.in;
   p.sn = q.in_stride_n ? q.in_stride_n : q.Cin;
   p.st = q.in_stride_t ? q.in_stride_t : (long long)q.N * q.Cin;
