@@ -707,10 +707,17 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
   if (!fc1_done) launch_tapgemm(t, c.stream);
   long long n1 = g.rows1 * d.c1;
   if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
-  TapArgs<T, float> t2{};
-  t2.in = s.r; t2.wt = w2t; t2.bias = p.fc2_b; t2.out = y; t2.rows = g.rows1; t2.Cin = d.c1; t2.Co = d.c_end;
-  t2.ntaps = 1; t2.ldo = d.c_end; t2.map = t.map;
-  launch_tapgemm(t2, c.stream);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && g.rows1 > 0) {
+    const int lanes = 256 / (d.c1 / 8);
+    const int blocks = (int)std::min<long long>(ceil_div(g.rows1, lanes), 148 * 8);
+    STGCN_LAUNCH(rowdot_fwd_kernel<T>, blocks, 256, 0, c.stream, (const T*)s.r, p.fc2_w, p.fc2_b, y, g.rows1, d.c1);
+  } else {
+    TapArgs<T, float> t2{};
+    t2.in = s.r; t2.wt = w2t; t2.bias = p.fc2_b; t2.out = y; t2.rows = g.rows1; t2.Cin = d.c1; t2.Co = d.c_end;
+    t2.ntaps = 1; t2.ldo = d.c_end; t2.map = t.map;
+    launch_tapgemm(t2, c.stream);
+  }
 }
 
 template <class T>
@@ -727,17 +734,26 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   T* dyT = c.ws.take<T>(sizeof(T) == sizeof(float) ? 0 : (size_t)g.rows1 * d.c_end);
   float* dw2 = c.ws.take<float>((size_t)(d.c1 + 1) * d.c_end);
   float* dw1 = c.ws.take<float>((size_t)(d.c0 + 1) * d.c1);
-  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
-                                          wgrad_partial_elems(g.rows1, d.c0 + 1, d.c1)));
+  float* part = c.ws.take<float>(std::max({wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
+                                           wgrad_partial_elems(g.rows1, d.c0 + 1, d.c1),
+                                           (size_t)(ceil_div(g.rows1, 256) + 1) * (d.c1 + 1)}));
   simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
   if (!c.dry()) {
     Tag t_fc("out.fc.bwd");
     RowMap rm{g.T1, g.T1, d.N, 0, 0};
     // fc2 (dy is fp32; the wgrad kernel wants it in the activation type)
-    TapArgs<float, T> t0{};
-    t0.in = dy; t0.wt = p.fc2_w; t0.bias = nullptr; t0.out = dr; t0.rows = g.rows1; t0.Cin = d.c_end; t0.Co = d.c1;
-    t0.ntaps = 1; t0.ldo = d.c1; t0.map = rm;
-    launch_tapgemm(t0, c.stream);
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool rowdot = d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && al16(dr) && g.rows1 > 0;
+    if (rowdot) {
+      const long long total = g.rows1 * (d.c1 / 8);
+      STGCN_LAUNCH(rowouter_bwd_kernel<T>, (int)std::min<long long>(ceil_div(total, 256), 148 * 8), 256, 0, c.stream, dy,
+                   p.fc2_w, dr, g.rows1, d.c1);
+    } else {
+      TapArgs<float, T> t0{};
+      t0.in = dy; t0.wt = p.fc2_w; t0.bias = nullptr; t0.out = dr; t0.rows = g.rows1; t0.Cin = d.c_end; t0.Co = d.c1;
+      t0.ntaps = 1; t0.ldo = d.c1; t0.map = rm;
+      launch_tapgemm(t0, c.stream);
+    }
     const T* dy_t;
     if constexpr (sizeof(T) == sizeof(float)) {
       dy_t = reinterpret_cast<const T*>(dy);
@@ -748,7 +764,17 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     }
     TapArgs<T> t{};
     t.bias = nullptr; t.rows = g.rows1; t.ntaps = 1; t.map = rm;
-    if (gr.fc2_w || gr.fc2_b) {
+    if ((gr.fc2_w || gr.fc2_b) && rowdot) {
+      zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
+      long long rpc = std::max<long long>(256, (g.rows1 + 148 * 4 - 1) / (148 * 4));
+      const int ctas = ceil_div(g.rows1, rpc);
+      STGCN_LAUNCH(rowdot_wgrad_kernel<T>, ctas, 256, 0, c.stream, (const T*)s.r, dy, part, g.rows1, d.c1, (int)rpc);
+      launch_reduce_partials(part, dw2, d.c1 + 1, ctas, c.stream);
+      GatherBatch gb(c.stream);
+      if (gr.fc2_w) gb.add(dw2, gr.fc2_w, 1, 1, d.c1, 0, 0, 0, 1);
+      if (gr.fc2_b) gb.add(dw2, gr.fc2_b, 1, 1, 1, (long long)d.c1, 0, 0, 1);
+      gb.flush();
+    } else if (gr.fc2_w || gr.fc2_b) {
       zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
       WgradArgs<T> w{};
       w.in = s.r; w.dz = dy_t; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;

@@ -769,6 +769,77 @@ inline void launch_gate_any(int act, bool bwd, const GateArgs<T>& a, cudaStream_
   }
 }
 
+// ---- single-output linear layer (fc2 of the output block, end_channel = 1; layers.py:271,281) ---------------------
+// forward: y[r] = b + sum_c in[r,c] w[c];  data gradient: din[r,c] = dy[r] w[c];  weight gradient: dw[c] = sum_r dy[r] in[r,c],
+// db = sum_r dy[r].  All three are bandwidth work over a [rows, C] tensor: 8 channels per thread, 16-byte accesses.
+template <class T>
+__global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* in, const float* w, const float* b, float* y, long long rows, int C) {
+  const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;   // G = power of two <= 32
+  float wv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wv[i] = w[g * 8 + i];
+  const float bias = b ? b[0] : 0.f;
+  for (long long r = (long long)blockIdx.x * lanes + rl; r < rows; r += (long long)gridDim.x * lanes) {
+    float x[8];
+    load8(in + r * C + g * 8, x);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s = fmaf(x[i], wv[i], s);
+    for (int o = 1; o < G; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (g == 0) y[r] = s + bias;
+  }
+}
+template <class T>
+__global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, const float* w, T* din, long long rows, int C) {
+  const int G = C / 8;
+  const long long total = rows * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / G;
+    const int g = (int)(idx - r * G);
+    const float d = dy[r];
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = d * w[g * 8 + i];
+    store8(din + r * C + g * 8, v);
+  }
+}
+// partial[cta][c] = sum over the CTA's rows of dy[r]*in[r,c]; partial[cta][C] = sum dy[r]
+template <class T>
+__global__ void __launch_bounds__(256) rowdot_wgrad_kernel(const T* in, const float* dy, float* partial, long long rows, int C,
+                                                           int rows_per_cta) {
+  __shared__ float red[8][257];
+  const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;
+  float acc[8], accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta, r1 = min(rows, r0 + rows_per_cta);
+  for (long long r = r0 + rl; r < r1; r += lanes) {
+    float x[8];
+    load8(in + r * C + g * 8, x);
+    const float d = dy[r];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(d, x[i], acc[i]);
+    if (g == 0) accb += d;
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    for (int o = G; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+  for (int o = G; o < 32; o <<= 1) accb += __shfl_xor_sync(0xffffffffu, accb, o);
+  if (lane < G) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[warp][lane * 8 + i] = acc[i];
+    if (lane == 0) red[warp][C] = accb;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e <= C; e += blockDim.x) {
+    float v = 0.f;
+    for (int w2 = 0; w2 < (int)(blockDim.x >> 5); ++w2) v += red[w2][e];
+    partial[(long long)blockIdx.x * (C + 1) + e] = v;
+  }
+}
+inline bool rowdot_supported(int C) { return C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256; }
+
 // ---- first-layer special: temporal conv with a tiny input width (Cin <= 4; the model input has Cin = 1) ------
 // The GEMM has K = Kt*Cin <= 16, so it is bandwidth work: one fused pass computes conv + bias + gate and writes the
 // saved pre-activation Z and the output H (8 output channels per thread, 16/32-byte stores).
