@@ -28,6 +28,7 @@ struct WgradParams {
   // M rows of the MMA the remaining chunk slots of the stage stay zero (narrow dZ, e.g. 16 channels)
   int a_cw, a_real;
   uint32_t a_swz, a_lbo, a_sbo, a_kadv, a_chunk_bytes;
+  int KR;                       // vertices (K rows) per tile: 128 (64 made the ~1.6 us per-step latency dominate)
   // plane mode: tap j reads batch coordinate b + j*plane_b at the SAME time step (stacked operands) instead of time t+j
   int plane_mode, plane_b;
 };
@@ -37,8 +38,8 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem;                               // [64 rows][16] bf16 1.0 (2 KB, padded to 1 KB multiple)
-  uint8_t* zring = smem + 2048;                       // Sz x [2 chunks][64 rows][128 B]
-  uint8_t* xring = zring + (size_t)p.Sz * p.z_bytes;  // Sx x [64 rows][Cin*2 B]
+  uint8_t* zring = smem + 2048;                       // Sz x [2 chunks][KR rows][128 B]
+  uint8_t* xring = zring + (size_t)p.Sz * p.z_bytes;  // Sx x [KR rows][Cin*2 B]
   __shared__ __align__(8) uint64_t xfull[kMaxStages], xempty[kMaxStages], zfull[kMaxStages], zempty[kMaxStages], done;
   __shared__ uint32_t tmem_base_s;
 
@@ -80,7 +81,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
         mbar_wait(&xempty[s], ph ^ 1);
         mbar_arrive_expect_tx(&xfull[s], p.x_bytes);
         uint8_t* dst = xring + (size_t)s * p.x_bytes;
-        for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * 64 * xcw * 2, &tmX, &xfull[s], c * xcw, n0, ti, bi);
+        for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * p.KR * xcw * 2, &tmX, &xfull[s], c * xcw, n0, ti, bi);
         ++gx;
       };
       auto load_z = [&](int t_o, int b, int n0) {
@@ -92,7 +93,7 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
         ++gz;
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int b = item / p.n_chunks, n0 = (item % p.n_chunks) * 64;
+        const int b = item / p.n_chunks, n0 = (item % p.n_chunks) * p.KR;
         if (p.plane_mode) {
           for (int t_o = 0; t_o < p.T_out; ++t_o) {
             for (int j = 0; j < p.Kt; ++j) load_x(t_o, b + j * p.plane_b, n0);
@@ -125,20 +126,18 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
             tc_fence_after();
             const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
             const uint32_t acc = (started >> j) & 1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < p.KR / 16; ++k) {
               const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
-              const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, 64u * xcw * 2, p.b_sbo, p.b_swz);
+              const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, (uint32_t)p.KR * xcw * 2, p.b_sbo, p.b_swz);
               mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, acc | (k != 0));
             }
             started |= 1u << j;
           }
           if (p.want_bias) {
             const uint32_t acc = (started >> 31) & 1;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < p.KR / 16; ++k) {
               const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
-              const uint64_t db = make_smem_desc(ones_a + k * 512, 2048, 256, SWZ_32B);
+              const uint64_t db = make_smem_desc(ones_a + (k & 3) * 512, 2048, 256, SWZ_32B);
               mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, acc | (k != 0));
             }
             started |= 1u << 31;
@@ -357,6 +356,7 @@ inline void launch_wgrad_flat(const bf16* x, const bf16* dz, float* dwt, long lo
   STGCN_LAUNCH(umma_wgrad_flat_kernel, gx, kTapThreads, pl.smem, stream, tmZ, tmX, p);
 }
 
+constexpr int kWgradKR = 128;
 struct WgradPlan { bool ok; int Sx, Sz, nMT, a_cw, a_real; uint32_t x_bytes, z_bytes; size_t smem; };
 
 // W: channels of dz (128-multiples: full tiles; 16/32/64: one narrow, zero-padded tile)
@@ -372,15 +372,18 @@ inline WgradPlan plan_wgrad(int Cin, int W, int Kt, int T_in, bool plane_mode) {
   }
   if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128)) return pl;
   if (Kt * Cin + 16 > 512 || Kt > 30) return pl;
-  pl.x_bytes = 64u * Cin * 2;
-  pl.z_bytes = 16384;
+  pl.x_bytes = (uint32_t)kWgradKR * Cin * 2;
+  pl.z_bytes = (uint32_t)kWgradKR * 128 * 2;       // 128 channel slots (real chunks + zero padding for narrow dZ)
   int live = plane_mode ? Kt : (Kt < T_in ? Kt : T_in);
-  pl.Sx = live + 3 > kMaxStages ? kMaxStages : live + 3;
-  if (pl.Sx < live) return pl;
-  pl.Sz = 3;
-  pl.smem = 2048 + (size_t)pl.Sz * pl.z_bytes + (size_t)pl.Sx * pl.x_bytes + 1024;
-  if (pl.smem > kSmemBudget) return pl;
-  pl.ok = true;
+  // deepest rings that fit: X needs the `live` window + >= 1 slot in flight, dZ >= 2 slots
+  for (int extra = 3; extra >= 1 && !pl.ok; --extra)
+    for (int sz = 3; sz >= 2 && !pl.ok; --sz) {
+      pl.Sx = live + extra > kMaxStages ? kMaxStages : live + extra;
+      if (pl.Sx < live + 1) continue;
+      pl.Sz = sz;
+      pl.smem = 2048 + (size_t)pl.Sz * pl.z_bytes + (size_t)pl.Sx * pl.x_bytes + 1024;
+      pl.ok = pl.smem <= kSmemBudget;
+    }
   return pl;
 }
 inline bool wgrad_supported(int Cin, int W, int Kt, int T_in, int B, bool plane_mode = false) {
@@ -397,7 +400,7 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
   const int T_out = plane_mode ? T_in : T_in - Kt + 1;
   uint64_t zd[4] = {(uint64_t)W, (uint64_t)N, (uint64_t)T_out, (uint64_t)B};
   uint64_t zs[3] = {(uint64_t)W * 2, (uint64_t)N * W * 2, (uint64_t)T_out * N * W * 2};
-  uint32_t zb[4] = {(uint32_t)pl.a_cw, 64, 1, 1};
+  uint32_t zb[4] = {(uint32_t)pl.a_cw, (uint32_t)kWgradKR, 1, 1};
   const CUtensorMapSwizzle zsw = pl.a_cw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : (pl.a_cw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmZ = make_tmap_bf16(dz, 4, zd, zs, zb, zsw);
@@ -405,18 +408,19 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
   const int xB = plane_mode ? Kt * B : B;
   uint64_t xd[4] = {(uint64_t)Cin, (uint64_t)N, (uint64_t)T_in, (uint64_t)xB};
   uint64_t xs[3] = {(uint64_t)Cin * 2, (uint64_t)N * Cin * 2, (uint64_t)T_in * N * Cin * 2};
-  uint32_t xb[4] = {(uint32_t)xcw, 64, 1, 1};
+  uint32_t xb[4] = {(uint32_t)xcw, (uint32_t)kWgradKR, 1, 1};
   const CUtensorMapSwizzle sw = xcw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (xcw == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUtensorMap tmX = make_tmap_bf16(x, 4, xd, xs, xb, sw);
   WgradParams p{};
   p.B = B; p.N = N; p.T_in = T_in; p.T_out = T_out; p.Kt = Kt; p.Cin = Cin; p.W = W;
-  p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + 63) / 64; p.n_items = B * p.n_chunks;
+  p.KR = kWgradKR;
+  p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + kWgradKR - 1) / kWgradKR; p.n_items = B * p.n_chunks;
   p.x_bytes = pl.x_bytes; p.z_bytes = pl.z_bytes;
   p.b_swz = xcw == 64 ? SWZ_128B : (xcw == 32 ? SWZ_64B : SWZ_32B);
   p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
   p.a_cw = pl.a_cw; p.a_real = pl.a_real;
   p.a_swz = pl.a_cw == 64 ? SWZ_128B : (pl.a_cw == 32 ? SWZ_64B : SWZ_32B);
-  p.a_chunk_bytes = 64u * pl.a_cw * 2;          // one chunk: 64 K-rows x a_cw channels
+  p.a_chunk_bytes = (uint32_t)kWgradKR * pl.a_cw * 2;          // one chunk: KR K-rows x a_cw channels
   p.a_lbo = p.a_chunk_bytes; p.a_sbo = 8u * pl.a_cw * 2; p.a_kadv = 16u * pl.a_cw * 2;
   p.plane_mode = plane_mode ? 1 : 0; p.plane_b = B;
   p.dwt = dwt; p.want_bias = want_bias;
