@@ -3,12 +3,14 @@
 // caller-provided arenas, then enqueues the SIMT kernels of simt_kernels.cuh on the stream.
 // "dry" arenas (null base) only measure: the *_sizes entry points run the same code paths.
 #pragma once
+#include <cstdlib>
 #include <type_traits>
 
 #include "simt_kernels.cuh"
 #include "umma_tap.cuh"
 #include "umma_gso.cuh"
 #include "umma_wgrad.cuh"
+#include "umma_cheb.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -308,6 +310,16 @@ inline size_t gconv_saved_elems(const stgcn_gconv_desc& d) {
   return (size_t)gconv_stack_depth(d) * d.B * d.T * d.N * d.c_out;
 }
 
+template <class T>
+inline bool gconv_fused(const stgcn_gconv_desc& d) {
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    static const bool off = std::getenv("STGCN_NO_FUSED_GCONV") != nullptr;      // A/B switch for profiling
+    const int depth = gconv_stack_depth(d), taps = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
+    return !off && depth >= 2 && umma::cheb_supported(d.N, d.c_out, depth, taps, (long long)d.B * d.T);
+  }
+  return false;
+}
+
 // stack: [depth][rows, C]; stack[0] = aligned input, stack[k] = T_k(L) stack[0] (cheb) / L stack[0] (gcn)
 template <class T>
 inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_params& p, T* y, T* stack, Ctx c) {
@@ -320,6 +332,10 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
   simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
                                               ? std::max((size_t)d.c_in * C, (size_t)(d.Ks > 1 ? d.Ks : 1) * C * C) : 0);
+  // fused Chebyshev / first-order kernel (umma_cheb.cuh): recurrence + weight GEMMs + bias/residual/ReLU in one pass
+  const int fdepth = gconv_stack_depth(d), ftaps = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
+  const bool fused = gconv_fused<T>(d);
+  uint8_t* cimg = c.ws.take<uint8_t>(fused ? umma::cheb_image_bytes(d.N) : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
   T* x0 = stack;
@@ -342,6 +358,17 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
     launch_tapgemm(t, c.stream);
   } else {
     launch_copy_cols(x, x0, rows, d.c_in, d.c_in, C, 0, c.stream);
+  }
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (fused) {
+      umma::launch_cheb_prep(p.gso, cimg, d.N, 0, c.stream);
+      umma::ChebProblem q{};
+      q.N = d.N; q.G = (long long)d.B * d.T; q.depth = fdepth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
+      q.n_taps = ftaps; q.relu = d.relu; q.residual = d.residual; q.a_img = cimg; q.w = p.w; q.bias = p.b;
+      q.in = x0; q.stack = stack; q.out = y;
+      umma::launch_cheb(q, false, c.stream);
+      return;
+    }
   }
   auto gso = make_gso_runner<T>(p.gso, 0, d.N, C, (long long)d.B * d.T, mbf, c.stream);
   TapArgs<T> t{};
@@ -398,10 +425,24 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
                                           d.c_in > C ? wgrad_partial_elems(rows, d.c_in + 1, C) : (size_t)0));
   simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
                                               ? std::max((size_t)d.c_in * C, (size_t)ntw * C * C) : 0);
+  const bool fused = gconv_fused<T>(d);
+  uint8_t* cimg = c.ws.take<uint8_t>(fused ? umma::cheb_image_bytes(d.N) : 0);
   if (c.dry()) return;
-  STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (fused) {
+      // dG, the adjoint recurrence and the residual gradient in one kernel; dst[0] = gradient w.r.t. the aligned input
+      umma::launch_cheb_prep(p.gso, cimg, d.N, 1, c.stream);
+      umma::ChebProblem q{};
+      q.N = d.N; q.G = (long long)d.B * d.T; q.depth = depth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
+      q.n_taps = ntw; q.relu = d.relu; q.residual = d.residual; q.a_img = cimg; q.w = p.w; q.bias = nullptr;
+      q.in = dy; q.in2 = y; q.out = dst; q.out2 = dg;
+      umma::launch_cheb(q, true, c.stream);
+    }
+  }
+  if (!fused)
+    STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
-  auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, mbf, c.stream);
+  auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, fused ? nullptr : mbf, c.stream);
   TapArgs<T> t{};
   t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
   t.map = RowMap{d.T, d.T, d.N, 0, 0};
@@ -411,9 +452,9 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
 
   if (d.gconv == STGCN_GCONV_CHEB) {
     // wT[k][j][i] = w[k][i][j];  d stack[k] = dG W_k^T
-    bool dstack_done = false;
+    bool dstack_done = fused;
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      if (umma_linear(dg, wbf, nullptr, dst, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
+      if (!fused && umma_linear(dg, wbf, nullptr, dst, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
         launch_gather3(p.w, wbf, 1, 1, d.Ks * C * C, 0, 0, 0, 1, 0, c.stream);      // [k][o=i][c=j] = w[k][i][j] as is
         for (int k = 0; k < d.Ks; ++k)
           umma_linear(dg, wbf + (size_t)k * C * C, nullptr, dst + (size_t)k * plane, d.B, d.T, d.T, d.N, C, C,
@@ -445,19 +486,19 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       }
     }
     // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
-    for (int k = d.Ks - 1; k >= 2; --k) {
+    for (int k = d.Ks - 1; k >= 2 && !fused; --k) {
       gso(dst + (size_t)k * plane, dst + (size_t)(k - 1) * plane, dst + (size_t)(k - 1) * plane, 2.f, 1.f);
       STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, -1.f, (const T*)(dst + (size_t)k * plane),
                    dst + (size_t)(k - 2) * plane, (long long)plane);
     }
-    if (d.Ks >= 2) {
+    if (d.Ks >= 2 && !fused) {
       gso(dst + plane, dst, dst, 1.f, 1.f);
     }
-    if (d.residual) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
+    if (d.residual && !fused) STGCN_LAUNCH(axpy_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, 1.f, (const T*)dg, dst, (long long)plane);
   } else {
-    bool dx1_done = false;
+    bool dx1_done = fused;
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      if (umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
+      if (!fused && umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
         launch_gather3(p.w, wbf, 1, 1, C * C, 0, 0, 0, 1, 0, c.stream);             // [o=i][c=j] = w[i][j] as is
         umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, false);
         dx1_done = true;
@@ -484,7 +525,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
         launch_wgrad(w, c.stream);
       }
     }
-    gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
+    if (!fused) gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
   }
   {
     GatherBatch gb(c.stream);

@@ -148,3 +148,43 @@ def test_bf16_tcgen05_temporal_conv(c_in, c_out, kt, T, act, cuda_device):
     for k, v in pr.items():
         if v.grad is not None:
             assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < tol, k
+
+
+@pytest.mark.parametrize("kind,ks", [("cheb_graph_conv", 2), ("cheb_graph_conv", 3), ("cheb_graph_conv", 5),
+                                      ("graph_conv", 3)])
+@pytest.mark.parametrize("c_in,N,B,T", [(16, 228, 3, 5), (64, 228, 2, 3), (16, 41, 2, 7), (64, 207, 1, 9),
+                                        (16, 130, 4, 3)])
+@pytest.mark.parametrize("relu", [0, 1])
+def test_bf16_fused_graph_conv_layer(kind, ks, c_in, N, B, T, relu, cuda_device):
+    """The fused tcgen05 graph-convolution kernels (csrc/umma_cheb.cuh): Chebyshev recurrence / first-order
+    propagation + weight GEMMs + bias + residual (+ ReLU) in one pass, and the adjoint in one pass.  The operator is
+    deliberately non-symmetric (catches a missing transpose); ragged last work item (B*T not a multiple of the
+    groups per item); N below / above one 128-row tile.  Oracle evaluated on the same bf16-rounded operands."""
+    from stgcn_b200 import layers
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(ks * 131 + c_in + N)
+    a = torch.randn(N, N, generator=gen)
+    gso = (a / torch.linalg.matrix_norm(a, ord=2)).float()
+    layer = layers.GraphConvLayer(kind, c_in, 16, ks, gso.to(dev), True).to(dev)
+    p = {"g." + k: v.detach().cpu().clone() for k, v in layer.state_dict().items()}
+    x = torch.randn(B, c_in, T, N, generator=gen)
+    xg = x.to(dev).requires_grad_(True)
+    y = layer(xg, _relu=relu)
+    assert y.dtype == torch.bfloat16
+    rb = lambda t: t.bfloat16().float()
+    pr = {k: (rb(v) if v.dim() > 1 else v.clone()).requires_grad_(True) for k, v in p.items()}
+    xr = rb(x).requires_grad_(True)
+    yr = O.graph_conv_layer(xr, pr, "g.", rb(gso), 16, kind)
+    if relu:
+        yr = torch.relu(yr)
+    assert tuple(y.shape) == tuple(yr.shape)
+    assert rel_l2(y.float().cpu(), yr) < 1e-2
+    dy = torch.randn(yr.shape, generator=gen)
+    y.backward(dy.to(dev).bfloat16())
+    yr.backward(rb(dy))
+    tol = 3e-2 if not relu else 6e-2            # ReLU mask recomputed from the bf16-rounded output
+    assert rel_l2(xg.grad.cpu(), xr.grad) < tol
+    named = dict(layer.named_parameters())
+    for k, v in pr.items():
+        if v.grad is not None:
+            assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < tol, k
