@@ -117,6 +117,7 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
     sa.explicit_res = (g.folded || g.linear) ? 0 : 1;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     if (smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved) && al16(y)) {
+      sa.skip_z = 1;         // the backward recomputes z from x (tconv_bwd); 2/3 of this kernel's traffic was the z store
       launch_smallc1_conv_gate_fwd(sa, c.stream);
       return;
     }
@@ -137,23 +138,27 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
   launch_gate_any(d.act, false, ga, c.stream);
 }
 
+// dz_ready: gradient w.r.t. the pre-activations already computed by the caller (fused LayerNorm + gate backward,
+// lnorm_gate_bwd); dy is then unused.
 template <class T>
 inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, const T* dy,
-                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c) {
+                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c, T* dz_ready = nullptr) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
-  T* dz = c.ws.take<T>((size_t)g.rows_out * g.W);
+  T* dz = dz_ready ? dz_ready : c.ws.take<T>((size_t)g.rows_out * g.W);
   float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
   float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
+  float* bias_f = c.ws.take<float>(g.W);
   simt::bf16* wdbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
   const long long sc_rpc = std::max<long long>(64, (g.rows_out + 148 * 8 - 1) / (148 * 8));
   const int sc_ctas = g.rows_out > 0 ? ceil_div(g.rows_out, sc_rpc) : 0;
   float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows_out, Kw + 1, g.W), (size_t)sc_ctas * (Kw + 1) * g.W));
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
-  const bool smallc = g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
-  if (smallc) {
+  const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
+  if (dz_ready) {
+  } else if (smallc) {
     // first-layer special: gate backward fused with the weight gradient (dz only materialised when dx is wanted)
     zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
     SmallCArgs<T> sa{};
@@ -165,9 +170,24 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     sa.rows_per_cta = (int)sc_rpc;
     sa.partial = part;
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    if (smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved) && al16(dy) && al16(sa.dz)) {
+    const bool z_skipped = smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved);   // what the forward may have done
+    if (z_skipped) {
+      // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]  (the forward's layout; c_in == 1 here)
+      launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
+      launch_gather3(p.conv_b, bias_f, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
+      sa.wt = wd; sa.bias = bias_f; sa.skip_z = 1;
+    }
+    if (z_skipped && al16(dy) && al16(sa.dz)) {
       launch_smallc1_gate_wgrad(sa, sc_ctas, c.stream);
     } else {
+      if (z_skipped) {       // rare (misaligned dy): regenerate z with the generic forward kernel, then proceed as before
+        SmallCArgs<T> sf = sa;
+        sf.h = nullptr; sf.skip_z = 0;
+        size_t fsmem = (size_t)(d.Kt * d.c_in + 1) * g.W * sizeof(float);
+        long long total = g.rows_out * (d.c_out / 8);
+        STGCN_LAUNCH(smallc_conv_gate_fwd_kernel<T>, (int)std::min<long long>(ceil_div(total, 256), 148 * 16), 256, fsmem, c.stream, sf);
+        sa.skip_z = 0;
+      }
       size_t smem = (size_t)lanes * 2 * (Kw + 1) * d.c_out * sizeof(float);
       STGCN_CUDA(cudaFuncSetAttribute(smallc_gate_wgrad_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       STGCN_LAUNCH(smallc_gate_wgrad_kernel<T>, sc_ctas, threads, smem, c.stream, sa);
@@ -624,6 +644,36 @@ inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats,
   }
 }
 
+// LayerNorm backward fused with the gate backward of the temporal conv that produced the LayerNorm input: writes
+// dz (gradient w.r.t. that conv's pre-activations) and the LayerNorm parameter gradients.  Returns false (nothing
+// launched) when the shape is not served; the caller then runs lnorm_bwd + the gate kernel separately.
+template <class T>
+inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc, const T* x, const float* stats,
+                           const T* dy, const float* w, float* dw, float* db, const T* z_saved, const T* tc_in, T* dz,
+                           float* sums, uint64_t seed, cudaStream_t s, bool dry) {
+  lnorm_check(d);
+  static const bool off = std::getenv("STGCN_NO_FUSED_LNGATE") != nullptr;      // A/B switch for profiling
+  TconvGeom g = tconv_geom(tc);
+  LnGateArgs<T> a{};
+  const long long G = (long long)d.B * d.T;
+  a.x = x; a.dy = dy; a.w = w; a.mean = stats; a.rstd = stats + G; a.dw = dw; a.db = db; a.M = d.N * d.C; a.G = G;
+  a.training = d.training; a.p = d.p_drop; a.seed = seed; a.z = z_saved; a.xin = tc_in; a.dz = dz; a.sums = sums;
+  a.N = d.N; a.C = d.C; a.W = g.W; a.Cin = tc.c_in; a.Kt = tc.Kt; a.T_out = g.T_out; a.T_in = tc.T;
+  a.explicit_res = (g.folded || g.linear) ? 0 : 1;
+  if (off || d.C != tc.c_out || g.T_out != d.T) return false;
+  if (dry) {   // alignment cannot be checked on a dry run; shapes decide (the arenas hand out 256-byte aligned blocks)
+    a.x = a.dy = a.z = a.xin = reinterpret_cast<const T*>(256); a.dz = reinterpret_cast<T*>(256); a.w = reinterpret_cast<const float*>(256);
+    a.G = 1;
+    return ln_gate_bwd_supported(a);
+  }
+  if (!ln_gate_bwd_supported(a)) return false;
+  const int M = d.N * d.C;
+  if (dw) zero(dw, M, s);
+  if (db) zero(db, M, s);
+  launch_ln_gate_bwd(tc.act, a, umma::sm_count(), s);
+  return true;
+}
+
 // ============================ ST-conv block ==================================================
 struct StGeom {
   int T1, T2;
@@ -681,8 +731,13 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   T* dh2 = c.ws.take<T>((size_t)g.rows1 * d.c2);
   T* dh1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
   const bool first = d.c_in == 1;
-  { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd"); lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
-  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c); }
+  T* dz2 = c.ws.take<T>(tconv_saved_elems(g.tc2));
+  float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2);
+  bool ln_fused;
+  { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c.stream, c.dry());
+    if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
+  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr); }
   { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
   { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c); }
 }
@@ -862,8 +917,13 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       gb.flush();
     }
   }
-  { Tag t("out.ln.bwd"); lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
-  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c); }
+  T* dz = c.ws.take<T>(tconv_saved_elems(g.tc));
+  float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T1);
+  bool ln_fused;
+  { Tag t("out.ln.bwd");
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c.stream, c.dry());
+    if (!ln_fused) lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
+  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr); }
 }
 
 }  // namespace ops

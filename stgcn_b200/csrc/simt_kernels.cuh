@@ -856,6 +856,7 @@ struct SmallCArgs {
   float* partial;      // bwd, optional: [gridDim.x][(Kt*Cin + 1)*W] per-CTA partial sums (reduced by reduce_partials_kernel)
   long long rows;
   int Cin, Cout, W, Kt, T_out, T_in, N, act, explicit_res, rows_per_cta;
+  int skip_z;          // Cin == 1 fast path: z is not stored by the forward and recomputed from x by the backward
 };
 
 
@@ -899,7 +900,7 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
     }
     store8(a.z + r * a.W + j0, zp);
     if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
-    store8(a.h + r * a.Cout + j0, hv);
+    if (a.h) store8(a.h + r * a.Cout + j0, hv);
   }
 }
 
@@ -942,8 +943,10 @@ __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T
       const float res = (a.explicit_res && j0 + i == 0) ? xv[K - 1] : 0.f;
       hv[i] = act_fwd(a.act, zp[i] + res, zq[i]);
     }
-    store8(a.z + r * a.W + j0, zp);
-    if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
+    if (!a.skip_z) {
+      store8(a.z + r * a.W + j0, zp);
+      if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
+    }
     store8(a.h + r * a.Cout + j0, hv);
   }
 }
@@ -1036,6 +1039,14 @@ __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a
   for (int k = 0; k <= K; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { accp[k][i] = 0.f; accq[k][i] = 0.f; }
+  // skip_z: the pre-activations were not stored; they are K FMAs per channel away from x.  The weights sit in shared
+  // memory (in registers they cost 64 more per thread and halved the occupancy of this bandwidth-bound kernel).
+  __shared__ __align__(16) float w_s[(K + 1) * 128];       // [k][W] then bias [W]; W <= 128
+  if (a.skip_z) {
+    for (int i = threadIdx.x; i < K * a.W; i += blockDim.x) w_s[i] = a.wt[i];
+    for (int i = threadIdx.x; i < a.W; i += blockDim.x) w_s[K * a.W + i] = a.bias[i];
+    __syncthreads();
+  }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   const long long r1 = min(a.rows, r0 + a.rows_per_cta);
   for (long long r = r0 + rl; r < r1; r += lanes) {
@@ -1045,8 +1056,21 @@ __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a
 #pragma unroll
     for (int k = 0; k < K; ++k) xv[k] = ldf(a.x + in0 + (long long)k * a.N);
     float zp[8], zq[8], dh[8], du[8], dq[8];
-    load8(a.z + r * a.W + j0, zp);
-    if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+    if (a.skip_z) {
+      const float* bs = w_s + K * a.W;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { zp[i] = bs[j0 + i]; zq[i] = gated ? bs[a.Cout + j0 + i] : 0.f; }
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          zp[i] = fmaf(xv[k], w_s[k * a.W + j0 + i], zp[i]);
+          if (gated) zq[i] = fmaf(xv[k], w_s[k * a.W + a.Cout + j0 + i], zq[i]);
+        }
+    } else {
+      load8(a.z + r * a.W + j0, zp);
+      if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+    }
     load8(a.dh + r * a.Cout + j0, dh);
     if (a.explicit_res && j0 == 0) zp[0] += xv[K - 1];        // residual = zero-padded input: channel 0 only
 #pragma unroll
@@ -1420,6 +1444,142 @@ __global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean,
   for (int k = 0; k < VEC; ++k) {
     if (dw) atomicAdd(dw + i + k, aw[k]);
     if (db) atomicAdd(db + i + k, ab[k]);
+  }
+}
+
+// ---- LayerNorm backward + LayerNorm parameter gradients + gate backward of the producing temporal conv ------------
+// (layers.py:255-256 backward through tc2_ln, then layers.py:92-115 backward through the GLU/GTU/... gate.)
+// Two launches.  ln_bwd_sums_kernel: the two per-group reductions of the LayerNorm backward (one CTA per (b, t) group,
+// read-only).  ln_gate_bwd_kernel: thread = one 8-element chunk (8 channels of one vertex) x a range of groups; for every
+// (group, chunk) it forms the LayerNorm data gradient from the group's scalars, sends it straight through the gate
+// derivative (P/Q halves of the saved pre-activation z, residual from the conv input) and stores dz -- the 64-channel
+// dH never reaches HBM -- while dw/db of its chunk accumulate in registers across the groups (one atomic per element per
+// CTA at the end).  Replaces ln_bwd + ln_param_grad + gate_vec: x and dy are read twice instead of three times, dH
+// (write + read) disappears.
+template <class T>
+struct LnGateArgs {
+  const T* x; const T* dy; const float* w; const float* mean; const float* rstd;
+  float* sums;                          // [G][2] scratch: (sum dy*w, sum dy*w*xhat) / M
+  float* dw; float* db;                 // pre-zeroed; may be null
+  int M; long long G;
+  int training; float p; uint64_t seed;
+  // gate
+  const T* z; const T* xin; T* dz;
+  int N, C, W, Cin, Kt, T_out, T_in, explicit_res;
+  int groups_per_cta;
+};
+__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
+  __syncthreads();   // protect red[] reuse
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) { red[w] = a; red[32 + w] = b; }
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (w == 0) {
+    float ta = l < nw ? red[l] : 0.f, tb = l < nw ? red[32 + l] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ta += __shfl_xor_sync(0xffffffffu, ta, o); tb += __shfl_xor_sync(0xffffffffu, tb, o); }
+    if (l == 0) { red[0] = ta; red[32] = tb; }
+  }
+  __syncthreads();
+  a = red[0]; b = red[32];
+}
+template <class T>
+__global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
+  __shared__ float red[64];
+  const long long g = blockIdx.x;
+  const T* xp = a.x + g * a.M;
+  const T* dp = a.dy + g * a.M;
+  const float mu = a.mean[g], rs = a.rstd[g];
+  const bool drop = a.training && a.p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - a.p) : 1.f;
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll 4
+  for (int i = threadIdx.x * 8; i < a.M; i += 256 * 8) {
+    float xv[8], dv[8], wv[8];
+    load8(xp + i, xv); load8(dp + i, dv); load8(a.w + i, wv);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float d = dv[k];
+      if (drop) d = dropout_keep(a.seed, (uint64_t)(g * a.M + i + k), a.p) ? d * keep_scale : 0.f;
+      const float gi = d * wv[k];
+      s1 += gi; s2 += gi * (xv[k] - mu) * rs;
+    }
+  }
+  block_sum2(s1, s2, red);
+  if (threadIdx.x == 0) { a.sums[2 * g] = s1 / (float)a.M; a.sums[2 * g + 1] = s2 / (float)a.M; }
+}
+template <class T, int ACT>
+__global__ void __launch_bounds__(128) ln_gate_bwd_kernel(LnGateArgs<T> a) {
+  constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch * 8 >= a.M) return;
+  const int i = ch * 8, Cout = a.C;
+  const int n = i / Cout, c0 = i - n * Cout;
+  const bool has_res = a.explicit_res && c0 < a.Cin;
+  const bool drop = a.training && a.p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - a.p) : 1.f;
+  float wv[8], aw[8], ab[8];
+  load8(a.w + i, wv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { aw[k] = 0.f; ab[k] = 0.f; }
+  const long long g0 = (long long)blockIdx.y * a.groups_per_cta;
+  const long long g1 = min(a.G, g0 + a.groups_per_cta);
+#pragma unroll 2
+  for (long long g = g0; g < g1; ++g) {
+    const float mu = a.mean[g], rs = a.rstd[g], s1 = a.sums[2 * g], s2 = a.sums[2 * g + 1];
+    const long long r = g * a.N + n;
+    float xv[8], dv[8], zp[8], zq[8], res[8], dh[8], du[8], dq[8];
+    load8(a.x + g * a.M + i, xv); load8(a.dy + g * a.M + i, dv);
+    load8(a.z + r * a.W + c0, zp);
+    if (gated) load8(a.z + r * a.W + Cout + c0, zq);
+    if (has_res) {
+      const long long b = g / a.T_out;
+      const int t = (int)(g - b * a.T_out);
+      load8(a.xin + ((b * a.T_in + t + a.Kt - 1) * a.N + n) * a.Cin + c0, res);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float d = dv[k];
+      if (drop) d = dropout_keep(a.seed, (uint64_t)(g * a.M + i + k), a.p) ? d * keep_scale : 0.f;
+      const float xh = (xv[k] - mu) * rs;
+      dh[k] = rs * (d * wv[k] - s1 - xh * s2);
+      aw[k] += d * xh;
+      ab[k] += d;
+      if (has_res) zp[k] += res[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) act_bwd(ACT, zp[k], gated ? zq[k] : 0.f, dh[k], du[k], dq[k]);
+    store8(a.dz + r * a.W + c0, du);
+    if (gated) store8(a.dz + r * a.W + Cout + c0, dq);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (a.dw) atomicAdd(a.dw + i + k, aw[k]);
+    if (a.db) atomicAdd(a.db + i + k, ab[k]);
+  }
+}
+template <class T>
+inline bool ln_gate_bwd_supported(const LnGateArgs<T>& a) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return a.G > 0 && a.M % 8 == 0 && a.C % 8 == 0 && a.W % 8 == 0 && a.M == a.N * a.C &&
+         (!a.explicit_res || a.Cin % 8 == 0) && al16(a.x) && al16(a.dy) && al16(a.w) && al16(a.z) && al16(a.xin) && al16(a.dz);
+}
+template <class T>
+inline void launch_ln_gate_bwd(int act, LnGateArgs<T> a, int sms, cudaStream_t s) {
+  STGCN_LAUNCH(ln_bwd_sums_kernel<T>, (unsigned)a.G, 256, 0, s, a);
+  const int xb = ceil_div(a.M / 8, 128);
+  int ychunks = (int)std::min<long long>(a.G, std::max<long long>(1, ((long long)sms * 16) / xb));
+  a.groups_per_cta = ceil_div(a.G, ychunks);
+  ychunks = ceil_div(a.G, a.groups_per_cta);
+  const dim3 grid(xb, ychunks);
+  switch (act) {
+    case STGCN_ACT_GLU: STGCN_LAUNCH((ln_gate_bwd_kernel<T, STGCN_ACT_GLU>), grid, 128, 0, s, a); break;
+    case STGCN_ACT_GTU: STGCN_LAUNCH((ln_gate_bwd_kernel<T, STGCN_ACT_GTU>), grid, 128, 0, s, a); break;
+    case STGCN_ACT_RELU: STGCN_LAUNCH((ln_gate_bwd_kernel<T, STGCN_ACT_RELU>), grid, 128, 0, s, a); break;
+    case STGCN_ACT_SILU: STGCN_LAUNCH((ln_gate_bwd_kernel<T, STGCN_ACT_SILU>), grid, 128, 0, s, a); break;
+    default: STGCN_LAUNCH((ln_gate_bwd_kernel<T, STGCN_ACT_LINEAR>), grid, 128, 0, s, a); break;
   }
 }
 

@@ -15,8 +15,9 @@
 // adds bias + residual, applies ReLU and stores y.  The backward kernel runs the adjoint recurrence the same way and
 // accumulates Lhat^T D_k directly on top of dG W_{k-1}^T in TMEM.
 //
-// Warps: 0 = operator load + cp.async producer, 1 = MMA issuer (+ TMEM allocation), 2..5 = epilogue (one vertex
-// row per thread per tile), 6..7 = cp.async producers.
+// A CTA runs kChebSlots independent item pipelines ("slots") that share the resident operator: while one slot's
+// epilogue warps drain TMEM, the other slot's MMAs run.  Warps: 0 = operator load + TMEM allocation; per slot: one MMA
+// issuer, four epilogue warps (one vertex row per thread per tile), two cp.async producer warps.
 #pragma once
 #include "umma_gso.cuh"
 
@@ -24,8 +25,10 @@ namespace stgcn {
 namespace umma {
 
 constexpr int kChebC = 16;
-constexpr int kChebThreads = 256;
-constexpr int kChebProducers = 3;          // warps 0, 6, 7
+constexpr int kChebSlots = 2;              // independent item pipelines per CTA (one's MMAs overlap the other's epilogue)
+constexpr int kChebSlotWarps = 7;          // per slot: 1 MMA issuer + 4 epilogue + 2 cp.async producer warps
+constexpr int kChebProducers = 2;
+constexpr int kChebThreads = 32 * (1 + kChebSlots * kChebSlotWarps);
 constexpr int kChebMaxMT = 4;
 constexpr int kChebMaxDepth = 8;
 
@@ -48,6 +51,7 @@ struct ChebParams {
   // forward: in = x_0 plane (= stack plane 0), stack = [depth][G][N][16] (planes 1.. written), out = y
   // backward: in = dy, in2 = y, out = dx_0, out2 = dG
   const bf16* in; const bf16* in2; bf16* stack; bf16* out; bf16* out2;
+  unsigned long long* dbg;              // optional timeline stamps (diagnostics)
 };
 
 // 16 bf16 of one 32-byte row in a 32B-swizzled buffer (rows 32 B apart; the two 16-byte halves swap when bit 2 of
@@ -57,6 +61,12 @@ __device__ __forceinline__ void row_store(uint8_t* buf, int row, const uint4& lo
   uint8_t* r = buf + row * 32;
   *reinterpret_cast<uint4*>(r + (sw << 4)) = lo;
   *reinterpret_cast<uint4*>(r + ((sw ^ 1) << 4)) = hi;
+}
+__device__ __forceinline__ void row_load_raw(const uint8_t* buf, int row, uint4& lo, uint4& hi) {
+  const int sw = (row >> 2) & 1;
+  const uint8_t* r = buf + row * 32;
+  lo = *reinterpret_cast<const uint4*>(r + (sw << 4));
+  hi = *reinterpret_cast<const uint4*>(r + ((sw ^ 1) << 4));
 }
 __device__ __forceinline__ void row_load(const uint8_t* buf, int row, float* v) {
   const int sw = (row >> 2) & 1;
@@ -104,22 +114,30 @@ __device__ __forceinline__ void cheb_issue_mix(uint32_t buf, uint32_t w_img, uin
     }
 }
 
-template <bool BWD>
+// Timeline stamps (diagnostics, stgcn_debug_timeline): CTA 0 records globaltimer for its first 3 items per slot at
+// dbg[slot*72 + item*24 + e]: e = 0 fill begin, 1 fill landed, 2+j MMA stage j issued, 8+2j / 9+2j epilogue stage j
+// begin / end; dbg[150] = kernel start, dbg[151] = operator resident.
+#define CHEB_STAMP(e) do { if (dbg_on && it < 3) p.dbg[slot * 72 + it * 24 + (e)] = gtime(); } while (0)
+
+template <bool BWD, int GB>
 __global__ void __launch_bounds__(kChebThreads, 1) umma_cheb_kernel(ChebParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_s = smem;                                   // operator image
   uint8_t* w_s = smem + p.a_bytes;                       // n_taps x [16][16] bf16, 32B-swizzled K-major
-  uint8_t* bufs = w_s + ((p.n_taps * 512 + 1023) & ~1023);   // depth plane buffers of Gb groups
-  __shared__ __align__(8) uint64_t afull, in_full, in_free, acc_full, xk_ready, mix_free;
+  uint8_t* bufs0 = w_s + ((p.n_taps * 512 + 1023) & ~1023);   // per slot: depth plane buffers of GB groups
+  __shared__ __align__(8) uint64_t afull, in_full_[2], in_free_[2], acc_full_[2], xk_ready_[2], mix_free_[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[kChebC];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int NC = p.Gb * kChebC;
+  constexpr int NC = GB * kChebC;
+  constexpr int SB = GB < 2 ? GB : 2;          // groups drained per TMEM round trip
   const int regions = BWD ? p.depth : 2;
+  const int slot_cols = regions * p.nMT * NC;
   uint32_t ncols = 32;
-  while ((int)ncols < regions * p.nMT * NC) ncols <<= 1;
+  while ((int)ncols < kChebSlots * slot_cols) ncols <<= 1;
+  if (p.dbg && blockIdx.x == 0 && threadIdx.x == 0) p.dbg[150] = gtime();
 
   // weight images: forward B[n = c_out][k = c_in] = w[c_in][c_out]; backward B[n = c_in][k = c_out] = w[c_in][c_out]
   for (int i = threadIdx.x; i < p.n_taps * 256; i += blockDim.x) {
@@ -131,226 +149,286 @@ __global__ void __launch_bounds__(kChebThreads, 1) umma_cheb_kernel(ChebParams p
   if (threadIdx.x < kChebC) bias_s[threadIdx.x] = p.bias ? p.bias[threadIdx.x] : 0.f;
   if (threadIdx.x == 0) {
     mbar_init(&afull, 1);
-    mbar_init(&in_full, kChebProducers);
-    mbar_init(&in_free, 4);
-    mbar_init(&acc_full, 1);
-    mbar_init(&xk_ready, 4);
-    mbar_init(&mix_free, 4);
+    for (int s = 0; s < kChebSlots; ++s) {
+      mbar_init(&in_full_[s], kChebProducers);
+      mbar_init(&in_free_[s], 4);
+      mbar_init(&acc_full_[s], 1);
+      mbar_init(&xk_ready_[s], 4);
+      mbar_init(&mix_free_[s], 4);
+    }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  if (warp == 0) tmem_alloc(&tmem_base_s, ncols);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = tmem_base_s;
 
-  const bool is_producer = warp == 0 || warp >= 6;
-  if (is_producer) {
-    // =========================== producers ===============================
-    if (warp == 0 && lane == 0) {
+  if (warp == 0) {
+    if (lane == 0) {
       mbar_arrive_expect_tx(&afull, p.a_bytes);
       for (uint32_t off = 0; off < p.a_bytes; off += 16384) {
         const uint32_t n = p.a_bytes - off < 16384 ? p.a_bytes - off : 16384;
         bulk_load_1d(a_s + off, p.a_img + off, n, &afull);
       }
     }
-    const int ptid = (warp == 0 ? 0 : warp - 5) * 32 + lane;
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const long long g0 = (long long)item * p.Gb;
-      mbar_wait(&in_free, (it & 1) ^ 1);
-      cheb_fill(bufs, p.in, g0, p, ptid, kChebProducers * 32);
-      if (BWD && p.relu) cheb_fill(bufs + p.buf_bytes, p.in2, g0, p, ptid, kChebProducers * 32);
-      cp_async_commit();
-      cp_async_wait<0>();
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&in_full);
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s), b_u = smem_u32(bufs);
-      mbar_wait(&afull, 0);
-      uint32_t it = 0, n_xk = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        if (!BWD) {
-          mbar_wait(&in_full, it & 1);
-          tc_fence_after();
-          for (int k = 1; k < p.depth; ++k) {
-            if (k >= 2) { mbar_wait(&xk_ready, n_xk & 1); ++n_xk; tc_fence_after(); }
-            cheb_issue_hop(a_u, b_u + (k - 1) * p.buf_bytes, tmem_base, NC, 0, p);
-            mma_commit(&acc_full);
-          }
-          mbar_wait(&xk_ready, n_xk & 1); ++n_xk;
-          mbar_wait(&mix_free, (it & 1) ^ 1);
-          tc_fence_after();
-          for (int t = 0; t < p.n_taps; ++t)
-            cheb_issue_mix(b_u + (p.tap_first + t) * p.buf_bytes, w_u + t * 512, tmem_base + p.nMT * NC, NC, t != 0, p);
-          mma_commit(&acc_full);
-        } else {
-          mbar_wait(&xk_ready, n_xk & 1); ++n_xk;         // dG in buffer 0
-          mbar_wait(&mix_free, (it & 1) ^ 1);             // previous item's accumulators drained
-          tc_fence_after();
-          for (int t = 0; t < p.n_taps; ++t)
-            cheb_issue_mix(b_u, w_u + t * 512, tmem_base + (p.tap_first + t) * p.nMT * NC, NC, 0, p);
-          mma_commit(&acc_full);
-          for (int k = p.depth - 1; k >= 1; --k) {
-            mbar_wait(&xk_ready, n_xk & 1); ++n_xk;       // P_k in buffer k
+  } else {
+    // ---- slot-local roles: warp 1 + 7*slot = MMA issuer, +1..+4 = epilogue, +5..+6 = cp.async producers ----
+    const int slot = (warp - 1) / kChebSlotWarps, role = (warp - 1) % kChebSlotWarps;
+    uint8_t* bufs = bufs0 + (size_t)slot * p.depth * p.buf_bytes;
+    const uint32_t tmem_base = tmem_base_s + slot * slot_cols;
+    uint64_t* in_full = &in_full_[slot]; uint64_t* in_free = &in_free_[slot]; uint64_t* acc_full = &acc_full_[slot];
+    uint64_t* xk_ready = &xk_ready_[slot]; uint64_t* mix_free = &mix_free_[slot];
+    const int item0 = blockIdx.x * kChebSlots + slot, item_step = gridDim.x * kChebSlots;
+    const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && lane == 0;
+
+    if (role >= 5) {
+      // =========================== producers ===============================
+      const int ptid = (role - 5) * 32 + lane;
+      uint32_t it = 0;
+      for (int item = item0; item < p.n_items; item += item_step, ++it) {
+        const long long g0 = (long long)item * GB;
+        mbar_wait(in_free, (it & 1) ^ 1);
+        if (role == 5) CHEB_STAMP(0);
+        cheb_fill(bufs, p.in, g0, p, ptid, kChebProducers * 32);
+        if (BWD && p.relu) cheb_fill(bufs + p.buf_bytes, p.in2, g0, p, ptid, kChebProducers * 32);
+        cp_async_commit();
+        cp_async_wait<0>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(in_full);
+        if (role == 5) CHEB_STAMP(1);
+      }
+    } else if (role == 0) {
+      // =========================== MMA issuer ==============================
+      if (lane == 0) {
+        const uint32_t a_u = smem_u32(a_s), w_u = smem_u32(w_s), b_u = smem_u32(bufs);
+        mbar_wait(&afull, 0);
+        if (dbg_on && slot == 0) p.dbg[151] = gtime();
+        uint32_t it = 0, n_xk = 0;
+        for (int item = item0; item < p.n_items; item += item_step, ++it) {
+          if (!BWD) {
+            mbar_wait(in_full, it & 1);
             tc_fence_after();
-            const uint32_t has_product = (k - 1 >= p.tap_first && k - 1 < p.tap_first + p.n_taps) ? 1u : 0u;
-            cheb_issue_hop(a_u, b_u + k * p.buf_bytes, tmem_base + (k - 1) * p.nMT * NC, NC, has_product, p);
-            mma_commit(&acc_full);
+            for (int k = 1; k < p.depth; ++k) {
+              if (k >= 2) { mbar_wait(xk_ready, n_xk & 1); ++n_xk; tc_fence_after(); }
+              cheb_issue_hop(a_u, b_u + (k - 1) * p.buf_bytes, tmem_base, NC, 0, p);
+              mma_commit(acc_full);
+              CHEB_STAMP(2 + k - 1);
+            }
+            mbar_wait(xk_ready, n_xk & 1); ++n_xk;
+            mbar_wait(mix_free, (it & 1) ^ 1);
+            tc_fence_after();
+            for (int t = 0; t < p.n_taps; ++t)
+              cheb_issue_mix(b_u + (p.tap_first + t) * p.buf_bytes, w_u + t * 512, tmem_base + p.nMT * NC, NC, t != 0, p);
+            mma_commit(acc_full);
+            CHEB_STAMP(2 + p.depth - 1);
+          } else {
+            mbar_wait(xk_ready, n_xk & 1); ++n_xk;         // dG in buffer 0
+            mbar_wait(mix_free, (it & 1) ^ 1);             // previous item's accumulators drained
+            tc_fence_after();
+            for (int t = 0; t < p.n_taps; ++t)
+              cheb_issue_mix(b_u, w_u + t * 512, tmem_base + (p.tap_first + t) * p.nMT * NC, NC, 0, p);
+            mma_commit(acc_full);
+            CHEB_STAMP(2);
+            for (int k = p.depth - 1; k >= 1; --k) {
+              mbar_wait(xk_ready, n_xk & 1); ++n_xk;       // P_k in buffer k
+              tc_fence_after();
+              const uint32_t has_product = (k - 1 >= p.tap_first && k - 1 < p.tap_first + p.n_taps) ? 1u : 0u;
+              cheb_issue_hop(a_u, b_u + k * p.buf_bytes, tmem_base + (k - 1) * p.nMT * NC, NC, has_product, p);
+              mma_commit(acc_full);
+              CHEB_STAMP(2 + p.depth - k);
+            }
           }
         }
       }
-    }
-  } else {
-    // =========================== epilogue warps ==========================
-    const int q = warp & 3;
-    const int r = q * 32 + lane;
-    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
-    uint32_t it = 0, n_acc = 0;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-      const long long g0 = (long long)item * p.Gb;
-      if (!BWD) {
-        for (int k = 1; k < p.depth; ++k) {
-          const float alpha = k == 1 ? 1.f : 2.f;
-          uint8_t* bk = bufs + (size_t)k * p.buf_bytes;
-          const uint8_t* bm2 = bufs + (size_t)(k >= 2 ? k - 2 : 0) * p.buf_bytes;
-          bf16* plane = p.stack + (size_t)k * p.plane;
-          mbar_wait(&acc_full, n_acc & 1); ++n_acc;
-          tc_fence_after();
-          for (int mt = 0; mt < p.nMT; ++mt) {
-            if (mt * 128 + q * 32 >= p.rows_pad) break;          // warp-uniform (tcgen05.ld is .sync.aligned)
-            const int n = mt * 128 + r;
-            const bool nvalid = n < p.N, inbuf = n < p.rows_pad;
+    } else {
+      // =========================== epilogue warps ==========================
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+      const bool stamp = role == 1;
+      uint32_t it = 0, n_acc = 0;
+      for (int item = item0; item < p.n_items; item += item_step, ++it) {
+        const long long g0 = (long long)item * GB;
+        if (!BWD) {
+          for (int k = 1; k < p.depth; ++k) {
+            const float alpha = k == 1 ? 1.f : 2.f;
+            uint8_t* bk = bufs + (size_t)k * p.buf_bytes;
+            const uint8_t* bm2 = bufs + (size_t)(k >= 2 ? k - 2 : 0) * p.buf_bytes;
+            bf16* plane = p.stack + (size_t)k * p.plane;
+            mbar_wait(acc_full, n_acc & 1); ++n_acc;
+            tc_fence_after();
+            if (stamp) CHEB_STAMP(8 + 2 * (k - 1));
+            for (int mt = 0; mt < p.nMT; ++mt) {
+              if (mt * 128 + q * 32 >= p.rows_pad) break;          // warp-uniform (tcgen05.ld is .sync.aligned)
+              const int n = mt * 128 + r;
+              const bool nvalid = n < p.N, inbuf = n < p.rows_pad;
 #pragma unroll 1
-            for (int g = 0; g < p.Gb; ++g) {
-              uint32_t a[16];
-              tmem_ld_32x32b_x16(t_lane + mt * NC + g * kChebC, a);
-              float v[16], m2[16];
-              if (k >= 2 && inbuf) row_load(bm2 + (size_t)g * p.gs, n, m2);
+              for (int gb = 0; gb < GB; gb += SB) {
+              uint32_t a[SB][16];
+              uint4 m2[SB][2];
+#pragma unroll
+              for (int j = 0; j < SB; ++j) tmem_ld_32x32b_x16(t_lane + mt * NC + (gb + j) * kChebC, a[j]);
+#pragma unroll
+              for (int j = 0; j < SB; ++j)
+                if (k >= 2 && inbuf) row_load_raw(bm2 + (size_t)(gb + j) * p.gs, n, m2[j][0], m2[j][1]);
               tmem_ld_wait();
 #pragma unroll
+              for (int j = 0; j < SB; ++j) {
+                const int g = gb + j;
+                float v[16], m[16];
+                if (k >= 2) { unpack8_bf16(m2[j][0], m); unpack8_bf16(m2[j][1], m + 8); }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                  v[i] = alpha * __uint_as_float(a[j][i]);
+                  if (k >= 2) v[i] -= m[i];
+                  if (!nvalid) v[i] = 0.f;
+                }
+                const uint4 lo = pack8_bf16(v), hi = pack8_bf16(v + 8);
+                if (inbuf) row_store(bk + (size_t)g * p.gs, n, lo, hi);
+                if (nvalid && g0 + g < p.G) {
+                  uint4* dst = reinterpret_cast<uint4*>(plane + ((g0 + g) * p.N + n) * kChebC);
+                  dst[0] = lo; dst[1] = hi;
+                }
+              }
+              }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(xk_ready);
+            if (stamp) CHEB_STAMP(9 + 2 * (k - 1));
+          }
+          // y = relu(acc + bias + x_0)
+          mbar_wait(acc_full, n_acc & 1); ++n_acc;
+          tc_fence_after();
+          if (stamp) CHEB_STAMP(8 + 2 * (p.depth - 1));
+          for (int mt = 0; mt < p.nMT; ++mt) {
+            if (mt * 128 + q * 32 >= p.N) break;                   // warp-uniform
+            const int n = mt * 128 + r;
+            const bool nvalid = n < p.N;
+#pragma unroll 1
+            for (int gb = 0; gb < GB; gb += SB) {
+            uint32_t a[SB][16];
+            uint4 x0[SB][2];
+#pragma unroll
+            for (int j = 0; j < SB; ++j) tmem_ld_32x32b_x16(t_lane + (p.nMT + mt) * NC + (gb + j) * kChebC, a[j]);
+#pragma unroll
+            for (int j = 0; j < SB; ++j)
+              if (p.residual && nvalid) row_load_raw(bufs + (size_t)(gb + j) * p.gs, n, x0[j][0], x0[j][1]);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < SB; ++j) {
+              const int g = gb + j;
+              float v[16], m[16];
+              if (p.residual) { unpack8_bf16(x0[j][0], m); unpack8_bf16(x0[j][1], m + 8); }
+#pragma unroll
               for (int i = 0; i < 16; ++i) {
-                v[i] = alpha * __uint_as_float(a[i]);
-                if (k >= 2) v[i] -= m2[i];
-                if (!nvalid) v[i] = 0.f;
+                v[i] = __uint_as_float(a[j][i]) + bias_s[i];
+                if (p.residual) v[i] += m[i];
+                if (p.relu) v[i] = fmaxf(v[i], 0.f);
               }
-              const uint4 lo = pack8_bf16(v), hi = pack8_bf16(v + 8);
-              if (inbuf) row_store(bk + (size_t)g * p.gs, n, lo, hi);
               if (nvalid && g0 + g < p.G) {
-                uint4* dst = reinterpret_cast<uint4*>(plane + ((g0 + g) * p.N + n) * kChebC);
-                dst[0] = lo; dst[1] = hi;
+                uint4* dst = reinterpret_cast<uint4*>(p.out + ((g0 + g) * p.N + n) * kChebC);
+                dst[0] = pack8_bf16(v); dst[1] = pack8_bf16(v + 8);
               }
+            }
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) { mbar_arrive(mix_free); mbar_arrive(in_free); }
+          if (stamp) CHEB_STAMP(9 + 2 * (p.depth - 1));
+        } else {
+          // S0: dG = dy * [y > 0] in place in buffer 0 (+ HBM copy for the weight-gradient kernels)
+          mbar_wait(in_full, it & 1);
+          for (int mt = 0; mt < p.nMT; ++mt) {
+            const int n = mt * 128 + r;
+            if (n >= p.N) break;                         // padded rows were zero-filled by the producers
+#pragma unroll
+            for (int g = 0; g < GB; ++g) {
+              if (g0 + g >= p.G) break;
+              float dy[16], y[16];
+              row_load(bufs + (size_t)g * p.gs, n, dy);
+              if (p.relu) {
+                row_load(bufs + p.buf_bytes + (size_t)g * p.gs, n, y);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) dy[i] = y[i] > 0.f ? dy[i] : 0.f;
+              }
+              const uint4 lo = pack8_bf16(dy), hi = pack8_bf16(dy + 8);
+              if (p.relu) row_store(bufs + (size_t)g * p.gs, n, lo, hi);
+              uint4* dst = reinterpret_cast<uint4*>(p.out2 + ((g0 + g) * p.N + n) * kChebC);
+              dst[0] = lo; dst[1] = hi;
             }
           }
           fence_proxy_async();
-          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&xk_ready);
-        }
-        // y = relu(acc + bias + x_0)
-        mbar_wait(&acc_full, n_acc & 1); ++n_acc;
-        tc_fence_after();
-        for (int mt = 0; mt < p.nMT; ++mt) {
-          if (mt * 128 + q * 32 >= p.N) break;                   // warp-uniform
-          const int n = mt * 128 + r;
-          const bool nvalid = n < p.N;
+          if (lane == 0) mbar_arrive(xk_ready);
+          // E_k, k = depth-1 .. 1: P_k = alpha_k * (R_k - D_{k+2}) -> buffer k ;  E_0: dx_0 = R_0 - D_2 + dG
+          for (int k = p.depth - 1; k >= 0; --k) {
+            const float alpha = k >= 2 ? 2.f : 1.f;
+            const bool sub = k + 2 <= p.depth - 1;
+            const bool addg = k == 0 && p.residual;
+            uint8_t* bk = bufs + (size_t)k * p.buf_bytes;
+            const uint8_t* bp2 = bufs + (size_t)(sub ? k + 2 : 0) * p.buf_bytes;
+            mbar_wait(acc_full, n_acc & 1); ++n_acc;
+            tc_fence_after();
+            if (stamp) CHEB_STAMP(8 + 2 * (p.depth - 1 - k));
+            for (int mt = 0; mt < p.nMT; ++mt) {
+              if (mt * 128 + q * 32 >= p.rows_pad) break;          // warp-uniform
+              const int n = mt * 128 + r;
+              const bool nvalid = n < p.N, inbuf = n < p.rows_pad;
 #pragma unroll 1
-          for (int g = 0; g < p.Gb; ++g) {
-            if (g0 + g >= p.G) break;
-            uint32_t a[16];
-            tmem_ld_32x32b_x16(t_lane + (p.nMT + mt) * NC + g * kChebC, a);
-            float v[16], x0[16];
-            if (p.residual && nvalid) row_load(bufs + (size_t)g * p.gs, n, x0);
-            tmem_ld_wait();
+              for (int gb = 0; gb < GB; gb += SB) {
+              uint32_t a[SB][16];
+              uint4 p2[SB][2], dg[SB][2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              v[i] = __uint_as_float(a[i]) + bias_s[i];
-              if (p.residual) v[i] += x0[i];
-              if (p.relu) v[i] = fmaxf(v[i], 0.f);
-            }
-            if (nvalid) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out + ((g0 + g) * p.N + n) * kChebC);
-              dst[0] = pack8_bf16(v); dst[1] = pack8_bf16(v + 8);
-            }
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) { mbar_arrive(&mix_free); mbar_arrive(&in_free); }
-      } else {
-        // S0: dG = dy * [y > 0] in place in buffer 0 (+ HBM copy for the weight-gradient kernels)
-        mbar_wait(&in_full, it & 1);
-        for (int mt = 0; mt < p.nMT; ++mt) {
-          const int n = mt * 128 + r;
-          if (n >= p.N) break;                         // padded rows were zero-filled by the producers
-#pragma unroll 1
-          for (int g = 0; g < p.Gb; ++g) {
-            if (g0 + g >= p.G) break;
-            float dy[16], y[16];
-            row_load(bufs + (size_t)g * p.gs, n, dy);
-            if (p.relu) {
-              row_load(bufs + p.buf_bytes + (size_t)g * p.gs, n, y);
+              for (int j = 0; j < SB; ++j) tmem_ld_32x32b_x16(t_lane + (k * p.nMT + mt) * NC + (gb + j) * kChebC, a[j]);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dy[i] = y[i] > 0.f ? dy[i] : 0.f;
-            }
-            const uint4 lo = pack8_bf16(dy), hi = pack8_bf16(dy + 8);
-            if (p.relu) row_store(bufs + (size_t)g * p.gs, n, lo, hi);
-            uint4* dst = reinterpret_cast<uint4*>(p.out2 + ((g0 + g) * p.N + n) * kChebC);
-            dst[0] = lo; dst[1] = hi;
-          }
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&xk_ready);
-        // E_k, k = depth-1 .. 1: P_k = alpha_k * (R_k - D_{k+2}) -> buffer k ;  E_0: dx_0 = R_0 - D_2 + dG
-        for (int k = p.depth - 1; k >= 0; --k) {
-          const float alpha = k >= 2 ? 2.f : 1.f;
-          const bool sub = k + 2 <= p.depth - 1;
-          uint8_t* bk = bufs + (size_t)k * p.buf_bytes;
-          const uint8_t* bp2 = bufs + (size_t)(sub ? k + 2 : 0) * p.buf_bytes;
-          mbar_wait(&acc_full, n_acc & 1); ++n_acc;
-          tc_fence_after();
-          for (int mt = 0; mt < p.nMT; ++mt) {
-            if (mt * 128 + q * 32 >= p.rows_pad) break;          // warp-uniform
-            const int n = mt * 128 + r;
-            const bool nvalid = n < p.N, inbuf = n < p.rows_pad;
-#pragma unroll 1
-            for (int g = 0; g < p.Gb; ++g) {
-              uint32_t a[16];
-              tmem_ld_32x32b_x16(t_lane + (k * p.nMT + mt) * NC + g * kChebC, a);
-              float v[16], p2[16], dg[16];
-              if (sub && inbuf) row_load(bp2 + (size_t)g * p.gs, n, p2);
-              if (k == 0 && p.residual && inbuf) row_load(bufs + (size_t)g * p.gs, n, dg);
+              for (int j = 0; j < SB; ++j) {
+                if (sub && inbuf) row_load_raw(bp2 + (size_t)(gb + j) * p.gs, n, p2[j][0], p2[j][1]);
+                if (addg && inbuf) row_load_raw(bufs + (size_t)(gb + j) * p.gs, n, dg[j][0], dg[j][1]);
+              }
               tmem_ld_wait();
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                v[i] = __uint_as_float(a[i]);
-                if (sub) v[i] -= 0.5f * p2[i];          // buffer k+2 holds 2 * D_{k+2}
-                if (k == 0 && p.residual) v[i] += dg[i];
-                v[i] = nvalid ? alpha * v[i] : 0.f;
+              for (int j = 0; j < SB; ++j) {
+                const int g = gb + j;
+                float v[16], m[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(a[j][i]);
+                if (sub) {
+                  unpack8_bf16(p2[j][0], m); unpack8_bf16(p2[j][1], m + 8);
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] -= 0.5f * m[i];     // buffer k+2 holds 2 * D_{k+2}
+                }
+                if (addg) {
+                  unpack8_bf16(dg[j][0], m); unpack8_bf16(dg[j][1], m + 8);
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) v[i] += m[i];
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = nvalid ? alpha * v[i] : 0.f;
+                const uint4 lo = pack8_bf16(v), hi = pack8_bf16(v + 8);
+                if (k > 0) {
+                  if (inbuf) row_store(bk + (size_t)g * p.gs, n, lo, hi);
+                } else if (nvalid && g0 + g < p.G) {
+                  uint4* dst = reinterpret_cast<uint4*>(p.out + ((g0 + g) * p.N + n) * kChebC);
+                  dst[0] = lo; dst[1] = hi;
+                }
               }
-              const uint4 lo = pack8_bf16(v), hi = pack8_bf16(v + 8);
-              if (k > 0) {
-                if (inbuf) row_store(bk + (size_t)g * p.gs, n, lo, hi);
-              } else if (nvalid && g0 + g < p.G) {
-                uint4* dst = reinterpret_cast<uint4*>(p.out + ((g0 + g) * p.N + n) * kChebC);
-                dst[0] = lo; dst[1] = hi;
               }
             }
-          }
-          tc_fence_before();
-          if (k > 0) {
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&xk_ready);
-          } else {
-            __syncwarp();
-            if (lane == 0) { mbar_arrive(&mix_free); mbar_arrive(&in_free); }
+            tc_fence_before();
+            if (k > 0) {
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(xk_ready);
+            } else {
+              __syncwarp();
+              if (lane == 0) { mbar_arrive(mix_free); mbar_arrive(in_free); }
+            }
+            if (stamp) CHEB_STAMP(9 + 2 * (p.depth - 1 - k));
           }
         }
       }
@@ -358,7 +436,7 @@ __global__ void __launch_bounds__(kChebThreads, 1) umma_cheb_kernel(ChebParams p
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+  if (warp == 0) tmem_dealloc(tmem_base_s, ncols);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,9 +470,9 @@ inline ChebPlan plan_cheb(int N, int C, int depth, int n_taps, bool bwd) {
   pl.w_bytes = (uint32_t)((n_taps * 512 + 1023) & ~1023);
   const int regions = bwd ? depth : 2;
   const size_t slack = 1024 + 4096;       // base alignment + operand over-read past the last buffer (never stored)
-  for (int Gb = 8; Gb >= 1; --Gb) {
-    if (regions * pl.nMT * Gb * kChebC > 512) continue;
-    const size_t need = (size_t)pl.a_bytes + pl.w_bytes + (size_t)depth * Gb * pl.gs + slack;
+  for (int Gb = 4; Gb >= 1; Gb /= 2) {
+    if (kChebSlots * regions * pl.nMT * Gb * kChebC > 512) continue;
+    const size_t need = (size_t)pl.a_bytes + pl.w_bytes + (size_t)kChebSlots * depth * Gb * pl.gs + slack;
     if (need > kSmemBudget) continue;
     pl.Gb = Gb; pl.buf_bytes = (uint32_t)Gb * pl.gs; pl.smem = need;
     pl.ok = true;
@@ -456,14 +534,20 @@ inline void launch_cheb(const ChebProblem& q, bool bwd, cudaStream_t stream) {
   for (int i = 0; i < pl.nMT; ++i) { p.mt_off[i] = pl.mt_off[i]; p.mt_rows[i] = pl.mt_rows[i]; }
   p.a_img = reinterpret_cast<const uint8_t*>(q.a_img); p.w = q.w; p.bias = q.bias;
   p.in = q.in; p.in2 = q.in2; p.stack = q.stack; p.out = q.out; p.out2 = q.out2;
-  int gx = p.n_items < sm_count() ? p.n_items : sm_count();
+  p.dbg = g_tap_dbg;
+  const int pairs = (p.n_items + kChebSlots - 1) / kChebSlots;
+  int gx = pairs < sm_count() ? pairs : sm_count();
   if (gx < 1) gx = 1;
+  auto go = [&](auto kern, const char* name) {
+    STGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    STGCN_LAUNCH_NAMED(name, kern, gx, kChebThreads, pl.smem, stream, p);
+  };
   if (bwd) {
-    STGCN_CUDA(cudaFuncSetAttribute(umma_cheb_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH_NAMED("umma_cheb_kernel<bwd>", umma_cheb_kernel<true>, gx, kChebThreads, pl.smem, stream, p);
+    const char* nm = "umma_cheb_kernel<bwd>";
+    if (pl.Gb == 4) go(umma_cheb_kernel<true, 4>, nm); else if (pl.Gb == 2) go(umma_cheb_kernel<true, 2>, nm); else go(umma_cheb_kernel<true, 1>, nm);
   } else {
-    STGCN_CUDA(cudaFuncSetAttribute(umma_cheb_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    STGCN_LAUNCH_NAMED("umma_cheb_kernel<fwd>", umma_cheb_kernel<false>, gx, kChebThreads, pl.smem, stream, p);
+    const char* nm = "umma_cheb_kernel<fwd>";
+    if (pl.Gb == 4) go(umma_cheb_kernel<false, 4>, nm); else if (pl.Gb == 2) go(umma_cheb_kernel<false, 2>, nm); else go(umma_cheb_kernel<false, 1>, nm);
   }
 }
 
