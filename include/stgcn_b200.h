@@ -206,6 +206,10 @@ int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M,
 /* Diagnostics: while a device buffer of 16 uint64 is registered (NULL to stop), every umma_tap launch has CTA (0,0)
  * write %globaltimer stamps of its pipeline milestones into it (see csrc/umma_tap.cuh STGCN_STAMP).          */
 int stgcn_debug_timeline(unsigned long long* device_buf16);
+/* Diagnostics: times `n_mma` tcgen05.mma instructions of one shape / operand layout on one SM.  cfg17 = {M, N, a_mn_major,
+ * b_mn_major, a_in_tmem, a_swizzle, a_lbo, a_sbo, a_k_advance, b_swizzle, b_lbo, b_sbo, b_k_advance, n_mma, n_chains,
+ * chain_cols, 0}; out3 (device) = {issue cycles, cycles to completion, n_mma}.  No reference counterpart. */
+int stgcn_umma_microbench(const int32_t* cfg17, unsigned long long* out3_dev, void* stream);
 
 /* ---- training-step helpers (main.py:166-168) ------------------------------------------ */
 /* loss = mean((pred - target)^2) over n elements, written to *loss (device, fp32);

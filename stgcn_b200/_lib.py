@@ -119,6 +119,7 @@ _SIGNATURES = [
     ("stgcn_umma_selftest", C.c_int, [C.c_int, _fp, _fp, _fp, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint32,
                                       C.c_uint32, C.c_uint32, _fp]),
     ("stgcn_debug_timeline", C.c_int, [_fp]),
+    ("stgcn_umma_microbench", C.c_int, [C.POINTER(C.c_int32), _fp, _fp]),
     ("stgcn_mse_fwd_bwd", C.c_int, [_fp, _fp, C.c_int64, C.c_float, _fp, _fp, _fp]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]

@@ -355,7 +355,6 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   // fused Chebyshev / first-order kernel (umma_cheb.cuh): recurrence + weight GEMMs + bias/residual/ReLU in one pass
   const int fdepth = gconv_stack_depth(d), ftaps = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   const bool fused = gconv_fused<T>(d);
-  uint8_t* cimg = c.ws.take<uint8_t>(fused ? umma::cheb_image_bytes(d.N) : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.w && p.gso, STGCN_E_INVALID, "gconv: missing weight or gso");
   T* x0 = stack;
@@ -381,10 +380,11 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   }
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (fused) {
-      umma::launch_cheb_prep(p.gso, cimg, d.N, 0, c.stream);
+      const int Kp = (d.N + 63) / 64 * 64;
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.stream, p.gso, mbf, d.N, Kp, 0);
       umma::ChebProblem q{};
       q.N = d.N; q.G = (long long)d.B * d.T; q.depth = fdepth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
-      q.n_taps = ftaps; q.relu = d.relu; q.residual = d.residual; q.a_img = cimg; q.w = p.w; q.bias = p.b;
+      q.n_taps = ftaps; q.relu = d.relu; q.residual = d.residual; q.a_mat = mbf; q.w = p.w; q.bias = p.b;
       q.in = x0; q.stack = stack; q.out = y;
       umma::launch_cheb(q, false, c.stream);
       return;
@@ -446,15 +446,15 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
                                               ? std::max((size_t)d.c_in * C, (size_t)ntw * C * C) : 0);
   const bool fused = gconv_fused<T>(d);
-  uint8_t* cimg = c.ws.take<uint8_t>(fused ? umma::cheb_image_bytes(d.N) : 0);
   if (c.dry()) return;
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (fused) {
       // dG, the adjoint recurrence and the residual gradient in one kernel; dst[0] = gradient w.r.t. the aligned input
-      umma::launch_cheb_prep(p.gso, cimg, d.N, 1, c.stream);
+      const int Kp = (d.N + 63) / 64 * 64;
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.stream, p.gso, mbf, d.N, Kp, 1);
       umma::ChebProblem q{};
       q.N = d.N; q.G = (long long)d.B * d.T; q.depth = depth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
-      q.n_taps = ntw; q.relu = d.relu; q.residual = d.residual; q.a_img = cimg; q.w = p.w; q.bias = nullptr;
+      q.n_taps = ntw; q.relu = d.relu; q.residual = d.residual; q.a_mat = mbf; q.w = p.w; q.bias = nullptr;
       q.in = dy; q.in2 = y; q.out = dst; q.out2 = dg;
       umma::launch_cheb(q, true, c.stream);
     }

@@ -1,6 +1,7 @@
 // stgcn_b200.cu -- C-ABI exports of libstgcn_b200.so (see include/stgcn_b200.h).
 #include "ops.cuh"
 #include "umma_selftest.cuh"
+#include "umma_bench.cuh"
 
 namespace stgcn {
 thread_local char g_last_error[512] = "";
@@ -254,6 +255,19 @@ int stgcn_umma_selftest(int mode, const void* A, const void* B, float* C, int M,
   return guarded([&] {
     STGCN_CHECK(A && B && C, STGCN_E_INVALID, "null argument");
     umma::run_selftest(mode, A, B, C, M, N, K, lbo_a, sbo_a, lbo_b, sbo_b, as_stream(stream));
+  });
+}
+
+int stgcn_umma_microbench(const int32_t* cfg17, unsigned long long* out3_dev, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(cfg17 && out3_dev, STGCN_E_INVALID, "null argument");
+    umma::MmaBenchCfg c{};
+    c.M = cfg17[0]; c.N = cfg17[1]; c.a_mn = cfg17[2]; c.b_mn = cfg17[3]; c.a_tmem = cfg17[4];
+    c.a_swz = (uint32_t)cfg17[5]; c.a_lbo = (uint32_t)cfg17[6]; c.a_sbo = (uint32_t)cfg17[7]; c.a_kadv = (uint32_t)cfg17[8];
+    c.b_swz = (uint32_t)cfg17[9]; c.b_lbo = (uint32_t)cfg17[10]; c.b_sbo = (uint32_t)cfg17[11]; c.b_kadv = (uint32_t)cfg17[12];
+    c.n_mma = cfg17[13]; c.n_chains = cfg17[14]; c.chain_cols = cfg17[15];
+    c.style = cfg17[16] & 15; c.n_warps = ((cfg17[16] >> 4) & 15) ? ((cfg17[16] >> 4) & 15) : 1;
+    umma::run_mma_bench(c, out3_dev, as_stream(stream));
   });
 }
 

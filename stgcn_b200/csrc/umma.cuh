@@ -150,6 +150,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 
+// descriptor of the same layout at another shared-memory address: proto = make_smem_desc(0, lbo, sbo, swz)
+__device__ __forceinline__ uint64_t desc_at(uint64_t proto, uint32_t saddr) { return proto + (uint64_t)((saddr & 0x3FFFF) >> 4); }
+
 // 32-bit instruction descriptor for kind::f16 (bf16 x bf16 -> fp32):
 //   [4,6) D format (1 = f32)  [7,10) A format (1 = bf16)  [10,13) B format (1 = bf16)
 //   [15] A major (0 = K, 1 = MN)  [16] B major  [17,23) N >> 3  [24,29) M >> 4
@@ -168,6 +171,46 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ISSUE COST (profiles/r01_mma_microbench_b.txt): a tcgen05.mma issued from inside `if (lane == 0)` costs ~175 cycles --
+// every operand is a per-thread value, so the compiler wraps each instruction in an ELECT / 3 x R2UR.BROADCAST /
+// BRA.U.ANY waterfall -- and 209 cycles with one elect.sync per instruction (the _w variants below).  Inside ONE
+// `if (elect_one()) { ... }` region the compiler knows a single lane is active, keeps descriptors in uniform registers
+// and the same instruction issues in 41 (N <= 16) .. 50 (N = 64) .. 123 (N = 256) cycles.  So: the whole MMA-issuer
+// role body sits under one elect_one(), and descriptors are advanced with desc_at() / adds.
+// Warp-collective variants (whole warp calls with uniform arguments, one elected lane issues) -- diagnostics only.
+__device__ __forceinline__ void mma_bf16_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (elect_one()) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+// A operand in tensor memory (lane = row, two 16-bit K elements per 32-bit column)
+__device__ __forceinline__ void mma_bf16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (elect_one()) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void mma_commit_w(uint64_t* bar) {
+  if (elect_one()) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  }
+}
+// warp index / a shared-memory word as provably warp-uniform values
+__device__ __forceinline__ int warp_idx_uniform() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // mbarrier arrives once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))

@@ -70,7 +70,7 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, NC, 0, 1);
       mbar_wait(&afull, 0);
       uint32_t g = 0, acc_cnt = 0;

@@ -255,8 +255,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.CoT, 0, 0);
+      const uint64_t dproto = make_smem_desc(0, 16, p.sbo, p.swz);
       const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2, ablk = 128u * p.KB * 2;
       const int nk16 = p.KB / 16;
       mbar_wait(&wfull, 0);
@@ -282,13 +283,14 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             tc_fence_after();
             const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes);
             const uint32_t b_base = smem_u32(w_s + (size_t)j * p.nKB * wblk);
-            for (int kb = 0; kb < p.nKB; ++kb)
+            for (int kb = 0; kb < p.nKB; ++kb) {
+              uint64_t da = desc_at(dproto, a_base + kb * ablk), db = desc_at(dproto, b_base + kb * wblk);
               for (int k = 0; k < nk16; ++k) {
-                const uint64_t da = make_smem_desc(a_base + kb * ablk + k * 32, 16, p.sbo, p.swz);
-                const uint64_t db = make_smem_desc(b_base + kb * wblk + k * 32, 16, p.sbo, p.swz);
                 mma_bf16_ss(d_tmem, da, db, idesc, accumulate);
                 accumulate = 1;
+                da += 2; db += 2;         // 32 bytes = one K = 16 step
               }
+            }
           }
           if (acc_cnt == 8) STGCN_STAMP(22);
           mma_commit(&tfull[ab]);

@@ -109,10 +109,14 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.Cin, 1, 1);
       const uint32_t idesc_b = make_idesc_bf16(128, 16, 1, 1);
       const uint32_t ones_a = smem_u32(ones);
+      const uint64_t pa = make_smem_desc(0, p.a_lbo, p.a_sbo, p.a_swz);
+      const uint64_t pb = make_smem_desc(0, (uint32_t)p.KR * xcw * 2, p.b_sbo, p.b_swz);
+      const uint64_t pones = make_smem_desc(0, 2048, 256, SWZ_32B);
+      const uint64_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       uint32_t gx_base = 0, gz = 0, started = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         for (int t_o = 0; t_o < p.T_out; ++t_o, ++gz) {
@@ -126,19 +130,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
             tc_fence_after();
             const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
             const uint32_t acc = (started >> j) & 1;
+            uint64_t da = desc_at(pa, a_base), db = desc_at(pb, b_base);
             for (int k = 0; k < p.KR / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
-              const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, (uint32_t)p.KR * xcw * 2, p.b_sbo, p.b_swz);
               mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, acc | (k != 0));
+              da += a_step; db += b_step;
             }
             started |= 1u << j;
           }
           if (p.want_bias) {
             const uint32_t acc = (started >> 31) & 1;
+            uint64_t da = desc_at(pa, a_base);
             for (int k = 0; k < p.KR / 16; ++k) {
-              const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, p.a_lbo, p.a_sbo, p.a_swz);
-              const uint64_t db = make_smem_desc(ones_a + (k & 3) * 512, 2048, 256, SWZ_32B);
-              mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, acc | (k != 0));
+              mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, desc_at(pones, ones_a + (k & 3) * 512), idesc_b, acc | (k != 0));
+              da += a_step;
             }
             started |= 1u << 31;
           }
@@ -249,9 +253,13 @@ umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.Cin, 1, 1), idesc_b = make_idesc_bf16(128, 16, 1, 1);
       const uint32_t ones_a = smem_u32(ones);
+      const uint64_t pa = make_smem_desc(0, 0, p.a_sbo, p.a_swz);                              // LBO 0: chunk aliased
+      const uint64_t pb = make_smem_desc(0, (uint32_t)kFlatRows * xcw * 2, p.b_sbo, p.b_swz);
+      const uint64_t pones = make_smem_desc(0, 2048, 256, SWZ_32B);
+      const uint64_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       uint32_t g = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
         const uint32_t s = g % p.S, ph = (g / p.S) & 1;
@@ -260,18 +268,21 @@ umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         const uint32_t a_base = smem_u32(ring + (size_t)s * p.stage_bytes);
         for (int j = 0; j < p.Kt; ++j) {
           const uint32_t b_base = a_base + p.z_bytes + j * p.x_bytes;
+          uint64_t da = desc_at(pa, a_base), db = desc_at(pb, b_base);
+#pragma unroll 4
           for (int k = 0; k < kFlatRows / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, 0, p.a_sbo, p.a_swz);      // LBO 0: chunk aliased
-            const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, (uint32_t)kFlatRows * xcw * 2, p.b_sbo, p.b_swz);
             mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, (g | (uint32_t)k) != 0);
+            da += a_step; db += b_step;
           }
         }
-        if (p.want_bias)
+        if (p.want_bias) {
+          uint64_t da = desc_at(pa, a_base);
+#pragma unroll 4
           for (int k = 0; k < kFlatRows / 16; ++k) {
-            const uint64_t da = make_smem_desc(a_base + k * p.a_kadv, 0, p.a_sbo, p.a_swz);
-            const uint64_t db = make_smem_desc(ones_a + (k & 3) * 512, 2048, 256, SWZ_32B);
-            mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, db, idesc_b, (g | (uint32_t)k) != 0);
+            mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, desc_at(pones, ones_a + (k & 3) * 512), idesc_b, (g | (uint32_t)k) != 0);
+            da += a_step;
           }
+        }
         mma_commit(&empty[s]);
       }
       mma_commit(&done);

@@ -21,7 +21,9 @@ def show(name):
             b = slot * 72 + it * 24
             print(f" slot {slot} item {it}: fill {us(t[b])}->{us(t[b+1])} | mma issued",
                   [us(t[b + 2 + j]) for j in range(depth)], "| epi",
-                  [(us(t[b + 8 + 2 * j]), us(t[b + 9 + 2 * j])) for j in range(depth)])
+                  [(us(t[b + 8 + 2 * j]), us(t[b + 9 + 2 * j])) for j in range(depth)],
+                  "| hop waits-done/issued", [(us(t[b + 16 + j]), us(t[b + 20 + j])) for j in range(depth - 1)],
+                  "| epi0 detail: tile0 tmem", us(t[b + 14]), "tile1 tmem", us(t[b + 19]), "stores issued", us(t[b + 15]), "fence done", us(t[b + 23]))
 
 
 gl = layers.GraphConvLayer("cheb_graph_conv", 16, 16, 3, torch.randn(N, N, device=dev) / 30, True).to(dev)
