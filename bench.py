@@ -398,7 +398,8 @@ def main():
             else:
                 ach, peak, bound, unit = fl / t_s / 1e12, peaks["bf16_tflops_sustained"], "tensor", "TFLOP/s"
             roofline = {"kernel": k0, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "traffic": None, "peak_source": peaks["source"], "alg_flops_per_step": fl,
+                        "traffic": _ncu_traffic(k0, a.workload, B, a.precision), "peak_source": peaks["source"],
+                        "alg_flops_per_step": fl,
                         "alg_bytes_per_step": by, "launches_per_step": c0 / psteps,
                         "avg_launch_ms": ms0 / c0, "share_of_step": ms0 / tot_ms}
             break
@@ -432,6 +433,21 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _ncu_traffic(key, workload, B, precision):
+    """DRAM bytes (read + write) per launch of this kernel from the committed `ncu --set full` captures
+    (profiles/r01_traffic.json; PeMSD7-M, B=256, bf16 only), or None when that kernel was not captured."""
+    import re
+    if workload != "pemsd7m" or B != 256 or precision != "bf16":
+        return None
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    tag, kern = key.split(":", 1)
+    m = re.search(r"[A-Za-z_][A-Za-z0-9_]*", kern)
+    row = json.load(open(path))["kernels"].get(f"{tag}:{m.group(0) if m else kern}")
+    return None if row is None else row["dram_read_bytes"] + row["dram_write_bytes"]
 
 
 def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
@@ -479,6 +495,10 @@ def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
         c1, c2, t1 = d["c1"], d["c2"], d["T1"]
         nk = (ks - 1) if kind == "cheb_graph_conv" else 1
         kmix = ks if kind == "cheb_graph_conv" else 1
+        if "umma_cheb" in kern:     # fused recurrence + weight GEMMs: fwd reads x0, writes the stack planes and y;
+            fl = nk * 2.0 * n * c2 * rows(t1) + 2.0 * kmix * c2 * c2 * rows(t1)     # bwd reads dy, y, writes dG, dx0
+            by = rows(t1) * c2 * e * ((1 + nk + 1) if direction == "fwd" else 4)
+            return fl, by
         if "gso" in kern:
             return nk * 2.0 * n * n * c2 * rows(t1) / n, nk * 3 * rows(t1) * c2 * e
         if "wgrad" in kern:
@@ -490,6 +510,8 @@ def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
         return 2.0 * rows(1) * d["c1"] * d["c2"], rows(1) * (d["c1"] + d["c2"]) * e
     if op == "ln":
         c, t = (d["c3"], d["T2"]) if st != "out" else (d["c1"], 1)
+        if direction == "bwd" and "gate" in kern and "sums" not in kern:
+            return 0.0, rows(t) * (2 * c + 4 * c) * e        # x, dy in; z (2c) in; dz (2c) out
         return 0.0, 2 * rows(t) * c * e
     return None
 

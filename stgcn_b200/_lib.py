@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libstgcn_b200.so")
+# STGCN_B200_LIB: developer knob to A/B another build of the SAME library (tools/build_variants.sh); never a fallback
+LIB_PATH = os.environ.get("STGCN_B200_LIB") or os.path.join(_HERE, "lib", "libstgcn_b200.so")
 
 ACT = {"glu": 0, "gtu": 1, "relu": 2, "silu": 3, "linear": 4}
 GCONV = {"cheb_graph_conv": 0, "graph_conv": 1}

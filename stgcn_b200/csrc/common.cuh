@@ -131,6 +131,15 @@ inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float sigmoidf_(float v) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * v)); }
+// bf16 storage mode only: sigma(v) = 0.5 + 0.5 tanh(v / 2) is ONE MUFU op (tanh.approx, |error| < 2^-11, far below the
+// bf16 the results are stored in) instead of ex2 + rcp; the gate epilogues are MUFU / issue bound.  The fp32 parity
+// path keeps sigmoidf_ (cancellation near sigma -> 0 would eat into its 1e-3 budget).
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_tanh_(float v) { return fmaf(0.5f, tanh_approx(0.5f * v), 0.5f); }
+template <bool FAST>
+__device__ __forceinline__ float sigmoid_t(float v) { return FAST ? sigmoid_tanh_(v) : sigmoidf_(v); }
+template <bool FAST>
+__device__ __forceinline__ float tanh_t(float v) { return FAST ? tanh_approx(v) : tanhf(v); }
 
 // Counter-based dropout keep-mask: splitmix64 finaliser over (seed, element index).
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {

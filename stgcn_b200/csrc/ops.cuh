@@ -11,6 +11,7 @@
 #include "umma_gso.cuh"
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
+#include "ln_gate_pipe.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -140,9 +141,21 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
 
 // dz_ready: gradient w.r.t. the pre-activations already computed by the caller (fused LayerNorm + gate backward,
 // lnorm_gate_bwd); dy is then unused.
+// lr: optional low-rank form of dy (GateArgs::lr_src / lr_w): dy = lr->src [rows_out, 16] . lr->w [16, c_out]; only the
+// generic gate path takes it (tconv_lowrank_dy_ok), dy is then unused.
+template <class T>
+struct LowRankDy { const T* src; const float* w; };
+template <class T>
+inline bool tconv_lowrank_dy_ok(const stgcn_tconv_desc& d) {
+  TconvGeom g = tconv_geom(d);
+  const bool res_ok = (g.folded || g.linear) || d.c_in % 8 == 0;
+  return g.rows_out > 0 && !smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt) && d.c_out % 8 == 0 && g.W % 8 == 0 && res_ok &&
+         g.rows_out * d.c_out / 8 < (1LL << 31);
+}
 template <class T>
 inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, const T* dy,
-                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c, T* dz_ready = nullptr) {
+                      const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c, T* dz_ready = nullptr,
+                      const LowRankDy<T>* lr = nullptr) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
@@ -157,6 +170,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
+  STGCN_CHECK(!lr || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: low-rank dy only on the generic gate path");
   if (dz_ready) {
   } else if (smallc) {
     // first-layer special: gate backward fused with the weight gradient (dz only materialised when dx is wanted)
@@ -197,6 +211,10 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     GateArgs<T> ga{};
     ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
     ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
+    if (lr) {
+      ga.lr_src = lr->src; ga.lr_w = lr->w; ga.dy = nullptr;
+      STGCN_CHECK(gate_vec_ok(ga), STGCN_E_UNSUPPORTED, "tconv_bwd: low-rank dy not served (misaligned buffers)");
+    }
     launch_gate_any(d.act, true, ga, c.stream);
   }
   if (want_w) {
@@ -425,9 +443,12 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   }
 }
 
+// dst_ext: optional caller-owned buffer [depth][rows, c_out] for the stack gradients; with it and c_in > c_out the
+// caller may pass dx == nullptr and apply the align conv's data gradient itself from dst_ext plane 0 (stblock_bwd
+// folds it into the gate backward of the preceding temporal conv).
 template <class T>
 inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, const T* y, const T* dy,
-                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c) {
+                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c, T* dst_ext = nullptr) {
   gconv_check(d);
   ScopedMark sm(c.ws);
   const long long rows = (long long)d.B * d.T * d.N;
@@ -436,7 +457,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   const int depth = gconv_stack_depth(d);
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   T* dg = c.ws.take<T>(plane);
-  T* dst = c.ws.take<T>((size_t)depth * plane);
+  T* dst = dst_ext ? dst_ext : c.ws.take<T>((size_t)depth * plane);
   float* wT = c.ws.take<float>((size_t)ntw * C * C);
   float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
@@ -612,7 +633,16 @@ inline void lnorm_fwd(const stgcn_lnorm_desc& d, const T* x, const float* w, con
   if (G == 0) return;
   const int M = d.N * d.C;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (M % 8 == 0 && al16(x) && al16(y) && al16(w) && al16(b))
+  const bool vec = M % 8 == 0 && al16(x) && al16(y) && al16(w) && al16(b);
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    static const bool off = std::getenv("STGCN_NO_LN_CACHED") != nullptr;      // A/B switch for profiling
+    if (vec && !off && M <= 512 * 8 * 8) {
+      if (M <= 512 * 8 * 4) STGCN_LAUNCH((ln_fwd_cached_kernel<4>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
+      else                  STGCN_LAUNCH((ln_fwd_cached_kernel<8>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
+      return;
+    }
+  }
+  if (vec)
     STGCN_LAUNCH((ln_fwd_kernel<T, 8>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
   else
     STGCN_LAUNCH((ln_fwd_kernel<T, 1>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
@@ -670,6 +700,13 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   const int M = d.N * d.C;
   if (dw) zero(dw, M, s);
   if (db) zero(db, M, s);
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    static const bool pipe_off = std::getenv("STGCN_NO_LN_PIPE") != nullptr;      // A/B switch for profiling
+    if (!pipe_off && ln_gate_pipe_supported(a)) {
+      launch_ln_gate_bwd_pipe(tc.act, a, umma::sm_count(), s);
+      return true;
+    }
+  }
   launch_ln_gate_bwd(tc.act, a, umma::sm_count(), s);
   return true;
 }
@@ -738,8 +775,15 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
     ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c.stream, c.dry());
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
   { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr); }
-  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
-  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c); }
+  // c1 > c2 (bottleneck): the align conv's data gradient dh1 = dst0 . Wa is formed inside tc1's gate backward from the
+  // 16-channel dst0 instead of being written to HBM at c1 channels and read back
+  static const bool lr_off = std::getenv("STGCN_NO_FUSED_ALIGNBWD") != nullptr;      // A/B switch for profiling
+  const bool lr_fuse = !lr_off && std::is_same<T, simt::bf16>::value && d.c1 > d.c2 && d.c2 == kGateLrC &&
+                       tconv_lowrank_dy_ok<T>(g.tc1);      // shapes only: the dry (sizing) run must take the same path
+  T* dst_ext = c.ws.take<T>(lr_fuse ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, lr_fuse ? nullptr : dh1, c, lr_fuse ? dst_ext : nullptr); }
+  LowRankDy<T> lr{dst_ext, p.gc.align_w};       // align_w is [c2][c1] row-major = lr_w[o * c1 + j]
+  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, lr_fuse ? &lr : nullptr); }
 }
 
 // ============================ output block ===================================================
@@ -772,6 +816,18 @@ inline OutSaved<T> out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Are
   return s;
 }
 
+// fc1 + ReLU in one tcgen05 launch: bf16 mode, no dropout to apply, shape served by the tap kernel (shapes only, so the
+// forward and the backward agree)
+template <class T>
+inline bool out_relu_fused(const stgcn_outblock_desc& d, const OutGeom& g) {
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    static const bool off = std::getenv("STGCN_NO_FUSED_FC1RELU") != nullptr;      // A/B switch for profiling
+    if (off || (d.training && d.p_drop > 0.f) || d.B <= 0) return false;
+    return umma_linear(nullptr, nullptr, nullptr, nullptr, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, nullptr, true);
+  }
+  return false;
+}
+
 // y (and dy in the backward) are ALWAYS fp32: the model output feeds the loss (main.py:166-167).
 template <class T>
 inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_outblock_params& p, float* y,
@@ -792,17 +848,22 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
   TapArgs<T> t{};
   t.in = s.l; t.wt = w1t; t.bias = p.fc1_b; t.out = s.f1; t.rows = g.rows1; t.Cin = d.c0; t.Co = d.c1; t.ntaps = 1;
   t.ldo = d.c1; t.map = RowMap{g.T1, g.T1, d.N, 0, 0};
-  bool fc1_done = false;
+  bool fc1_done = false, relu_done = false;
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, true)) {
       launch_gather3(p.fc1_w, wbf, 1, 1, d.c1 * d.c0, 0, 0, 0, 1, 0, c.stream);      // [o][c] as is
-      umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, false);
+      // without dropout the ReLU rides in the GEMM epilogue and only r = relu(f1) is kept (r > 0 <=> f1 > 0 is all the
+      // backward needs, outblock_bwd / out_relu_fused)
+      UmmaLinearOpts o{};
+      relu_done = out_relu_fused<T>(d, g);
+      o.relu = relu_done ? 1 : 0;
+      umma_linear(s.l, wbf, p.fc1_b, relu_done ? s.r : s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, o, c.stream, false);
       fc1_done = true;
     }
   }
   if (!fc1_done) launch_tapgemm(t, c.stream);
   long long n1 = g.rows1 * d.c1;
-  if (n1) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
+  if (n1 && !relu_done) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && g.rows1 > 0) {
     const int lanes = 256 / (d.c1 / 8);
@@ -882,7 +943,8 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       gb.flush();
     }
     long long n1 = g.rows1 * d.c1;
-    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, (const T*)s.f1, df1, n1, d.training, d.p_drop, seed);
+    const T* relu_ref = out_relu_fused<T>(d, g) ? s.r : s.f1;        // the forward kept only r = relu(f1) when it fused the ReLU
+    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, relu_ref, df1, n1, d.training, d.p_drop, seed);
     // fc1
     bool dl_done = false;
     if constexpr (std::is_same<T, simt::bf16>::value) {

@@ -605,22 +605,26 @@ inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   if (a.partial) launch_reduce_partials(a.partial, a.dwt, Mtot * a.Co, chunks, s);
 }
 
+template <bool FAST = false>
 __device__ __forceinline__ float act_fwd(int act, float u, float q) {
-  if (act == STGCN_ACT_GLU) return u * sigmoidf_(q);
-  if (act == STGCN_ACT_GTU) return tanhf(u) * sigmoidf_(q);
+  if (act == STGCN_ACT_GLU) return u * sigmoid_t<FAST>(q);
+  if (act == STGCN_ACT_GTU) return tanh_t<FAST>(u) * sigmoid_t<FAST>(q);
   if (act == STGCN_ACT_RELU) return fmaxf(u, 0.f);
-  if (act == STGCN_ACT_SILU) return u * sigmoidf_(u);
+  if (act == STGCN_ACT_SILU) return u * sigmoid_t<FAST>(u);
   return u;
 }
 // gradients of act_fwd w.r.t. (u, q) times g
+template <bool FAST = false>
 __device__ __forceinline__ void act_bwd(int act, float u, float q, float g, float& du, float& dq) {
   dq = 0.f;
-  if (act == STGCN_ACT_GLU) { float s = sigmoidf_(q); du = g * s; dq = g * u * s * (1.f - s); }
-  else if (act == STGCN_ACT_GTU) { float s = sigmoidf_(q), th = tanhf(u); du = g * s * (1.f - th * th); dq = g * th * s * (1.f - s); }
+  if (act == STGCN_ACT_GLU) { float s = sigmoid_t<FAST>(q); du = g * s; dq = g * u * s * (1.f - s); }
+  else if (act == STGCN_ACT_GTU) { float s = sigmoid_t<FAST>(q), th = tanh_t<FAST>(u); du = g * s * (1.f - th * th); dq = g * th * s * (1.f - s); }
   else if (act == STGCN_ACT_RELU) { du = u > 0.f ? g : 0.f; }
-  else if (act == STGCN_ACT_SILU) { float s = sigmoidf_(u); du = g * (s + u * s * (1.f - s)); }
+  else if (act == STGCN_ACT_SILU) { float s = sigmoid_t<FAST>(u); du = g * (s + u * s * (1.f - s)); }
   else { du = g; }
 }
+// bf16 storage mode uses the one-MUFU sigmoid / tanh (common.cuh)
+template <class T> constexpr bool kFastAct = std::is_same<T, bf16>::value;
 
 // ---- gating / activation of the temporal conv (layers.py:92-115) ---------------------------
 template <class T>
@@ -634,7 +638,12 @@ struct GateArgs {
   int Cin, Cout, W, Kt;
   int T_out, T_in, N;
   int explicit_res;    // 1: residual = xin[(b,t+Kt-1,n), j] for j < Cin (zero pad / identity)
+  // bwd, optional low-rank dy: dy[r, j] = sum_{o<16} lr_src[r, o] * lr_w[o * Cout + j]  (the 1x1 align conv of the
+  // graph-conv layer that consumed this layer's output, layers.py:16,225: its data gradient is formed on the fly
+  // instead of being written to HBM as a [rows, Cout] tensor and read back here)
+  const T* lr_src; const float* lr_w;
 };
+constexpr int kGateLrC = 16;
 
 template <class T>
 __device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r, int j) {
@@ -712,6 +721,11 @@ __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres
 // 8 channels per thread (requires Cout, W and Cin to be multiples of 8 when a residual is read)
 template <class T, int ACT>
 __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
+  extern __shared__ __align__(16) float lrw_s[];        // [kGateLrC][Cout] when a.lr_src (launcher sizes it)
+  if (a.lr_src) {
+    for (int i = threadIdx.x; i < kGateLrC * a.Cout; i += blockDim.x) lrw_s[i] = a.lr_w[i];
+    __syncthreads();
+  }
   const int groups = a.Cout / 8;
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * groups) return;
@@ -731,28 +745,50 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
   if (!bwd) {
     float h[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = act_fwd(ACT, zp[i] + res[i], gated ? zq[i] : 0.f);
+    for (int i = 0; i < 8; ++i) h[i] = act_fwd<kFastAct<T>>(ACT, zp[i] + res[i], gated ? zq[i] : 0.f);
     store8(a.y + r * a.Cout + j0, h);
   } else {
     float g[8], du[8], dq[8];
-    load8(a.dy + r * a.Cout + j0, g);
+    if (a.lr_src) {
+      float d[kGateLrC];
+      load8(a.lr_src + r * kGateLrC, d); load8(a.lr_src + r * kGateLrC + 8, d + 8);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) act_bwd(ACT, zp[i] + res[i], gated ? zq[i] : 0.f, g[i], du[i], dq[i]);
+      for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+      for (int o = 0; o < kGateLrC; ++o) {
+        const float4 w0 = *reinterpret_cast<const float4*>(lrw_s + o * a.Cout + j0);
+        const float4 w1 = *reinterpret_cast<const float4*>(lrw_s + o * a.Cout + j0 + 4);
+        g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
+        g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
+      }
+    } else {
+      load8(a.dy + r * a.Cout + j0, g);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) act_bwd<kFastAct<T>>(ACT, zp[i] + res[i], gated ? zq[i] : 0.f, g[i], du[i], dq[i]);
     store8(a.dz + r * a.W + j0, du);
     if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
   }
 }
 
+// does the 8-channels-per-thread kernel serve these arguments?  (tconv_bwd asks before it commits to a low-rank dy)
+template <class T>
+inline bool gate_vec_ok(const GateArgs<T>& a) {
+  const long long n = a.rows * a.Cout;
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return a.Cout % 8 == 0 && a.W % 8 == 0 && n / 8 < (1LL << 31) && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
+         al16(a.dy) && al16(a.y) && al16(a.dz) && al16(a.lr_src) && al16(a.lr_w);
+}
 template <class T, int ACT>
 inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   long long n = a.rows * a.Cout;
   if (n == 0) return;
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (a.Cout % 8 == 0 && a.W % 8 == 0 && n / 8 < (1LL << 31) && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
-      al16(a.dy) && al16(a.y) && al16(a.dz)) {
-    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, 0, s, a, bwd ? 1 : 0);
+  if (gate_vec_ok(a)) {
+    const size_t lr_smem = a.lr_src ? (size_t)kGateLrC * a.Cout * sizeof(float) : 0;
+    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, lr_smem, s, a, bwd ? 1 : 0);
     return;
   }
+  STGCN_CHECK(!a.lr_src, STGCN_E_UNSUPPORTED, "low-rank dy needs the vectorised gate kernel");
   if (bwd) STGCN_LAUNCH((gate_bwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
   else     STGCN_LAUNCH((gate_fwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
 }
@@ -907,7 +943,7 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
 // Cin == 1 specialisation: the K = Kt weights of this thread's 8 (+8 gate) channels live in registers; each thread
 // walks rows with a grid stride (its channel group never changes), so the loop body is K loads of x, K*16 FMAs, the
 // gate, and three 16-byte stores.
-template <class T, int K>
+template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
   const int groups = a.Cout / 8;
   const bool gated = a.W == 2 * a.Cout;
@@ -941,7 +977,7 @@ __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float res = (a.explicit_res && j0 + i == 0) ? xv[K - 1] : 0.f;
-      hv[i] = act_fwd(a.act, zp[i] + res, zq[i]);
+      hv[i] = act_fwd<kFastAct<T>>(ACT, zp[i] + res, zq[i]);
     }
     if (!a.skip_z) {
       store8(a.z + r * a.W + j0, zp);
@@ -954,9 +990,19 @@ template <class T>
 inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s) {
   const int lanes = 256 / (a.Cout / 8);
   const int blocks = (int)std::min<long long>(ceil_div(a.rows, lanes), 148 * 8);
-  if (a.Kt == 2) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 2>), blocks, 256, 0, s, a);
-  else if (a.Kt == 3) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 3>), blocks, 256, 0, s, a);
-  else STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 4>), blocks, 256, 0, s, a);
+  // the activation is a template parameter: a runtime switch inside the 8-wide unrolled gate cost a branch chain per element
+#define STGCN_SC1F(ACTV) do { \
+    if (a.Kt == 2) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 2, ACTV>), blocks, 256, 0, s, a); \
+    else if (a.Kt == 3) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 3, ACTV>), blocks, 256, 0, s, a); \
+    else STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 4, ACTV>), blocks, 256, 0, s, a); } while (0)
+  switch (a.act) {
+    case STGCN_ACT_GLU: STGCN_SC1F(STGCN_ACT_GLU); break;
+    case STGCN_ACT_GTU: STGCN_SC1F(STGCN_ACT_GTU); break;
+    case STGCN_ACT_RELU: STGCN_SC1F(STGCN_ACT_RELU); break;
+    case STGCN_ACT_SILU: STGCN_SC1F(STGCN_ACT_SILU); break;
+    default: STGCN_SC1F(STGCN_ACT_LINEAR); break;
+  }
+#undef STGCN_SC1F
 }
 
 // Fused gate-backward + weight gradient for the same layer: per CTA a row range, thread = (channel j, row lane);
@@ -1027,7 +1073,7 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
 
 // Cin == 1 specialisation of the above (the model input): 8 channels per thread with 16-byte loads, K = Kt taps known
 // at compile time, shuffle + shared-memory reduction, per-CTA partials.
-template <class T, int K>
+template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
   __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
   const bool gated = a.W == 2 * a.Cout;
@@ -1074,7 +1120,7 @@ __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a
     load8(a.dh + r * a.Cout + j0, dh);
     if (a.explicit_res && j0 == 0) zp[0] += xv[K - 1];        // residual = zero-padded input: channel 0 only
 #pragma unroll
-    for (int i = 0; i < 8; ++i) act_bwd(a.act, zp[i], gated ? zq[i] : 0.f, dh[i], du[i], dq[i]);
+    for (int i = 0; i < 8; ++i) act_bwd<kFastAct<T>>(ACT, zp[i], gated ? zq[i] : 0.f, dh[i], du[i], dq[i]);
     if (a.dz) {
       store8(a.dz + r * a.W + j0, du);
       if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
@@ -1123,9 +1169,18 @@ inline bool smallc1_supported(int Cin, int Cout, int Kt) {
 }
 template <class T>
 inline void launch_smallc1_gate_wgrad(const SmallCArgs<T>& a, int ctas, cudaStream_t s) {
-  if (a.Kt == 2) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 2>), ctas, 256, 0, s, a);
-  else if (a.Kt == 3) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3>), ctas, 256, 0, s, a);
-  else STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 4>), ctas, 256, 0, s, a);
+#define STGCN_SC1B(ACTV) do { \
+    if (a.Kt == 2) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 2, ACTV>), ctas, 256, 0, s, a); \
+    else if (a.Kt == 3) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3, ACTV>), ctas, 256, 0, s, a); \
+    else STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 4, ACTV>), ctas, 256, 0, s, a); } while (0)
+  switch (a.act) {
+    case STGCN_ACT_GLU: STGCN_SC1B(STGCN_ACT_GLU); break;
+    case STGCN_ACT_GTU: STGCN_SC1B(STGCN_ACT_GTU); break;
+    case STGCN_ACT_RELU: STGCN_SC1B(STGCN_ACT_RELU); break;
+    case STGCN_ACT_SILU: STGCN_SC1B(STGCN_ACT_SILU); break;
+    default: STGCN_SC1B(STGCN_ACT_LINEAR); break;
+  }
+#undef STGCN_SC1B
 }
 
 template <class T>
@@ -1369,6 +1424,69 @@ __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w,
   }
 }
 
+// bf16 single-read variant: the group (M <= 512 * 8 * NCH elements) is loaded ONCE into registers (NCH 16-byte chunks
+// per thread, all loads in flight together) and the mean / variance / normalise passes run from there -- the generic
+// kernel above re-reads the group twice through L1/L2 with a block reduction between the passes (2.4 TB/s measured).
+// Same element-to-thread mapping and summation order as ln_fwd_kernel<bf16, 8>: bit-identical results.
+__device__ __forceinline__ void unpack8(const uint4& a, float* v) {
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <int NCH>
+__global__ void __launch_bounds__(512) ln_fwd_cached_kernel(const bf16* x, const float* w, const float* b, bf16* y,
+                                                            float* mean, float* rstd, int M, float eps, int training,
+                                                            float p, uint64_t seed) {
+  __shared__ float red[32];
+  const long long g = blockIdx.x;
+  const bf16* xp = x + g * M;
+  uint4 xr[NCH];
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = (c * 512 + (int)threadIdx.x) * 8;
+    xr[c] = make_uint4(0, 0, 0, 0);
+    if (i < M) xr[c] = *reinterpret_cast<const uint4*>(xp + i);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if ((c * 512 + (int)threadIdx.x) * 8 < M) {
+      float v[8]; unpack8(xr[c], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
+  }
+  const float mu = block_sum(s, red) / M;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if ((c * 512 + (int)threadIdx.x) * 8 < M) {
+      float v[8]; unpack8(xr[c], v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const float d = v[k] - mu; q += d * d; }
+    }
+  }
+  const float var = block_sum(q, red) / M;
+  const float rs = rsqrtf(var + eps);
+  if (threadIdx.x == 0) { mean[g] = mu; rstd[g] = rs; }
+  const bool drop = training && p > 0.f;
+  const float keep_scale = drop ? 1.f / (1.f - p) : 1.f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int i = (c * 512 + (int)threadIdx.x) * 8;
+    if (i < M) {
+      float v[8], wv[8], bv[8], o[8];
+      unpack8(xr[c], v); load8(w + i, wv); load8(b + i, bv);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        o[k] = (v[k] - mu) * rs * wv[k] + bv[k];
+        if (drop) o[k] = dropout_keep(seed, (uint64_t)(g * M + i + k), p) ? o[k] * keep_scale : 0.f;
+      }
+      store8(y + g * M + i, o);
+    }
+  }
+}
+
 template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
                                                      const float* rstd, T* dx, int M, int training, float p,
@@ -1510,8 +1628,14 @@ __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
   block_sum2(s1, s2, red);
   if (threadIdx.x == 0) { a.sums[2 * g] = s1 / (float)a.M; a.sums[2 * g + 1] = s2 / (float)a.M; }
 }
+#ifndef STGCN_LNGATE_MINB
+#define STGCN_LNGATE_MINB 4
+#endif
+#ifndef STGCN_LNGATE_UNROLL
+#define STGCN_LNGATE_UNROLL 2
+#endif
 template <class T, int ACT>
-__global__ void __launch_bounds__(128) ln_gate_bwd_kernel(LnGateArgs<T> a) {
+__global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnGateArgs<T> a) {
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch * 8 >= a.M) return;
@@ -1526,7 +1650,8 @@ __global__ void __launch_bounds__(128) ln_gate_bwd_kernel(LnGateArgs<T> a) {
   for (int k = 0; k < 8; ++k) { aw[k] = 0.f; ab[k] = 0.f; }
   const long long g0 = (long long)blockIdx.y * a.groups_per_cta;
   const long long g1 = min(a.G, g0 + a.groups_per_cta);
-#pragma unroll 2
+  constexpr int kUnroll = STGCN_LNGATE_UNROLL;
+#pragma unroll kUnroll
   for (long long g = g0; g < g1; ++g) {
     const float mu = a.mean[g], rs = a.rstd[g], s1 = a.sums[2 * g], s2 = a.sums[2 * g + 1];
     const long long r = g * a.N + n;
@@ -1550,7 +1675,7 @@ __global__ void __launch_bounds__(128) ln_gate_bwd_kernel(LnGateArgs<T> a) {
       if (has_res) zp[k] += res[k];
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) act_bwd(ACT, zp[k], gated ? zq[k] : 0.f, dh[k], du[k], dq[k]);
+    for (int k = 0; k < 8; ++k) act_bwd<kFastAct<T>>(ACT, zp[k], gated ? zq[k] : 0.f, dh[k], du[k], dq[k]);
     store8(a.dz + r * a.W + c0, du);
     if (gated) store8(a.dz + r * a.W + Cout + c0, dq);
   }

@@ -130,7 +130,11 @@ __device__ __forceinline__ void cheb_issue_mix(uint32_t buf, uint32_t w_img, uin
 // dbg[slot*72 + item*24 + e]: e = 0 fill begin, 1 fill landed, 2+j MMA stage j issued, 8+2j / 9+2j epilogue stage j
 // begin / end, 16+j / 20+j forward hop j: waits done / instructions issued; dbg[150] = kernel start, dbg[151] = operator
 // resident.
+#ifdef STGCN_TIMELINE
 #define CHEB_STAMP(e) do { if (dbg_on && it < 3) p.dbg[slot * 72 + it * 24 + (e)] = gtime(); } while (0)
+#else
+#define CHEB_STAMP(e) do { (void)dbg_on; } while (0)
+#endif
 
 // Shared-memory plane buffers of one slot (each GB groups x rows_pad rows x 32 B):
 //   forward : [0],[1] = x_0 of even / odd items (filled one item ahead), [1 + k] = x_k (k >= 1)

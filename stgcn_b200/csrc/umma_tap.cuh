@@ -12,14 +12,19 @@
 // shared memory for the life of the CTA.  Two TMEM accumulators are ping-ponged between the MMA
 // issuer and the epilogue warps.
 //
-// Warp roles (320 threads): warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one
-// lane) + TMEM allocation, warps 2..9 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31: one
-// vertex row per thread; the two warps of a lane quarter take alternate 16-column chunks).
+// Warp roles: warp 0 = TMA producer (one elected lane), warp 1 = MMA issuer (one lane) + TMEM
+// allocation, warps 2..2+kTapEpiWarps-1 = epilogue (warp w reads TMEM lanes 32*(w%4)..+31: one vertex row
+// per thread; the kTapEpiGroups warps of a lane quarter take alternate 16-column chunks, or alternate
+// tiles when the output is narrow), then kTapProducers-1 extra cp.async producer warps.  The epilogue is
+// instruction-issue bound (~15 instructions per output element), so it gets as many warps as the register
+// file allows: 16 (4 per scheduler) instead of the 8 that left 3/4 of the issue slots empty.
 //
 // Epilogues:
 //   EPI_LINEAR: out = acc + bias (+ aux rows: residual / residual-gradient), stored bf16
 //   EPI_GATE  : z = acc + bias stored (saved for backward); h = act(z, residual) stored
 #pragma once
+#include <cstdlib>
+
 #include "umma.cuh"
 #include "simt_kernels.cuh"
 
@@ -31,8 +36,16 @@ enum { EPI_LINEAR = 0, EPI_GATE = 1 };
 constexpr int kMaxStages = 12;
 constexpr int kCpDepth = 6;            // cp.async producer: slices published this many groups late (copies in flight)
 constexpr int kTapThreads = 192;       // gso / wgrad kernels: 4 epilogue warps
-constexpr int kTapEpiWarps = 8;        // tap kernel: two epilogue warps per TMEM lane quarter (column halves)
-constexpr int kTapProducers = 4;        // cp.async producer warps for narrow inputs: warp 0 and warps 10..12
+#ifndef STGCN_TAP_EPI_WARPS
+#define STGCN_TAP_EPI_WARPS 16
+#endif
+constexpr int kTapEpiWarps = STGCN_TAP_EPI_WARPS;   // tap kernel: kTapEpiGroups epilogue warps per TMEM lane quarter
+constexpr int kTapEpiGroups = kTapEpiWarps / 4;     // a group = 4 warps covering the 128 TMEM lanes
+static_assert(kTapEpiWarps % 4 == 0 && kTapEpiGroups >= 1 && kTapEpiGroups <= 4, "epilogue warps come in groups of 4");
+#ifndef STGCN_TAP_PRODUCERS
+#define STGCN_TAP_PRODUCERS 4
+#endif
+constexpr int kTapProducers = STGCN_TAP_PRODUCERS;  // cp.async producer warps for narrow inputs: warp 0 and the warps after the epilogue
 constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps + 32 * (kTapProducers - 1);
 
 struct TapParams {
@@ -48,9 +61,16 @@ struct TapParams {
   int ld_out, co_valid;
   bf16* out_z;                // gate: z [rows_out, W]
   int n_items, n_node_tiles;
+  // Output-time split: a work item is (sample, 128-vertex tile, time chunk): output steps [ts*t_chunk, +t_chunk).
+  // 512 (sample, tile) items over 148 CTAs quantise to 4 rounds for 3.46 rounds of work; halving the items'
+  // length costs Kt-1 re-loaded slices per cut and gets 7 rounds of half the length (13% fewer tiles per CTA).
+  int n_tsplit, t_chunk;
   int relu;                   // linear epilogue: clamp at 0 after bias/aux
   int NB, nb_shift;           // TMEM accumulator ring depth (power of two) and its log2
-  int split_tiles;            // 1: the two epilogue warp groups take alternate tiles (narrow outputs); 0: alternate column chunks
+  // epilogue work split: the kTapEpiGroups warp groups form col_parts x tile_parts; group g handles the 16-column
+  // chunks {g % col_parts, + col_parts, ...} of the tiles with acc_cnt % tile_parts == g / col_parts (narrow outputs
+  // alternate tiles instead of columns)
+  int col_parts, tile_parts;
   // output staging: tiles are assembled in 128B-swizzled shared memory and written with TMA bulk tensor stores
   // (per-thread 32-byte stores to 128 different rows cost ~32 LSU wavefronts per instruction and made the epilogue
   // the bottleneck: 3.6 us per 128x128 tile, profiles/r01_bf16_summary.md)
@@ -85,7 +105,7 @@ __device__ __forceinline__ void load16_bf16(const bf16* src, float* v) {
   }
 }
 // epilogue math: MUFU-based (ex2 / rcp / tanh.approx), accurate far beyond the bf16 the results are stored in
-__device__ __forceinline__ float fast_sigmoid(float x) { return sigmoidf_(x); }   // branch-free ex2/rcp.approx
+__device__ __forceinline__ float fast_sigmoid(float x) { return sigmoid_tanh_(x); }   // one MUFU.TANH (common.cuh)
 __device__ __forceinline__ float fast_tanh(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -112,7 +132,13 @@ __device__ __forceinline__ unsigned long long gtime() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+// Timeline stamps are compiled in only with -DSTGCN_TIMELINE (tools/build_variants.sh): their predicate chains cost
+// ~15 instructions per tile per warp in the issue-bound epilogue.
+#ifdef STGCN_TIMELINE
 #define STGCN_STAMP(i) do { if (dbg_on) p.dbg[i] = gtime(); } while (0)
+#else
+#define STGCN_STAMP(i) do { (void)dbg_on; } while (0)
+#endif
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
   uint4 a;
@@ -128,6 +154,12 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& a, float* v) {
 __device__ __forceinline__ void stage_store8(uint8_t* sub, int row, int c, const uint4& v) {
   *reinterpret_cast<uint4*>(sub + row * 128 + (((c >> 3) ^ (row & 7)) << 4)) = v;
 }
+// same through a 32-bit shared-window address: st.shared instead of a generic 64-bit-addressed store (the generic form
+// cost ~10 integer instructions per store in the epilogue loop, which is instruction-issue bound)
+__device__ __forceinline__ void stage_store8_s(uint32_t sub, int row, int c, const uint4& v) {
+  const uint32_t a = sub + row * 128 + (((c >> 3) ^ (row & 7)) << 4);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void add_bias8(float* v, const float* bias_smem) {
   const float4 b0 = reinterpret_cast<const float4*>(bias_smem)[0], b1 = reinterpret_cast<const float4*>(bias_smem)[1];
   v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
@@ -141,6 +173,21 @@ __device__ __forceinline__ void stage_store16(uint8_t* sub, int row, int c, cons
   uint8_t* r = sub + row * 128;
   *reinterpret_cast<uint4*>(r + ((cc ^ sw) << 4)) = a;
   *reinterpret_cast<uint4*>(r + (((cc + 1) ^ sw) << 4)) = b;
+}
+
+// work item -> (sample, vertex tile origin, output steps [t_begin, t_end), source slices [s_lo, s_hi))
+struct TapItem { int b, n0, t_begin, t_end, s_lo, s_hi; };
+__device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
+  TapItem it;
+  const int ts = item % p.n_tsplit, rest = item / p.n_tsplit;
+  it.b = rest / p.n_node_tiles;
+  it.n0 = (rest - it.b * p.n_node_tiles) * 128;
+  it.t_begin = ts * p.t_chunk;
+  it.t_end = it.t_begin + p.t_chunk < p.T_out ? it.t_begin + p.t_chunk : p.T_out;
+  const int lo = it.t_begin + p.t0, hi = it.t_end + p.t0 + p.Kt - 1;     // slices [lo, hi) are touched
+  it.s_lo = lo > 0 ? lo : 0;
+  it.s_hi = hi < p.T_src ? hi : p.T_src;
+  return it;
 }
 
 template <int EPI, int ACT>
@@ -162,7 +209,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
   uint32_t ncols = 32;
   while ((int)ncols < p.NB * p.CoT) ncols <<= 1;
-  const int epi_arrivals = p.split_tiles ? kTapEpiWarps / 2 : kTapEpiWarps;
+  const int epi_arrivals = 4 * p.col_parts;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -194,8 +241,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint32_t g = 0;
         const uint32_t ablk = 128u * p.KB * 2;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-          const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
-          for (int ti = 0; ti < p.T_src; ++ti, ++g) {
+          const TapItem wi = tap_item(p, item);
+          const int b = wi.b, n0 = wi.n0;
+          for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g) {
             const uint32_t s = g % p.S, ph = (g / p.S) & 1;
             if (g == 24) STGCN_STAMP(25);
             mbar_wait(&empty[s], ph ^ 1);
@@ -217,8 +265,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t g = 0;
       int pending = -1;                                  // this warp's issued-but-unpublished slice (stage index)
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
-        for (int ti = 0; ti < p.T_src; ++ti, ++g) {
+        const TapItem wi = tap_item(p, item);
+        const int b = wi.b, n0 = wi.n0;
+        for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g) {
           if ((int)(g % kTapProducers) != prod_idx) continue;
           const uint32_t s = g % p.S, ph = (g / p.S) & 1;
           if (g == 24) STGCN_STAMP(25);
@@ -264,7 +313,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       STGCN_STAMP(2);
       uint32_t g_base = 0, acc_cnt = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
+        const TapItem wi = tap_item(p, item);
+        for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
           const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
           if (acc_cnt == 8) STGCN_STAMP(16);
           mbar_wait(&tempty[ab], aph ^ 1);
@@ -275,7 +325,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           for (int j = 0; j < p.Kt; ++j) {
             const int ti = t_o + j + p.t0;
             if (ti < 0 || ti >= p.T_src) continue;
-            const uint32_t g = g_base + ti, s = g % p.S, ph = (g / p.S) & 1;
+            const uint32_t g = g_base + (ti - wi.s_lo), s = g % p.S, ph = (g / p.S) & 1;
             mbar_wait(&full[s], ph);
             if (acc_cnt == 0) STGCN_STAMP(3);
             if (acc_cnt == 8) STGCN_STAMP(8);
@@ -296,34 +346,41 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           mma_commit(&tfull[ab]);
           if (acc_cnt == 8) STGCN_STAMP(23);
           // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
-          const int t_rel = t_o + p.t0;
-          if (t_rel >= 0 && t_rel < p.T_src) mma_commit(&empty[(g_base + t_rel) % p.S]);
-          if (t_o == p.T_out - 1)
-            for (int ti = (t_rel + 1 > 0 ? t_rel + 1 : 0); ti < p.T_src; ++ti) mma_commit(&empty[(g_base + ti) % p.S]);
+          const int t_rel = t_o + p.t0;                      // t_rel >= 0 implies t_rel >= s_lo; t_rel < s_hi always
+          if (t_rel >= 0 && t_rel < p.T_src) mma_commit(&empty[(g_base + (t_rel - wi.s_lo)) % p.S]);
+          if (t_o == wi.t_end - 1)
+            for (int ti = (t_rel + 1 > wi.s_lo ? t_rel + 1 : wi.s_lo); ti < wi.s_hi; ++ti)
+              mma_commit(&empty[(g_base + (ti - wi.s_lo)) % p.S]);
           if (acc_cnt == 8) STGCN_STAMP(24);
         }
-        g_base += p.T_src;
+        g_base += wi.s_hi - wi.s_lo;
       }
     }
   } else {
     // =========================== epilogue warps ==========================
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;           // which alternate 16-column chunks this warp handles
+    const int grp = (warp - 2) >> 2;            // warp group (4 warps = 128 TMEM lanes)
+    const int cpart = grp % p.col_parts, tpart = grp / p.col_parts;
     const int row = q * 32 + lane;
     uint32_t acc_cnt = 0;
+    // first aux chunk of the NEXT tile, requested while the current tile is still being finished: loaded at the top of
+    // its own tile the L2 round trip (~0.3 us of a ~2 us tile) sat exposed in front of every tile's column loop
+    uint4 rpre = make_uint4(0, 0, 0, 0);
+    bool have_pre = false;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int b = item / p.n_node_tiles, n0 = (item % p.n_node_tiles) * 128;
+      const TapItem wi = tap_item(p, item);
+      const int b = wi.b, n0 = wi.n0;
       const int n = n0 + row;
       const bool valid = n < p.N;
-      for (int t_o = 0; t_o < p.T_out; ++t_o, ++acc_cnt) {
-        if (p.split_tiles && (int)(acc_cnt & 1) != half) continue;      // narrow outputs: warp groups alternate tiles
+      for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
+        if (p.tile_parts > 1 && (int)(acc_cnt % p.tile_parts) != tpart) continue;   // warp groups alternate tiles
         const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
         const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
         const int t_aux = t_o + p.aux_dt;
         const bool aux_ok = p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
         const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
-        const int cfirst = p.split_tiles ? 0 : half * 16;
-        const int cstep = p.split_tiles ? 16 : 32;
+        const int cfirst = cpart * 16;
+        const int cstep = p.col_parts * 16;
         // Columns are processed in 8-wide groups by a ROLLED loop: the fully unrolled 16-wide version was ~60 KB of
         // SASS and thrashed the instruction caches (144 cycles per element, profiles/r01_bf16_summary.md).  The
         // residual / aux operand of the next group is fetched one iteration ahead.
@@ -331,13 +388,16 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int width = EPI == EPI_LINEAR ? p.CoT : p.Cout;
         const int n_aux = aux_row ? p.aux_cols - cbase : 0;         // aux covers local columns [0, n_aux)
         uint4 rnext = make_uint4(0, 0, 0, 0);
-        if (cfirst < n_aux) rnext = *reinterpret_cast<const uint4*>(aux_row + cbase + cfirst);
+        if (cfirst < n_aux) rnext = have_pre ? rpre : *reinterpret_cast<const uint4*>(aux_row + cbase + cfirst);
+        have_pre = false;
         uint8_t* stg = nullptr;
+        uint32_t stg_s = 0;
         if (p.store_tma) {
           // the staging buffer used nbuf tiles ago must have been read out by its TMA store
           if (threadIdx.x == 64) { if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
           named_bar_sync(1, 32 * kTapEpiWarps);
-          stg = smem + p.stage_off + (size_t)(acc_cnt % p.nbuf) * p.stage_bytes;
+          stg = smem + p.stage_off + (size_t)(p.nbuf == 2 ? (acc_cnt & 1) : 0) * p.stage_bytes;      // nbuf is 1 or 2
+          stg_s = smem_u32(stg);
         }
         mbar_wait(&tfull[ab], aph);
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(4);
@@ -378,7 +438,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               for (int i = 0; i < 8; ++i) zp[i] = fmaxf(zp[i], 0.f);
             }
             const uint4 o = pack8_bf16(zp);
-            if (stg) stage_store8(stg + (size_t)(cc >> 6) * 16384, row, cc & 63, o);
+            if (stg) stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, o);
             else if (valid && co0 + cc < p.co_valid) *reinterpret_cast<uint4*>(p.out + orow * p.ld_out + co0 + cc) = o;
           } else {
             float h[8];
@@ -386,9 +446,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>(has_aux ? zp[i] + av[i] : zp[i], zq[i]);
             const uint4 op = pack8_bf16(zp), oh = pack8_bf16(h);
             if (stg) {
-              stage_store8(stg + (size_t)(cc >> 6) * 16384, row, cc & 63, op);
-              if (gated) stage_store8(stg + (size_t)((p.Cout + cc) >> 6) * 16384, row, cc & 63, pack8_bf16(zq));
-              stage_store8(stg + (size_t)(p.nZ + (cc >> 6)) * 16384, row, cc & 63, oh);
+              stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, op);
+              if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + cc) >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
+              stage_store8_s(stg_s + (uint32_t)(p.nZ + (cc >> 6)) * 16384u, row, cc & 63, oh);
             } else if (valid) {
               *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = op;
               if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
@@ -397,6 +457,22 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
         }
         if (warp == 2 && acc_cnt == 8) STGCN_STAMP(14);
+#ifndef STGCN_TAP_NO_AUX_PREFETCH
+        if (p.tile_parts == 1 && p.aux != nullptr && cfirst < p.aux_cols - cbase) {
+          int nt = t_o + 1, nb = b, nn = n;
+          bool more = true;
+          if (nt >= wi.t_end) {
+            const int nitem = item + (int)gridDim.x;
+            more = nitem < p.n_items;
+            if (more) { const TapItem w2 = tap_item(p, nitem); nb = w2.b; nn = w2.n0 + row; nt = w2.t_begin; }
+          }
+          const int ta = nt + p.aux_dt;
+          if (more && ta >= 0 && ta < p.T_aux && nn < p.N) {
+            rpre = *reinterpret_cast<const uint4*>(p.aux + (((long long)nb * p.T_aux + ta) * p.N + nn) * p.C_aux + cbase + cfirst);
+            have_pre = true;
+          }
+        }
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -561,12 +637,38 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     nb = nb >= 8 ? 8 : (nb >= 4 ? 4 : 2);
     p.NB = nb; p.nb_shift = nb == 8 ? 3 : (nb == 4 ? 2 : 1);
     const int width = q.epi == EPI_GATE ? q.Cout : pl.CoT;
-    p.split_tiles = width < 32 ? 1 : 0;
-    if (p.split_tiles) p.store_tma = 0;
+    // TMA-store staging synchronises ALL epilogue warps per tile, so staged tiles are split by columns only
+    // (staged widths are multiples of 64 >= 16 * kTapEpiGroups); otherwise the widest column split that divides
+    // the group count, the remaining factor alternating tiles
+    int cp = 1;
+    for (int d = 1; d <= kTapEpiGroups; ++d)
+      if (kTapEpiGroups % d == 0 && d * 16 <= width) cp = d;
+    if (p.store_tma && cp != kTapEpiGroups) p.store_tma = 0;
+    p.col_parts = cp; p.tile_parts = kTapEpiGroups / cp;
   }
   p.n_node_tiles = (q.N + 127) / 128;
-  p.n_items = q.B * p.n_node_tiles;
-  int gx = p.n_items < sm_count() / pl.nCoT ? p.n_items : sm_count() / pl.nCoT;
+  const int ctas = sm_count() / pl.nCoT > 0 ? sm_count() / pl.nCoT : 1;
+  {   // time split (see TapParams): minimise [tiles per CTA x bytes written per tile + slices per CTA x bytes per slice]
+    static const char* force = std::getenv("STGCN_TAP_TSPLIT");        // A/B knob: forced split count
+    const long long base_items = (long long)q.B * p.n_node_tiles;
+    const long long out_b = 256LL * ((q.epi == EPI_GATE ? q.Co + q.Cout : pl.CoT) > 32 ? (q.epi == EPI_GATE ? q.Co + q.Cout : pl.CoT) : 32);
+    const long long in_b = 256LL * q.Cin;
+    long long best = -1;
+    p.n_tsplit = 1; p.t_chunk = q.T_out;
+    for (int ns = 1; ns <= 4 && ns <= q.T_out; ++ns) {
+      const int chunk = (q.T_out + ns - 1) / ns, ns_eff = (q.T_out + chunk - 1) / chunk;
+      if (ns_eff != ns) continue;
+      if (force && std::atoi(force) > 0 && std::atoi(force) != ns && std::atoi(force) <= q.T_out) continue;
+      const long long items = base_items * ns, g = items < ctas ? items : ctas;
+      const long long rounds = (items + g - 1) / g;
+      int slices = chunk + q.Kt - 1;
+      if (slices > q.T_src) slices = q.T_src;
+      const long long cost = rounds * (chunk * out_b + slices * in_b);
+      if (best < 0 || cost < best) { best = cost; p.n_tsplit = ns; p.t_chunk = chunk; }
+    }
+  }
+  p.n_items = q.B * p.n_node_tiles * p.n_tsplit;
+  int gx = p.n_items < ctas ? p.n_items : ctas;
   if (gx < 1) gx = 1;
   dim3 grid(gx, pl.nCoT);
   const char* kname = q.epi == EPI_GATE ? "umma_tap_kernel<EPI_GATE>" : "umma_tap_kernel<EPI_LINEAR>";

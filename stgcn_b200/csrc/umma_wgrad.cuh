@@ -21,6 +21,9 @@ namespace umma {
 struct WgradParams {
   int B, N, T_in, T_out, Kt, Cin, W;
   int Sx, Sz, n_items, n_chunks;
+  // time split (as in umma_tap.cuh): item = (sample, vertex chunk, output steps [ts*t_chunk, +t_chunk)); the partial sums
+  // all land in the same TMEM accumulators, so a cut only costs the Kt-1 re-loaded X slices
+  int n_tsplit, t_chunk;
   uint32_t x_bytes, z_bytes, b_swz, b_sbo, b_kadv;
   float* dwt;
   int want_bias;
@@ -93,17 +96,19 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
         ++gz;
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int b = item / p.n_chunks, n0 = (item % p.n_chunks) * p.KR;
+        const int ts = item % p.n_tsplit, rest = item / p.n_tsplit;
+        const int b = rest / p.n_chunks, n0 = (rest % p.n_chunks) * p.KR;
+        const int t_begin = ts * p.t_chunk, t_end = t_begin + p.t_chunk < p.T_out ? t_begin + p.t_chunk : p.T_out;
         if (p.plane_mode) {
-          for (int t_o = 0; t_o < p.T_out; ++t_o) {
+          for (int t_o = t_begin; t_o < t_end; ++t_o) {
             for (int j = 0; j < p.Kt; ++j) load_x(t_o, b + j * p.plane_b, n0);
             load_z(t_o, b, n0);
           }
         } else {
-          for (int ti = 0; ti < p.T_in; ++ti) {
+          for (int ti = t_begin; ti < t_end + p.Kt - 1; ++ti) {
             load_x(ti, b, n0);
             const int t_o = ti - (p.Kt - 1);
-            if (t_o >= 0 && t_o < p.T_out) load_z(t_o, b, n0);
+            if (t_o >= t_begin && t_o < t_end) load_z(t_o, b, n0);
           }
         }
       }
@@ -119,13 +124,16 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       const uint64_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       uint32_t gx_base = 0, gz = 0, started = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        for (int t_o = 0; t_o < p.T_out; ++t_o, ++gz) {
+        const int ts = item % p.n_tsplit;
+        const int t_begin = ts * p.t_chunk, t_end = t_begin + p.t_chunk < p.T_out ? t_begin + p.t_chunk : p.T_out;
+        const int t_len = t_end - t_begin;
+        for (int t_r = 0; t_r < t_len; ++t_r, ++gz) {                 // t_r: output step relative to the item's first
           const uint32_t sz = gz % p.Sz, phz = (gz / p.Sz) & 1;
           mbar_wait(&zfull[sz], phz);
           tc_fence_after();
           const uint32_t a_base = smem_u32(zring + (size_t)sz * p.z_bytes);
           for (int j = 0; j < p.Kt; ++j) {
-            const uint32_t gx = gx_base + (p.plane_mode ? t_o * p.Kt + j : t_o + j), sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
+            const uint32_t gx = gx_base + (p.plane_mode ? t_r * p.Kt + j : t_r + j), sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
             mbar_wait(&xfull[sx], phx);
             tc_fence_after();
             const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
@@ -148,14 +156,14 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
           }
           mma_commit(&zempty[sz]);
           if (p.plane_mode) {
-            for (int j = 0; j < p.Kt; ++j) mma_commit(&xempty[(gx_base + t_o * p.Kt + j) % p.Sx]);
+            for (int j = 0; j < p.Kt; ++j) mma_commit(&xempty[(gx_base + t_r * p.Kt + j) % p.Sx]);
           } else {
-            mma_commit(&xempty[(gx_base + t_o) % p.Sx]);
-            if (t_o == p.T_out - 1)
-              for (int ti = p.T_out; ti < p.T_in; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
+            mma_commit(&xempty[(gx_base + t_r) % p.Sx]);
+            if (t_r == t_len - 1)
+              for (int ti = t_len; ti < t_len + p.Kt - 1; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
           }
         }
-        gx_base += p.plane_mode ? p.T_out * p.Kt : p.T_in;
+        gx_base += p.plane_mode ? t_len * p.Kt : t_len + p.Kt - 1;
       }
       mma_commit(&done);
     }
@@ -425,7 +433,25 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
   WgradParams p{};
   p.B = B; p.N = N; p.T_in = T_in; p.T_out = T_out; p.Kt = Kt; p.Cin = Cin; p.W = W;
   p.KR = kWgradKR;
-  p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + kWgradKR - 1) / kWgradKR; p.n_items = B * p.n_chunks;
+  p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + kWgradKR - 1) / kWgradKR;
+  {   // time split: minimise rounds x bytes loaded per item (dZ slices + X slices incl. the Kt-1 re-loaded ones)
+    static const char* force = std::getenv("STGCN_WGRAD_TSPLIT");      // A/B knob: forced split count
+    const long long base_items = (long long)B * p.n_chunks;
+    const int ctas = sm_count() / pl.nMT > 0 ? sm_count() / pl.nMT : 1;
+    long long best = -1;
+    p.n_tsplit = 1; p.t_chunk = T_out;
+    for (int ns = 1; ns <= 4 && ns <= T_out; ++ns) {
+      const int chunk = (T_out + ns - 1) / ns, ns_eff = (T_out + chunk - 1) / chunk;
+      if (ns_eff != ns) continue;
+      if (force && std::atoi(force) > 0 && std::atoi(force) != ns && std::atoi(force) <= T_out) continue;
+      const long long items = base_items * ns, g = items < ctas ? items : ctas;
+      const long long rounds = (items + g - 1) / g;
+      const long long xs_n = plane_mode ? (long long)chunk * Kt : chunk + Kt - 1;
+      const long long cost = rounds * (chunk * (long long)(W < 128 ? W : 128) + xs_n * Cin);
+      if (best < 0 || cost < best) { best = cost; p.n_tsplit = ns; p.t_chunk = chunk; }
+    }
+  }
+  p.n_items = B * p.n_chunks * p.n_tsplit;
   p.x_bytes = pl.x_bytes; p.z_bytes = pl.z_bytes;
   p.b_swz = xcw == 64 ? SWZ_128B : (xcw == 32 ? SWZ_64B : SWZ_32B);
   p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
