@@ -12,7 +12,11 @@
  *   - All pointers are DEVICE pointers owned by the caller (workspace and saved-state
  *     buffers included).  The library allocates no device memory.
  *   - Work is enqueued asynchronously on the given stream (a cudaStream_t passed as
- *     void*); no call synchronises the host.
+ *     void*); no call synchronises the host.  The block-level calls (stgcn_stblock_*,
+ *     stgcn_outblock_*) also use internal helper streams for parameter-only preparation and
+ *     gradient scatters; these are forked from and joined back into the given stream inside
+ *     the call (events), so ordering on the given stream -- and CUDA-graph capture of it --
+ *     behave as if everything ran there.
  *   - Activations cross this boundary channels-last: a tensor the reference sees as
  *     (B, C, T, N) is stored as contiguous (B, T, N, C).  This is the memory layout the
  *     reference's own STConvBlock returns (a permuted view of a (B,T,N,C) buffer,

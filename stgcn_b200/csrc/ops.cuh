@@ -18,10 +18,57 @@ namespace ops {
 
 using namespace simt;
 
+// Helper streams of the block-level entry points (stblock / outblock).  Everything that depends only on PARAMETERS --
+// weight re-layouts, the bf16 operator image, zeroing of gradient accumulators -- is enqueued on `p`, forked from the
+// caller's stream at entry, so it runs while earlier compute kernels are still busy (the persistent tcgen05 kernels leave
+// room for a 256-thread CTA on every SM); gradient scatters / partial reductions go to `q` behind the kernel that
+// produced them.  Both are joined back into the caller's stream before the entry point returns, so the caller still sees
+// plain stream semantics and the whole call is capturable in a CUDA graph.  A dozen 2-3 us dependent launches per layer
+// on the critical path were ~7% of the bf16 step.
+struct Side {
+  static constexpr int kEvents = 64;
+  cudaStream_t p = nullptr, q = nullptr;
+  cudaEvent_t ev[kEvents];
+  int next = 0;
+  bool q_forked = false;     // q joined this call's work (a capturing stream must not wait on a never-forked one)
+  cudaEvent_t event() { cudaEvent_t e = ev[next]; next = (next + 1) % kEvents; return e; }
+  static Side* get() {                     // one per host thread (forward and autograd-backward threads differ)
+    static thread_local Side* s = nullptr;
+    static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;      // A/B switch for profiling
+    if (off) return nullptr;
+    if (!s) {
+      s = new Side();
+      STGCN_CUDA(cudaStreamCreateWithFlags(&s->p, cudaStreamNonBlocking));
+      STGCN_CUDA(cudaStreamCreateWithFlags(&s->q, cudaStreamNonBlocking));
+      for (int i = 0; i < kEvents; ++i) STGCN_CUDA(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
+    }
+    return s;
+  }
+};
+
 struct Ctx {
   Arena& ws;
   cudaStream_t stream;
+  Arena* keep = nullptr;     // buffers that must outlive the op that fills them (prepared weights, gradient accumulators)
+  Side* side = nullptr;      // null: everything on `stream`
   bool dry() const { return ws.dry; }
+  Arena& K() const { return keep ? *keep : ws; }
+  cudaStream_t ps() const { return side ? side->p : stream; }      // parameter-only preparation
+  cudaStream_t qs() const { return side ? side->q : stream; }      // post-processing of gradients
+  static void order(cudaStream_t first, cudaStream_t then, Side* sd) {
+    cudaEvent_t e = sd->event();
+    STGCN_CUDA(cudaEventRecord(e, first));
+    STGCN_CUDA(cudaStreamWaitEvent(then, e, 0));
+  }
+  void begin() const { if (side && !dry()) { order(stream, side->p, side); side->q_forked = false; } }   // p sees the caller's prior work
+  void prep_ready() const { if (side && !dry()) order(side->p, stream, side); }       // stream waits for the prep enqueued so far
+  void post_after() const { if (side && !dry()) { order(stream, side->q, side); side->q_forked = true; } }   // q waits for the compute so far
+  void end() const {
+    if (side && !dry()) {
+      order(side->p, stream, side);
+      if (side->q_forked) order(side->q, stream, side);
+    }
+  }
 };
 
 inline void zero(float* p, size_t n, cudaStream_t s) {
@@ -67,11 +114,12 @@ template <class T>
 inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_params& p, T* y, T* z_saved, Ctx c) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
-  float* wt = c.ws.take<float>((size_t)d.Kt * d.c_in * g.W);
-  float* bias = c.ws.take<float>(g.W);
-  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * d.c_in * g.W : 0);
+  float* wt = c.K().take<float>((size_t)d.Kt * d.c_in * g.W);
+  float* bias = c.K().take<float>(g.W);
+  simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * d.c_in * g.W : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.conv_w && p.conv_b, STGCN_E_INVALID, "tconv: missing conv weight/bias");
+  const cudaStream_t ps = c.ps();          // weight re-layouts depend on parameters only (Ctx)
   if constexpr (std::is_same<T, simt::bf16>::value) {
     // ---- tcgen05 path: conv + bias + gate/residual fused in one kernel (umma_tap.cuh)
     umma::TapProblem q{};
@@ -84,32 +132,34 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
     if (d.B > 0 && umma::tap_supported(q)) {
       // window-ordered K-major weights: w[(j*W + o)*c_in + c] = conv_w[o][c][j] (+ align fold on tap Kt-1)
       if (!g.folded) {
-        GatherBatch gb(c.stream);
+        GatherBatch gb(ps);
         gb.add(p.conv_w, wbf, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt);
         gb.add(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1);
       } else {
         STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "tconv: c_in > c_out needs align conv parameters");
-        launch_gather3(p.conv_w, wt, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
-        launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
-        launch_gather3(p.align_w, wt + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
-        launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
+        launch_gather3(p.conv_w, wt, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, ps);
+        launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, ps);
+        launch_gather3(p.align_w, wt + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, ps);
+        launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, ps);
         long long nw = (long long)d.Kt * g.W * d.c_in;
-        STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wt, wbf, nw);
+        STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, ps, (const float*)wt, wbf, nw);
       }
+      c.prep_ready();
       umma::launch_tap(q, c.stream);
       return;
     }
   }
   // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]
-  launch_gather3(p.conv_w, wt, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
-  launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
+  launch_gather3(p.conv_w, wt, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, ps);
+  launch_gather3(p.conv_b, bias, 1, 1, g.W, 0, 0, 0, 1, 0, ps);
   if (g.folded) {
     STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "tconv: c_in > c_out needs align conv parameters");
     // tap Kt-1, linear half: wt[((Kt-1)*c_in + c)*W + o] += align_w[o][c]  
-    STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, c.stream,
+    STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, ps,
                  wt + (size_t)(d.Kt - 1) * d.c_in * g.W, g.W, p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
-    launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, c.stream);
+    launch_gather3(p.align_b, bias, 1, 1, d.c_out, 0, 0, 0, 1, 1, ps);
   }
+  c.prep_ready();
   if (g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt)) {
     // first-layer special (tiny K): fused conv + bias + gate, one pass
     SmallCArgs<T> sa{};
@@ -160,10 +210,11 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
   T* dz = dz_ready ? dz_ready : c.ws.take<T>((size_t)g.rows_out * g.W);
-  float* dwt = c.ws.take<float>((size_t)(Kw + 1) * g.W);
-  float* wd = c.ws.take<float>((size_t)d.Kt * g.W * d.c_in);
-  float* bias_f = c.ws.take<float>(g.W);
-  simt::bf16* wdbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
+  float* dwt = c.K().take<float>((size_t)(Kw + 1) * g.W);
+  float* wd = c.K().take<float>((size_t)d.Kt * g.W * d.c_in);
+  float* wfw = c.K().take<float>((size_t)d.Kt * g.W * d.c_in);        // forward-layout weights (z recompute of the first layer)
+  float* bias_f = c.K().take<float>(g.W);
+  simt::bf16* wdbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
   const long long sc_rpc = std::max<long long>(64, (g.rows_out + 148 * 8 - 1) / (148 * 8));
   const int sc_ctas = g.rows_out > 0 ? ceil_div(g.rows_out, sc_rpc) : 0;
   float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows_out, Kw + 1, g.W), (size_t)sc_ctas * (Kw + 1) * g.W));
@@ -171,10 +222,54 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
   STGCN_CHECK(!lr || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: low-rank dy only on the generic gate path");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  const bool z_skipped = smallc && smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved);   // what the forward may have done
+  // data gradient through the tcgen05 tap kernel?
+  umma::TapProblem qd{};
+  bool dgrad_umma = false;
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    if (dx) {
+      qd.in = dz; qd.w = wdbf; qd.bias = nullptr; qd.B = d.B; qd.N = d.N; qd.T_src = g.T_out; qd.T_out = d.T; qd.Kt = d.Kt;
+      qd.t0 = -(d.Kt - 1); qd.Cin = g.W; qd.Co = d.c_in; qd.epi = umma::EPI_LINEAR; qd.act = 0; qd.Cout = 0;
+      const bool explicit_res = !(g.folded || g.linear);
+      qd.aux = explicit_res ? dz : nullptr; qd.aux_dt = -(d.Kt - 1); qd.T_aux = g.T_out; qd.C_aux = g.W;
+      qd.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
+      qd.out = dx; qd.ld_out = d.c_in; qd.out_z = nullptr;
+      dgrad_umma = d.B > 0 && umma::tap_supported(qd);
+    }
+  }
+  // ---- parameter-only preparation (helper stream, Ctx): accumulator zeroing and weight re-layouts
+  const cudaStream_t ps = c.ps();
+  if (smallc || want_w) zero(dwt, (size_t)(Kw + 1) * g.W, ps);
+  if (z_skipped) {
+    // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]  (the forward's layout; c_in == 1 here)
+    launch_gather3(p.conv_w, wfw, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, ps);
+    launch_gather3(p.conv_b, bias_f, 1, 1, g.W, 0, 0, 0, 1, 0, ps);
+  }
+  if (dgrad_umma) {
+    // window-ordered weights of the transposed conv: wd[(j*c_in + c)*W + o] = conv_w[o][c][Kt-1-j]
+    if (!g.folded) {
+      launch_gather3(p.conv_w, wdbf, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, ps);
+    } else {
+      launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, ps);
+      // align conv acts at tap Kt-1, i.e. window position j = 0
+      STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, ps, wd, g.W,
+                   p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
+      long long nw = (long long)d.Kt * g.W * d.c_in;
+      STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, ps, (const float*)wd, wdbf, nw);
+    }
+  } else if (dx) {
+    // wd[(k*W + o)*c_in + c] = conv_w[o][c][k]
+    launch_gather3(p.conv_w, wd, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, ps);
+    if (g.folded)
+      launch_gather3(p.align_w, wd + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, ps);
+  }
+  c.prep_ready();
+
+  // ---- dz: gradient w.r.t. the pre-activations
   if (dz_ready) {
   } else if (smallc) {
     // first-layer special: gate backward fused with the weight gradient (dz only materialised when dx is wanted)
-    zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
     SmallCArgs<T> sa{};
     sa.x = x; sa.z = const_cast<T*>(z_saved); sa.dh = dy; sa.dz = dx ? dz : nullptr; sa.dwt = dwt; sa.rows = g.rows_out;
     sa.Cin = d.c_in; sa.Cout = d.c_out; sa.W = g.W; sa.Kt = d.Kt; sa.T_out = g.T_out; sa.T_in = d.T; sa.N = d.N;
@@ -183,14 +278,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     const int lanes = threads / d.c_out;
     sa.rows_per_cta = (int)sc_rpc;
     sa.partial = part;
-    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    const bool z_skipped = smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved);   // what the forward may have done
-    if (z_skipped) {
-      // wt[(k*c_in + c)*W + o] = conv_w[o][c][k]  (the forward's layout; c_in == 1 here)
-      launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
-      launch_gather3(p.conv_b, bias_f, 1, 1, g.W, 0, 0, 0, 1, 0, c.stream);
-      sa.wt = wd; sa.bias = bias_f; sa.skip_z = 1;
-    }
+    if (z_skipped) { sa.wt = wfw; sa.bias = bias_f; sa.skip_z = 1; }
     if (z_skipped && al16(dy) && al16(sa.dz)) {
       launch_smallc1_gate_wgrad(sa, sc_ctas, c.stream);
     } else {
@@ -217,8 +305,8 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     }
     launch_gate_any(d.act, true, ga, c.stream);
   }
+  // ---- weight gradients
   if (want_w) {
-    if (!smallc) zero(dwt, (size_t)(Kw + 1) * g.W, c.stream);
     bool done_w = smallc;
     if constexpr (std::is_same<T, simt::bf16>::value) {
       if (!done_w && umma::wgrad_supported(d.c_in, g.W, d.Kt, d.T, d.B)) {
@@ -232,8 +320,9 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
       w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0}; w.partial = part;
       launch_wgrad(w, c.stream);
     }
-    // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]
-    GatherBatch gb(c.stream);
+    // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]      (helper stream: the data gradient below does not wait for it)
+    c.post_after();
+    GatherBatch gb(c.qs());
     if (gr.conv_w) gb.add(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W);
     if (gr.conv_b) gb.add(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1);
     if (g.folded) {
@@ -242,37 +331,10 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     }
     gb.flush();
   }
-  if constexpr (std::is_same<T, simt::bf16>::value) {
-    if (dx) {
-      umma::TapProblem q{};
-      q.in = dz; q.w = wdbf; q.bias = nullptr; q.B = d.B; q.N = d.N; q.T_src = g.T_out; q.T_out = d.T; q.Kt = d.Kt;
-      q.t0 = -(d.Kt - 1); q.Cin = g.W; q.Co = d.c_in; q.epi = umma::EPI_LINEAR; q.act = 0; q.Cout = 0;
-      const bool explicit_res = !(g.folded || g.linear);
-      q.aux = explicit_res ? dz : nullptr; q.aux_dt = -(d.Kt - 1); q.T_aux = g.T_out; q.C_aux = g.W;
-      q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
-      q.out = dx; q.ld_out = d.c_in; q.out_z = nullptr;
-      if (d.B > 0 && umma::tap_supported(q)) {
-        // window-ordered weights of the transposed conv: wd[(j*c_in + c)*W + o] = conv_w[o][c][Kt-1-j]
-        if (!g.folded) {
-          launch_gather3(p.conv_w, wdbf, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
-        } else {
-          launch_gather3(p.conv_w, wd, d.Kt, d.c_in, g.W, d.Kt - 1, -1, d.Kt, (long long)d.c_in * d.Kt, 0, c.stream);
-          // align conv acts at tap Kt-1, i.e. window position j = 0
-          STGCN_LAUNCH(add_block_kernel, ceil_div((long long)d.c_in * d.c_out, 256), 256, 0, c.stream, wd, g.W,
-                       p.align_w, d.c_in, d.c_out, 1LL, (long long)d.c_in);
-          long long nw = (long long)d.Kt * g.W * d.c_in;
-          STGCN_LAUNCH((convert_kernel<float, simt::bf16>), ceil_div(nw, 256), 256, 0, c.stream, (const float*)wd, wdbf, nw);
-        }
-        umma::launch_tap(q, c.stream);
-        dx = nullptr;   // done
-      }
-    }
-  }
-  if (dx) {
-    // wd[(k*W + o)*c_in + c] = conv_w[o][c][k]
-    launch_gather3(p.conv_w, wd, d.Kt, g.W, d.c_in, 0, 1, (long long)d.c_in * d.Kt, d.Kt, 0, c.stream);
-    if (g.folded)
-      launch_gather3(p.align_w, wd + (size_t)(d.Kt - 1) * g.W * d.c_in, 1, d.c_out, d.c_in, 0, 0, d.c_in, 1, 1, c.stream);
+  // ---- data gradient
+  if (dgrad_umma) {
+    if constexpr (std::is_same<T, simt::bf16>::value) umma::launch_tap(qd, c.stream);
+  } else if (dx) {
     TapArgs<T> t{};
     t.in = dz; t.wt = wd; t.bias = nullptr; t.out = dx; t.rows = g.rows_in;
     t.Cin = g.W; t.Co = d.c_in; t.ntaps = d.Kt; t.ldo = d.c_in; t.accumulate = 0;
@@ -322,12 +384,12 @@ struct GsoRunner {
 };
 template <class T>
 inline GsoRunner<T> make_gso_runner(const float* M, int trans, int N, int C, long long G, simt::bf16* mbf_buf,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, cudaStream_t prep_stream) {
   GsoRunner<T> r{M, trans, N, C, G, stream};
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (mbf_buf && umma::gso_supported(N, C, G)) {
       int Kp = (N + 63) / 64 * 64;
-      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)N * Kp, 256), 256, 0, stream, M, mbf_buf, N, Kp, trans);
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)N * Kp, 256), 256, 0, prep_stream, M, mbf_buf, N, Kp, trans);
       r.mbf = mbf_buf;
     }
   }
@@ -366,10 +428,10 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   const long long rows = (long long)d.B * d.T * d.N;
   const int C = d.c_out;
   const size_t plane = (size_t)rows * C;
-  float* wat = c.ws.take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
-  simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
-  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
-                                              ? std::max((size_t)d.c_in * C, (size_t)(d.Ks > 1 ? d.Ks : 1) * C * C) : 0);
+  float* wat = c.K().take<float>(d.c_in > C ? (size_t)d.c_in * C : 0);
+  simt::bf16* mbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
+  simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c_in * C : 0);
+  simt::bf16* wbf2 = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)(d.Ks > 1 ? d.Ks : 1) * C * C : 0);
   // fused Chebyshev / first-order kernel (umma_cheb.cuh): recurrence + weight GEMMs + bias/residual/ReLU in one pass
   const int fdepth = gconv_stack_depth(d), ftaps = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   const bool fused = gconv_fused<T>(d);
@@ -380,7 +442,8 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (d.c_in > C && umma_linear(x, wbf, p.align_b, x0, d.B, d.T, d.T, d.N, d.c_in, C, UmmaLinearOpts{}, c.stream, true)) {
       STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
-      launch_gather3(p.align_w, wbf, 1, 1, C * d.c_in, 0, 0, 0, 1, 0, c.stream);            // [o][c] as is
+      launch_gather3(p.align_w, wbf, 1, 1, C * d.c_in, 0, 0, 0, 1, 0, c.ps());            // [o][c] as is
+      c.prep_ready();
       umma_linear(x, wbf, p.align_b, x0, d.B, d.T, d.T, d.N, d.c_in, C, UmmaLinearOpts{}, c.stream, false);
       align_done = true;
     }
@@ -388,7 +451,8 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   if (align_done) {
   } else if (d.c_in > C) {
     STGCN_CHECK(p.align_w && p.align_b, STGCN_E_INVALID, "gconv: c_in > c_out needs align conv parameters");
-    launch_gather3(p.align_w, wat, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // wat[c][o] = align_w[o][c]
+    launch_gather3(p.align_w, wat, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.ps());   // wat[c][o] = align_w[o][c]
+    c.prep_ready();
     TapArgs<T> t{};
     t.in = x; t.wt = wat; t.bias = p.align_b; t.out = x0; t.rows = rows; t.Cin = d.c_in; t.Co = C; t.ntaps = 1;
     t.ldo = C; t.map = RowMap{d.T, d.T, d.N, 0, 0};
@@ -399,7 +463,8 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (fused) {
       const int Kp = (d.N + 63) / 64 * 64;
-      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.stream, p.gso, mbf, d.N, Kp, 0);
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.ps(), p.gso, mbf, d.N, Kp, 0);
+      c.prep_ready();
       umma::ChebProblem q{};
       q.N = d.N; q.G = (long long)d.B * d.T; q.depth = fdepth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
       q.n_taps = ftaps; q.relu = d.relu; q.residual = d.residual; q.a_mat = mbf; q.w = p.w; q.bias = p.b;
@@ -408,7 +473,8 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
       return;
     }
   }
-  auto gso = make_gso_runner<T>(p.gso, 0, d.N, C, (long long)d.B * d.T, mbf, c.stream);
+  auto gso = make_gso_runner<T>(p.gso, 0, d.N, C, (long long)d.B * d.T, mbf, c.stream, c.ps());
+  c.prep_ready();
   TapArgs<T> t{};
   t.bias = p.b; t.out = y; t.rows = rows; t.Cin = C; t.Co = C; t.ldo = C;
   if (d.gconv == STGCN_GCONV_CHEB) {
@@ -430,10 +496,11 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
     const bool cheb = d.gconv == STGCN_GCONV_CHEB;
     o.Kt = cheb ? d.Ks : 1;
     const simt::bf16* src = cheb ? stack : stack + plane;
-    if (umma_linear(src, wbf, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, true)) {
+    if (umma_linear(src, wbf2, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, true)) {
       // W_j[o][c] = w[j][c][o]
-      launch_gather3(p.w, wbf, o.Kt, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
-      umma_linear(src, wbf, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, false);
+      launch_gather3(p.w, wbf2, o.Kt, C, C, 0, (long long)C * C, 1, C, 0, c.ps());
+      c.prep_ready();
+      umma_linear(src, wbf2, p.b, y, BT, o.Kt, 1, d.N, C, C, o, c.stream, false);
       mix_done = true;
     }
   }
@@ -458,21 +525,24 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   T* dg = c.ws.take<T>(plane);
   T* dst = dst_ext ? dst_ext : c.ws.take<T>((size_t)depth * plane);
-  float* wT = c.ws.take<float>((size_t)ntw * C * C);
-  float* dwt = c.ws.take<float>((size_t)(ntw * C + 1) * C);
-  float* dwa = c.ws.take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
-  simt::bf16* mbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
+  float* wT = c.K().take<float>((size_t)ntw * C * C);
+  float* dwt = c.K().take<float>((size_t)(ntw * C + 1) * C);
+  float* dwa = c.K().take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
+  simt::bf16* mbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
   float* part = c.ws.take<float>(std::max(wgrad_partial_elems(rows, ntw * C + 1, C),
                                           d.c_in > C ? wgrad_partial_elems(rows, d.c_in + 1, C) : (size_t)0));
-  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value
-                                              ? std::max((size_t)d.c_in * C, (size_t)ntw * C * C) : 0);
+  simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)ntw * C * C : 0);       // stack-gradient weights
+  simt::bf16* wbfa = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c_in * C : 0);      // align data-gradient weights
   const bool fused = gconv_fused<T>(d);
   if (c.dry()) return;
   if constexpr (std::is_same<T, simt::bf16>::value) {
     if (fused) {
       // dG, the adjoint recurrence and the residual gradient in one kernel; dst[0] = gradient w.r.t. the aligned input
       const int Kp = (d.N + 63) / 64 * 64;
-      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.stream, p.gso, mbf, d.N, Kp, 1);
+      STGCN_LAUNCH(umma::gso_prep_kernel, ceil_div((long long)d.N * Kp, 256), 256, 0, c.ps(), p.gso, mbf, d.N, Kp, 1);
+      zero(dwt, (size_t)(ntw * C + 1) * C, c.ps());
+      if (d.c_in > C && (gr.align_w || gr.align_b)) zero(dwa, (size_t)(d.c_in + 1) * C, c.ps());
+      c.prep_ready();
       umma::ChebProblem q{};
       q.N = d.N; q.G = (long long)d.B * d.T; q.depth = depth; q.tap_first = d.gconv == STGCN_GCONV_CHEB ? 0 : 1;
       q.n_taps = ntw; q.relu = d.relu; q.residual = d.residual; q.a_mat = mbf; q.w = p.w; q.bias = nullptr;
@@ -483,20 +553,25 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   if (!fused)
     STGCN_LAUNCH(relu_bwd_kernel<T>, ceil_div(ceil_div(plane, 8), 256), 256, 0, c.stream, dy, y, dg, (long long)plane, d.relu);
 
-  auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, fused ? nullptr : mbf, c.stream);
+  auto gso = make_gso_runner<T>(p.gso, 1, d.N, C, (long long)d.B * d.T, fused ? nullptr : mbf, c.stream, c.ps());
   TapArgs<T> t{};
   t.in = dg; t.bias = nullptr; t.rows = rows; t.Cin = C; t.Co = C; t.ntaps = 1; t.ldo = C;
   t.map = RowMap{d.T, d.T, d.N, 0, 0};
   WgradArgs<T> w{};
   w.dz = dg; w.dwt = dwt; w.rows = rows; w.Cin = C; w.Co = C; w.ldz = C; w.bias_row = 1; w.partial = part;
-  zero(dwt, (size_t)(ntw * C + 1) * C, c.stream);
+  if (!fused) {
+    zero(dwt, (size_t)(ntw * C + 1) * C, c.ps());
+    if (d.c_in > C && (gr.align_w || gr.align_b)) zero(dwa, (size_t)(d.c_in + 1) * C, c.ps());
+    c.prep_ready();
+  }
 
   if (d.gconv == STGCN_GCONV_CHEB) {
     // wT[k][j][i] = w[k][i][j];  d stack[k] = dG W_k^T
     bool dstack_done = fused;
     if constexpr (std::is_same<T, simt::bf16>::value) {
       if (!fused && umma_linear(dg, wbf, nullptr, dst, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
-        launch_gather3(p.w, wbf, 1, 1, d.Ks * C * C, 0, 0, 0, 1, 0, c.stream);      // [k][o=i][c=j] = w[k][i][j] as is
+        launch_gather3(p.w, wbf, 1, 1, d.Ks * C * C, 0, 0, 0, 1, 0, c.ps());      // [k][o=i][c=j] = w[k][i][j] as is
+        c.prep_ready();
         for (int k = 0; k < d.Ks; ++k)
           umma_linear(dg, wbf + (size_t)k * C * C, nullptr, dst + (size_t)k * plane, d.B, d.T, d.T, d.N, C, C,
                       UmmaLinearOpts{}, c.stream, false);
@@ -504,7 +579,8 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       }
     }
     if (!dstack_done) {
-      launch_gather3(p.w, wT, d.Ks, C, C, 0, (long long)C * C, 1, C, 0, c.stream);
+      launch_gather3(p.w, wT, d.Ks, C, C, 0, (long long)C * C, 1, C, 0, c.ps());
+      c.prep_ready();
       for (int k = 0; k < d.Ks; ++k) {
         t.wt = wT + (size_t)k * C * C; t.out = dst + (size_t)k * plane;
         launch_tapgemm(t, c.stream);
@@ -540,13 +616,15 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     bool dx1_done = fused;
     if constexpr (std::is_same<T, simt::bf16>::value) {
       if (!fused && umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, true)) {
-        launch_gather3(p.w, wbf, 1, 1, C * C, 0, 0, 0, 1, 0, c.stream);             // [o=i][c=j] = w[i][j] as is
+        launch_gather3(p.w, wbf, 1, 1, C * C, 0, 0, 0, 1, 0, c.ps());             // [o=i][c=j] = w[i][j] as is
+        c.prep_ready();
         umma_linear(dg, wbf, nullptr, dst + plane, d.B, d.T, d.T, d.N, C, C, UmmaLinearOpts{}, c.stream, false);
         dx1_done = true;
       }
     }
     if (!dx1_done) {
-      launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.stream);   // wT[j][i] = w[i][j]
+      launch_gather3(p.w, wT, 1, C, C, 0, 0, 1, C, 0, c.ps());   // wT[j][i] = w[i][j]
+      c.prep_ready();
       t.wt = wT; t.out = dst + plane;
       launch_tapgemm(t, c.stream);
     }
@@ -569,7 +647,8 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
     if (!fused) gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
   }
   {
-    GatherBatch gb(c.stream);
+    c.post_after();                      // behind the weight-gradient kernels; nothing on the caller's stream waits for it
+    GatherBatch gb(c.qs());
     if (gr.w) gb.add(dwt, gr.w, 1, 1, ntw * C * C, 0, 0, 0, 1);
     if (gr.b) gb.add(dwt, gr.b, 1, 1, C, (long long)ntw * C * C, 0, 0, 1);
   }
@@ -577,7 +656,6 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   // dst[0] now holds the gradient w.r.t. the aligned input
   if (d.c_in > C) {
     if (gr.align_w || gr.align_b) {
-      zero(dwa, (size_t)(d.c_in + 1) * C, c.stream);
       bool done_wa = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_flat_supported(d.c_in, C, 1, rows)) {
@@ -594,15 +672,17 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
         wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
         launch_wgrad(wa, c.stream);
       }
-      GatherBatch gb(c.stream);
+      c.post_after();
+      GatherBatch gb(c.qs());
       if (gr.align_w) gb.add(dwa, gr.align_w, 1, C, d.c_in, 0, 0, 1, C);
       if (gr.align_b) gb.add(dwa, gr.align_b, 1, 1, C, (long long)d.c_in * C, 0, 0, 1);
       gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      if (dx && umma_linear(dst, wbf, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, true)) {
-        launch_gather3(p.align_w, wbf, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.stream);   // [o=i][c] = align_w[c][i]
-        umma_linear(dst, wbf, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, false);
+      if (dx && umma_linear(dst, wbfa, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, true)) {
+        launch_gather3(p.align_w, wbfa, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.ps());   // [o=i][c] = align_w[c][i]
+        c.prep_ready();
+        umma_linear(dst, wbfa, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, false);
         dx = nullptr;
       }
     }
@@ -680,7 +760,9 @@ inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats,
 template <class T>
 inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc, const T* x, const float* stats,
                            const T* dy, const float* w, float* dw, float* db, const T* z_saved, const T* tc_in, T* dz,
-                           float* sums, uint64_t seed, cudaStream_t s, bool dry) {
+                           float* sums, uint64_t seed, Ctx c) {
+  const cudaStream_t s = c.stream;
+  const bool dry = c.dry();
   lnorm_check(d);
   static const bool off = std::getenv("STGCN_NO_FUSED_LNGATE") != nullptr;      // A/B switch for profiling
   TconvGeom g = tconv_geom(tc);
@@ -698,8 +780,9 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   }
   if (!ln_gate_bwd_supported(a)) return false;
   const int M = d.N * d.C;
-  if (dw) zero(dw, M, s);
-  if (db) zero(db, M, s);
+  if (dw) zero(dw, M, c.ps());       // parameter-gradient accumulators: zeroed on the helper stream (Ctx)
+  if (db) zero(db, M, c.ps());
+  c.prep_ready();
   if constexpr (std::is_same<T, simt::bf16>::value) {
     static const bool pipe_off = std::getenv("STGCN_NO_LN_PIPE") != nullptr;      // A/B switch for profiling
     if (!pipe_off && ln_gate_pipe_supported(a)) {
@@ -772,7 +855,7 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2);
   bool ln_fused;
   { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
-    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c.stream, c.dry());
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c);
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
   { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr); }
   // c1 > c2 (bottleneck): the align conv's data gradient dh1 = dst0 . Wa is formed inside tc1's gate backward from the
@@ -838,20 +921,27 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
   { Tag t("out.ln.fwd"); lnorm_fwd<T>(g.ln, s.h, p.ln_w, p.ln_b, s.l, s.stats, 0, c.stream, c.dry()); }
   Tag t_fc("out.fc.fwd");
   ScopedMark sm(c.ws);
-  float* w1t = c.ws.take<float>((size_t)d.c0 * d.c1);
-  float* w2t = c.ws.take<float>((size_t)d.c1 * d.c_end);
-  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
+  float* w1t = c.K().take<float>((size_t)d.c0 * d.c1);
+  float* w2t = c.K().take<float>((size_t)d.c1 * d.c_end);
+  simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
   if (c.dry()) return;
   STGCN_CHECK(p.fc1_w && p.fc2_w, STGCN_E_INVALID, "outblock: missing fc weights");
-  launch_gather3(p.fc1_w, w1t, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);      // w1t[c][o] = fc1_w[o][c]
-  launch_gather3(p.fc2_w, w2t, 1, d.c1, d.c_end, 0, 0, 1, d.c1, 0, c.stream);
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  bool fc1_umma = false;
+  if constexpr (std::is_same<T, simt::bf16>::value)
+    fc1_umma = umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, true);
+  const bool fc2_rowdot = d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && g.rows1 > 0;
+  // only the layouts the chosen kernels read are produced
+  if (!fc1_umma) launch_gather3(p.fc1_w, w1t, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.ps());      // w1t[c][o] = fc1_w[o][c]
+  if (!fc2_rowdot) launch_gather3(p.fc2_w, w2t, 1, d.c1, d.c_end, 0, 0, 1, d.c1, 0, c.ps());
   TapArgs<T> t{};
   t.in = s.l; t.wt = w1t; t.bias = p.fc1_b; t.out = s.f1; t.rows = g.rows1; t.Cin = d.c0; t.Co = d.c1; t.ntaps = 1;
   t.ldo = d.c1; t.map = RowMap{g.T1, g.T1, d.N, 0, 0};
   bool fc1_done = false, relu_done = false;
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    if (umma_linear(s.l, wbf, p.fc1_b, s.f1, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, c.stream, true)) {
-      launch_gather3(p.fc1_w, wbf, 1, 1, d.c1 * d.c0, 0, 0, 0, 1, 0, c.stream);      // [o][c] as is
+    if (fc1_umma) {
+      launch_gather3(p.fc1_w, wbf, 1, 1, d.c1 * d.c0, 0, 0, 0, 1, 0, c.ps());      // [o][c] as is
+      c.prep_ready();
       // without dropout the ReLU rides in the GEMM epilogue and only r = relu(f1) is kept (r > 0 <=> f1 > 0 is all the
       // backward needs, outblock_bwd / out_relu_fused)
       UmmaLinearOpts o{};
@@ -861,11 +951,10 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
       fc1_done = true;
     }
   }
-  if (!fc1_done) launch_tapgemm(t, c.stream);
+  if (!fc1_done) { c.prep_ready(); launch_tapgemm(t, c.stream); }
   long long n1 = g.rows1 * d.c1;
   if (n1 && !relu_done) STGCN_LAUNCH(relu_dropout_fwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)s.f1, s.r, n1, d.training, d.p_drop, seed);
-  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && g.rows1 > 0) {
+  if (fc2_rowdot) {
     const int lanes = 256 / (d.c1 / 8);
     const int blocks = (int)std::min<long long>(ceil_div(g.rows1, lanes), 148 * 8);
     STGCN_LAUNCH(rowdot_fwd_kernel<T>, blocks, 256, 0, c.stream, (const T*)s.r, p.fc2_w, p.fc2_b, y, g.rows1, d.c1);
@@ -873,6 +962,7 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
     TapArgs<T, float> t2{};
     t2.in = s.r; t2.wt = w2t; t2.bias = p.fc2_b; t2.out = y; t2.rows = g.rows1; t2.Cin = d.c1; t2.Co = d.c_end;
     t2.ntaps = 1; t2.ldo = d.c_end; t2.map = t.map;
+    c.prep_ready();
     launch_tapgemm(t2, c.stream);
   }
 }
@@ -889,14 +979,23 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   T* dl = c.ws.take<T>((size_t)g.rows1 * d.c0);
   T* dh = c.ws.take<T>((size_t)g.rows1 * d.c0);
   T* dyT = c.ws.take<T>(sizeof(T) == sizeof(float) ? 0 : (size_t)g.rows1 * d.c_end);
-  float* dw2 = c.ws.take<float>((size_t)(d.c1 + 1) * d.c_end);
-  float* dw1 = c.ws.take<float>((size_t)(d.c0 + 1) * d.c1);
+  float* dw2 = c.K().take<float>((size_t)(d.c1 + 1) * d.c_end);
+  float* dw1 = c.K().take<float>((size_t)(d.c0 + 1) * d.c1);
   float* part = c.ws.take<float>(std::max({wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
                                            wgrad_partial_elems(g.rows1, d.c0 + 1, d.c1),
                                            (size_t)(ceil_div(g.rows1, 256) + 1) * (d.c1 + 1)}));
-  simt::bf16* wbf = c.ws.take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
+  simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
   if (!c.dry()) {
     Tag t_fc("out.fc.bwd");
+    // parameter-only preparation on the helper stream (Ctx): accumulators zeroed, fc1 data-gradient weights laid out
+    if (gr.fc2_w || gr.fc2_b) zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.ps());
+    if (gr.fc1_w || gr.fc1_b) zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.ps());
+    bool dl_umma = false;
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      dl_umma = umma_linear(df1, wbf, nullptr, dl, d.B, g.T1, g.T1, d.N, d.c1, d.c0, UmmaLinearOpts{}, c.stream, true);
+      if (dl_umma) launch_gather3(p.fc1_w, wbf, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.ps());     // [o=c0 idx][c=c1 idx] = fc1_w[c][o]
+    }
+    c.prep_ready();
     RowMap rm{g.T1, g.T1, d.N, 0, 0};
     // fc2 (dy is fp32; the wgrad kernel wants it in the activation type)
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
@@ -922,22 +1021,22 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     TapArgs<T> t{};
     t.bias = nullptr; t.rows = g.rows1; t.ntaps = 1; t.map = rm;
     if ((gr.fc2_w || gr.fc2_b) && rowdot) {
-      zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
       long long rpc = std::max<long long>(256, (g.rows1 + 148 * 4 - 1) / (148 * 4));
       const int ctas = ceil_div(g.rows1, rpc);
       STGCN_LAUNCH(rowdot_wgrad_kernel<T>, ctas, 256, 0, c.stream, (const T*)s.r, dy, part, g.rows1, d.c1, (int)rpc);
       launch_reduce_partials(part, dw2, d.c1 + 1, ctas, c.stream);
-      GatherBatch gb(c.stream);
+      c.post_after();
+      GatherBatch gb(c.qs());
       if (gr.fc2_w) gb.add(dw2, gr.fc2_w, 1, 1, d.c1, 0, 0, 0, 1);
       if (gr.fc2_b) gb.add(dw2, gr.fc2_b, 1, 1, 1, (long long)d.c1, 0, 0, 1);
       gb.flush();
     } else if (gr.fc2_w || gr.fc2_b) {
-      zero(dw2, (size_t)(d.c1 + 1) * d.c_end, c.stream);
       WgradArgs<T> w{};
       w.in = s.r; w.dz = dy_t; w.dwt = dw2; w.rows = g.rows1; w.Cin = d.c1; w.Co = d.c_end; w.ntaps = 1; w.ldz = d.c_end;
       w.bias_row = 1; w.map = rm; w.partial = part;
       launch_wgrad(w, c.stream);
-      GatherBatch gb(c.stream);
+      c.post_after();
+      GatherBatch gb(c.qs());
       if (gr.fc2_w) gb.add(dw2, gr.fc2_w, 1, d.c_end, d.c1, 0, 0, 1, d.c_end);
       if (gr.fc2_b) gb.add(dw2, gr.fc2_b, 1, 1, d.c_end, (long long)d.c1 * d.c_end, 0, 0, 1);
       gb.flush();
@@ -948,8 +1047,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     // fc1
     bool dl_done = false;
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      if (umma_linear(df1, wbf, nullptr, dl, d.B, g.T1, g.T1, d.N, d.c1, d.c0, UmmaLinearOpts{}, c.stream, true)) {
-        launch_gather3(p.fc1_w, wbf, 1, d.c0, d.c1, 0, 0, 1, d.c0, 0, c.stream);     // [o=c0 idx][c=c1 idx] = fc1_w[c][o]
+      if (dl_umma) {
         umma_linear(df1, wbf, nullptr, dl, d.B, g.T1, g.T1, d.N, d.c1, d.c0, UmmaLinearOpts{}, c.stream, false);
         dl_done = true;
       }
@@ -959,7 +1057,6 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       launch_tapgemm(t, c.stream);
     }
     if (gr.fc1_w || gr.fc1_b) {
-      zero(dw1, (size_t)(d.c0 + 1) * d.c1, c.stream);
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_supported(d.c0, d.c1, 1, g.T1, d.B)) {
@@ -973,7 +1070,8 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
         w.bias_row = 1; w.map = rm; w.partial = part;
         launch_wgrad(w, c.stream);
       }
-      GatherBatch gb(c.stream);
+      c.post_after();
+      GatherBatch gb(c.qs());
       if (gr.fc1_w) gb.add(dw1, gr.fc1_w, 1, d.c1, d.c0, 0, 0, 1, d.c1);
       if (gr.fc1_b) gb.add(dw1, gr.fc1_b, 1, 1, d.c1, (long long)d.c0 * d.c1, 0, 0, 1);
       gb.flush();
@@ -983,7 +1081,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T1);
   bool ln_fused;
   { Tag t("out.ln.bwd");
-    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c.stream, c.dry());
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c);
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
   { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr); }
 }

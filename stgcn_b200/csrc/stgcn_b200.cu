@@ -27,6 +27,35 @@ using bf16 = __nv_bfloat16;
   } while (0)
 inline size_t elem_size(int precision) { return precision == STGCN_PREC_FP32 ? sizeof(float) : sizeof(bf16); }
 inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
+
+// Block-level calls (stblock / outblock).  The workspace is split into a "keep" region -- prepared weights and gradient
+// accumulators, which helper-stream work reads and writes asynchronously and which therefore live for the whole call
+// (ops::Ctx, ops::Side) -- and the scoped scratch arena.  The keep size comes from a dry pass of the same host code.
+// body(ctx): runs the block; it is invoked twice (dry, then live).
+template <class F>
+inline void run_block(void* workspace, size_t workspace_bytes, cudaStream_t stream, F&& body) {
+  size_t keep_bytes = 0;
+  {
+    Arena ws_d(nullptr, 0), keep_d(nullptr, 0);
+    ops::Ctx cd{ws_d, nullptr};
+    cd.keep = &keep_d;
+    body(cd);
+    keep_bytes = Arena::align_up(keep_d.peak);
+  }
+  STGCN_CHECK(keep_bytes <= workspace_bytes, STGCN_E_WORKSPACE, "workspace/saved buffer too small");
+  Arena keep(workspace, keep_bytes), ws(static_cast<char*>(workspace) + keep_bytes, workspace_bytes - keep_bytes);
+  ops::Ctx c{ws, stream};
+  c.keep = &keep;
+  c.side = ops::Side::get();
+  c.begin();
+  try {
+    body(c);
+  } catch (...) {
+    c.end();        // never leave the helper streams forked (a stream capture could not be ended)
+    throw;
+  }
+  c.end();
+}
 }  // namespace
 
 extern "C" {
@@ -185,23 +214,25 @@ int stgcn_lnorm_bwd(const stgcn_lnorm_desc* d, const void* x, const void* saved,
 int stgcn_stblock_sizes(const stgcn_stblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
-    ops::Ctx c{ws, nullptr};
+    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0), keep_f(nullptr, 0), keep_b(nullptr, 0);
+    ops::Ctx cf{ws, nullptr}, cb{ws, nullptr};
+    cf.keep = &keep_f; cb.keep = &keep_b;
     stgcn_stblock_params p{};
     stgcn_stblock_grads g{};
-    STGCN_DISPATCH(d->precision, ops::stblock_fwd<T>(*d, nullptr, p, nullptr, sv, c, 0);
-                   ops::stblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0));
+    STGCN_DISPATCH(d->precision, ops::stblock_fwd<T>(*d, nullptr, p, nullptr, sv, cf, 0);
+                   ops::stblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, cb, 0));
     if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
-    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
+    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256) + Arena::align_up(max2(keep_f.peak, keep_b.peak));
   });
 }
 int stgcn_stblock_fwd(const stgcn_stblock_desc* d, const void* x, const stgcn_stblock_params* p, void* y, void* saved,
                       void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
-    STGCN_DISPATCH(d->precision,
-                   ops::stblock_fwd<T>(*d, (const T*)x, *p, (T*)y, sv, ops::Ctx{ws, as_stream(stream)}, dropout_seed));
+    STGCN_DISPATCH(d->precision, run_block(workspace, workspace_bytes, as_stream(stream), [&](ops::Ctx c) {
+                     Arena sv(c.dry() ? nullptr : saved, (size_t)-1);
+                     ops::stblock_fwd<T>(*d, (const T*)x, *p, (T*)y, sv, c, dropout_seed);
+                   }));
   });
 }
 int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* saved, const void* dy,
@@ -209,9 +240,10 @@ int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* sa
                       size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
-    STGCN_DISPATCH(d->precision, ops::stblock_bwd<T>(*d, (const T*)x, sv, (const T*)dy, *p, *g, (T*)dx,
-                                                     ops::Ctx{ws, as_stream(stream)}, dropout_seed));
+    STGCN_DISPATCH(d->precision, run_block(workspace, workspace_bytes, as_stream(stream), [&](ops::Ctx c) {
+                     Arena sv(c.dry() ? nullptr : const_cast<void*>(saved), (size_t)-1);
+                     ops::stblock_bwd<T>(*d, (const T*)x, sv, (const T*)dy, *p, *g, (T*)dx, c, dropout_seed);
+                   }));
   });
 }
 
@@ -219,23 +251,25 @@ int stgcn_stblock_bwd(const stgcn_stblock_desc* d, const void* x, const void* sa
 int stgcn_outblock_sizes(const stgcn_outblock_desc* d, size_t* saved_bytes, size_t* workspace_bytes) {
   return guarded([&] {
     STGCN_CHECK(d, STGCN_E_INVALID, "null desc");
-    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0);
-    ops::Ctx c{ws, nullptr};
+    Arena ws(nullptr, 0), sv(nullptr, 0), sv2(nullptr, 0), keep_f(nullptr, 0), keep_b(nullptr, 0);
+    ops::Ctx cf{ws, nullptr}, cb{ws, nullptr};
+    cf.keep = &keep_f; cb.keep = &keep_b;
     stgcn_outblock_params p{};
     stgcn_outblock_grads g{};
-    STGCN_DISPATCH(d->precision, ops::outblock_fwd<T>(*d, nullptr, p, nullptr, sv, c, 0);
-                   ops::outblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, c, 0));
+    STGCN_DISPATCH(d->precision, ops::outblock_fwd<T>(*d, nullptr, p, nullptr, sv, cf, 0);
+                   ops::outblock_bwd<T>(*d, nullptr, sv2, nullptr, p, g, nullptr, cb, 0));
     if (saved_bytes) *saved_bytes = max2(sv.peak, 256);
-    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256);
+    if (workspace_bytes) *workspace_bytes = max2(ws.peak, 256) + Arena::align_up(max2(keep_f.peak, keep_b.peak));
   });
 }
 int stgcn_outblock_fwd(const stgcn_outblock_desc* d, const void* x, const stgcn_outblock_params* p, void* y,
                        void* saved, void* workspace, size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && x && y && saved && workspace, STGCN_E_INVALID, "null argument");
-    Arena ws(workspace, workspace_bytes), sv(saved, (size_t)-1);
-    STGCN_DISPATCH(d->precision, ops::outblock_fwd<T>(*d, (const T*)x, *p, (float*)y, sv,
-                                                      ops::Ctx{ws, as_stream(stream)}, dropout_seed));
+    STGCN_DISPATCH(d->precision, run_block(workspace, workspace_bytes, as_stream(stream), [&](ops::Ctx c) {
+                     Arena sv(c.dry() ? nullptr : saved, (size_t)-1);
+                     ops::outblock_fwd<T>(*d, (const T*)x, *p, (float*)y, sv, c, dropout_seed);
+                   }));
   });
 }
 int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* saved, const void* dy,
@@ -243,9 +277,10 @@ int stgcn_outblock_bwd(const stgcn_outblock_desc* d, const void* x, const void* 
                        size_t workspace_bytes, uint64_t dropout_seed, void* stream) {
   return guarded([&] {
     STGCN_CHECK(d && p && g && x && saved && dy && workspace, STGCN_E_INVALID, "null argument");
-    Arena ws(workspace, workspace_bytes), sv(const_cast<void*>(saved), (size_t)-1);
-    STGCN_DISPATCH(d->precision, ops::outblock_bwd<T>(*d, (const T*)x, sv, (const float*)dy, *p, *g, (T*)dx,
-                                                      ops::Ctx{ws, as_stream(stream)}, dropout_seed));
+    STGCN_DISPATCH(d->precision, run_block(workspace, workspace_bytes, as_stream(stream), [&](ops::Ctx c) {
+                     Arena sv(c.dry() ? nullptr : const_cast<void*>(saved), (size_t)-1);
+                     ops::outblock_bwd<T>(*d, (const T*)x, sv, (const float*)dy, *p, *g, (T*)dx, c, dropout_seed);
+                   }));
   });
 }
 
