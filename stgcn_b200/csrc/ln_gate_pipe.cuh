@@ -39,7 +39,7 @@ inline LnPipeGeom ln_pipe_geom(int M, int N, int Cin, int explicit_res) {
   return g;
 }
 
-template <int ACT>
+template <int ACT, bool QONLY>
 __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnGateArgs<bf16> a, LnPipeGeom geo) {
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   extern __shared__ __align__(128) uint8_t smraw[];
@@ -57,6 +57,8 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
   }
   __syncthreads();
   const int M = a.M, C = a.C, W = a.W;
+  constexpr bool q_only = QONLY && ACT == STGCN_ACT_GLU;     // z = Q only, [rows, C]; h = x (the LayerNorm input)
+  const int zrow = q_only ? C : W;                             // channels per row of the saved tensor
   auto issue = [&](long long g, int s) {                           // thread 0 only
     uint8_t* st = sm + (size_t)s * geo.stage_bytes;
     umma::mbar_arrive_expect_tx(&full[s], 2 * geo.m_bytes + geo.res_bytes);
@@ -73,13 +75,14 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
     if (g0 + 1 < g1) issue(g0 + 1, 1);
   }
   // this thread's chunks: element offset i, vertex n, first channel c0 (fixed for the whole kernel)
-  int ci[kLnPipeChunks], cz[kLnPipeChunks], cres[kLnPipeChunks];   // cz: offset of the chunk's P half inside the group's z slab
+  int ci[kLnPipeChunks], cz[kLnPipeChunks], cdz[kLnPipeChunks], cres[kLnPipeChunks];   // cz / cdz: chunk offset inside the group's z / dz slab
 #pragma unroll
   for (int k = 0; k < kLnPipeChunks; ++k) {
     const int i = (k * kLnPipeThreads + tid) * 8;
     ci[k] = i < M ? i : -1;
     const int n = i / C, c0 = i - n * C;
-    cz[k] = n * W + c0;
+    cz[k] = q_only ? n * C + c0 : n * W + c0;
+    cdz[k] = n * W + c0;
     cres[k] = (geo.res_bytes && c0 < a.Cin) ? n * a.Cin + c0 : -1;
   }
   float aw[kLnPipeChunks][8], ab[kLnPipeChunks][8];
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
   for (long long g = g0; g < g1; ++g, ++it) {
     const int s = it & 1;
     const uint32_t ph = (it >> 1) & 1;
-    const bf16* zg = a.z + g * a.N * W;
+    const bf16* zg = a.z + g * a.N * zrow;
     bf16* dzg = a.dz + g * a.N * W;
     // z of the first two chunks is requested before anything else: the wait and the reduction hide its latency
     uint4 zq_p[2], zq_q[2];
@@ -103,8 +106,8 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
     for (int k = 0; k < 2; ++k) {
       zq_p[k] = make_uint4(0, 0, 0, 0); zq_q[k] = make_uint4(0, 0, 0, 0);
       if (ci[k] >= 0) {
-        zq_p[k] = ldg16(zg + cz[k]);
-        if (gated) zq_q[k] = ldg16(zg + cz[k] + C);
+        zq_p[k] = ldg16(zg + cz[k]);                               // q_only: this IS the Q chunk
+        if (gated && !q_only) zq_q[k] = ldg16(zg + cz[k] + C);
       }
     }
     const float mu = a.mean[g], rs = a.rstd[g];
@@ -139,16 +142,16 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
       const uint4 zp_raw = zq_p[k & 1], zq_raw = zq_q[k & 1];
       if (k + 2 < kLnPipeChunks && ci[k + 2] >= 0) {               // refill the slot two chunks ahead
         zq_p[k & 1] = ldg16(zg + cz[k + 2]);
-        if (gated) zq_q[k & 1] = ldg16(zg + cz[k + 2] + C);
+        if (gated && !q_only) zq_q[k & 1] = ldg16(zg + cz[k + 2] + C);
       }
       if (ci[k] >= 0) {
         float xv[8], dv[8], wv[8], zp[8], zq[8], dh[8], du[8], dq[8];
         unpack8(*reinterpret_cast<const uint4*>(xs + ci[k]), xv);
         unpack8(*reinterpret_cast<const uint4*>(ds + ci[k]), dv);
         load8(a.w + ci[k], wv);
-        unpack8(zp_raw, zp);
-        if (gated) unpack8(zq_raw, zq);
-        if (cres[k] >= 0) {
+        if (q_only) unpack8(zp_raw, zq); else unpack8(zp_raw, zp);
+        if (gated && !q_only) unpack8(zq_raw, zq);
+        if (cres[k] >= 0 && !q_only) {
           float res[8];
           unpack8(*reinterpret_cast<const uint4*>(rsd + cres[k]), res);
 #pragma unroll
@@ -163,10 +166,19 @@ __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnG
           aw[k][e] += d * xh;
           ab[k][e] += d;
         }
+        if (q_only) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) act_bwd<true>(ACT, zp[e], gated ? zq[e] : 0.f, dh[e], du[e], dq[e]);
-        store8(dzg + cz[k], du);
-        if (gated) store8(dzg + cz[k] + C, dq);
+          for (int e = 0; e < 8; ++e) {
+            const float sg = sigmoid_tanh_(zq[e]);
+            du[e] = dh[e] * sg;
+            dq[e] = dh[e] * xv[e] * (1.f - sg);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) act_bwd<true>(ACT, zp[e], gated ? zq[e] : 0.f, dh[e], du[e], dq[e]);
+        }
+        store8(dzg + cdz[k], du);
+        if (gated) store8(dzg + cdz[k] + C, dq);
       }
     }
     __syncthreads();                                               // every thread is done with stage s
@@ -189,11 +201,11 @@ inline bool ln_gate_pipe_supported(const LnGateArgs<bf16>& a) {
   if (!(a.G > 0 && a.M % 8 == 0 && a.M <= kLnPipeMaxM && a.C % 8 == 0 && a.W % 8 == 0 && a.M == a.N * a.C)) return false;
   if (a.explicit_res && (a.Cin % 8 != 0 || ((long long)a.N * a.Cin * 2) % 16 != 0)) return false;
   if (!(al16(a.x) && al16(a.dy) && al16(a.w) && al16(a.z) && al16(a.xin) && al16(a.dz))) return false;
-  return ln_pipe_geom(a.M, a.N, a.Cin, a.explicit_res).smem <= 225 * 1024;
+  return ln_pipe_geom(a.M, a.N, a.Cin, a.explicit_res && !a.q_only).smem <= 225 * 1024;
 }
 
 inline void launch_ln_gate_bwd_pipe(int act, LnGateArgs<bf16> a, int sms, cudaStream_t s) {
-  const LnPipeGeom geo = ln_pipe_geom(a.M, a.N, a.Cin, a.explicit_res);
+  const LnPipeGeom geo = ln_pipe_geom(a.M, a.N, a.Cin, a.explicit_res && !a.q_only);      // q-only: no residual slab needed
   a.groups_per_cta = ceil_div(a.G, sms);
   const int grid = ceil_div(a.G, a.groups_per_cta);
   auto go = [&](auto kern, const char* name) {
@@ -201,11 +213,14 @@ inline void launch_ln_gate_bwd_pipe(int act, LnGateArgs<bf16> a, int sms, cudaSt
     STGCN_LAUNCH_NAMED(name, kern, grid, kLnPipeThreads, geo.smem, s, a, geo);
   };
   switch (act) {
-    case STGCN_ACT_GLU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_GLU>, "ln_gate_bwd_pipe_kernel<GLU>"); break;
-    case STGCN_ACT_GTU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_GTU>, "ln_gate_bwd_pipe_kernel<GTU>"); break;
-    case STGCN_ACT_RELU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_RELU>, "ln_gate_bwd_pipe_kernel<RELU>"); break;
-    case STGCN_ACT_SILU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_SILU>, "ln_gate_bwd_pipe_kernel<SILU>"); break;
-    default: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_LINEAR>, "ln_gate_bwd_pipe_kernel<LINEAR>"); break;
+    case STGCN_ACT_GLU:
+      if (a.q_only) go(ln_gate_bwd_pipe_kernel<STGCN_ACT_GLU, true>, "ln_gate_bwd_pipe_kernel<GLU,q>");
+      else go(ln_gate_bwd_pipe_kernel<STGCN_ACT_GLU, false>, "ln_gate_bwd_pipe_kernel<GLU>");
+      break;
+    case STGCN_ACT_GTU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_GTU, false>, "ln_gate_bwd_pipe_kernel<GTU>"); break;
+    case STGCN_ACT_RELU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_RELU, false>, "ln_gate_bwd_pipe_kernel<RELU>"); break;
+    case STGCN_ACT_SILU: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_SILU, false>, "ln_gate_bwd_pipe_kernel<SILU>"); break;
+    default: go(ln_gate_bwd_pipe_kernel<STGCN_ACT_LINEAR, false>, "ln_gate_bwd_pipe_kernel<LINEAR>"); break;
   }
 }
 

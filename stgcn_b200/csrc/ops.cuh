@@ -107,11 +107,35 @@ inline TconvGeom tconv_geom(const stgcn_tconv_desc& d) {
   g.folded = !g.linear && d.c_in > d.c_out;   // residual 1x1 conv folded into tap Kt-1 of the linear half
   return g;
 }
-inline size_t tconv_saved_elems(const stgcn_tconv_desc& d) { auto g = tconv_geom(d); return (size_t)g.rows_out * g.W; }
+inline size_t tconv_saved_elems(const stgcn_tconv_desc& d, bool q_only = false) {
+  auto g = tconv_geom(d);
+  return (size_t)g.rows_out * (q_only ? d.c_out : g.W);
+}
+// GLU "q-only" saved state (block-level callers that own both directions): the tcgen05 forward stores only the gate
+// half Q of the pre-activation; the backward gets du = dy*s, dq = dy*h*(1-s) from Q and the layer output h, which the
+// block keeps anyway.  Saves a 64-channel store + load per gated conv.  Shapes only, so forward and backward agree.
+template <class T>
+inline bool tconv_qonly(const stgcn_tconv_desc& d) {
+  if constexpr (std::is_same<T, simt::bf16>::value) {
+    static const bool on = std::getenv("STGCN_GLU_QONLY") != nullptr;      // opt-in until validated on the GPU
+    if (!on || d.act != STGCN_ACT_GLU || d.B <= 0) return false;
+    TconvGeom g = tconv_geom(d);
+    umma::TapProblem q{};
+    q.B = d.B; q.N = d.N; q.T_src = d.T; q.T_out = g.T_out; q.Kt = d.Kt; q.t0 = 0;
+    q.Cin = d.c_in; q.Co = g.W; q.epi = umma::EPI_GATE; q.act = d.act; q.Cout = d.c_out;
+    const bool explicit_res = !(g.folded || g.linear);
+    q.aux = explicit_res ? reinterpret_cast<const simt::bf16*>(256) : nullptr; q.C_aux = d.c_in;
+    q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
+    q.q_only = 1;
+    return umma::tap_supported(q) && d.c_out % 8 == 0;
+  }
+  return false;
+}
 
 // z_saved: [rows_out, W] pre-activations
 template <class T>
-inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_params& p, T* y, T* z_saved, Ctx c) {
+inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_params& p, T* y, T* z_saved, Ctx c,
+                      bool q_only = false) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   float* wt = c.K().take<float>((size_t)d.Kt * d.c_in * g.W);
@@ -128,7 +152,8 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
     const bool explicit_res = !(g.folded || g.linear);
     q.aux = explicit_res ? x : nullptr; q.aux_dt = d.Kt - 1; q.T_aux = d.T; q.C_aux = d.c_in;
     q.aux_cols = d.c_in < d.c_out ? d.c_in : d.c_out;
-    q.out = y; q.ld_out = d.c_out; q.out_z = z_saved;
+    q.out = y; q.ld_out = d.c_out; q.out_z = z_saved; q.q_only = q_only ? 1 : 0;
+    STGCN_CHECK(!q_only || (d.B > 0 && umma::tap_supported(q)), STGCN_E_INVALID, "tconv_fwd: q-only state needs the tcgen05 path");
     if (d.B > 0 && umma::tap_supported(q)) {
       // window-ordered K-major weights: w[(j*W + o)*c_in + c] = conv_w[o][c][j] (+ align fold on tap Kt-1)
       if (!g.folded) {
@@ -205,7 +230,7 @@ inline bool tconv_lowrank_dy_ok(const stgcn_tconv_desc& d) {
 template <class T>
 inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, const T* dy,
                       const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c, T* dz_ready = nullptr,
-                      const LowRankDy<T>* lr = nullptr) {
+                      const LowRankDy<T>* lr = nullptr, const T* h_qonly = nullptr) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
@@ -221,7 +246,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
-  STGCN_CHECK(!lr || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: low-rank dy only on the generic gate path");
+  STGCN_CHECK((!lr && !h_qonly) || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: low-rank dy / q-only state only on the generic gate path");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool z_skipped = smallc && smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved);   // what the forward may have done
   // data gradient through the tcgen05 tap kernel?
@@ -299,10 +324,10 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     GateArgs<T> ga{};
     ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
     ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
-    if (lr) {
-      ga.lr_src = lr->src; ga.lr_w = lr->w; ga.dy = nullptr;
-      STGCN_CHECK(gate_vec_ok(ga), STGCN_E_UNSUPPORTED, "tconv_bwd: low-rank dy not served (misaligned buffers)");
-    }
+    if (lr) { ga.lr_src = lr->src; ga.lr_w = lr->w; ga.dy = nullptr; }
+    if (h_qonly) { ga.h = h_qonly; ga.q_only = 1; }       // z_saved holds only Q (tconv_qonly); h = this layer's output
+    if (lr || h_qonly)
+      STGCN_CHECK(gate_vec_ok(ga), STGCN_E_UNSUPPORTED, "tconv_bwd: low-rank dy / q-only state not served (misaligned buffers)");
     launch_gate_any(d.act, true, ga, c.stream);
   }
   // ---- weight gradients
@@ -679,6 +704,11 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
+      static const bool simt_off = std::getenv("STGCN_NO_SIMT_ALIGNBWD") != nullptr;      // A/B switch for profiling
+      if (dx && !simt_off && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
+        launch_lowrank_expand<T>(dst, p.align_w, dx, rows, d.c_in, c.stream);      // align_w is [C][c_in] row-major
+        dx = nullptr;
+      }
       if (dx && umma_linear(dst, wbfa, nullptr, dx, d.B, d.T, d.T, d.N, C, d.c_in, UmmaLinearOpts{}, c.stream, true)) {
         launch_gather3(p.align_w, wbfa, 1, d.c_in, C, 0, 0, 1, d.c_in, 0, c.ps());   // [o=i][c] = align_w[c][i]
         c.prep_ready();
@@ -760,7 +790,7 @@ inline void lnorm_bwd(const stgcn_lnorm_desc& d, const T* x, const float* stats,
 template <class T>
 inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc, const T* x, const float* stats,
                            const T* dy, const float* w, float* dw, float* db, const T* z_saved, const T* tc_in, T* dz,
-                           float* sums, uint64_t seed, Ctx c) {
+                           float* sums, uint64_t seed, Ctx c, bool q_only = false) {
   const cudaStream_t s = c.stream;
   const bool dry = c.dry();
   lnorm_check(d);
@@ -772,6 +802,7 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   a.training = d.training; a.p = d.p_drop; a.seed = seed; a.z = z_saved; a.xin = tc_in; a.dz = dz; a.sums = sums;
   a.N = d.N; a.C = d.C; a.W = g.W; a.Cin = tc.c_in; a.Kt = tc.Kt; a.T_out = g.T_out; a.T_in = tc.T;
   a.explicit_res = (g.folded || g.linear) ? 0 : 1;
+  a.q_only = q_only ? 1 : 0;
   if (off || d.C != tc.c_out || g.T_out != d.T) return false;
   if (dry) {   // alignment cannot be checked on a dry run; shapes decide (the arenas hand out 256-byte aligned blocks)
     a.x = a.dy = a.z = a.xin = reinterpret_cast<const T*>(256); a.dz = reinterpret_cast<T*>(256); a.w = reinterpret_cast<const float*>(256);
@@ -819,11 +850,11 @@ struct StSaved { T *z1, *h1, *stack, *h2, *z2, *h3; float* stats; };
 template <class T>
 inline StSaved<T> st_saved(const stgcn_stblock_desc& d, const StGeom& g, Arena& sv) {
   StSaved<T> s;
-  s.z1 = sv.take<T>(tconv_saved_elems(g.tc1));
+  s.z1 = sv.take<T>(tconv_saved_elems(g.tc1, tconv_qonly<T>(g.tc1)));
   s.h1 = sv.take<T>((size_t)g.rows1 * d.c1);
   s.stack = sv.take<T>(gconv_saved_elems(g.gc));
   s.h2 = sv.take<T>((size_t)g.rows1 * d.c2);
-  s.z2 = sv.take<T>(tconv_saved_elems(g.tc2));
+  s.z2 = sv.take<T>(tconv_saved_elems(g.tc2, tconv_qonly<T>(g.tc2)));
   s.h3 = sv.take<T>((size_t)g.rows2 * d.c3);
   s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
   return s;
@@ -835,9 +866,9 @@ inline void stblock_fwd(const stgcn_stblock_desc& d, const T* x, const stgcn_stb
   StGeom g = st_geom(d);
   StSaved<T> s = st_saved<T>(d, g, sv);
   const bool first = d.c_in == 1;   // label only: distinguishes the two blocks of the default model in profiles
-  { Tag t(first ? "st0.tc1.fwd" : "st1.tc1.fwd"); tconv_fwd<T>(g.tc1, x, p.tc1, s.h1, s.z1, c); }
+  { Tag t(first ? "st0.tc1.fwd" : "st1.tc1.fwd"); tconv_fwd<T>(g.tc1, x, p.tc1, s.h1, s.z1, c, tconv_qonly<T>(g.tc1)); }
   { Tag t(first ? "st0.gc.fwd" : "st1.gc.fwd"); gconv_fwd<T>(g.gc, s.h1, p.gc, s.h2, s.stack, c); }
-  { Tag t(first ? "st0.tc2.fwd" : "st1.tc2.fwd"); tconv_fwd<T>(g.tc2, s.h2, p.tc2, s.h3, s.z2, c); }
+  { Tag t(first ? "st0.tc2.fwd" : "st1.tc2.fwd"); tconv_fwd<T>(g.tc2, s.h2, p.tc2, s.h3, s.z2, c, tconv_qonly<T>(g.tc2)); }
   { Tag t(first ? "st0.ln.fwd" : "st1.ln.fwd"); lnorm_fwd<T>(g.ln, s.h3, p.ln_w, p.ln_b, y, s.stats, seed, c.stream, c.dry()); }
 }
 
@@ -855,9 +886,10 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2);
   bool ln_fused;
   { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
-    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c);
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c, tconv_qonly<T>(g.tc2));
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
-  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr); }
+  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr, nullptr,
+                                                                  (!ln_fused && tconv_qonly<T>(g.tc2)) ? s.h3 : nullptr); }
   // c1 > c2 (bottleneck): the align conv's data gradient dh1 = dst0 . Wa is formed inside tc1's gate backward from the
   // 16-channel dst0 instead of being written to HBM at c1 channels and read back
   static const bool lr_off = std::getenv("STGCN_NO_FUSED_ALIGNBWD") != nullptr;      // A/B switch for profiling
@@ -866,7 +898,8 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   T* dst_ext = c.ws.take<T>(lr_fuse ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
   { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, lr_fuse ? nullptr : dh1, c, lr_fuse ? dst_ext : nullptr); }
   LowRankDy<T> lr{dst_ext, p.gc.align_w};       // align_w is [c2][c1] row-major = lr_w[o * c1 + j]
-  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, lr_fuse ? &lr : nullptr); }
+  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, lr_fuse ? &lr : nullptr,
+                                                                  tconv_qonly<T>(g.tc1) ? s.h1 : nullptr); }
 }
 
 // ============================ output block ===================================================
@@ -890,7 +923,7 @@ struct OutSaved { T *z, *h, *l, *f1, *r; float* stats; };
 template <class T>
 inline OutSaved<T> out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Arena& sv) {
   OutSaved<T> s;
-  s.z = sv.take<T>(tconv_saved_elems(g.tc));
+  s.z = sv.take<T>(tconv_saved_elems(g.tc, tconv_qonly<T>(g.tc)));
   s.h = sv.take<T>((size_t)g.rows1 * d.c0);
   s.stats = sv.take<float>(lnorm_saved_floats(g.ln));
   s.l = sv.take<T>((size_t)g.rows1 * d.c0);
@@ -917,7 +950,7 @@ inline void outblock_fwd(const stgcn_outblock_desc& d, const T* x, const stgcn_o
                          Arena& sv, Ctx c, uint64_t seed) {
   OutGeom g = out_geom(d);
   OutSaved<T> s = out_saved<T>(d, g, sv);
-  { Tag t("out.tc1.fwd"); tconv_fwd<T>(g.tc, x, p.tc1, s.h, s.z, c); }
+  { Tag t("out.tc1.fwd"); tconv_fwd<T>(g.tc, x, p.tc1, s.h, s.z, c, tconv_qonly<T>(g.tc)); }
   { Tag t("out.ln.fwd"); lnorm_fwd<T>(g.ln, s.h, p.ln_w, p.ln_b, s.l, s.stats, 0, c.stream, c.dry()); }
   Tag t_fc("out.fc.fwd");
   ScopedMark sm(c.ws);
@@ -1081,9 +1114,10 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T1);
   bool ln_fused;
   { Tag t("out.ln.bwd");
-    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c);
+    ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c, tconv_qonly<T>(g.tc));
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
-  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr); }
+  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr, nullptr,
+                                           (!ln_fused && tconv_qonly<T>(g.tc)) ? s.h : nullptr); }
 }
 
 }  // namespace ops

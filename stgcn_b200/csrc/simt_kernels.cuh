@@ -642,6 +642,9 @@ struct GateArgs {
   // graph-conv layer that consumed this layer's output, layers.py:16,225: its data gradient is formed on the fly
   // instead of being written to HBM as a [rows, Cout] tensor and read back here)
   const T* lr_src; const float* lr_w;
+  // bwd, GLU "q-only" saved state: z holds just the gate half Q as [rows, Cout]; with the layer OUTPUT h = u * sigma(Q)
+  // the gradients are du = dy * s, dq = dy * h * (1 - s) -- neither P nor the residual is needed
+  const T* h; int q_only;
 };
 constexpr int kGateLrC = 16;
 
@@ -733,11 +736,17 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
   const int j0 = (int)(idx - r * groups) * 8;
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   float zp[8], zq[8], res[8];
-  load8(a.z + r * a.W + j0, zp);
-  if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+  const bool q_only = ACT == STGCN_ACT_GLU && a.q_only;
+  if (q_only) {
+    load8(a.z + r * a.Cout + j0, zq);
+    load8(a.h + r * a.Cout + j0, zp);          // zp carries h here
+  } else {
+    load8(a.z + r * a.W + j0, zp);
+    if (gated) load8(a.z + r * a.W + a.Cout + j0, zq);
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) res[i] = 0.f;
-  if (a.explicit_res && j0 < a.Cin) {
+  if (!q_only && a.explicit_res && j0 < a.Cin) {
     long long base; int t;
     row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, base, t);
     load8(a.xin + (base + (long long)(a.Kt - 1) * a.N) * a.Cin + j0, res);      // Cin % 8 == 0 is checked by the launcher
@@ -764,8 +773,17 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
     } else {
       load8(a.dy + r * a.Cout + j0, g);
     }
+    if (q_only) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) act_bwd<kFastAct<T>>(ACT, zp[i] + res[i], gated ? zq[i] : 0.f, g[i], du[i], dq[i]);
+      for (int i = 0; i < 8; ++i) {
+        const float sg = sigmoid_t<kFastAct<T>>(zq[i]);
+        du[i] = g[i] * sg;
+        dq[i] = g[i] * zp[i] * (1.f - sg);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) act_bwd<kFastAct<T>>(ACT, zp[i] + res[i], gated ? zq[i] : 0.f, g[i], du[i], dq[i]);
+    }
     store8(a.dz + r * a.W + j0, du);
     if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
   }
@@ -777,7 +795,7 @@ inline bool gate_vec_ok(const GateArgs<T>& a) {
   const long long n = a.rows * a.Cout;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   return a.Cout % 8 == 0 && a.W % 8 == 0 && n / 8 < (1LL << 31) && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
-         al16(a.dy) && al16(a.y) && al16(a.dz) && al16(a.lr_src) && al16(a.lr_w);
+         al16(a.dy) && al16(a.y) && al16(a.dz) && al16(a.lr_src) && al16(a.lr_w) && al16(a.h);
 }
 template <class T, int ACT>
 inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
@@ -788,9 +806,46 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
     STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, lr_smem, s, a, bwd ? 1 : 0);
     return;
   }
-  STGCN_CHECK(!a.lr_src, STGCN_E_UNSUPPORTED, "low-rank dy needs the vectorised gate kernel");
+  STGCN_CHECK(!a.lr_src && !a.q_only, STGCN_E_UNSUPPORTED, "low-rank dy / q-only saved state need the vectorised gate kernel");
   if (bwd) STGCN_LAUNCH((gate_bwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
   else     STGCN_LAUNCH((gate_fwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
+}
+
+// out[r, j0..j0+7] = sum_{o<16} src[r, o] * w[o * Cout + j]: data gradient of a 1x1 conv with 16 output channels
+// (the graph-conv layer's align conv, layers.py:16,225) as plain FMAs -- with K = 16 the tensor-core tile kernel spends
+// its time in per-tile epilogue bookkeeping (66 us for 75 MB), this is bandwidth work.  8 channels per thread.
+template <class T>
+__global__ void __launch_bounds__(256) lowrank_expand_kernel(const T* src, const float* w, T* out, long long rows, int Cout) {
+  extern __shared__ __align__(16) float lrx_s[];         // [kGateLrC][Cout]
+  for (int i = threadIdx.x; i < kGateLrC * Cout; i += blockDim.x) lrx_s[i] = w[i];
+  __syncthreads();
+  const int groups = Cout / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * groups) return;
+  const long long r = (long long)((unsigned)idx / (unsigned)groups);
+  const int j0 = (int)(idx - r * groups) * 8;
+  float d[kGateLrC], g[8];
+  load8(src + r * kGateLrC, d); load8(src + r * kGateLrC + 8, d + 8);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = 0.f;
+#pragma unroll
+  for (int o = 0; o < kGateLrC; ++o) {
+    const float4 w0 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0);
+    const float4 w1 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0 + 4);
+    g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
+    g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
+  }
+  store8(out + r * Cout + j0, g);
+}
+template <class T>
+inline bool lowrank_expand_supported(const T* src, const float* w, const T* out, long long rows, int Csrc, int Cout) {
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  return Csrc == kGateLrC && Cout % 8 == 0 && Cout <= 512 && rows > 0 && rows * (Cout / 8) < (1LL << 31) && al16(src) && al16(w) && al16(out);
+}
+template <class T>
+inline void launch_lowrank_expand(const T* src, const float* w, T* out, long long rows, int Cout, cudaStream_t s) {
+  const long long n = rows * (Cout / 8);
+  STGCN_LAUNCH(lowrank_expand_kernel<T>, ceil_div(n, 256), 256, (size_t)kGateLrC * Cout * sizeof(float), s, src, w, out, rows, Cout);
 }
 
 template <class T>
@@ -1585,6 +1640,7 @@ struct LnGateArgs {
   const T* z; const T* xin; T* dz;
   int N, C, W, Cin, Kt, T_out, T_in, explicit_res;
   int groups_per_cta;
+  int q_only;                           // GLU: z holds only Q as [rows, C]; x (the LayerNorm input) is h = u * sigma(Q)
 };
 __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
   __syncthreads();   // protect red[] reuse
@@ -1657,9 +1713,14 @@ __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnG
     const long long r = g * a.N + n;
     float xv[8], dv[8], zp[8], zq[8], res[8], dh[8], du[8], dq[8];
     load8(a.x + g * a.M + i, xv); load8(a.dy + g * a.M + i, dv);
-    load8(a.z + r * a.W + c0, zp);
-    if (gated) load8(a.z + r * a.W + Cout + c0, zq);
-    if (has_res) {
+    const bool q_only = ACT == STGCN_ACT_GLU && a.q_only;
+    if (q_only) {
+      load8(a.z + r * Cout + c0, zq);
+    } else {
+      load8(a.z + r * a.W + c0, zp);
+      if (gated) load8(a.z + r * a.W + Cout + c0, zq);
+    }
+    if (has_res && !q_only) {
       const long long b = g / a.T_out;
       const int t = (int)(g - b * a.T_out);
       load8(a.xin + ((b * a.T_in + t + a.Kt - 1) * a.N + n) * a.Cin + c0, res);
@@ -1672,10 +1733,19 @@ __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnG
       dh[k] = rs * (d * wv[k] - s1 - xh * s2);
       aw[k] += d * xh;
       ab[k] += d;
-      if (has_res) zp[k] += res[k];
+      if (has_res && !q_only) zp[k] += res[k];
     }
+    if (q_only) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) act_bwd<kFastAct<T>>(ACT, zp[k], gated ? zq[k] : 0.f, dh[k], du[k], dq[k]);
+      for (int k = 0; k < 8; ++k) {
+        const float sg = sigmoid_t<kFastAct<T>>(zq[k]);
+        du[k] = dh[k] * sg;
+        dq[k] = dh[k] * xv[k] * (1.f - sg);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) act_bwd<kFastAct<T>>(ACT, zp[k], gated ? zq[k] : 0.f, dh[k], du[k], dq[k]);
+    }
     store8(a.dz + r * a.W + c0, du);
     if (gated) store8(a.dz + r * a.W + Cout + c0, dq);
   }

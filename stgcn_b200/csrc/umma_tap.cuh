@@ -59,7 +59,8 @@ struct TapParams {
   int aux_dt, T_aux, C_aux, aux_cols;
   bf16* out;                  // linear: [rows_out, ld_out] ; gate: h [rows_out, Cout]
   int ld_out, co_valid;
-  bf16* out_z;                // gate: z [rows_out, W]
+  bf16* out_z;                // gate: z [rows_out, W]; q_only: the gate half alone, [rows_out, Cout]
+  int q_only;                 // GLU: the backward rebuilds everything from (h, sigma(Q)); the P half is not stored
   int n_items, n_node_tiles;
   // Output-time split: a work item is (sample, 128-vertex tile, time chunk): output steps [ts*t_chunk, +t_chunk).
   // 512 (sample, tile) items over 148 CTAs quantise to 4 rounds for 3.46 rounds of work; halving the items'
@@ -446,12 +447,20 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>(has_aux ? zp[i] + av[i] : zp[i], zq[i]);
             const uint4 op = pack8_bf16(zp), oh = pack8_bf16(h);
             if (stg) {
-              stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, op);
-              if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + cc) >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
+              if (gated && p.q_only) {
+                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
+              } else {
+                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, op);
+                if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + cc) >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
+              }
               stage_store8_s(stg_s + (uint32_t)(p.nZ + (cc >> 6)) * 16384u, row, cc & 63, oh);
             } else if (valid) {
-              *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = op;
-              if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
+              if (gated && p.q_only) {
+                *reinterpret_cast<uint4*>(p.out_z + orow * p.Cout + cc) = pack8_bf16(zq);
+              } else {
+                *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = op;
+                if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
+              }
               *reinterpret_cast<uint4*>(p.out + orow * p.Cout + cc) = oh;
             }
           }
@@ -513,6 +522,7 @@ struct TapProblem {
   const bf16* aux; int aux_dt, T_aux, C_aux, aux_cols;
   bf16* out; int ld_out;
   bf16* out_z;
+  int q_only;              // gate (GLU): store only the Q half of z ([rows, Cout])
   // optional element strides of `in` for the vertex / time / batch axes (0 = dense [B,T_src,N,Cin]); lets a stack of
   // planes [Kt][B*T][N][C] be read with the plane index as the "time" axis
   long long in_stride_n, in_stride_t, in_stride_b;
@@ -527,7 +537,7 @@ struct TapPlan {
 };
 
 // gate: the epilogue needs the whole pre-activation width W = Co in one CTA; Cout = its output channels.
-inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout = 0) {
+inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout = 0, bool q_only = false) {
   TapPlan pl{};
   pl.ok = false;
   if (Cin % 16 || Co % 16 || Cin < 16 || Co < 16) return pl;
@@ -548,7 +558,7 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout 
     // output staging for TMA stores (64-column sub-tiles of 16 KB); two buffers if they fit next to >= live+1 stages
     int nZ = 0, nO = 0;
     const bool stageable = gate ? (Co % 64 == 0 && Cout % 64 == 0) : (CoT % 64 == 0);
-    if (stageable) { nZ = gate ? Co / 64 : 0; nO = gate ? Cout / 64 : CoT / 64; }
+    if (stageable) { nZ = gate ? (q_only ? Cout : Co) / 64 : 0; nO = gate ? Cout / 64 : CoT / 64; }
     const size_t per_buf = (size_t)(nZ + nO) * 16384;
     int nbuf = 0;
     for (int cand = 2; cand >= 1 && stageable; --cand)
@@ -572,7 +582,7 @@ inline bool tap_supported(const TapProblem& q) {
   if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
   if (q.aux && (q.aux_cols % 16 != 0 || q.C_aux % 16 != 0)) return false;      // vector residual loads
   if (q.T_out < 1 || q.T_src < 1 || q.N < 1 || q.B < 1) return false;
-  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout).ok;
+  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0).ok;
 }
 
 inline int sm_count() {
@@ -586,7 +596,7 @@ inline int sm_count() {
 }
 
 inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
-  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout);
+  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0);
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma tap GEMM: unsupported shape");
   const CUtensorMapSwizzle tsw = pl.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : (pl.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -611,8 +621,9 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     uint32_t ob[4] = {64, 128, 1, 1};
     tmO = make_tmap_bf16(q.out, 4, od, os, ob, CU_TENSOR_MAP_SWIZZLE_128B);
     if (q.epi == EPI_GATE) {
-      uint64_t zd[4] = {(uint64_t)q.Co, (uint64_t)q.N, (uint64_t)q.T_out, (uint64_t)q.B};
-      uint64_t zs[3] = {(uint64_t)q.Co * 2, (uint64_t)q.N * q.Co * 2, (uint64_t)q.T_out * q.N * q.Co * 2};
+      const uint64_t zc = q.q_only ? q.Cout : q.Co;        // channels per row of the saved tensor
+      uint64_t zd[4] = {zc, (uint64_t)q.N, (uint64_t)q.T_out, (uint64_t)q.B};
+      uint64_t zs[3] = {zc * 2, (uint64_t)q.N * zc * 2, (uint64_t)q.T_out * q.N * zc * 2};
       tmZ = make_tmap_bf16(q.out_z, 4, zd, zs, ob, CU_TENSOR_MAP_SWIZZLE_128B);
     }
   }
@@ -625,6 +636,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
   p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
+  p.q_only = (q.epi == EPI_GATE && q.act == STGCN_ACT_GLU && q.q_only) ? 1 : 0;
   p.dbg = g_tap_dbg;
   // a stage is recycled only after a window of Kt published slices was consumed: S >= depth + Kt + 1 or it deadlocks
   p.narrow_cp = (pl.KB == 16 && pl.nKB == 1 && pl.S >= kTapProducers + q.Kt + 2) ? 1 : 0;

@@ -214,6 +214,11 @@ struct WgradFlatParams {
   uint32_t z_bytes, x_bytes, stage_bytes, a_swz, a_sbo, a_kadv, b_swz, b_sbo, b_kadv;
   float* dwt;
   int want_bias;
+  // merge_taps: the Kt plane tiles of a stage sit x_bytes apart, which is exactly the leading-dimension stride of the
+  // MN-major B descriptor, so ONE instruction with N = Kt*Cin covers all planes (accumulator columns [j*Cin, +Cin) are
+  // contiguous too).  With Cin = 16 the per-tap N = 16 instructions cost the same ~45 cycles each and made the kernel
+  // issue bound (64 instructions per 32 KB tile).
+  int merge_taps;
 };
 constexpr int kFlatRows = 256;
 
@@ -274,7 +279,16 @@ umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(ring + (size_t)s * p.stage_bytes);
-        for (int j = 0; j < p.Kt; ++j) {
+        if (p.merge_taps) {
+          const uint32_t idesc_m = make_idesc_bf16(128, p.Kt * p.Cin, 1, 1);
+          uint64_t da = desc_at(pa, a_base), db = desc_at(pb, a_base + p.z_bytes);
+#pragma unroll 4
+          for (int k = 0; k < kFlatRows / 16; ++k) {
+            mma_bf16_ss(tmem_base, da, db, idesc_m, (g | (uint32_t)k) != 0);
+            da += a_step; db += b_step;
+          }
+        }
+        for (int j = 0; j < (p.merge_taps ? 0 : p.Kt); ++j) {
           const uint32_t b_base = a_base + p.z_bytes + j * p.x_bytes;
           uint64_t da = desc_at(pa, a_base), db = desc_at(pb, b_base);
 #pragma unroll 4
@@ -370,6 +384,8 @@ inline void launch_wgrad_flat(const bf16* x, const bf16* dz, float* dwt, long lo
   p.a_swz = dsw_of(W); p.a_sbo = 8u * W * 2; p.a_kadv = 16u * W * 2;
   p.b_swz = dsw_of(xcw); p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
   p.dwt = dwt; p.want_bias = want_bias;
+  static const bool merge_off = std::getenv("STGCN_NO_WGRAD_MERGE") != nullptr;      // A/B switch for profiling
+  p.merge_taps = (!merge_off && Kt > 1 && Cin <= 64 && Kt * Cin <= 256 && (Kt * Cin) % 16 == 0) ? 1 : 0;
   int gx = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   STGCN_CUDA(cudaFuncSetAttribute(umma_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   STGCN_LAUNCH(umma_wgrad_flat_kernel, gx, kTapThreads, pl.smem, stream, tmZ, tmX, p);
