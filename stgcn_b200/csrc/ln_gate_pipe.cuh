@@ -41,6 +41,7 @@ inline LnPipeGeom ln_pipe_geom(int M, int N, int Cin, int explicit_res) {
 
 template <int ACT, bool QONLY>
 __global__ void __launch_bounds__(kLnPipeThreads, 1) ln_gate_bwd_pipe_kernel(LnGateArgs<bf16> a, LnPipeGeom geo) {
+  pdl_begin();
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   extern __shared__ __align__(128) uint8_t smraw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smraw) + 127) & ~uintptr_t(127));

@@ -35,7 +35,9 @@ struct Side {
   static Side* get() {                     // one per host thread (forward and autograd-backward threads differ)
     static thread_local Side* s = nullptr;
     static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;      // A/B switch for profiling
-    if (off) return nullptr;
+    // the per-kernel event profiler (stgcn_profile_begin/end) wants one kernel at a time: events on a helper stream would
+    // include the time that stream spent waiting for its dependencies
+    if (off || g_prof.on.load(std::memory_order_relaxed)) return nullptr;
     if (!s) {
       s = new Side();
       STGCN_CUDA(cudaStreamCreateWithFlags(&s->p, cudaStreamNonBlocking));
@@ -55,6 +57,16 @@ struct Ctx {
   Arena& K() const { return keep ? *keep : ws; }
   cudaStream_t ps() const { return side ? side->p : stream; }      // parameter-only preparation
   cudaStream_t qs() const { return side ? side->q : stream; }      // post-processing of gradients
+  // Weight-gradient kernels on q (opt-in, STGCN_WGRAD_STREAM): nothing on the caller's stream consumes a parameter
+  // gradient, so the wgrad kernel of a layer can run beside that layer's data-gradient kernel and its launch/drain
+  // bubbles leave the critical path.  Everything such a kernel reads must then outlive the op: KW() hands those
+  // buffers out of the keep arena (decided by the flag alone, so the sizing pass and the live pass agree).
+  static bool wgrad_stream() {
+    static const bool on = std::getenv("STGCN_WGRAD_STREAM") != nullptr && std::getenv("STGCN_NO_SIDE_STREAMS") == nullptr;
+    return on;
+  }
+  Arena& KW() const { return (wgrad_stream() && keep) ? *keep : ws; }
+  cudaStream_t wstream() const { return (wgrad_stream() && side) ? side->q : stream; }
   static void order(cudaStream_t first, cudaStream_t then, Side* sd) {
     cudaEvent_t e = sd->event();
     STGCN_CUDA(cudaEventRecord(e, first));
@@ -117,8 +129,8 @@ inline size_t tconv_saved_elems(const stgcn_tconv_desc& d, bool q_only = false) 
 template <class T>
 inline bool tconv_qonly(const stgcn_tconv_desc& d) {
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool on = std::getenv("STGCN_GLU_QONLY") != nullptr;      // opt-in until validated on the GPU
-    if (!on || d.act != STGCN_ACT_GLU || d.B <= 0) return false;
+    static const bool off = std::getenv("STGCN_NO_GLU_QONLY") != nullptr;      // A/B switch (validated: +5.8%, batch g)
+    if (off || d.act != STGCN_ACT_GLU || d.B <= 0) return false;
     TconvGeom g = tconv_geom(d);
     umma::TapProblem q{};
     q.B = d.B; q.N = d.N; q.T_src = d.T; q.T_out = g.T_out; q.Kt = d.Kt; q.t0 = 0;
@@ -234,7 +246,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
-  T* dz = dz_ready ? dz_ready : c.ws.take<T>((size_t)g.rows_out * g.W);
+  T* dz = dz_ready ? dz_ready : c.KW().take<T>((size_t)g.rows_out * g.W);
   float* dwt = c.K().take<float>((size_t)(Kw + 1) * g.W);
   float* wd = c.K().take<float>((size_t)d.Kt * g.W * d.c_in);
   float* wfw = c.K().take<float>((size_t)d.Kt * g.W * d.c_in);        // forward-layout weights (z recompute of the first layer)
@@ -242,7 +254,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   simt::bf16* wdbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.Kt * g.W * d.c_in : 0);
   const long long sc_rpc = std::max<long long>(64, (g.rows_out + 148 * 8 - 1) / (148 * 8));
   const int sc_ctas = g.rows_out > 0 ? ceil_div(g.rows_out, sc_rpc) : 0;
-  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(g.rows_out, Kw + 1, g.W), (size_t)sc_ctas * (Kw + 1) * g.W));
+  float* part = c.KW().take<float>(std::max(wgrad_partial_elems(g.rows_out, Kw + 1, g.W), (size_t)sc_ctas * (Kw + 1) * g.W));
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
@@ -333,9 +345,11 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   // ---- weight gradients
   if (want_w) {
     bool done_w = smallc;
+    if (!done_w) c.post_after();                 // q (if the wgrad runs there) sees dz
+    const cudaStream_t wst = c.wstream();
     if constexpr (std::is_same<T, simt::bf16>::value) {
       if (!done_w && umma::wgrad_supported(d.c_in, g.W, d.Kt, d.T, d.B)) {
-        umma::launch_wgrad_umma(x, dz, dwt, d.B, d.N, d.T, d.Kt, d.c_in, g.W, 1, c.stream);
+        umma::launch_wgrad_umma(x, dz, dwt, d.B, d.N, d.T, d.Kt, d.c_in, g.W, 1, wst);
         done_w = true;
       }
     }
@@ -343,7 +357,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
       WgradArgs<T> w{};
       w.in = x; w.dz = dz; w.dwt = dwt; w.rows = g.rows_out; w.Cin = d.c_in; w.Co = g.W; w.ntaps = d.Kt; w.ldz = g.W;
       w.bias_row = 1; w.map = RowMap{g.T_out, d.T, d.N, 1, 0}; w.partial = part;
-      launch_wgrad(w, c.stream);
+      launch_wgrad(w, wst);
     }
     // conv_w grad [o][c][k] = dwt[(k*c_in + c)*W + o]      (helper stream: the data gradient below does not wait for it)
     c.post_after();
@@ -548,13 +562,13 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   const size_t plane = (size_t)rows * C;
   const int depth = gconv_stack_depth(d);
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
-  T* dg = c.ws.take<T>(plane);
-  T* dst = dst_ext ? dst_ext : c.ws.take<T>((size_t)depth * plane);
+  T* dg = c.KW().take<T>(plane);
+  T* dst = dst_ext ? dst_ext : c.KW().take<T>((size_t)depth * plane);
   float* wT = c.K().take<float>((size_t)ntw * C * C);
   float* dwt = c.K().take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.K().take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
   simt::bf16* mbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? umma::gso_prep_elems(d.N) : 0);
-  float* part = c.ws.take<float>(std::max(wgrad_partial_elems(rows, ntw * C + 1, C),
+  float* part = c.KW().take<float>(std::max(wgrad_partial_elems(rows, ntw * C + 1, C),
                                           d.c_in > C ? wgrad_partial_elems(rows, d.c_in + 1, C) : (size_t)0));
   simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)ntw * C * C : 0);       // stack-gradient weights
   simt::bf16* wbfa = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c_in * C : 0);      // align data-gradient weights
@@ -615,16 +629,16 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_flat_supported(C, C, d.Ks, rows)) {          // stack planes as taps over flat 256-row tiles
-          umma::launch_wgrad_flat(stack, dg, dwt, rows, rows, d.Ks, C, C, 1, c.stream);
+          { c.post_after(); umma::launch_wgrad_flat(stack, dg, dwt, rows, rows, d.Ks, C, C, 1, c.wstream()); }
           done_w = true;
         } else if (umma::wgrad_supported(C, C, d.Ks, d.T, d.B, true)) {
-          umma::launch_wgrad_umma(stack, dg, dwt, d.B, d.N, d.T, d.Ks, C, C, 1, c.stream, true);
+          { c.post_after(); umma::launch_wgrad_umma(stack, dg, dwt, d.B, d.N, d.T, d.Ks, C, C, 1, c.wstream(), true); }
           done_w = true;
         }
       }
       if (!done_w) {
         w.in = stack; w.ntaps = d.Ks; w.map = RowMap{d.T, d.T, d.N, 0, rows};
-        launch_wgrad(w, c.stream);
+        { c.post_after(); launch_wgrad(w, c.wstream()); }
       }
     }
     // reverse Chebyshev recurrence: x_k = 2 L x_{k-1} - x_{k-2}
@@ -657,16 +671,16 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_flat_supported(C, C, 1, rows)) {
-          umma::launch_wgrad_flat(stack + plane, dg, dwt, rows, 0, 1, C, C, 1, c.stream);
+          { c.post_after(); umma::launch_wgrad_flat(stack + plane, dg, dwt, rows, 0, 1, C, C, 1, c.wstream()); }
           done_w = true;
         } else if (umma::wgrad_supported(C, C, 1, d.T, d.B)) {
-          umma::launch_wgrad_umma(stack + plane, dg, dwt, d.B, d.N, d.T, 1, C, C, 1, c.stream);
+          { c.post_after(); umma::launch_wgrad_umma(stack + plane, dg, dwt, d.B, d.N, d.T, 1, C, C, 1, c.wstream()); }
           done_w = true;
         }
       }
       if (!done_w) {
         w.in = stack + plane; w.ntaps = 1; w.map = RowMap{d.T, d.T, d.N, 0, 0};
-        launch_wgrad(w, c.stream);
+        { c.post_after(); launch_wgrad(w, c.wstream()); }
       }
     }
     if (!fused) gso(dst + plane, d.residual ? dg : nullptr, dst, 1.f, 1.f);
@@ -684,10 +698,10 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       bool done_wa = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_flat_supported(d.c_in, C, 1, rows)) {
-          umma::launch_wgrad_flat(x, dst, dwa, rows, 0, 1, d.c_in, C, 1, c.stream);
+          { c.post_after(); umma::launch_wgrad_flat(x, dst, dwa, rows, 0, 1, d.c_in, C, 1, c.wstream()); }
           done_wa = true;
         } else if (umma::wgrad_supported(d.c_in, C, 1, d.T, d.B)) {
-          umma::launch_wgrad_umma(x, dst, dwa, d.B, d.N, d.T, 1, d.c_in, C, 1, c.stream);
+          { c.post_after(); umma::launch_wgrad_umma(x, dst, dwa, d.B, d.N, d.T, 1, d.c_in, C, 1, c.wstream()); }
           done_wa = true;
         }
       }
@@ -695,7 +709,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
         WgradArgs<T> wa{};
         wa.in = x; wa.dz = dst; wa.dwt = dwa; wa.rows = rows; wa.Cin = d.c_in; wa.Co = C; wa.ntaps = 1; wa.ldz = C;
         wa.bias_row = 1; wa.map = RowMap{d.T, d.T, d.N, 0, 0}; wa.partial = part;
-        launch_wgrad(wa, c.stream);
+        { c.post_after(); launch_wgrad(wa, c.wstream()); }
       }
       c.post_after();
       GatherBatch gb(c.qs());
@@ -704,8 +718,8 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      static const bool simt_off = std::getenv("STGCN_NO_SIMT_ALIGNBWD") != nullptr;      // A/B switch for profiling
-      if (dx && !simt_off && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
+      static const bool simt_on = std::getenv("STGCN_SIMT_ALIGNBWD") != nullptr;      // opt-in (first version measured -8%)
+      if (dx && simt_on && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
         launch_lowrank_expand<T>(dst, p.align_w, dx, rows, d.c_in, c.stream);      // align_w is [C][c_in] row-major
         dx = nullptr;
       }
@@ -816,7 +830,9 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   c.prep_ready();
   if constexpr (std::is_same<T, simt::bf16>::value) {
     static const bool pipe_off = std::getenv("STGCN_NO_LN_PIPE") != nullptr;      // A/B switch for profiling
-    if (!pipe_off && ln_gate_pipe_supported(a)) {
+    // the persistent kernel needs enough groups per CTA to amortise its prologue (first bulk load) and its final
+    // flush of 2*M atomics: measured on PeMSD7-M, 14 groups per CTA 154 vs 158 us, 7 groups per CTA 120 vs 95 us
+    if (!pipe_off && ln_gate_pipe_supported(a) && a.G >= 10LL * umma::sm_count()) {
       launch_ln_gate_bwd_pipe(tc.act, a, umma::sm_count(), s);
       return true;
     }
@@ -882,7 +898,7 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   T* dh2 = c.ws.take<T>((size_t)g.rows1 * d.c2);
   T* dh1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
   const bool first = d.c_in == 1;
-  T* dz2 = c.ws.take<T>(tconv_saved_elems(g.tc2));
+  T* dz2 = c.KW().take<T>(tconv_saved_elems(g.tc2));
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2);
   bool ln_fused;
   { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
@@ -892,10 +908,12 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
                                                                   (!ln_fused && tconv_qonly<T>(g.tc2)) ? s.h3 : nullptr); }
   // c1 > c2 (bottleneck): the align conv's data gradient dh1 = dst0 . Wa is formed inside tc1's gate backward from the
   // 16-channel dst0 instead of being written to HBM at c1 channels and read back
-  static const bool lr_off = std::getenv("STGCN_NO_FUSED_ALIGNBWD") != nullptr;      // A/B switch for profiling
-  const bool lr_fuse = !lr_off && std::is_same<T, simt::bf16>::value && d.c1 > d.c2 && d.c2 == kGateLrC &&
+  // (opt-in: measured -0.4% on PeMSD7-M -- the 128 FMAs per 8 outputs turn the bandwidth-bound gate kernel into an
+  // issue-bound one, 52 -> 125 us, for a 46 us kernel saved; profiles/r01_ab_batch_f.md)
+  static const bool lr_on = std::getenv("STGCN_FUSED_ALIGNBWD") != nullptr;
+  const bool lr_fuse = lr_on && std::is_same<T, simt::bf16>::value && d.c1 > d.c2 && d.c2 == kGateLrC &&
                        tconv_lowrank_dy_ok<T>(g.tc1);      // shapes only: the dry (sizing) run must take the same path
-  T* dst_ext = c.ws.take<T>(lr_fuse ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
+  T* dst_ext = c.KW().take<T>(lr_fuse ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
   { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, lr_fuse ? nullptr : dh1, c, lr_fuse ? dst_ext : nullptr); }
   LowRankDy<T> lr{dst_ext, p.gc.align_w};       // align_w is [c2][c1] row-major = lr_w[o * c1 + j]
   { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, lr_fuse ? &lr : nullptr,
@@ -1008,13 +1026,13 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   OutSaved<T> s = out_saved<T>(d, g, sv);
   ScopedMark sm(c.ws);
   T* dr = c.ws.take<T>((size_t)g.rows1 * d.c1);
-  T* df1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
+  T* df1 = c.KW().take<T>((size_t)g.rows1 * d.c1);
   T* dl = c.ws.take<T>((size_t)g.rows1 * d.c0);
   T* dh = c.ws.take<T>((size_t)g.rows1 * d.c0);
   T* dyT = c.ws.take<T>(sizeof(T) == sizeof(float) ? 0 : (size_t)g.rows1 * d.c_end);
   float* dw2 = c.K().take<float>((size_t)(d.c1 + 1) * d.c_end);
   float* dw1 = c.K().take<float>((size_t)(d.c0 + 1) * d.c1);
-  float* part = c.ws.take<float>(std::max({wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
+  float* part = c.KW().take<float>(std::max({wgrad_partial_elems(g.rows1, d.c1 + 1, d.c_end),
                                            wgrad_partial_elems(g.rows1, d.c0 + 1, d.c1),
                                            (size_t)(ceil_div(g.rows1, 256) + 1) * (d.c1 + 1)}));
   simt::bf16* wbf = c.K().take<simt::bf16>(std::is_same<T, simt::bf16>::value ? (size_t)d.c0 * d.c1 : 0);
@@ -1033,10 +1051,14 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     // fc2 (dy is fp32; the wgrad kernel wants it in the activation type)
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool rowdot = d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && al16(dr) && g.rows1 > 0;
+    // without dropout the ReLU backward rides in the fc2 data-gradient kernel (df1 written directly)
+    static const bool relu_bwd_off = std::getenv("STGCN_NO_FUSED_RELUBWD") != nullptr;      // A/B switch for profiling
+    const T* relu_ref = out_relu_fused<T>(d, g) ? s.r : s.f1;        // the forward kept only r = relu(f1) when it fused the ReLU
+    const bool relu_bwd_fused = rowdot && !relu_bwd_off && !(d.training && d.p_drop > 0.f) && al16(relu_ref) && al16(df1);
     if (rowdot) {
       const long long total = g.rows1 * (d.c1 / 8);
       STGCN_LAUNCH(rowouter_bwd_kernel<T>, (int)std::min<long long>(ceil_div(total, 256), 148 * 8), 256, 0, c.stream, dy,
-                   p.fc2_w, dr, g.rows1, d.c1);
+                   p.fc2_w, relu_bwd_fused ? df1 : dr, g.rows1, d.c1, relu_bwd_fused ? relu_ref : (const T*)nullptr);
     } else {
       TapArgs<float, T> t0{};
       t0.in = dy; t0.wt = p.fc2_w; t0.bias = nullptr; t0.out = dr; t0.rows = g.rows1; t0.Cin = d.c_end; t0.Co = d.c1;
@@ -1048,7 +1070,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       dy_t = reinterpret_cast<const T*>(dy);
     } else {
       long long ne = g.rows1 * d.c_end;
-      if (ne) STGCN_LAUNCH(convert_kernel, ceil_div(ne, 256), 256, 0, c.stream, dy, dyT, ne);
+      if (ne) STGCN_LAUNCH((convert_kernel<float, T>), ceil_div(ne, 256), 256, 0, c.stream, dy, dyT, ne);
       dy_t = dyT;
     }
     TapArgs<T> t{};
@@ -1056,8 +1078,9 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     if ((gr.fc2_w || gr.fc2_b) && rowdot) {
       long long rpc = std::max<long long>(256, (g.rows1 + 148 * 4 - 1) / (148 * 4));
       const int ctas = ceil_div(g.rows1, rpc);
-      STGCN_LAUNCH(rowdot_wgrad_kernel<T>, ctas, 256, 0, c.stream, (const T*)s.r, dy, part, g.rows1, d.c1, (int)rpc);
-      launch_reduce_partials(part, dw2, d.c1 + 1, ctas, c.stream);
+      c.post_after();                       // reads only saved state and dy: runs beside the data-gradient chain
+      STGCN_LAUNCH(rowdot_wgrad_kernel<T>, ctas, 256, 0, c.wstream(), (const T*)s.r, dy, part, g.rows1, d.c1, (int)rpc);
+      launch_reduce_partials(part, dw2, d.c1 + 1, ctas, c.wstream());
       c.post_after();
       GatherBatch gb(c.qs());
       if (gr.fc2_w) gb.add(dw2, gr.fc2_w, 1, 1, d.c1, 0, 0, 0, 1);
@@ -1075,8 +1098,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       gb.flush();
     }
     long long n1 = g.rows1 * d.c1;
-    const T* relu_ref = out_relu_fused<T>(d, g) ? s.r : s.f1;        // the forward kept only r = relu(f1) when it fused the ReLU
-    if (n1) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, relu_ref, df1, n1, d.training, d.p_drop, seed);
+    if (n1 && !relu_bwd_fused) STGCN_LAUNCH(relu_dropout_bwd_kernel<T>, ceil_div(n1, 256), 256, 0, c.stream, (const T*)dr, relu_ref, df1, n1, d.training, d.p_drop, seed);
     // fc1
     bool dl_done = false;
     if constexpr (std::is_same<T, simt::bf16>::value) {
@@ -1093,7 +1115,8 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       bool done_w = false;
       if constexpr (std::is_same<T, simt::bf16>::value) {
         if (umma::wgrad_supported(d.c0, d.c1, 1, g.T1, d.B)) {
-          umma::launch_wgrad_umma(s.l, df1, dw1, d.B, d.N, g.T1, 1, d.c0, d.c1, 1, c.stream);
+          c.post_after();
+          umma::launch_wgrad_umma(s.l, df1, dw1, d.B, d.N, g.T1, 1, d.c0, d.c1, 1, c.wstream());
           done_w = true;
         }
       }
@@ -1110,7 +1133,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
       gb.flush();
     }
   }
-  T* dz = c.ws.take<T>(tconv_saved_elems(g.tc));
+  T* dz = c.KW().take<T>(tconv_saved_elems(g.tc));
   float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T1);
   bool ln_fused;
   { Tag t("out.ln.bwd");

@@ -92,6 +92,7 @@ struct TapArgs {
 
 template <class TI, class TO, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs<TI, TO> a) {
+  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -213,6 +214,7 @@ struct GsoArgs {
 
 template <class T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) gso_kernel(GsoArgs<T> a) {
+  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -320,6 +322,7 @@ struct WgradArgs {
 
 template <class T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
+  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -426,6 +429,7 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
 
 // out[e] += sum_c partial[c][e]: one warp per 8 elements x 4 lanes-groups; lanes stride over the chunks, shuffle-reduce
 __global__ void reduce_partials_kernel(const float* partial, float* out, int n, int chunks) {
+  pdl_begin();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * (blockDim.x >> 5) + warp;
   if (e >= n) return;
@@ -448,6 +452,7 @@ inline void launch_reduce_partials(const float* partial, float* out, int n, int 
 constexpr int kSkR = 128;     // rows per tile: the three block barriers per tile were the bottleneck at 32
 template <class T, bool VEC>
 __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
+  pdl_begin();
   extern __shared__ __align__(16) float sk[];
   const int Kw = a.ntaps * a.Cin;
   const int Mtot = Kw + (a.bias_row ? 1 : 0);
@@ -658,6 +663,7 @@ __device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r
 
 template <class T, int ACT>
 __global__ void gate_fwd_kernel(GateArgs<T> a) {
+  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = (long long)((unsigned long long)idx / (unsigned)a.Cout);
@@ -681,6 +687,7 @@ __global__ void gate_fwd_kernel(GateArgs<T> a) {
 
 template <class T, int ACT>
 __global__ void gate_bwd_kernel(GateArgs<T> a) {
+  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = idx / a.Cout;
@@ -711,6 +718,7 @@ __global__ void gate_bwd_kernel(GateArgs<T> a) {
 template <class T>
 __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres, int W, int Cin, int Kt,
                                     int T_out, int T_in, int N) {
+  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cres) return;
   long long r = idx / Cres;
@@ -724,14 +732,16 @@ __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres
 // 8 channels per thread (requires Cout, W and Cin to be multiples of 8 when a residual is read)
 template <class T, int ACT>
 __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
+  pdl_begin();
   extern __shared__ __align__(16) float lrw_s[];        // [kGateLrC][Cout] when a.lr_src (launcher sizes it)
   if (a.lr_src) {
     for (int i = threadIdx.x; i < kGateLrC * a.Cout; i += blockDim.x) lrw_s[i] = a.lr_w[i];
     __syncthreads();
   }
   const int groups = a.Cout / 8;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= a.rows * groups) return;
+  const long long total = a.rows * groups;
+  // one chunk per thread normally; with a low-rank dy the grid is persistent (weights staged once per CTA)
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
   const long long r = (long long)((unsigned)idx / (unsigned)groups);    // rows * groups < 2^31 (launcher)
   const int j0 = (int)(idx - r * groups) * 8;
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
@@ -787,6 +797,7 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
     store8(a.dz + r * a.W + j0, du);
     if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
   }
+  }
 }
 
 // does the 8-channels-per-thread kernel serve these arguments?  (tconv_bwd asks before it commits to a low-rank dy)
@@ -803,7 +814,8 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   if (n == 0) return;
   if (gate_vec_ok(a)) {
     const size_t lr_smem = a.lr_src ? (size_t)kGateLrC * a.Cout * sizeof(float) : 0;
-    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, lr_smem, s, a, bwd ? 1 : 0);
+    const int blocks = a.lr_src ? (int)std::min<long long>(ceil_div(n / 8, 256), 148 * 8) : ceil_div(n / 8, 256);
+    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), blocks, 256, lr_smem, s, a, bwd ? 1 : 0);
     return;
   }
   STGCN_CHECK(!a.lr_src && !a.q_only, STGCN_E_UNSUPPORTED, "low-rank dy / q-only saved state need the vectorised gate kernel");
@@ -816,26 +828,30 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
 // its time in per-tile epilogue bookkeeping (66 us for 75 MB), this is bandwidth work.  8 channels per thread.
 template <class T>
 __global__ void __launch_bounds__(256) lowrank_expand_kernel(const T* src, const float* w, T* out, long long rows, int Cout) {
+  pdl_begin();
   extern __shared__ __align__(16) float lrx_s[];         // [kGateLrC][Cout]
   for (int i = threadIdx.x; i < kGateLrC * Cout; i += blockDim.x) lrx_s[i] = w[i];
   __syncthreads();
+  // persistent grid-stride loop: staging the weights once per 8-output chunk (one-shot CTAs) made the first version
+  // 150 us for 37 MB (profiles/r01_ab_batch_g.md)
   const int groups = Cout / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * groups) return;
-  const long long r = (long long)((unsigned)idx / (unsigned)groups);
-  const int j0 = (int)(idx - r * groups) * 8;
-  float d[kGateLrC], g[8];
-  load8(src + r * kGateLrC, d); load8(src + r * kGateLrC + 8, d + 8);
+  const long long total = rows * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = (long long)((unsigned)idx / (unsigned)groups);
+    const int j0 = (int)(idx - r * groups) * 8;
+    float d[kGateLrC], g[8];
+    load8(src + r * kGateLrC, d); load8(src + r * kGateLrC + 8, d + 8);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] = 0.f;
+    for (int i = 0; i < 8; ++i) g[i] = 0.f;
 #pragma unroll
-  for (int o = 0; o < kGateLrC; ++o) {
-    const float4 w0 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0);
-    const float4 w1 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0 + 4);
-    g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
-    g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
+    for (int o = 0; o < kGateLrC; ++o) {
+      const float4 w0 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0);
+      const float4 w1 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0 + 4);
+      g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
+      g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
+    }
+    store8(out + r * Cout + j0, g);
   }
-  store8(out + r * Cout + j0, g);
 }
 template <class T>
 inline bool lowrank_expand_supported(const T* src, const float* w, const T* out, long long rows, int Csrc, int Cout) {
@@ -845,7 +861,8 @@ inline bool lowrank_expand_supported(const T* src, const float* w, const T* out,
 template <class T>
 inline void launch_lowrank_expand(const T* src, const float* w, T* out, long long rows, int Cout, cudaStream_t s) {
   const long long n = rows * (Cout / 8);
-  STGCN_LAUNCH(lowrank_expand_kernel<T>, ceil_div(n, 256), 256, (size_t)kGateLrC * Cout * sizeof(float), s, src, w, out, rows, Cout);
+  const int blocks = (int)std::min<long long>(ceil_div(n, 256), 148 * 8);
+  STGCN_LAUNCH(lowrank_expand_kernel<T>, blocks, 256, (size_t)kGateLrC * Cout * sizeof(float), s, src, w, out, rows, Cout);
 }
 
 template <class T>
@@ -865,6 +882,7 @@ inline void launch_gate_any(int act, bool bwd, const GateArgs<T>& a, cudaStream_
 // db = sum_r dy[r].  All three are bandwidth work over a [rows, C] tensor: 8 channels per thread, 16-byte accesses.
 template <class T>
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* in, const float* w, const float* b, float* y, long long rows, int C) {
+  pdl_begin();
   const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;   // G = power of two <= 32
   float wv[8];
 #pragma unroll
@@ -880,8 +898,13 @@ __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* in, const floa
     if (g == 0) y[r] = s + bias;
   }
 }
+// relu_ref (optional): the ReLU that sat in front of this layer's input is applied on the way out,
+// din[r, c] = relu_ref[r, c] > 0 ? dy[r] * w[c] : 0 (no dropout): one pass instead of a [rows, C] round trip through a
+// separate ReLU-backward kernel.
 template <class T>
-__global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, const float* w, T* din, long long rows, int C) {
+__global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, const float* w, T* din, long long rows, int C,
+                                                           const T* relu_ref) {
+  pdl_begin();
   const int G = C / 8;
   const long long total = rows * G;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -891,6 +914,12 @@ __global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, cons
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = d * w[g * 8 + i];
+    if (relu_ref) {
+      float f[8];
+      load8(relu_ref + r * C + g * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = f[i] > 0.f ? v[i] : 0.f;
+    }
     store8(din + r * C + g * 8, v);
   }
 }
@@ -898,6 +927,7 @@ __global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, cons
 template <class T>
 __global__ void __launch_bounds__(256) rowdot_wgrad_kernel(const T* in, const float* dy, float* partial, long long rows, int C,
                                                            int rows_per_cta) {
+  pdl_begin();
   __shared__ float red[8][257];
   const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;
   float acc[8], accb = 0.f;
@@ -953,6 +983,7 @@ struct SmallCArgs {
 
 template <class T>
 __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T> a) {
+  pdl_begin();
   extern __shared__ float sm[];          // wt [K][W] then bias [W]
   const int K = a.Kt * a.Cin;
   for (int i = threadIdx.x; i < K * a.W; i += blockDim.x) sm[i] = a.wt[i];
@@ -1000,6 +1031,7 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
 // gate, and three 16-byte stores.
 template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
+  pdl_begin();
   const int groups = a.Cout / 8;
   const bool gated = a.W == 2 * a.Cout;
   const int j0 = (threadIdx.x % groups) * 8;
@@ -1065,6 +1097,7 @@ inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s)
 // global buffer with one atomic per element per CTA.  Optionally also materialises dz (when dx is needed).
 template <class T>
 __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a) {
+  pdl_begin();
   extern __shared__ float red[];         // [lanes][2][K+1][Cout]
   const int K = a.Kt * a.Cin;
   const bool gated = a.W == 2 * a.Cout;
@@ -1130,6 +1163,7 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
 // at compile time, shuffle + shared-memory reduction, per-CTA partials.
 template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
+  pdl_begin();
   __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
   const bool gated = a.W == 2 * a.Cout;
   const int G = a.Cout / 8;                         // channel groups (power of two <= 32 checked by the launcher)
@@ -1248,6 +1282,7 @@ inline bool smallc_supported(int Cin, int Cout, int W, int Kt) {
 template <class TO>
 __global__ void gather3_kernel(const float* in, TO* out, int d0, int d1, int d2, long long off,
                                long long s0, long long s1, long long s2, int accumulate) {
+  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (long long)d0 * d1 * d2;
   if (idx >= tot) return;
@@ -1276,6 +1311,7 @@ struct GatherJob {
 constexpr int kMaxGatherJobs = 8;
 struct GatherJobs { GatherJob j[kMaxGatherJobs]; int n; };
 __global__ void gather3_multi_kernel(GatherJobs jobs) {
+  pdl_begin();
   const GatherJob& g = jobs.j[blockIdx.y];
   const long long tot = (long long)g.d0 * g.d1 * g.d2;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
@@ -1310,6 +1346,7 @@ struct GatherBatch {
 
 // out[i*ldo + j] += in[i*si + j*sj]   (strided block accumulate; used to fold 1x1 align weights)
 __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, int d1, long long si, long long sj) {
+  pdl_begin();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d0 * d1) return;
   int i = idx / d1, j = idx - i * d1;
@@ -1319,6 +1356,7 @@ __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, i
 // out[r, j] = j < Cin ? in[r*ldi + j] : 0   for j < Cout   (zero-pad or column slice copy)
 template <class T>
 __global__ void copy_cols_kernel(const T* in, T* out, long long rows, int Cin, int ldi, int Cout, int accumulate) {
+  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cout) return;
   long long r = idx / Cout;
@@ -1337,6 +1375,7 @@ inline void launch_copy_cols(const T* in, T* out, long long rows, int Cin, int l
 // dtype conversion of an activation tensor
 template <class TI, class TO>
 __global__ void convert_kernel(const TI* in, TO* out, long long n) {
+  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) stf(out + i, ldf(in + i));
 }
@@ -1344,6 +1383,7 @@ __global__ void convert_kernel(const TI* in, TO* out, long long n) {
 // y = relu?(g + a)
 template <class T>
 __global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int relu) {
+  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
@@ -1366,6 +1406,7 @@ __global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int r
 // dg = relu ? dy * (y > 0) : dy
 template <class T>
 __global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int relu) {
+  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dg)) & 15) == 0) {
@@ -1382,6 +1423,7 @@ __global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int
 // y += alpha * x
 template <class T>
 __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
+  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
@@ -1397,6 +1439,7 @@ __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
 // y = relu(x), with optional dropout; and its backward
 template <class T>
 __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int training, float p, uint64_t seed) {
+  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = fmaxf(ldf(x + i), 0.f);
@@ -1406,6 +1449,7 @@ __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int train
 template <class T>
 __global__ void relu_dropout_bwd_kernel(const T* dy, const T* x, T* dx, long long n, int training, float p,
                                         uint64_t seed) {
+  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = ldf(x + i) > 0.f ? ldf(dy + i) : 0.f;
@@ -1437,6 +1481,7 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w, const float* b, T* y,
                                                      float* mean, float* rstd, int M, float eps, int training,
                                                      float p, uint64_t seed) {
+  pdl_begin();
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1492,6 +1537,7 @@ template <int NCH>
 __global__ void __launch_bounds__(512) ln_fwd_cached_kernel(const bf16* x, const float* w, const float* b, bf16* y,
                                                             float* mean, float* rstd, int M, float eps, int training,
                                                             float p, uint64_t seed) {
+  pdl_begin();
   __shared__ float red[32];
   const long long g = blockIdx.x;
   const bf16* xp = x + g * M;
@@ -1546,6 +1592,7 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
                                                      const float* rstd, T* dx, int M, int training, float p,
                                                      uint64_t seed) {
+  pdl_begin();
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1591,6 +1638,7 @@ template <class T, int VEC>
 __global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean, const float* rstd, float* dw,
                                      float* db, int M, long long G, int groups_per_cta, int training, float p,
                                      uint64_t seed) {
+  pdl_begin();
   int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i >= M) return;
   long long g0 = (long long)blockIdx.y * groups_per_cta;
@@ -1661,6 +1709,7 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
 }
 template <class T>
 __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
+  pdl_begin();
   __shared__ float red[64];
   const long long g = blockIdx.x;
   const T* xp = a.x + g * a.M;
@@ -1692,6 +1741,7 @@ __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
 #endif
 template <class T, int ACT>
 __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnGateArgs<T> a) {
+  pdl_begin();
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch * 8 >= a.M) return;
@@ -1780,6 +1830,7 @@ inline void launch_ln_gate_bwd(int act, LnGateArgs<T> a, int sms, cudaStream_t s
 
 // loss = mean((pred-target)^2); dpred = 2 (pred-target)/n * scale
 __global__ void mse_kernel(const float* pred, const float* target, long long n, float scale, float* loss, float* dpred) {
+  pdl_begin();
   __shared__ float red[32];
   float s = 0.f;
   float inv = 1.f / (float)n;

@@ -195,6 +195,7 @@ template <int EPI, int ACT>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmZ, TapParams p) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;

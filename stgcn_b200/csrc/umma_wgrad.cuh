@@ -38,6 +38,7 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem;                               // [64 rows][16] bf16 1.0 (2 KB, padded to 1 KB multiple)
@@ -224,6 +225,7 @@ constexpr int kFlatRows = 256;
 
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradFlatParams p) {
+  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem;                       // [64 rows][16] bf16 1.0
