@@ -57,12 +57,12 @@ struct Ctx {
   Arena& K() const { return keep ? *keep : ws; }
   cudaStream_t ps() const { return side ? side->p : stream; }      // parameter-only preparation
   cudaStream_t qs() const { return side ? side->q : stream; }      // post-processing of gradients
-  // Weight-gradient kernels on q (opt-in, STGCN_WGRAD_STREAM): nothing on the caller's stream consumes a parameter
+  // Weight-gradient kernels on q (validated +5%, batch h; STGCN_NO_WGRAD_STREAM=1 switches it off): nothing on the caller's stream consumes a parameter
   // gradient, so the wgrad kernel of a layer can run beside that layer's data-gradient kernel and its launch/drain
   // bubbles leave the critical path.  Everything such a kernel reads must then outlive the op: KW() hands those
   // buffers out of the keep arena (decided by the flag alone, so the sizing pass and the live pass agree).
   static bool wgrad_stream() {
-    static const bool on = std::getenv("STGCN_WGRAD_STREAM") != nullptr && std::getenv("STGCN_NO_SIDE_STREAMS") == nullptr;
+    static const bool on = std::getenv("STGCN_NO_WGRAD_STREAM") == nullptr && std::getenv("STGCN_NO_SIDE_STREAMS") == nullptr;
     return on;
   }
   Arena& KW() const { return (wgrad_stream() && keep) ? *keep : ws; }

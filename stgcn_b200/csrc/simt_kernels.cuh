@@ -59,6 +59,13 @@ __device__ __forceinline__ void load8(const bf16* p, float* v) {
   }
 }
 
+// 8 packed bf16 (16 bytes) -> 8 floats (bf16 -> fp32 is a 16-bit shift)
+__device__ __forceinline__ void unpack8(const uint4& a, float* v) {
+  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
 // (b, rem) = divmod(r, TN_out), t = rem / N with 32-bit arithmetic (64-bit integer division costs ~100 instructions on
 // the GPU and dominated the elementwise kernels); the host guarantees rows < 2^31.
 __device__ __forceinline__ void row_decode(long long r, int TN_out, int N, long long TN_in, long long& base, int& t) {
@@ -829,40 +836,50 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
 template <class T>
 __global__ void __launch_bounds__(256) lowrank_expand_kernel(const T* src, const float* w, T* out, long long rows, int Cout) {
   pdl_begin();
-  extern __shared__ __align__(16) float lrx_s[];         // [kGateLrC][Cout]
-  for (int i = threadIdx.x; i < kGateLrC * Cout; i += blockDim.x) lrx_s[i] = w[i];
-  __syncthreads();
-  // persistent grid-stride loop: staging the weights once per 8-output chunk (one-shot CTAs) made the first version
-  // 150 us for 37 MB (profiles/r01_ab_batch_g.md)
+  // thread = (8-channel group, row lane); its 16 x 8 weights live in REGISTERS for the whole (persistent) kernel: from
+  // shared memory the 32 LDS.128 per 128 FMAs made the kernel shared-memory-bandwidth bound (146 us for 37 MB,
+  // profiles/r01_ab_batch_h.md); the rows' 32-byte inputs are broadcast through L1 to the 8 threads that share a row
   const int groups = Cout / 8;
-  const long long total = rows * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = (long long)((unsigned)idx / (unsigned)groups);
-    const int j0 = (int)(idx - r * groups) * 8;
-    float d[kGateLrC], g[8];
-    load8(src + r * kGateLrC, d); load8(src + r * kGateLrC + 8, d + 8);
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups, lanes = blockDim.x / groups;
+  const int j0 = g * 8;
+  float wr[kGateLrC][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) g[i] = 0.f;
-#pragma unroll
-    for (int o = 0; o < kGateLrC; ++o) {
-      const float4 w0 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0);
-      const float4 w1 = *reinterpret_cast<const float4*>(lrx_s + o * Cout + j0 + 4);
-      g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
-      g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
+  for (int o = 0; o < kGateLrC; ++o) {
+    const float4 w0 = *reinterpret_cast<const float4*>(w + o * Cout + j0);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + o * Cout + j0 + 4);
+    wr[o][0] = w0.x; wr[o][1] = w0.y; wr[o][2] = w0.z; wr[o][3] = w0.w;
+    wr[o][4] = w1.x; wr[o][5] = w1.y; wr[o][6] = w1.z; wr[o][7] = w1.w;
+  }
+  const long long stride = (long long)gridDim.x * lanes;
+  long long r = (long long)blockIdx.x * lanes + lane;
+  uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0;                     // next row's 16 inputs, requested one iteration ahead
+  if (r < rows) { n0 = reinterpret_cast<const uint4*>(src + r * kGateLrC)[0]; n1 = reinterpret_cast<const uint4*>(src + r * kGateLrC)[1]; }
+  for (; r < rows; r += stride) {
+    float d[kGateLrC], v[8];
+    unpack8(n0, d); unpack8(n1, d + 8);
+    if (r + stride < rows) {
+      n0 = reinterpret_cast<const uint4*>(src + (r + stride) * kGateLrC)[0];
+      n1 = reinterpret_cast<const uint4*>(src + (r + stride) * kGateLrC)[1];
     }
-    store8(out + r * Cout + j0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int o = 0; o < kGateLrC; ++o)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(d[o], wr[o][i], v[i]);
+    store8(out + r * Cout + j0, v);
   }
 }
 template <class T>
 inline bool lowrank_expand_supported(const T* src, const float* w, const T* out, long long rows, int Csrc, int Cout) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  return Csrc == kGateLrC && Cout % 8 == 0 && Cout <= 512 && rows > 0 && rows * (Cout / 8) < (1LL << 31) && al16(src) && al16(w) && al16(out);
+  return Csrc == kGateLrC && Cout % 8 == 0 && 256 % (Cout / 8) == 0 && rows > 0 && al16(src) && al16(w) && al16(out);
 }
 template <class T>
 inline void launch_lowrank_expand(const T* src, const float* w, T* out, long long rows, int Cout, cudaStream_t s) {
-  const long long n = rows * (Cout / 8);
-  const int blocks = (int)std::min<long long>(ceil_div(n, 256), 148 * 8);
-  STGCN_LAUNCH(lowrank_expand_kernel<T>, blocks, 256, (size_t)kGateLrC * Cout * sizeof(float), s, src, w, out, rows, Cout);
+  const int lanes = 256 / (Cout / 8);
+  const int blocks = (int)std::min<long long>(ceil_div(rows, lanes), 148);       // 154 registers: one CTA per SM
+  STGCN_LAUNCH(lowrank_expand_kernel<T>, blocks, 256, 0, s, src, w, out, rows, Cout);
 }
 
 template <class T>
@@ -1528,11 +1545,6 @@ __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w,
 // per thread, all loads in flight together) and the mean / variance / normalise passes run from there -- the generic
 // kernel above re-reads the group twice through L1/L2 with a block reduction between the passes (2.4 TB/s measured).
 // Same element-to-thread mapping and summation order as ln_fwd_kernel<bf16, 8>: bit-identical results.
-__device__ __forceinline__ void unpack8(const uint4& a, float* v) {
-  const uint32_t w[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
 template <int NCH>
 __global__ void __launch_bounds__(512) ln_fwd_cached_kernel(const bf16* x, const float* w, const float* b, bf16* y,
                                                             float* mean, float* rstd, int M, float eps, int training,
