@@ -718,7 +718,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      static const bool simt_on = std::getenv("STGCN_SIMT_ALIGNBWD") != nullptr;      // opt-in (first version measured -8%)
+      static const bool simt_on = std::getenv("STGCN_NO_SIMT_ALIGNBWD") == nullptr;   // A/B switch (register-resident weights: +0.9%, batch i)
       if (dx && simt_on && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
         launch_lowrank_expand<T>(dst, p.align_w, dx, rows, d.c_in, c.stream);      // align_w is [C][c_in] row-major
         dx = nullptr;
@@ -829,10 +829,13 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   if (db) zero(db, M, c.ps());
   c.prep_ready();
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool pipe_off = std::getenv("STGCN_NO_LN_PIPE") != nullptr;      // A/B switch for profiling
+    // opt-in (STGCN_LN_PIPE=1): with the q-only saved state the two-launch kernels are faster everywhere on PeMSD7-M
+    // (171.1 k vs 168.6 k samples/s, profiles/r01_ab_batch_i.md); kept for larger N*C where its single read of x, dy pays
+    static const bool pipe_off = std::getenv("STGCN_LN_PIPE") == nullptr;
     // the persistent kernel needs enough groups per CTA to amortise its prologue (first bulk load) and its final
     // flush of 2*M atomics: measured on PeMSD7-M, 14 groups per CTA 154 vs 158 us, 7 groups per CTA 120 vs 95 us
-    if (!pipe_off && ln_gate_pipe_supported(a) && a.G >= 10LL * umma::sm_count()) {
+    static const long long min_groups = std::getenv("STGCN_LN_PIPE_MIN_GROUPS") ? std::atoll(std::getenv("STGCN_LN_PIPE_MIN_GROUPS")) : 10;
+    if (!pipe_off && ln_gate_pipe_supported(a) && a.G >= min_groups * umma::sm_count()) {
       launch_ln_gate_bwd_pipe(tc.act, a, umma::sm_count(), s);
       return true;
     }

@@ -191,3 +191,50 @@ def test_bf16_fused_graph_conv_layer(kind, ks, c_in, N, B, T, relu, cuda_device)
     for k, v in pr.items():
         if v.grad is not None:
             assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < tol, k
+
+
+@pytest.mark.parametrize("dataset,kind,B", [("pemsd7m", "cheb_graph_conv", 8), ("metrla", "graph_conv", 4)])
+def test_bf16_graphed_step_matches_eager(dataset, kind, B, cuda_device):
+    """The whole step (forward + MSE + backward) is captured in ONE CUDA graph although the block-level calls fork helper
+    streams for parameter-only work and for the weight-gradient kernels (csrc/ops.cuh: Side): the forks are joined back
+    inside every call.  Replays must reproduce the eagerly computed loss and gradients (fp32 atomics in the weight
+    gradients make them equal only up to summation order) and must follow new inputs."""
+    import ctypes as C
+    from stgcn_b200 import models, _lib as L
+    from stgcn_b200.graph import GraphedStep
+    dev = cuda_device
+    gso = load_gso(dataset, "cheb" if kind == "cheb_graph_conv" else "gcn")
+    n = gso.shape[0]
+    blocks = [[1], [64, 16, 64], [64, 16, 64], [128, 128], [1]]
+    args = SimpleNamespace(Kt=3, Ks=3, act_func="glu", graph_conv_type=kind, gso=gso.to(dev), enable_bias=True,
+                           droprate=0.0, n_his=12)
+    cls = models.STGCNChebGraphConv if kind == "cheb_graph_conv" else models.STGCNGraphConv
+    model = cls(args, blocks, n).to(dev)
+    model.load_state_dict(O.init_params(blocks=blocks, kt=3, ks=3, n_his=12, n_vertex=n, kind=kind, seed=5))
+    model.train()
+    gen = torch.Generator().manual_seed(11)
+    xs = [torch.randn(B, 1, 12, n, generator=gen).to(dev) for _ in range(2)]
+    ys = [torch.randn(B, n, generator=gen).to(dev) for _ in range(2)]
+
+    def eager(x, y):
+        model.zero_grad(set_to_none=True)
+        pred = model(x).reshape(B, -1).float()
+        dpred = torch.empty_like(pred)
+        loss = torch.zeros(1, device=dev)
+        L.check(L.lib().stgcn_mse_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), C.c_float(1.0), loss.data_ptr(),
+                                          dpred.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+        pred.backward(dpred)
+        torch.cuda.synchronize()
+        return loss.item(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    ref = [eager(x, y) for x, y in zip(xs, ys)]
+    step = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2)
+    for rep in range(2):                       # second pass: replays are repeatable
+        for (x, y), (loss_ref, grads_ref) in zip(zip(xs, ys), ref):
+            loss = step(x, y)
+            torch.cuda.synchronize()
+            assert abs(loss.item() - loss_ref) <= 1e-5 * abs(loss_ref) + 1e-7, (rep, loss.item(), loss_ref)
+            got = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+            assert set(got) == set(grads_ref)
+            for k, g_ref in grads_ref.items():
+                assert rel_l2(got[k].cpu(), g_ref.cpu()) <= 1e-4, (rep, k, rel_l2(got[k].cpu(), g_ref.cpu()))
