@@ -485,6 +485,8 @@ def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
             return gemm, (rows(tout) * W + rows(tin) * cin) * e                      # data gradient
         if "wgrad" in kern and "smallc" not in kern:
             return gemm, (rows(tin) * cin + rows(tout) * W) * e
+        if "smallc1" in kern:      # Cin = 1 first layer: z is never stored (recomputed), so only x and h / dh move
+            return gemm, (rows(tin) * cin + rows(tout) * cout) * e
         if "smallc_conv" in kern:
             return gemm, (rows(tin) * cin + rows(tout) * (W + cout)) * e
         if "smallc" in kern:                                                         # gate bwd + wgrad fused
