@@ -201,6 +201,24 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, t
                 steps=len(times), batch=batch, host_threads_available=avail)
 
 
+def _arm_watchdog(seconds, rank):
+    """A hung collective or a kernel that never returns must not eat the whole time budget of a measurement pass: after
+    `seconds` a daemon thread dumps every Python stack to stderr and ends the process with status 124."""
+    if seconds <= 0:
+        return
+    import faulthandler
+
+    def fire():
+        sys.stderr.write(f"[bench watchdog] rank {rank}: not finished after {seconds} s -- stacks follow, exiting 124\n")
+        faulthandler.dump_traceback(file=sys.stderr, all_threads=True)
+        sys.stderr.flush()
+        os._exit(124)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -216,11 +234,21 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "600")),
+                    help="watchdog: dump all Python stacks to stderr and exit 124 if the run has not finished by then")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    _arm_watchdog(a.max_seconds, rank)
+    # Multi-process runs keep every kernel of the library on the caller's stream: the last round-1 attempt at N=2 with the
+    # helper streams on did not finish (no diagnostics; GPU budget exhausted before it could be bisected), while the same
+    # step without them ran 165.6 k samples/s on 2 GPUs earlier in the round.  STGCN_MULTI_GPU_STREAMS=1 overrides.
+    helper_streams = True
+    if world > 1 and not os.environ.get("STGCN_MULTI_GPU_STREAMS"):
+        os.environ["STGCN_NO_SIDE_STREAMS"] = "1"          # read once by the library, before its first call
+        helper_streams = False
     tag, kind, ks, default_b, desc = WORKLOADS[a.workload]
     B = a.batch or default_b
     steps, warmup = a.steps, max(a.warmup, 3)
@@ -424,7 +452,8 @@ def main():
                 "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
                 "config": {**cfg_common, "precision": a.precision,
                            "l2": f"{POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
-                           "parallelism": f"dp{world}", "cuda_graph": graphed is not None},
+                           "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
+                           "helper_streams": helper_streams},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,

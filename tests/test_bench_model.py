@@ -1,0 +1,44 @@
+"""Host-side checks of bench.py's work model (no GPU): the closed-form algorithmic FLOPs / bytes of SURVEY.md §8(d),
+the per-kernel attribution used for the `roofline` object, and the committed ncu traffic table."""
+import json
+import os
+
+import pytest
+
+import bench
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("n,kind,ks,fwd_m,tot_m", [
+    (228, "cheb_graph_conv", 3, 206.33, 564.01),      # PeMSD7-M   (= FlopCounterMode on the reference)
+    (207, "graph_conv", 3, 157.55, 449.11),           # METR-LA
+    (325, "cheb_graph_conv", 3, 326.39, 868.52),      # PEMS-BAY
+])
+def test_algorithmic_flops_match_survey(n, kind, ks, fwd_m, tot_m):
+    fwd, tot, stages = bench.flops_per_sample(n, kind, ks)
+    assert abs(fwd / 1e6 - fwd_m) < 0.01
+    assert abs(tot / 1e6 - tot_m) < 0.01
+    assert abs(sum(sum(v.values()) for v in stages.values()) - tot) < 1.0      # the per-stage split adds up
+
+
+@pytest.mark.parametrize("n,mb", [(228, 1.763), (207, 1.601), (325, 2.513)])
+def test_algorithmic_bytes_match_survey(n, mb):
+    assert abs(bench.bytes_per_sample(n, 2) / 1e6 - mb) < 0.001
+    assert bench.bytes_per_sample(n, 4) == 2 * bench.bytes_per_sample(n, 2)
+
+
+def test_kernel_work_model_and_traffic_table():
+    table = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["kernels"]
+    assert table, "empty traffic table"
+    for key, row in table.items():
+        work = bench._kernel_work(key, 228, 256, "cheb_graph_conv", 3, 2)
+        assert work is not None, key                       # every captured kernel is modelled
+        fl, by = work
+        assert fl >= 0 and by > 0, key
+        measured = row["dram_read_bytes"] + row["dram_write_bytes"]
+        assert bench._ncu_traffic(key, "pemsd7m", 256, "bf16") == measured
+        # DRAM traffic of one launch never exceeds ~1.3x the algorithmic bytes of its stage (no re-reads); it may be
+        # far below when the output stayed in the 126 MB L2 at capture time
+        assert measured <= 1.3 * by, (key, measured, by)
+    assert bench._ncu_traffic("st0.tc2.fwd:umma_tap_kernel<EPI_GATE>", "metrla", 512, "bf16") is None

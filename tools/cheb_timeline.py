@@ -1,5 +1,8 @@
 """In-kernel timeline of the fused graph-convolution kernels (CTA 0, first 3 items of each slot), from the
 globaltimer stamps of csrc/umma_cheb.cuh.  Diagnostics only: prints microseconds relative to the kernel start."""
+# NOTE: the in-kernel globaltimer stamps are compiled in only with -DSTGCN_TIMELINE:
+#   tools/build_variants.sh tl="-DSTGCN_TIMELINE" && STGCN_B200_LIB=$PWD/build/variants/tl.so python <this script>
+
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, stgcn_b200
