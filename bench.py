@@ -242,9 +242,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     _arm_watchdog(a.max_seconds, rank)
-    # Multi-process runs keep every kernel of the library on the caller's stream: the last round-1 attempt at N=2 with the
-    # helper streams on did not finish (no diagnostics; GPU budget exhausted before it could be bisected), while the same
-    # step without them ran 165.6 k samples/s on 2 GPUs earlier in the round.  STGCN_MULTI_GPU_STREAMS=1 overrides.
+    # Multi-process runs keep every kernel of the library on the caller's stream.  The last round-1 attempt at N=2 did not
+    # finish; the likely cause is the rank-0-only profile pass issuing gradient all-reduces without partners (fixed below),
+    # but the GPU budget was exhausted before the helper streams could be exercised together with NCCL, so they stay off for
+    # N > 1 until that is measured (the step without them ran 165.6 k samples/s on 2 GPUs earlier in the round).
+    # STGCN_MULTI_GPU_STREAMS=1 overrides.
     helper_streams = True
     if world > 1 and not os.environ.get("STGCN_MULTI_GPU_STREAMS"):
         os.environ["STGCN_NO_SIDE_STREAMS"] = "1"          # read once by the library, before its first call
@@ -318,14 +320,15 @@ def main():
     loss_buf = torch.zeros(1, device=dev)
     loss_host = torch.zeros(1).pin_memory()
 
-    def eager_step(x, y):
+    def eager_step(x, y, reduce=True):
         model.zero_grad(set_to_none=True)
         pred = model(x).reshape(B, -1)                      # (B,1,1,N) view -> (B,N), main.py:166
         dpred = torch.empty_like(pred)
         L.check(lib.stgcn_mse_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), 1.0, loss_buf.data_ptr(),
                                       dpred.data_ptr(), torch.cuda.current_stream().cuda_stream))
         pred.backward(dpred)
-        reducer()
+        if reduce:
+            reducer()
 
     # The public API for a launch-free step: the whole forward + loss + backward captured once in a CUDA graph
     # (stgcn_b200.graph.GraphedStep); the gradient all-reduce (N > 1) is issued right after the replay.
@@ -405,7 +408,10 @@ def main():
         psteps = 3
         L.profile_begin()
         for i in range(psteps):
-            eager_step(xs[i % POOL], ys[i % POOL])        # eager: the event profiler brackets individual launches
+            # eager: the event profiler brackets individual launches.  NO collective here: this pass runs on rank 0 only,
+            # an all-reduce without its partners pairs up with the other ranks' final barrier and hangs the job (the N=2
+            # run of round 1 did exactly that)
+            eager_step(xs[i % POOL], ys[i % POOL], reduce=False)
         prof = L.profile_end()
         tot_ms = sum(v[1] for v in prof.values())
         rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
