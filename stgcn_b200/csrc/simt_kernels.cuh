@@ -1178,7 +1178,11 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
 
 // Cin == 1 specialisation of the above (the model input): 8 channels per thread with 16-byte loads, K = Kt taps known
 // at compile time, shuffle + shared-memory reduction, per-CTA partials.
-template <class T, int K, int ACT>
+// PF (opt-in, STGCN_SMALLC1_PREFETCH=1; bf16, z recomputed, no dz output): the next row's x taps and dh chunk are
+// requested one iteration ahead and the weights are read from shared memory as float4 -- ncu showed the loop waiting on
+// the x loads (long scoreboard 33 %) and on scalar LDS (short scoreboard 14 %, MIO 7 %).  PF = false is the validated
+// round-1 kernel, unchanged.
+template <class T, int K, int ACT, bool PF = false>
 __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
   pdl_begin();
   __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
@@ -1201,6 +1205,61 @@ __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a
   }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   const long long r1 = min(a.rows, r0 + a.rows_per_cta);
+  if constexpr (PF && std::is_same<T, bf16>::value) {
+    long long r = r0 + rl;
+    float xn[K];
+    uint4 dhn = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int k = 0; k < K; ++k) xn[k] = 0.f;
+    auto fetch = [&](long long rr) {
+      long long in0; int t_unused;
+      row_decode(rr, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
+#pragma unroll
+      for (int k = 0; k < K; ++k) xn[k] = ldf(a.x + in0 + (long long)k * a.N);
+      dhn = *reinterpret_cast<const uint4*>(a.dh + rr * a.Cout + j0);
+    };
+    if (r < r1) fetch(r);
+    for (; r < r1; r += lanes) {
+      float xv[K], zp[8], zq[8], dh[8], du[8], dq[8];
+#pragma unroll
+      for (int k = 0; k < K; ++k) xv[k] = xn[k];
+      unpack8(dhn, dh);
+      if (r + lanes < r1) fetch(r + lanes);
+      {
+        const float4 b0 = *reinterpret_cast<const float4*>(w_s + K * a.W + j0), b1 = *reinterpret_cast<const float4*>(w_s + K * a.W + j0 + 4);
+        zp[0] = b0.x; zp[1] = b0.y; zp[2] = b0.z; zp[3] = b0.w; zp[4] = b1.x; zp[5] = b1.y; zp[6] = b1.z; zp[7] = b1.w;
+        if (gated) {
+          const float4 c0 = *reinterpret_cast<const float4*>(w_s + K * a.W + a.Cout + j0), c1 = *reinterpret_cast<const float4*>(w_s + K * a.W + a.Cout + j0 + 4);
+          zq[0] = c0.x; zq[1] = c0.y; zq[2] = c0.z; zq[3] = c0.w; zq[4] = c1.x; zq[5] = c1.y; zq[6] = c1.z; zq[7] = c1.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) zq[i] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        const float4 p0 = *reinterpret_cast<const float4*>(w_s + k * a.W + j0), p1 = *reinterpret_cast<const float4*>(w_s + k * a.W + j0 + 4);
+        const float wp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) zp[i] = fmaf(xv[k], wp[i], zp[i]);
+        if (gated) {
+          const float4 q0 = *reinterpret_cast<const float4*>(w_s + k * a.W + a.Cout + j0), q1 = *reinterpret_cast<const float4*>(w_s + k * a.W + a.Cout + j0 + 4);
+          const float wq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) zq[i] = fmaf(xv[k], wq[i], zq[i]);
+        }
+      }
+      if (a.explicit_res && j0 == 0) zp[0] += xv[K - 1];        // residual = zero-padded input: channel 0 only
+#pragma unroll
+      for (int i = 0; i < 8; ++i) act_bwd<true>(ACT, zp[i], gated ? zq[i] : 0.f, dh[i], du[i], dq[i]);
+#pragma unroll
+      for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { accp[k][i] = fmaf(xv[k], du[i], accp[k][i]); accq[k][i] = fmaf(xv[k], dq[i], accq[k][i]); }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { accp[K][i] += du[i]; accq[K][i] += dq[i]; }
+    }
+  } else
   for (long long r = r0 + rl; r < r1; r += lanes) {
     long long in0; int t_unused;
     row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
@@ -1275,6 +1334,11 @@ inline bool smallc1_supported(int Cin, int Cout, int Kt) {
 }
 template <class T>
 inline void launch_smallc1_gate_wgrad(const SmallCArgs<T>& a, int ctas, cudaStream_t s) {
+  static const bool pf_on = std::getenv("STGCN_SMALLC1_PREFETCH") != nullptr;      // opt-in variant (see the kernel)
+  if (pf_on && std::is_same<T, bf16>::value && a.skip_z && a.dz == nullptr && a.Kt == 3 && a.act == STGCN_ACT_GLU) {
+    STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3, STGCN_ACT_GLU, true>), ctas, 256, 0, s, a);
+    return;
+  }
 #define STGCN_SC1B(ACTV) do { \
     if (a.Kt == 2) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 2, ACTV>), ctas, 256, 0, s, a); \
     else if (a.Kt == 3) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3, ACTV>), ctas, 256, 0, s, a); \
