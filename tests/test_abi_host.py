@@ -147,3 +147,53 @@ def test_reference_models_py_loads_our_layers_unchanged():
                 sys.modules.pop(k, None)
             else:
                 sys.modules[k] = v
+
+
+def _sizes_in_subprocess(env_extra):
+    """(saved, workspace) bytes of the default model's two ST blocks and output block in bf16 mode, from a fresh process
+    (the library reads its A/B knobs once per process)."""
+    import json
+    import subprocess
+    import sys
+    code = r'''
+import ctypes as C, json, sys
+sys.path.insert(0, %r)
+from stgcn_b200 import _lib as L
+lib = L.lib()
+out = {}
+for name, desc in [("st0", L.StblockDesc(256, 12, 228, 1, 64, 16, 64, 3, 3, 0, 0, 1, 0.0, 1e-12, 1)),
+                   ("st1", L.StblockDesc(256, 8, 228, 64, 64, 16, 64, 3, 3, 0, 0, 1, 0.0, 1e-12, 1))]:
+    sv, ws = C.c_size_t(), C.c_size_t()
+    L.check(lib.stgcn_stblock_sizes(C.byref(desc), C.byref(sv), C.byref(ws)))
+    out[name] = (sv.value, ws.value)
+o = L.OutblockDesc(256, 4, 228, 64, 128, 128, 1, 4, 0, 1, 0.0, 1e-12, 1)
+sv, ws = C.c_size_t(), C.c_size_t()
+L.check(lib.stgcn_outblock_sizes(C.byref(o), C.byref(sv), C.byref(ws)))
+out["out"] = (sv.value, ws.value)
+print(json.dumps(out))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("STGCN_")}
+    env.update(env_extra)
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=120)
+    assert res.returncode == 0, res.stderr[-800:]
+    return json.loads(res.stdout.strip().splitlines()[-1])
+
+
+def test_bf16_buffer_planning_follows_the_knobs():
+    """Sizing (dry) passes of the block-level calls in bf16 mode, on the CPU: every A/B configuration plans without
+    error; the GLU q-only saved state is smaller than the full pre-activations; running the weight-gradient kernels
+    on the helper stream keeps their inputs in the non-recycled region, so the workspace grows."""
+    base = _sizes_in_subprocess({})
+    full_z = _sizes_in_subprocess({"STGCN_NO_GLU_QONLY": "1"})
+    no_wq = _sizes_in_subprocess({"STGCN_NO_WGRAD_STREAM": "1"})
+    serial = _sizes_in_subprocess({"STGCN_NO_SIDE_STREAMS": "1"})
+    opt = _sizes_in_subprocess({"STGCN_FUSED_ALIGNBWD": "1", "STGCN_LN_PIPE": "1", "STGCN_PDL": "1"})
+    rows2_st0, rows1_st1, rows2_st1 = 256 * 8 * 228, 256 * 6 * 228, 256 * 4 * 228
+    # st0: only tc2 has a stored gate half (tc1, Cin = 1, recomputes z); st1: tc1 and tc2; 64 channels x 2 bytes each
+    assert full_z["st0"][0] - base["st0"][0] >= rows2_st0 * 64 * 2
+    assert full_z["st1"][0] - base["st1"][0] >= (rows1_st1 + rows2_st1) * 64 * 2
+    assert full_z["out"][0] > base["out"][0]
+    for blk in ("st0", "st1", "out"):
+        assert base[blk][1] >= no_wq[blk][1] > 0           # dz & co. move to the keep region
+        assert serial[blk][1] == no_wq[blk][1]             # no helper streams -> no wgrad stream either
+        assert opt[blk][0] == base[blk][0] and opt[blk][1] > 0
