@@ -12,6 +12,7 @@
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
 #include "ln_gate_pipe.cuh"
+#include "ln_gate_group.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -829,6 +830,22 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   if (db) zero(db, M, c.ps());
   c.prep_ready();
   if constexpr (std::is_same<T, simt::bf16>::value) {
+    // opt-in (STGCN_LN_GROUP=1, ln_gate_group.cuh): one CTA per group produces dz in a single pass on the caller's stream;
+    // the parameter gradients, which nothing on that stream waits for, go to helper stream q
+    static const bool group_on = std::getenv("STGCN_LN_GROUP") != nullptr;
+    if (group_on && ln_gate_group_supported(a)) {
+      launch_ln_gate_bwd_group(tc.act, a, s);
+      if (dw || db) {
+        c.post_after();                  // q sees the zeroed accumulators (joined into the caller's stream above)
+        const int xb = ceil_div(M, 128 * 8);
+        int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 16) / xb));
+        const int gpc = ceil_div(G, ychunks);
+        ychunks = ceil_div(G, gpc);
+        STGCN_LAUNCH((ln_param_grad_kernel<T, 8>), dim3(xb, ychunks), 128, 0, c.qs(), x, dy, stats, stats + G, dw, db, M, G, gpc,
+                     d.training, d.p_drop, seed);
+      }
+      return true;
+    }
     // opt-in (STGCN_LN_PIPE=1): with the q-only saved state the two-launch kernels are faster everywhere on PeMSD7-M
     // (171.1 k vs 168.6 k samples/s, profiles/r01_ab_batch_i.md); kept for larger N*C where its single read of x, dy pays
     static const bool pipe_off = std::getenv("STGCN_LN_PIPE") == nullptr;
