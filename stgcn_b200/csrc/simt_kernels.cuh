@@ -1046,7 +1046,9 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
 // Cin == 1 specialisation: the K = Kt weights of this thread's 8 (+8 gate) channels live in registers; each thread
 // walks rows with a grid stride (its channel group never changes), so the loop body is K loads of x, K*16 FMAs, the
 // gate, and three 16-byte stores.
-template <class T, int K, int ACT>
+// PF (opt-in with STGCN_SMALLC1_PREFETCH=1, unmeasured): the next row's taps are requested one iteration ahead (ncu: long
+// scoreboard 49 % on the x loads).  PF = false is the validated round-1 kernel, unchanged.
+template <class T, int K, int ACT, bool PF = false>
 __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
   pdl_begin();
   const int groups = a.Cout / 8;
@@ -1064,6 +1066,43 @@ __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T
       wq[k][i] = gated ? a.wt[k * a.W + a.Cout + j0 + i] : 0.f;
     }
   }
+  if constexpr (PF) {
+    const long long stride = (long long)gridDim.x * lanes;
+    long long r = (long long)blockIdx.x * lanes + rl;
+    float xn[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) xn[k] = 0.f;
+    auto fetch = [&](long long rr) {
+      long long in0; int t_unused;
+      row_decode(rr, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
+#pragma unroll
+      for (int k = 0; k < K; ++k) xn[k] = ldf(a.x + in0 + (long long)k * a.N);
+    };
+    if (r < a.rows) fetch(r);
+    for (; r < a.rows; r += stride) {
+      float xv[K], zp[8], zq[8], hv[8];
+#pragma unroll
+      for (int k = 0; k < K; ++k) xv[k] = xn[k];
+      if (r + stride < a.rows) fetch(r + stride);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float p = bp[i], q = bq[i];
+#pragma unroll
+        for (int k = 0; k < K; ++k) { p = fmaf(xv[k], wp[k][i], p); q = fmaf(xv[k], wq[k][i], q); }
+        zp[i] = p; zq[i] = q;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float res = (a.explicit_res && j0 + i == 0) ? xv[K - 1] : 0.f;
+        hv[i] = act_fwd<kFastAct<T>>(ACT, zp[i] + res, zq[i]);
+      }
+      if (!a.skip_z) {
+        store8(a.z + r * a.W + j0, zp);
+        if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
+      }
+      store8(a.h + r * a.Cout + j0, hv);
+    }
+  } else
   for (long long r = (long long)blockIdx.x * lanes + rl; r < a.rows; r += (long long)gridDim.x * lanes) {
     long long in0; int t_unused;
     row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
@@ -1094,6 +1133,11 @@ template <class T>
 inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s) {
   const int lanes = 256 / (a.Cout / 8);
   const int blocks = (int)std::min<long long>(ceil_div(a.rows, lanes), 148 * 8);
+  static const bool pf_on = std::getenv("STGCN_SMALLC1_PREFETCH") != nullptr;      // opt-in variant (see the kernel)
+  if (pf_on && a.Kt == 3 && a.act == STGCN_ACT_GLU) {
+    STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 3, STGCN_ACT_GLU, true>), blocks, 256, 0, s, a);
+    return;
+  }
   // the activation is a template parameter: a runtime switch inside the 8-wide unrolled gate cost a branch chain per element
 #define STGCN_SC1F(ACTV) do { \
     if (a.Kt == 2) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 2, ACTV>), blocks, 256, 0, s, a); \
