@@ -33,7 +33,7 @@ if __name__ == "__main__":
         json.dump(fp, open(path, "w"), indent=0, sort_keys=True)
         print(f"{len(fp)} kernels -> {path}")
     else:
-        ref = {k: v for k, v in json.load(open(path)).items() if not k.startswith("_")}
+        ref = {k: v for k, v in json.load(open(path)).items() if k not in ("_note", "_unvalidated_opt_in")}
         changed = sorted(k for k in ref if k in fp and fp[k] != ref[k])
         removed = sorted(k for k in ref if k not in fp)
         new = sorted(k for k in fp if k not in ref)
