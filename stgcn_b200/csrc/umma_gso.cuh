@@ -139,6 +139,125 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem_base, ncols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K-tiled variant for operators that do not fit shared memory (N > ~1500; BASELINE configs[4], N = 2048): the A tile
+// [128 x 64] of every K block travels through the ring next to its B block instead of staying resident.  Lhat (8 MB
+// in bf16 at N = 2048) stays in the 126 MB L2, so the re-reads per group set are L2 traffic.  Opt-in
+// (STGCN_GSO_KTILED=1; also forces this kernel for small N so the existing graph-conv tests can exercise it); written
+// after the GPU budget of round 1 was spent: NOT yet run on a GPU.  Same roles / accumulator handling as umma_gso_kernel.
+// Next step for the roofline at N = 2048: cta_group::2 (M = 256) with TMA multicast of the B block across the pair.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTapThreads, 1)
+umma_gso_ktiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GsoParams p) {
+  pdl_begin();
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;                   // S stages of { A [128 rows][128 B] (16 KB) , B [Gb][64 rows][C*2 B] }
+  __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t stage_total = 16384u + p.stage_bytes;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h0 = blockIdx.y * 128;
+  const int NC = p.Gb * p.C;              // accumulator width
+  uint32_t ncols = 32;
+  while ((int)ncols < 2 * NC) ncols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&tmA);
+      tma_prefetch_desc(&tmB);
+      uint32_t g = 0;
+      for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x) {
+        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
+          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], stage_total);
+          uint8_t* st = ring + (size_t)s * stage_total;
+          tma_load_2d(st, &tmA, &full[s], kb * 64, h0);
+          tma_load_3d(st + 16384, &tmB, &full[s], 0, kb * 64, set * p.Gb);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16(128, NC, 0, 1);
+      uint32_t g = 0, acc_cnt = 0;
+      for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x, ++acc_cnt) {
+        const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
+        mbar_wait(&tempty[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + ab * NC;
+        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
+          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(ring + (size_t)s * stage_total);
+          const uint32_t b_base = a_base + 16384;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc(a_base + k * 32, 16, 1024, SWZ_128B);
+            const uint64_t db = make_smem_desc(b_base + k * p.b_kadv, p.b_lbo, p.b_sbo, p.b_swz);
+            mma_bf16_ss(d_tmem, da, db, idesc, (kb | k) != 0);
+          }
+          mma_commit(&empty[s]);
+        }
+        mma_commit(&tfull[ab]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int h = h0 + q * 32 + lane;
+    const bool hvalid = h < p.N;
+    uint32_t acc_cnt = 0;
+    for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x, ++acc_cnt) {
+      const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
+      mbar_wait(&tfull[ab], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * NC;
+      for (int gl = 0; gl < p.Gb; ++gl) {
+        const long long g = (long long)set * p.Gb + gl;
+        const bool ok = hvalid && g < p.G;
+        const long long base = (g * p.N + h) * p.C;
+        for (int c0 = 0; c0 < p.C; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(t_addr + gl * p.C + c0, r);
+          tmem_ld_wait();
+          if (ok) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = p.alpha * __uint_as_float(r[i]);
+            if (p.aux) {
+              float av[16];
+              load16_bf16(p.aux + base + c0, av);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += p.beta * av[i];
+            }
+            store16_bf16(p.out + base + c0, v);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[ab]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, ncols);
+}
+
 // Lhat (fp32 [N,N]) -> bf16 [N][Kp], Kp = N rounded up to 64, zero padded; optionally transposed
 __global__ void gso_prep_kernel(const float* M, bf16* out, int N, int Kp, int trans) {
   pdl_begin();
@@ -169,13 +288,40 @@ inline GsoPlan plan_gso(int N, int C) {
   pl.ok = true;
   return pl;
 }
-inline bool gso_supported(int N, int C, long long G) { return G > 0 && plan_gso(N, C).ok; }
+inline bool gso_ktiled_enabled() {
+  static const bool on = std::getenv("STGCN_GSO_KTILED") != nullptr;      // opt-in: not yet validated on a GPU
+  return on;
+}
+// K-tiled plan: stages of (16 KB A block + B block); nothing resident
+inline GsoPlan plan_gso_ktiled(int N, int C) {
+  GsoPlan pl{};
+  pl.ok = false;
+  if (C != 16 && C != 32 && C != 64) return pl;
+  pl.Kp = (N + 63) / 64 * 64;
+  pl.nKB = pl.Kp / 64;
+  pl.a_bytes = 0;
+  pl.Gb = 256 / C;
+  pl.stage_bytes = (uint32_t)pl.Gb * 64 * C * 2;      // = 32 KB
+  int S = (int)(kSmemBudget / (16384 + pl.stage_bytes));
+  pl.S = S > kMaxStages ? kMaxStages : S;
+  if (pl.S < 2) return pl;
+  pl.nMT = (N + 127) / 128;
+  pl.smem = (size_t)pl.S * (16384 + pl.stage_bytes) + 1024;
+  pl.ok = true;
+  return pl;
+}
+inline bool gso_supported(int N, int C, long long G) {
+  if (G <= 0) return false;
+  if (gso_ktiled_enabled()) return plan_gso_ktiled(N, C).ok;
+  return plan_gso(N, C).ok;
+}
 inline size_t gso_prep_elems(int N) { return (size_t)N * ((N + 63) / 64 * 64); }
 
 // mbf: bf16 [N][Kp] prepared operator (gso_prep_kernel)
 inline void launch_gso_umma(const bf16* mbf, const bf16* in, const bf16* aux, bf16* out, int N, int C, long long G,
                             float alpha, float beta, cudaStream_t stream) {
-  GsoPlan pl = plan_gso(N, C);
+  const bool ktiled = gso_ktiled_enabled();
+  GsoPlan pl = ktiled ? plan_gso_ktiled(N, C) : plan_gso(N, C);
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma gso: unsupported shape");
   uint64_t ad[2] = {(uint64_t)pl.Kp, (uint64_t)N};
   uint64_t as[1] = {(uint64_t)pl.Kp * 2};
@@ -198,6 +344,11 @@ inline void launch_gso_umma(const bf16* mbf, const bf16* in, const bf16* aux, bf
   int per = sm_count() / pl.nMT;
   int gx = p.n_sets < per ? p.n_sets : per;
   if (gx < 1) gx = 1;
+  if (ktiled) {
+    STGCN_CUDA(cudaFuncSetAttribute(umma_gso_ktiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    STGCN_LAUNCH(umma_gso_ktiled_kernel, dim3(gx, pl.nMT), kTapThreads, pl.smem, stream, tmA, tmB, p);
+    return;
+  }
   STGCN_CUDA(cudaFuncSetAttribute(umma_gso_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   STGCN_LAUNCH(umma_gso_kernel, dim3(gx, pl.nMT), kTapThreads, pl.smem, stream, tmA, tmB, p);
 }
