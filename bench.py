@@ -30,7 +30,25 @@ WORKLOADS = {
     "pemsd7m": ("pemsd7m", "cheb_graph_conv", 3, 256, "PeMSD7-M N=228 Kt=3 Ks=3 ChebGraphConv T=12"),
     "metrla": ("metrla", "graph_conv", 3, 512, "METR-LA N=207 GraphConv Kt=3 T=12"),
     "pemsbay": ("pemsbay", "cheb_graph_conv", 3, 128, "PEMS-BAY N=325 ChebGraphConv Ks=3 Kt=3 T=12"),
+    # BASELINE configs[4] (roofline sweep): seeded dense symmetric operator with spectral norm 1, 64 graph-conv channels.
+    # NOT measured in round 1; the node contraction needs STGCN_GSO_KTILED=1 to run on tensor cores.
+    "syn2048": ("syn2048", "cheb_graph_conv", 5, 512, "synthetic N=2048 dense operator ChebGraphConv Ks=5 channels=64 Kt=3 T=12"),
 }
+WORKLOAD_BLOCKS = {"syn2048": [[1], [64, 64, 64], [64, 64, 64], [128, 128], [1]]}
+
+
+def workload_blocks(workload):
+    return WORKLOAD_BLOCKS.get(workload, BLOCKS)
+
+
+def load_operator(tag, kind):
+    """Dense graph operator of a workload: the reference-derived matrices committed under tests/golden/, or the seeded
+    synthetic operator of SURVEY.md §8(d) for the N=2048 sweep."""
+    if tag.startswith("syn"):
+        from oracle import stgcn_oracle as O        # operator construction only (same helper the tests use)
+        return O.synthetic_gso(int(tag[3:]), seed=0)
+    return torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
+                                                 f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
 
 
 # ---- algorithmic work per sample (SURVEY.md §8d closed form; MAC = 2 FLOP) ---------------------------------------
@@ -148,19 +166,19 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, t
     layer_norm, autograd) on all host cores.  Returns dict(samples_per_s, ms_per_step, cores, steps)."""
     from oracle import stgcn_oracle as O
     tag, kind, ks, _, _ = WORKLOADS[workload]
-    gso = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
-                                                f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
+    blocks = workload_blocks(workload)
+    gso = load_operator(tag, kind)
     n = gso.shape[0]
     try:
         avail = len(os.sched_getaffinity(0))
     except AttributeError:
         avail = os.cpu_count() or 1
     params = {k: v.requires_grad_(True) for k, v in
-              O.init_params(blocks=BLOCKS, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
+              O.init_params(blocks=blocks, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
     gen = torch.Generator().manual_seed(0)
     x = torch.randn(batch, 1, 12, n, generator=gen)
     y = torch.randn(batch, n, generator=gen)
-    cfg = dict(blocks=BLOCKS, kt=3, n_his=12, act="glu", kind=kind, p_drop=droprate, training=True)
+    cfg = dict(blocks=blocks, kt=3, n_his=12, act="glu", kind=kind, p_drop=droprate, training=True)
 
     def step():
         for p in params.values():
@@ -262,7 +280,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cpu_b = min(B, 32)
+        cpu_b = min(B, 32 if a.workload != "syn2048" else 2)       # ~1 GFLOP of conv/bmm per sample-step at N=2048
         r = cpu_reference_run(a.workload, cpu_b, steps, warmup, a.droprate)
         sample = (f"{r['steps']} steps of B={cpu_b} (a bounded sample of the B={B} workload), oracle port of the "
                   f"reference step (same ATen ops), {r['cores']} host threads (fastest of a sweep; "
@@ -298,14 +316,14 @@ def main():
     from oracle import stgcn_oracle as O   # parameter init only (same shapes/keys as the reference)
     stgcn_b200.set_precision(a.precision)
 
-    gso = torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
-                                                f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
+    blocks = workload_blocks(a.workload)
+    gso = load_operator(tag, kind)
     n = gso.shape[0]
     args = SimpleNamespace(Kt=3, Ks=ks, act_func="glu", graph_conv_type=kind, gso=gso.to(dev), enable_bias=True,
                            droprate=a.droprate, n_his=12)
     cls = models.STGCNChebGraphConv if kind == "cheb_graph_conv" else models.STGCNGraphConv
-    model = cls(args, BLOCKS, n).to(dev)
-    model.load_state_dict(O.init_params(blocks=BLOCKS, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0))
+    model = cls(args, blocks, n).to(dev)
+    model.load_state_dict(O.init_params(blocks=blocks, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0))
     model.train()
     reducer = FlatGradAllReducer(model)
 
@@ -398,7 +416,7 @@ def main():
 
     # live per-kernel CUDA-event profile of the same step (separate short pass so the timed loop is unperturbed)
     roofline, top = None, []
-    fwd_f, tot_f, stages = flops_per_sample(n, kind, ks)
+    fwd_f, tot_f, stages = flops_per_sample(n, kind, ks, blocks=blocks)
     peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
@@ -422,7 +440,7 @@ def main():
         esize = 4 if a.precision == "fp32" else 2
         ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
         for k0, (c0, ms0) in rows:
-            work = _kernel_work(k0, n, B, kind, ks, esize)
+            work = _kernel_work(k0, n, B, kind, ks, esize, blocks=blocks)
             if not work:
                 continue
             fl, by = work
@@ -440,14 +458,14 @@ def main():
     step_tflops = tot_f * value / world / 1e12          # per GPU
     roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
-                     "flops_per_sample": tot_f, "alg_bytes_per_sample": bytes_per_sample(n, 4 if a.precision == "fp32" else 2),
+                     "flops_per_sample": tot_f, "alg_bytes_per_sample": bytes_per_sample(n, 4 if a.precision == "fp32" else 2, blocks=blocks),
                      "peak_source": peaks["source"]}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = cpu_reference_run(a.workload, 32, 60, 3, a.droprate, budget_s=15.0)
+        r = cpu_reference_run(a.workload, 32 if a.workload != "syn2048" else 2, 60, 3, a.droprate, budget_s=15.0)
         cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                        "sample": f"{r['steps']} steps of B=32 (BASELINE configs[0] batch), oracle port of the "
+                        "sample": f"{r['steps']} steps of B={r['batch']} (BASELINE configs[0] batch), oracle port of the "
                                   f"reference step on {r['cores']} host threads (fastest of a sweep; "
                                   f"{r['host_threads_available']} available), dropout {a.droprate}"}
 

@@ -42,3 +42,16 @@ def test_kernel_work_model_and_traffic_table():
         # far below when the output stayed in the 126 MB L2 at capture time
         assert measured <= 1.3 * by, (key, measured, by)
     assert bench._ncu_traffic("st0.tc2.fwd:umma_tap_kernel<EPI_GATE>", "metrla", 512, "bf16") is None
+
+
+def test_synthetic_sweep_workload_model():
+    """BASELINE configs[4] (N=2048, Ks=5, 64 graph-conv channels): FLOPs / bytes of SURVEY.md §8(d) with the workload's
+    own block table, and the seeded operator has spectral norm 1 (checked at a small size; same constructor)."""
+    import torch
+    blocks = bench.workload_blocks("syn2048")
+    fwd, tot, _ = bench.flops_per_sample(2048, "cheb_graph_conv", 5, blocks=blocks)
+    assert abs(fwd / 1e6 - 37865.65) < 0.01 and abs(tot / 1e6 - 79221.49) < 0.01
+    assert abs(bench.bytes_per_sample(2048, 2, blocks=blocks) / 1e6 - 15.835) < 0.001
+    op = bench.load_operator("syn96", "cheb_graph_conv")
+    assert op.shape == (96, 96) and torch.allclose(op, op.T)
+    assert abs(float(torch.linalg.matrix_norm(op.double(), ord=2)) - 1.0) < 1e-5
