@@ -1,7 +1,11 @@
-// ops.cuh -- host orchestration of the modular path, templated on the activation storage type T
-// (float: parity path; __nv_bfloat16: throughput path): each op carves its buffers from
-// caller-provided arenas, then enqueues the SIMT kernels of simt_kernels.cuh on the stream.
-// "dry" arenas (null base) only measure: the *_sizes entry points run the same code paths.
+// ops.cuh -- host orchestration, templated on the activation storage type T (float: parity path on the CUDA-core
+// kernels of simt_kernels.cuh; __nv_bfloat16: throughput path on the tcgen05 kernels of umma_*.cuh plus the CUDA-core
+// kernels that remain).  Each op carves its buffers from caller-provided arenas and enqueues its kernels; the
+// block-level ops (stblock_*, outblock_*) chain the layer ops, keep buffers that asynchronous work touches in a
+// non-recycled "keep" region, and spread parameter-only preparation and weight-gradient kernels over two helper
+// streams (Side / Ctx below).  "dry" arenas (null base) only measure: the *_sizes entry points and the sizing pass of
+// every block-level call run the same code paths, so any decision that changes an allocation must depend on shapes
+// and process-wide switches only, never on pointers.
 #pragma once
 #include <cstdlib>
 #include <type_traits>
