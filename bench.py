@@ -252,6 +252,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--micro-streams", type=int, default=1,
+                    help="experimental (unmeasured in round 1): run that many batch chunks as parallel chains on separate "
+                         "streams inside the captured step (stgcn_b200.graph.GraphedStep)")
     ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "600")),
                     help="watchdog: dump all Python stacks to stderr and exit 124 if the run has not finished by then")
     a = ap.parse_args()
@@ -266,6 +269,8 @@ def main():
     # N > 1 until that is measured (the step without them ran 165.6 k samples/s on 2 GPUs earlier in the round).
     # STGCN_MULTI_GPU_STREAMS=1 overrides.
     helper_streams = True
+    if a.micro_streams > 1:
+        os.environ.setdefault("STGCN_SIDE_PER_STREAM", "1")     # one pair of library helper streams per chain
     if world > 1 and not os.environ.get("STGCN_MULTI_GPU_STREAMS"):
         os.environ["STGCN_NO_SIDE_STREAMS"] = "1"          # read once by the library, before its first call
         helper_streams = False
@@ -355,7 +360,7 @@ def main():
     if not a.no_graph:
         from stgcn_b200.graph import GraphedStep
         n_before = L.launch_count()
-        graphed = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=3)
+        graphed = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=3, micro_streams=a.micro_streams)
         launches_per_step = (L.launch_count() - n_before) // 4       # 3 warm-up bodies + 1 capture
         loss_buf = graphed.loss
 
@@ -477,7 +482,7 @@ def main():
                 "config": {**cfg_common, "precision": a.precision,
                            "l2": f"{POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
                            "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                           "helper_streams": helper_streams},
+                           "helper_streams": helper_streams, "micro_streams": a.micro_streams},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / steps},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,

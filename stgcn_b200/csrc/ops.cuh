@@ -51,6 +51,34 @@ struct Side {
     }
     return s;
   }
+  // Opt-in (STGCN_SIDE_PER_STREAM=1, unmeasured): one pair of helper streams per CALLER stream, for hosts that run
+  // independent chains (e.g. two half-batches) on different streams of one thread -- with the single thread-local pair
+  // above, chain B's parameter preparation would queue behind chain A's forks.  All kPool pairs are created at the first
+  // call (a warm-up), none later, so a stream capture never sees a stream or event being created.
+  static constexpr int kPool = 4;
+  static bool per_stream() {
+    static const bool on = std::getenv("STGCN_SIDE_PER_STREAM") != nullptr;
+    return on;
+  }
+  static Side* get_for(cudaStream_t caller) {
+    static thread_local Side* pool[kPool] = {nullptr, nullptr, nullptr, nullptr};
+    static thread_local cudaStream_t owner[kPool];
+    static thread_local int used = 0;
+    static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;
+    if (off || g_prof.on.load(std::memory_order_relaxed)) return nullptr;
+    if (!pool[0]) {
+      for (int k = 0; k < kPool; ++k) {
+        pool[k] = new Side();
+        STGCN_CUDA(cudaStreamCreateWithFlags(&pool[k]->p, cudaStreamNonBlocking));
+        STGCN_CUDA(cudaStreamCreateWithFlags(&pool[k]->q, cudaStreamNonBlocking));
+        for (int i = 0; i < kEvents; ++i) STGCN_CUDA(cudaEventCreateWithFlags(&pool[k]->ev[i], cudaEventDisableTiming));
+      }
+    }
+    for (int k = 0; k < used; ++k)
+      if (owner[k] == caller) return pool[k];
+    if (used < kPool) { owner[used] = caller; return pool[used++]; }
+    return pool[0];        // more caller streams than pairs: share one (correct, merely more serialised)
+  }
 };
 
 struct Ctx {

@@ -46,7 +46,7 @@ inline void run_block(void* workspace, size_t workspace_bytes, cudaStream_t stre
   Arena keep(workspace, keep_bytes), ws(static_cast<char*>(workspace) + keep_bytes, workspace_bytes - keep_bytes);
   ops::Ctx c{ws, stream};
   c.keep = &keep;
-  c.side = ops::Side::get();
+  c.side = ops::Side::per_stream() ? ops::Side::get_for(stream) : ops::Side::get();
   c.begin();
   try {
     body(c);
