@@ -75,28 +75,9 @@ inline void prof_end(const char* kernel, cudaEvent_t a, cudaStream_t s) {
   g_prof.recs.push_back(ProfRec{key, a, b});
 }
 
-// Programmatic dependent launch (opt-in, STGCN_PDL): with the launch attribute the NEXT kernel of the stream may be
-// set up while this one is still running -- its grid is processed, its CTAs become resident as SMs free up -- and only its
-// pdl_begin() waits for this kernel to have completed and flushed.  Every kernel calls pdl_begin() before it touches global
-// memory; without the attribute both instructions are no-ops.  The ~40 persistent kernels of a step each paid a full
-// drain + launch bubble at their boundaries (removing ONE 21 us kernel bought 36 us, profiles/r01_ab_batch_f.md).
-__device__ __forceinline__ void pdl_begin() {
-  asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
-}
 template <class... KArgs, class... Args>
 inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
-  static const bool pdl = std::getenv("STGCN_PDL") != nullptr;
-  if (!pdl) {
-    kernel<<<grid, block, smem, stream>>>(std::forward<Args>(args)...);
-    return;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  STGCN_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+  kernel<<<grid, block, smem, stream>>>(std::forward<Args>(args)...);
 }
 
 // Every kernel launch goes through this: counts it and checks the launch status.

@@ -15,7 +15,6 @@
 #include "umma_gso.cuh"
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
-#include "ln_gate_pipe.cuh"
 #include "ln_gate_group.cuh"
 
 namespace stgcn {
@@ -90,12 +89,12 @@ struct Ctx {
   Arena& K() const { return keep ? *keep : ws; }
   cudaStream_t ps() const { return side ? side->p : stream; }      // parameter-only preparation
   cudaStream_t qs() const { return side ? side->q : stream; }      // post-processing of gradients
-  // Weight-gradient kernels on q (validated +5%, batch h; STGCN_NO_WGRAD_STREAM=1 switches it off): nothing on the caller's stream consumes a parameter
+  // Weight-gradient kernels on q (validated +5%, profiles/r01_ab_batch_h.md): nothing on the caller's stream consumes a parameter
   // gradient, so the wgrad kernel of a layer can run beside that layer's data-gradient kernel and its launch/drain
   // bubbles leave the critical path.  Everything such a kernel reads must then outlive the op: KW() hands those
   // buffers out of the keep arena (decided by the flag alone, so the sizing pass and the live pass agree).
   static bool wgrad_stream() {
-    static const bool on = std::getenv("STGCN_NO_WGRAD_STREAM") == nullptr && std::getenv("STGCN_NO_SIDE_STREAMS") == nullptr;
+    static const bool on = std::getenv("STGCN_NO_SIDE_STREAMS") == nullptr;
     return on;
   }
   Arena& KW() const { return (wgrad_stream() && keep) ? *keep : ws; }
@@ -162,8 +161,7 @@ inline size_t tconv_saved_elems(const stgcn_tconv_desc& d, bool q_only = false) 
 template <class T>
 inline bool tconv_qonly(const stgcn_tconv_desc& d) {
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool off = std::getenv("STGCN_NO_GLU_QONLY") != nullptr;      // A/B switch (validated: +5.8%, batch g)
-    if (off || d.act != STGCN_ACT_GLU || d.B <= 0) return false;
+    if (d.act != STGCN_ACT_GLU || d.B <= 0) return false;      // validated +5.8% (profiles/r01_ab_batch_g.md)
     TconvGeom g = tconv_geom(d);
     umma::TapProblem q{};
     q.B = d.B; q.N = d.N; q.T_src = d.T; q.T_out = g.T_out; q.Kt = d.Kt; q.t0 = 0;
@@ -261,21 +259,10 @@ inline void tconv_fwd(const stgcn_tconv_desc& d, const T* x, const stgcn_tconv_p
 
 // dz_ready: gradient w.r.t. the pre-activations already computed by the caller (fused LayerNorm + gate backward,
 // lnorm_gate_bwd); dy is then unused.
-// lr: optional low-rank form of dy (GateArgs::lr_src / lr_w): dy = lr->src [rows_out, 16] . lr->w [16, c_out]; only the
-// generic gate path takes it (tconv_lowrank_dy_ok), dy is then unused.
-template <class T>
-struct LowRankDy { const T* src; const float* w; };
-template <class T>
-inline bool tconv_lowrank_dy_ok(const stgcn_tconv_desc& d) {
-  TconvGeom g = tconv_geom(d);
-  const bool res_ok = (g.folded || g.linear) || d.c_in % 8 == 0;
-  return g.rows_out > 0 && !smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt) && d.c_out % 8 == 0 && g.W % 8 == 0 && res_ok &&
-         g.rows_out * d.c_out / 8 < (1LL << 31);
-}
 template <class T>
 inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, const T* dy,
                       const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, T* dx, Ctx c, T* dz_ready = nullptr,
-                      const LowRankDy<T>* lr = nullptr, const T* h_qonly = nullptr) {
+                      const T* h_qonly = nullptr) {
   TconvGeom g = tconv_geom(d);
   ScopedMark sm(c.ws);
   const int Kw = d.Kt * d.c_in;
@@ -291,7 +278,7 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
   if (c.dry()) return;
   bool want_w = gr.conv_w || gr.conv_b || (g.folded && (gr.align_w || gr.align_b));
   const bool smallc = !dz_ready && g.rows_out > 0 && smallc_supported<T>(d.c_in, d.c_out, g.W, d.Kt);
-  STGCN_CHECK((!lr && !h_qonly) || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: low-rank dy / q-only state only on the generic gate path");
+  STGCN_CHECK(!h_qonly || (!dz_ready && !smallc), STGCN_E_INVALID, "tconv_bwd: q-only state only on the generic gate path");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool z_skipped = smallc && smallc1_supported<T>(d.c_in, d.c_out, d.Kt) && al16(z_saved);   // what the forward may have done
   // data gradient through the tcgen05 tap kernel?
@@ -369,10 +356,9 @@ inline void tconv_bwd(const stgcn_tconv_desc& d, const T* x, const T* z_saved, c
     GateArgs<T> ga{};
     ga.z = z_saved; ga.xin = x; ga.dy = dy; ga.dz = dz; ga.rows = g.rows_out; ga.Cin = d.c_in; ga.Cout = d.c_out;
     ga.W = g.W; ga.Kt = d.Kt; ga.T_out = g.T_out; ga.T_in = d.T; ga.N = d.N; ga.explicit_res = (g.folded || g.linear) ? 0 : 1;
-    if (lr) { ga.lr_src = lr->src; ga.lr_w = lr->w; ga.dy = nullptr; }
     if (h_qonly) { ga.h = h_qonly; ga.q_only = 1; }       // z_saved holds only Q (tconv_qonly); h = this layer's output
-    if (lr || h_qonly)
-      STGCN_CHECK(gate_vec_ok(ga), STGCN_E_UNSUPPORTED, "tconv_bwd: low-rank dy / q-only state not served (misaligned buffers)");
+    if (h_qonly)
+      STGCN_CHECK(gate_vec_ok(ga), STGCN_E_UNSUPPORTED, "tconv_bwd: q-only state not served (misaligned buffers)");
     launch_gate_any(d.act, true, ga, c.stream);
   }
   // ---- weight gradients
@@ -485,9 +471,8 @@ inline size_t gconv_saved_elems(const stgcn_gconv_desc& d) {
 template <class T>
 inline bool gconv_fused(const stgcn_gconv_desc& d) {
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool off = std::getenv("STGCN_NO_FUSED_GCONV") != nullptr;      // A/B switch for profiling
     const int depth = gconv_stack_depth(d), taps = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
-    return !off && depth >= 2 && umma::cheb_supported(d.N, d.c_out, depth, taps, (long long)d.B * d.T);
+    return depth >= 2 && umma::cheb_supported(d.N, d.c_out, depth, taps, (long long)d.B * d.T);
   }
   return false;
 }
@@ -582,12 +567,9 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
   }
 }
 
-// dst_ext: optional caller-owned buffer [depth][rows, c_out] for the stack gradients; with it and c_in > c_out the
-// caller may pass dx == nullptr and apply the align conv's data gradient itself from dst_ext plane 0 (stblock_bwd
-// folds it into the gate backward of the preceding temporal conv).
 template <class T>
 inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, const T* y, const T* dy,
-                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c, T* dst_ext = nullptr) {
+                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c) {
   gconv_check(d);
   ScopedMark sm(c.ws);
   const long long rows = (long long)d.B * d.T * d.N;
@@ -596,7 +578,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   const int depth = gconv_stack_depth(d);
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   T* dg = c.KW().take<T>(plane);
-  T* dst = dst_ext ? dst_ext : c.KW().take<T>((size_t)depth * plane);
+  T* dst = c.KW().take<T>((size_t)depth * plane);
   float* wT = c.K().take<float>((size_t)ntw * C * C);
   float* dwt = c.K().take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.K().take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
@@ -751,8 +733,8 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
       gb.flush();
     }
     if constexpr (std::is_same<T, simt::bf16>::value) {
-      static const bool simt_on = std::getenv("STGCN_NO_SIMT_ALIGNBWD") == nullptr;   // A/B switch (register-resident weights: +0.9%, batch i)
-      if (dx && simt_on && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
+      // register-resident 16 x c_in weights on CUDA cores: +0.9% over the tcgen05 1-tap GEMM (profiles/r01_ab_batch_i.md)
+      if (dx && lowrank_expand_supported<T>(dst, p.align_w, dx, rows, C, d.c_in)) {
         launch_lowrank_expand<T>(dst, p.align_w, dx, rows, d.c_in, c.stream);      // align_w is [C][c_in] row-major
         dx = nullptr;
       }
@@ -792,8 +774,7 @@ inline void lnorm_fwd(const stgcn_lnorm_desc& d, const T* x, const float* w, con
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   const bool vec = M % 8 == 0 && al16(x) && al16(y) && al16(w) && al16(b);
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool off = std::getenv("STGCN_NO_LN_CACHED") != nullptr;      // A/B switch for profiling
-    if (vec && !off && M <= 512 * 8 * 8) {
+    if (vec && M <= 512 * 8 * 8) {
       if (M <= 512 * 8 * 4) STGCN_LAUNCH((ln_fwd_cached_kernel<4>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
       else                  STGCN_LAUNCH((ln_fwd_cached_kernel<8>), (unsigned)G, 512, 0, s, x, w, b, y, stats, stats + G, M, d.eps, d.training, d.p_drop, seed);
       return;
@@ -841,7 +822,6 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   const cudaStream_t s = c.stream;
   const bool dry = c.dry();
   lnorm_check(d);
-  static const bool off = std::getenv("STGCN_NO_FUSED_LNGATE") != nullptr;      // A/B switch for profiling
   TconvGeom g = tconv_geom(tc);
   LnGateArgs<T> a{};
   const long long G = (long long)d.B * d.T;
@@ -850,7 +830,7 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   a.N = d.N; a.C = d.C; a.W = g.W; a.Cin = tc.c_in; a.Kt = tc.Kt; a.T_out = g.T_out; a.T_in = tc.T;
   a.explicit_res = (g.folded || g.linear) ? 0 : 1;
   a.q_only = q_only ? 1 : 0;
-  if (off || d.C != tc.c_out || g.T_out != d.T) return false;
+  if (d.C != tc.c_out || g.T_out != d.T) return false;
   if (dry) {   // alignment cannot be checked on a dry run; shapes decide (the arenas hand out 256-byte aligned blocks)
     a.x = a.dy = a.z = a.xin = reinterpret_cast<const T*>(256); a.dz = reinterpret_cast<T*>(256); a.w = reinterpret_cast<const float*>(256);
     a.G = 1;
@@ -876,16 +856,6 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
         STGCN_LAUNCH((ln_param_grad_kernel<T, 8>), dim3(xb, ychunks), 128, 0, c.qs(), x, dy, stats, stats + G, dw, db, M, G, gpc,
                      d.training, d.p_drop, seed);
       }
-      return true;
-    }
-    // opt-in (STGCN_LN_PIPE=1): with the q-only saved state the two-launch kernels are faster everywhere on PeMSD7-M
-    // (171.1 k vs 168.6 k samples/s, profiles/r01_ab_batch_i.md); kept for larger N*C where its single read of x, dy pays
-    static const bool pipe_off = std::getenv("STGCN_LN_PIPE") == nullptr;
-    // the persistent kernel needs enough groups per CTA to amortise its prologue (first bulk load) and its final
-    // flush of 2*M atomics: measured on PeMSD7-M, 14 groups per CTA 154 vs 158 us, 7 groups per CTA 120 vs 95 us
-    static const long long min_groups = std::getenv("STGCN_LN_PIPE_MIN_GROUPS") ? std::atoll(std::getenv("STGCN_LN_PIPE_MIN_GROUPS")) : 10;
-    if (!pipe_off && ln_gate_pipe_supported(a) && a.G >= min_groups * umma::sm_count()) {
-      launch_ln_gate_bwd_pipe(tc.act, a, umma::sm_count(), s);
       return true;
     }
   }
@@ -956,19 +926,10 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
     ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c, tconv_qonly<T>(g.tc2));
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
-  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr, nullptr,
+  { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr,
                                                                   (!ln_fused && tconv_qonly<T>(g.tc2)) ? s.h3 : nullptr); }
-  // c1 > c2 (bottleneck): the align conv's data gradient dh1 = dst0 . Wa is formed inside tc1's gate backward from the
-  // 16-channel dst0 instead of being written to HBM at c1 channels and read back
-  // (opt-in: measured -0.4% on PeMSD7-M -- the 128 FMAs per 8 outputs turn the bandwidth-bound gate kernel into an
-  // issue-bound one, 52 -> 125 us, for a 46 us kernel saved; profiles/r01_ab_batch_f.md)
-  static const bool lr_on = std::getenv("STGCN_FUSED_ALIGNBWD") != nullptr;
-  const bool lr_fuse = lr_on && std::is_same<T, simt::bf16>::value && d.c1 > d.c2 && d.c2 == kGateLrC &&
-                       tconv_lowrank_dy_ok<T>(g.tc1);      // shapes only: the dry (sizing) run must take the same path
-  T* dst_ext = c.KW().take<T>(lr_fuse ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
-  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, lr_fuse ? nullptr : dh1, c, lr_fuse ? dst_ext : nullptr); }
-  LowRankDy<T> lr{dst_ext, p.gc.align_w};       // align_w is [c2][c1] row-major = lr_w[o * c1 + j]
-  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, lr_fuse ? &lr : nullptr,
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
+  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr,
                                                                   tconv_qonly<T>(g.tc1) ? s.h1 : nullptr); }
 }
 
@@ -1007,8 +968,7 @@ inline OutSaved<T> out_saved(const stgcn_outblock_desc& d, const OutGeom& g, Are
 template <class T>
 inline bool out_relu_fused(const stgcn_outblock_desc& d, const OutGeom& g) {
   if constexpr (std::is_same<T, simt::bf16>::value) {
-    static const bool off = std::getenv("STGCN_NO_FUSED_FC1RELU") != nullptr;      // A/B switch for profiling
-    if (off || (d.training && d.p_drop > 0.f) || d.B <= 0) return false;
+    if ((d.training && d.p_drop > 0.f) || d.B <= 0) return false;
     return umma_linear(nullptr, nullptr, nullptr, nullptr, d.B, g.T1, g.T1, d.N, d.c0, d.c1, UmmaLinearOpts{}, nullptr, true);
   }
   return false;
@@ -1104,9 +1064,8 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
     const bool rowdot = d.c_end == 1 && rowdot_supported(d.c1) && al16(s.r) && al16(dr) && g.rows1 > 0;
     // without dropout the ReLU backward rides in the fc2 data-gradient kernel (df1 written directly)
-    static const bool relu_bwd_off = std::getenv("STGCN_NO_FUSED_RELUBWD") != nullptr;      // A/B switch for profiling
     const T* relu_ref = out_relu_fused<T>(d, g) ? s.r : s.f1;        // the forward kept only r = relu(f1) when it fused the ReLU
-    const bool relu_bwd_fused = rowdot && !relu_bwd_off && !(d.training && d.p_drop > 0.f) && al16(relu_ref) && al16(df1);
+    const bool relu_bwd_fused = rowdot && !(d.training && d.p_drop > 0.f) && al16(relu_ref) && al16(df1);
     if (rowdot) {
       const long long total = g.rows1 * (d.c1 / 8);
       STGCN_LAUNCH(rowouter_bwd_kernel<T>, (int)std::min<long long>(ceil_div(total, 256), 148 * 8), 256, 0, c.stream, dy,
@@ -1191,7 +1150,7 @@ inline void outblock_bwd(const stgcn_outblock_desc& d, const T* x, Arena& sv, co
   { Tag t("out.ln.bwd");
     ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, s.z, x, dz, lnsums, 0, c, tconv_qonly<T>(g.tc));
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h, s.stats, dl, p.ln_w, gr.ln_w, gr.ln_b, dh, 0, c.stream, c.dry()); }
-  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr, nullptr,
+  { Tag t("out.tc1.bwd"); tconv_bwd<T>(g.tc, x, s.z, dh, p.tc1, gr.tc1, dx, c, ln_fused ? dz : nullptr,
                                            (!ln_fused && tconv_qonly<T>(g.tc)) ? s.h : nullptr); }
 }
 

@@ -99,7 +99,6 @@ struct TapArgs {
 
 template <class TI, class TO, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs<TI, TO> a) {
-  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -221,7 +220,6 @@ struct GsoArgs {
 
 template <class T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) gso_kernel(GsoArgs<T> a) {
-  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -329,7 +327,6 @@ struct WgradArgs {
 
 template <class T, int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
-  pdl_begin();
   constexpr int TX = BN / TN, TY = BM / TM;
   static_assert(TX * TY == NT, "tile/thread mismatch");
   constexpr int A_PER = BM * BK / NT;
@@ -436,7 +433,6 @@ __global__ void __launch_bounds__(NT) wgrad_kernel(WgradArgs<T> a) {
 
 // out[e] += sum_c partial[c][e]: one warp per 8 elements x 4 lanes-groups; lanes stride over the chunks, shuffle-reduce
 __global__ void reduce_partials_kernel(const float* partial, float* out, int n, int chunks) {
-  pdl_begin();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int e = blockIdx.x * (blockDim.x >> 5) + warp;
   if (e >= n) return;
@@ -459,7 +455,6 @@ inline void launch_reduce_partials(const float* partial, float* out, int n, int 
 constexpr int kSkR = 128;     // rows per tile: the three block barriers per tile were the bottleneck at 32
 template <class T, bool VEC>
 __global__ void __launch_bounds__(320) wgrad_skinny_kernel(WgradArgs<T> a) {
-  pdl_begin();
   extern __shared__ __align__(16) float sk[];
   const int Kw = a.ntaps * a.Cin;
   const int Mtot = Kw + (a.bias_row ? 1 : 0);
@@ -650,15 +645,11 @@ struct GateArgs {
   int Cin, Cout, W, Kt;
   int T_out, T_in, N;
   int explicit_res;    // 1: residual = xin[(b,t+Kt-1,n), j] for j < Cin (zero pad / identity)
-  // bwd, optional low-rank dy: dy[r, j] = sum_{o<16} lr_src[r, o] * lr_w[o * Cout + j]  (the 1x1 align conv of the
-  // graph-conv layer that consumed this layer's output, layers.py:16,225: its data gradient is formed on the fly
-  // instead of being written to HBM as a [rows, Cout] tensor and read back here)
-  const T* lr_src; const float* lr_w;
   // bwd, GLU "q-only" saved state: z holds just the gate half Q as [rows, Cout]; with the layer OUTPUT h = u * sigma(Q)
   // the gradients are du = dy * s, dq = dy * h * (1 - s) -- neither P nor the residual is needed
   const T* h; int q_only;
 };
-constexpr int kGateLrC = 16;
+constexpr int kGateLrC = 16;      // channel count of the low-rank expansion kernel below
 
 template <class T>
 __device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r, int j) {
@@ -670,7 +661,6 @@ __device__ __forceinline__ float gate_residual(const GateArgs<T>& a, long long r
 
 template <class T, int ACT>
 __global__ void gate_fwd_kernel(GateArgs<T> a) {
-  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = (long long)((unsigned long long)idx / (unsigned)a.Cout);
@@ -694,7 +684,6 @@ __global__ void gate_fwd_kernel(GateArgs<T> a) {
 
 template <class T, int ACT>
 __global__ void gate_bwd_kernel(GateArgs<T> a) {
-  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.rows * a.Cout) return;
   long long r = idx / a.Cout;
@@ -725,7 +714,6 @@ __global__ void gate_bwd_kernel(GateArgs<T> a) {
 template <class T>
 __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres, int W, int Cin, int Kt,
                                     int T_out, int T_in, int N) {
-  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cres) return;
   long long r = idx / Cres;
@@ -739,16 +727,10 @@ __global__ void residual_add_kernel(const T* dz, T* dx, long long rows, int Cres
 // 8 channels per thread (requires Cout, W and Cin to be multiples of 8 when a residual is read)
 template <class T, int ACT>
 __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
-  pdl_begin();
-  extern __shared__ __align__(16) float lrw_s[];        // [kGateLrC][Cout] when a.lr_src (launcher sizes it)
-  if (a.lr_src) {
-    for (int i = threadIdx.x; i < kGateLrC * a.Cout; i += blockDim.x) lrw_s[i] = a.lr_w[i];
-    __syncthreads();
-  }
   const int groups = a.Cout / 8;
   const long long total = a.rows * groups;
-  // one chunk per thread normally; with a low-rank dy the grid is persistent (weights staged once per CTA)
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;       // one 8-channel chunk per thread
+  if (idx >= total) return;
   const long long r = (long long)((unsigned)idx / (unsigned)groups);    // rows * groups < 2^31 (launcher)
   const int j0 = (int)(idx - r * groups) * 8;
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
@@ -775,21 +757,7 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
     store8(a.y + r * a.Cout + j0, h);
   } else {
     float g[8], du[8], dq[8];
-    if (a.lr_src) {
-      float d[kGateLrC];
-      load8(a.lr_src + r * kGateLrC, d); load8(a.lr_src + r * kGateLrC + 8, d + 8);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) g[i] = 0.f;
-#pragma unroll
-      for (int o = 0; o < kGateLrC; ++o) {
-        const float4 w0 = *reinterpret_cast<const float4*>(lrw_s + o * a.Cout + j0);
-        const float4 w1 = *reinterpret_cast<const float4*>(lrw_s + o * a.Cout + j0 + 4);
-        g[0] = fmaf(d[o], w0.x, g[0]); g[1] = fmaf(d[o], w0.y, g[1]); g[2] = fmaf(d[o], w0.z, g[2]); g[3] = fmaf(d[o], w0.w, g[3]);
-        g[4] = fmaf(d[o], w1.x, g[4]); g[5] = fmaf(d[o], w1.y, g[5]); g[6] = fmaf(d[o], w1.z, g[6]); g[7] = fmaf(d[o], w1.w, g[7]);
-      }
-    } else {
-      load8(a.dy + r * a.Cout + j0, g);
-    }
+    load8(a.dy + r * a.Cout + j0, g);
     if (q_only) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -804,28 +772,25 @@ __global__ void gate_vec_kernel(GateArgs<T> a, int bwd) {
     store8(a.dz + r * a.W + j0, du);
     if (gated) store8(a.dz + r * a.W + a.Cout + j0, dq);
   }
-  }
 }
 
-// does the 8-channels-per-thread kernel serve these arguments?  (tconv_bwd asks before it commits to a low-rank dy)
+// does the 8-channels-per-thread kernel serve these arguments?  (tconv_bwd asks before it commits to the q-only state)
 template <class T>
 inline bool gate_vec_ok(const GateArgs<T>& a) {
   const long long n = a.rows * a.Cout;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   return a.Cout % 8 == 0 && a.W % 8 == 0 && n / 8 < (1LL << 31) && (!a.explicit_res || a.Cin % 8 == 0) && al16(a.z) && al16(a.xin) &&
-         al16(a.dy) && al16(a.y) && al16(a.dz) && al16(a.lr_src) && al16(a.lr_w) && al16(a.h);
+         al16(a.dy) && al16(a.y) && al16(a.dz) && al16(a.h);
 }
 template <class T, int ACT>
 inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
   long long n = a.rows * a.Cout;
   if (n == 0) return;
   if (gate_vec_ok(a)) {
-    const size_t lr_smem = a.lr_src ? (size_t)kGateLrC * a.Cout * sizeof(float) : 0;
-    const int blocks = a.lr_src ? (int)std::min<long long>(ceil_div(n / 8, 256), 148 * 8) : ceil_div(n / 8, 256);
-    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), blocks, 256, lr_smem, s, a, bwd ? 1 : 0);
+    STGCN_LAUNCH((gate_vec_kernel<T, ACT>), ceil_div(n / 8, 256), 256, 0, s, a, bwd ? 1 : 0);
     return;
   }
-  STGCN_CHECK(!a.lr_src && !a.q_only, STGCN_E_UNSUPPORTED, "low-rank dy / q-only saved state need the vectorised gate kernel");
+  STGCN_CHECK(!a.q_only, STGCN_E_UNSUPPORTED, "the q-only saved state needs the vectorised gate kernel");
   if (bwd) STGCN_LAUNCH((gate_bwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
   else     STGCN_LAUNCH((gate_fwd_kernel<T, ACT>), ceil_div(n, 256), 256, 0, s, a);
 }
@@ -835,7 +800,6 @@ inline void launch_gate(bool bwd, const GateArgs<T>& a, cudaStream_t s) {
 // its time in per-tile epilogue bookkeeping (66 us for 75 MB), this is bandwidth work.  8 channels per thread.
 template <class T>
 __global__ void __launch_bounds__(256) lowrank_expand_kernel(const T* src, const float* w, T* out, long long rows, int Cout) {
-  pdl_begin();
   // thread = (8-channel group, row lane); its 16 x 8 weights live in REGISTERS for the whole (persistent) kernel: from
   // shared memory the 32 LDS.128 per 128 FMAs made the kernel shared-memory-bandwidth bound (146 us for 37 MB,
   // profiles/r01_ab_batch_h.md); the rows' 32-byte inputs are broadcast through L1 to the 8 threads that share a row
@@ -899,7 +863,6 @@ inline void launch_gate_any(int act, bool bwd, const GateArgs<T>& a, cudaStream_
 // db = sum_r dy[r].  All three are bandwidth work over a [rows, C] tensor: 8 channels per thread, 16-byte accesses.
 template <class T>
 __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* in, const float* w, const float* b, float* y, long long rows, int C) {
-  pdl_begin();
   const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;   // G = power of two <= 32
   float wv[8];
 #pragma unroll
@@ -921,7 +884,6 @@ __global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T* in, const floa
 template <class T>
 __global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, const float* w, T* din, long long rows, int C,
                                                            const T* relu_ref) {
-  pdl_begin();
   const int G = C / 8;
   const long long total = rows * G;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -944,7 +906,6 @@ __global__ void __launch_bounds__(256) rowouter_bwd_kernel(const float* dy, cons
 template <class T>
 __global__ void __launch_bounds__(256) rowdot_wgrad_kernel(const T* in, const float* dy, float* partial, long long rows, int C,
                                                            int rows_per_cta) {
-  pdl_begin();
   __shared__ float red[8][257];
   const int G = C / 8, g = threadIdx.x % G, rl = threadIdx.x / G, lanes = blockDim.x / G;
   float acc[8], accb = 0.f;
@@ -1000,7 +961,6 @@ struct SmallCArgs {
 
 template <class T>
 __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T> a) {
-  pdl_begin();
   extern __shared__ float sm[];          // wt [K][W] then bias [W]
   const int K = a.Kt * a.Cin;
   for (int i = threadIdx.x; i < K * a.W; i += blockDim.x) sm[i] = a.wt[i];
@@ -1050,7 +1010,6 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
 // scoreboard 49 % on the x loads).  PF = false is the validated round-1 kernel, unchanged.
 template <class T, int K, int ACT, bool PF = false>
 __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
-  pdl_begin();
   const int groups = a.Cout / 8;
   const bool gated = a.W == 2 * a.Cout;
   const int j0 = (threadIdx.x % groups) * 8;
@@ -1158,7 +1117,6 @@ inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s)
 // global buffer with one atomic per element per CTA.  Optionally also materialises dz (when dx is needed).
 template <class T>
 __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a) {
-  pdl_begin();
   extern __shared__ float red[];         // [lanes][2][K+1][Cout]
   const int K = a.Kt * a.Cin;
   const bool gated = a.W == 2 * a.Cout;
@@ -1228,7 +1186,6 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
 // round-1 kernel, unchanged.
 template <class T, int K, int ACT, bool PF = false>
 __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
-  pdl_begin();
   __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
   const bool gated = a.W == 2 * a.Cout;
   const int G = a.Cout / 8;                         // channel groups (power of two <= 32 checked by the launcher)
@@ -1407,7 +1364,6 @@ inline bool smallc_supported(int Cin, int Cout, int W, int Kt) {
 template <class TO>
 __global__ void gather3_kernel(const float* in, TO* out, int d0, int d1, int d2, long long off,
                                long long s0, long long s1, long long s2, int accumulate) {
-  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long tot = (long long)d0 * d1 * d2;
   if (idx >= tot) return;
@@ -1436,7 +1392,6 @@ struct GatherJob {
 constexpr int kMaxGatherJobs = 8;
 struct GatherJobs { GatherJob j[kMaxGatherJobs]; int n; };
 __global__ void gather3_multi_kernel(GatherJobs jobs) {
-  pdl_begin();
   const GatherJob& g = jobs.j[blockIdx.y];
   const long long tot = (long long)g.d0 * g.d1 * g.d2;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long long)gridDim.x * blockDim.x) {
@@ -1471,7 +1426,6 @@ struct GatherBatch {
 
 // out[i*ldo + j] += in[i*si + j*sj]   (strided block accumulate; used to fold 1x1 align weights)
 __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, int d1, long long si, long long sj) {
-  pdl_begin();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= d0 * d1) return;
   int i = idx / d1, j = idx - i * d1;
@@ -1481,7 +1435,6 @@ __global__ void add_block_kernel(float* out, int ldo, const float* in, int d0, i
 // out[r, j] = j < Cin ? in[r*ldi + j] : 0   for j < Cout   (zero-pad or column slice copy)
 template <class T>
 __global__ void copy_cols_kernel(const T* in, T* out, long long rows, int Cin, int ldi, int Cout, int accumulate) {
-  pdl_begin();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * Cout) return;
   long long r = idx / Cout;
@@ -1500,7 +1453,6 @@ inline void launch_copy_cols(const T* in, T* out, long long rows, int Cin, int l
 // dtype conversion of an activation tensor
 template <class TI, class TO>
 __global__ void convert_kernel(const TI* in, TO* out, long long n) {
-  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) stf(out + i, ldf(in + i));
 }
@@ -1508,7 +1460,6 @@ __global__ void convert_kernel(const TI* in, TO* out, long long n) {
 // y = relu?(g + a)
 template <class T>
 __global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int relu) {
-  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
@@ -1531,7 +1482,6 @@ __global__ void add_relu_kernel(const T* g, const T* a, T* y, long long n, int r
 // dg = relu ? dy * (y > 0) : dy
 template <class T>
 __global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int relu) {
-  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(dg)) & 15) == 0) {
@@ -1548,7 +1498,6 @@ __global__ void relu_bwd_kernel(const T* dy, const T* y, T* dg, long long n, int
 // y += alpha * x
 template <class T>
 __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
-  pdl_begin();
   long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i >= n) return;
   if (i + 8 <= n && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
@@ -1564,7 +1513,6 @@ __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
 // y = relu(x), with optional dropout; and its backward
 template <class T>
 __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int training, float p, uint64_t seed) {
-  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = fmaxf(ldf(x + i), 0.f);
@@ -1574,7 +1522,6 @@ __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int train
 template <class T>
 __global__ void relu_dropout_bwd_kernel(const T* dy, const T* x, T* dx, long long n, int training, float p,
                                         uint64_t seed) {
-  pdl_begin();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = ldf(x + i) > 0.f ? ldf(dy + i) : 0.f;
@@ -1606,7 +1553,6 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w, const float* b, T* y,
                                                      float* mean, float* rstd, int M, float eps, int training,
                                                      float p, uint64_t seed) {
-  pdl_begin();
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1657,7 +1603,6 @@ template <int NCH>
 __global__ void __launch_bounds__(512) ln_fwd_cached_kernel(const bf16* x, const float* w, const float* b, bf16* y,
                                                             float* mean, float* rstd, int M, float eps, int training,
                                                             float p, uint64_t seed) {
-  pdl_begin();
   __shared__ float red[32];
   const long long g = blockIdx.x;
   const bf16* xp = x + g * M;
@@ -1712,7 +1657,6 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
                                                      const float* rstd, T* dx, int M, int training, float p,
                                                      uint64_t seed) {
-  pdl_begin();
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1758,7 +1702,6 @@ template <class T, int VEC>
 __global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean, const float* rstd, float* dw,
                                      float* db, int M, long long G, int groups_per_cta, int training, float p,
                                      uint64_t seed) {
-  pdl_begin();
   int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i >= M) return;
   long long g0 = (long long)blockIdx.y * groups_per_cta;
@@ -1829,7 +1772,6 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
 }
 template <class T>
 __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
-  pdl_begin();
   __shared__ float red[64];
   const long long g = blockIdx.x;
   const T* xp = a.x + g * a.M;
@@ -1861,7 +1803,6 @@ __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
 #endif
 template <class T, int ACT>
 __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnGateArgs<T> a) {
-  pdl_begin();
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch * 8 >= a.M) return;
@@ -1950,7 +1891,6 @@ inline void launch_ln_gate_bwd(int act, LnGateArgs<T> a, int sms, cudaStream_t s
 
 // loss = mean((pred-target)^2); dpred = 2 (pred-target)/n * scale
 __global__ void mse_kernel(const float* pred, const float* target, long long n, float scale, float* loss, float* dpred) {
-  pdl_begin();
   __shared__ float red[32];
   float s = 0.f;
   float inv = 1.f / (float)n;

@@ -20,7 +20,6 @@ struct MmaBenchCfg {
 };                                         //    advanced by adds only; n_warps issuing warps, each with its own accumulators
 
 __global__ void __launch_bounds__(192, 1) umma_bench_kernel(MmaBenchCfg c, unsigned long long* out) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t done;

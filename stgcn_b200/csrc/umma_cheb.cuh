@@ -141,7 +141,6 @@ __device__ __forceinline__ void cheb_issue_mix(uint32_t buf, uint32_t w_img, uin
 //   backward: [2b], [2b+1] = dy (becomes dG in place) and y of items with parity b, [3 + k] = P_k (k >= 1)
 template <bool BWD, int GB>
 __global__ void __launch_bounds__(kChebThreads, 1) umma_cheb_kernel(ChebParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;                                   // n_taps x [16][16] bf16, 32B-swizzled K-major

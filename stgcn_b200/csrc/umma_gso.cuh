@@ -28,7 +28,6 @@ struct GsoParams {
 
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GsoParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* a_s = smem;                    // [nKB][128 rows][128 B]
@@ -149,7 +148,6 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_gso_ktiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GsoParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;                   // S stages of { A [128 rows][128 B] (16 KB) , B [Gb][64 rows][C*2 B] }
@@ -260,7 +258,6 @@ umma_gso_ktiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 
 // Lhat (fp32 [N,N]) -> bf16 [N][Kp], Kp = N rounded up to 64, zero padded; optionally transposed
 __global__ void gso_prep_kernel(const float* M, bf16* out, int N, int Kp, int trans) {
-  pdl_begin();
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N * Kp) return;
   int h = idx / Kp, i = idx - h * Kp;

@@ -20,7 +20,6 @@ struct SelftestArgs {
 
 __global__ void __launch_bounds__(128) umma_selftest_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB, SelftestArgs a) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* As = smem;                 // <= 16 KB

@@ -195,7 +195,6 @@ template <int EPI, int ACT>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmZ, TapParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
@@ -662,7 +661,6 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.n_node_tiles = (q.N + 127) / 128;
   const int ctas = sm_count() / pl.nCoT > 0 ? sm_count() / pl.nCoT : 1;
   {   // time split (see TapParams): minimise [tiles per CTA x bytes written per tile + slices per CTA x bytes per slice]
-    static const char* force = std::getenv("STGCN_TAP_TSPLIT");        // A/B knob: forced split count
     const long long base_items = (long long)q.B * p.n_node_tiles;
     const long long out_b = 256LL * ((q.epi == EPI_GATE ? q.Co + q.Cout : pl.CoT) > 32 ? (q.epi == EPI_GATE ? q.Co + q.Cout : pl.CoT) : 32);
     const long long in_b = 256LL * q.Cin;
@@ -671,7 +669,6 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     for (int ns = 1; ns <= 4 && ns <= q.T_out; ++ns) {
       const int chunk = (q.T_out + ns - 1) / ns, ns_eff = (q.T_out + chunk - 1) / chunk;
       if (ns_eff != ns) continue;
-      if (force && std::atoi(force) > 0 && std::atoi(force) != ns && std::atoi(force) <= q.T_out) continue;
       const long long items = base_items * ns, g = items < ctas ? items : ctas;
       const long long rounds = (items + g - 1) / g;
       int slices = chunk + q.Kt - 1;

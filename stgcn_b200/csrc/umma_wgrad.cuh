@@ -38,7 +38,6 @@ struct WgradParams {
 
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem;                               // [64 rows][16] bf16 1.0 (2 KB, padded to 1 KB multiple)
@@ -225,7 +224,6 @@ constexpr int kFlatRows = 256;
 
 __global__ void __launch_bounds__(kTapThreads, 1)
 umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmX, WgradFlatParams p) {
-  pdl_begin();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem;                       // [64 rows][16] bf16 1.0
@@ -386,8 +384,7 @@ inline void launch_wgrad_flat(const bf16* x, const bf16* dz, float* dwt, long lo
   p.a_swz = dsw_of(W); p.a_sbo = 8u * W * 2; p.a_kadv = 16u * W * 2;
   p.b_swz = dsw_of(xcw); p.b_sbo = 8u * xcw * 2; p.b_kadv = 16u * xcw * 2;
   p.dwt = dwt; p.want_bias = want_bias;
-  static const bool merge_off = std::getenv("STGCN_NO_WGRAD_MERGE") != nullptr;      // A/B switch for profiling
-  p.merge_taps = (!merge_off && Kt > 1 && Cin <= 64 && Kt * Cin <= 256 && (Kt * Cin) % 16 == 0) ? 1 : 0;
+  p.merge_taps = (Kt > 1 && Cin <= 64 && Kt * Cin <= 256 && (Kt * Cin) % 16 == 0) ? 1 : 0;
   int gx = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   STGCN_CUDA(cudaFuncSetAttribute(umma_wgrad_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
   STGCN_LAUNCH(umma_wgrad_flat_kernel, gx, kTapThreads, pl.smem, stream, tmZ, tmX, p);
@@ -453,7 +450,6 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
   p.KR = kWgradKR;
   p.Sx = pl.Sx; p.Sz = pl.Sz; p.n_chunks = (N + kWgradKR - 1) / kWgradKR;
   {   // time split: minimise rounds x bytes loaded per item (dZ slices + X slices incl. the Kt-1 re-loaded ones)
-    static const char* force = std::getenv("STGCN_WGRAD_TSPLIT");      // A/B knob: forced split count
     const long long base_items = (long long)B * p.n_chunks;
     const int ctas = sm_count() / pl.nMT > 0 ? sm_count() / pl.nMT : 1;
     long long best = -1;
@@ -461,7 +457,6 @@ inline void launch_wgrad_umma(const bf16* x, const bf16* dz, float* dwt, int B, 
     for (int ns = 1; ns <= 4 && ns <= T_out; ++ns) {
       const int chunk = (T_out + ns - 1) / ns, ns_eff = (T_out + chunk - 1) / chunk;
       if (ns_eff != ns) continue;
-      if (force && std::atoi(force) > 0 && std::atoi(force) != ns && std::atoi(force) <= T_out) continue;
       const long long items = base_items * ns, g = items < ctas ? items : ctas;
       const long long rounds = (items + g - 1) / g;
       const long long xs_n = plane_mode ? (long long)chunk * Kt : chunk + Kt - 1;

@@ -180,20 +180,17 @@ print(json.dumps(out))
 
 
 def test_bf16_buffer_planning_follows_the_knobs():
-    """Sizing (dry) passes of the block-level calls in bf16 mode, on the CPU: every A/B configuration plans without
-    error; the GLU q-only saved state is smaller than the full pre-activations; running the weight-gradient kernels
-    on the helper stream keeps their inputs in the non-recycled region, so the workspace grows."""
+    """Sizing (dry) passes of the block-level calls in bf16 mode, on the CPU: both stream configurations plan without
+    error; running the weight-gradient kernels on the helper stream keeps their inputs in the non-recycled region, so
+    the workspace grows; the saved state does not depend on the stream configuration."""
     base = _sizes_in_subprocess({})
-    full_z = _sizes_in_subprocess({"STGCN_NO_GLU_QONLY": "1"})
-    no_wq = _sizes_in_subprocess({"STGCN_NO_WGRAD_STREAM": "1"})
     serial = _sizes_in_subprocess({"STGCN_NO_SIDE_STREAMS": "1"})
-    opt = _sizes_in_subprocess({"STGCN_FUSED_ALIGNBWD": "1", "STGCN_LN_PIPE": "1", "STGCN_PDL": "1"})
-    rows2_st0, rows1_st1, rows2_st1 = 256 * 8 * 228, 256 * 6 * 228, 256 * 4 * 228
-    # st0: only tc2 has a stored gate half (tc1, Cin = 1, recomputes z); st1: tc1 and tc2; 64 channels x 2 bytes each
-    assert full_z["st0"][0] - base["st0"][0] >= rows2_st0 * 64 * 2
-    assert full_z["st1"][0] - base["st1"][0] >= (rows1_st1 + rows2_st1) * 64 * 2
-    assert full_z["out"][0] > base["out"][0]
+    rows1, rows2 = 256 * 10 * 228, 256 * 8 * 228
+    # st0 plans (bf16): z1 128ch (reserved; the Cin = 1 kernels recompute it and never touch the buffer) + h1 64ch +
+    # stack 3 x 16ch + h2 16ch over T1 steps, gate half Q of tc2 64ch + h3 64ch over T2 steps, LayerNorm statistics; the
+    # full 128-channel pre-activation of tc2 would add another 64 channels over T2
+    full = (rows1 * (128 + 64 + 48 + 16) + rows2 * (64 + 64)) * 2
+    assert full <= base["st0"][0] < full + rows2 * 64 * 2
     for blk in ("st0", "st1", "out"):
-        assert base[blk][1] >= no_wq[blk][1] > 0           # dz & co. move to the keep region
-        assert serial[blk][1] == no_wq[blk][1]             # no helper streams -> no wgrad stream either
-        assert opt[blk][0] == base[blk][0] and opt[blk][1] > 0
+        assert base[blk][1] >= serial[blk][1] > 0           # dz & co. move to the keep region
+        assert base[blk][0] == serial[blk][0]
