@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define STGCN_ABI_VERSION 1
+#define STGCN_ABI_VERSION 2
 
 enum { STGCN_OK = 0, STGCN_E_INVALID = 10001, STGCN_E_WORKSPACE = 10002, STGCN_E_UNSUPPORTED = 10003 };
 enum { STGCN_ACT_GLU = 0, STGCN_ACT_GTU = 1, STGCN_ACT_RELU = 2, STGCN_ACT_SILU = 3,   /* layers.py:104-115 */
@@ -151,6 +151,14 @@ uint64_t    stgcn_launch_count(void);
  * buf (NUL-terminated, truncated to cap); *needed receives the full size.                                    */
 int         stgcn_profile_begin(void);
 int         stgcn_profile_end(char* buf, size_t cap, size_t* needed);
+
+/* Dropout under CUDA-graph replay: the dropout_seed arguments below cross the ABI by value, so a captured graph would
+ * replay the mask of its capture pass for ever.  Register a device-side 64-bit step counter here (NULL unregisters) and
+ * increment it once per training step from inside the graph: every kernel that draws a keep-mask adds the counter to its
+ * seed, so the forward and backward of one step agree and successive replays draw fresh masks.  Per device, process-wide;
+ * synchronises the host once (setup call, not for the step loop).  No reference counterpart (nn.Dropout draws from the
+ * global Philox stream, layers.py:248,274).                                                                       */
+int         stgcn_set_dropout_step(const uint64_t* device_counter);
 
 /* ---- per-layer entry points ---------------------------------------------------------- */
 /* Sizes (bytes) of the caller-provided buffers: `saved` is written by fwd and must be

@@ -98,6 +98,7 @@ _SIGNATURES = [
     ("stgcn_version", C.c_int, []),
     ("stgcn_last_error", C.c_char_p, []),
     ("stgcn_launch_count", C.c_uint64, []),
+    ("stgcn_set_dropout_step", C.c_int, [_fp]),
     ("stgcn_profile_begin", C.c_int, []),
     ("stgcn_profile_end", C.c_int, [C.c_char_p, _sz, _P(_sz)]),
     ("stgcn_tconv_sizes", C.c_int, [_P(TconvDesc), _P(_sz), _P(_sz)]),

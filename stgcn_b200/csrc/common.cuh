@@ -148,6 +148,16 @@ __device__ __forceinline__ float sigmoid_t(float v) { return FAST ? sigmoid_tanh
 template <bool FAST>
 __device__ __forceinline__ float tanh_t(float v) { return FAST ? tanh_approx(v) : tanhf(v); }
 
+// Dropout seeds cross the ABI by value, which a CUDA-graph capture freezes: every replay would draw the mask of the
+// capture pass.  A caller that replays graphs registers a device-side 64-bit step counter (stgcn_set_dropout_step) and
+// bumps it once per step from inside the graph; every kernel that draws a mask adds it to its by-value seed, so the
+// forward and the backward of one step agree and successive replays differ.
+__device__ const unsigned long long* g_dropout_step = nullptr;
+__device__ __forceinline__ uint64_t live_seed(uint64_t seed) {
+  const unsigned long long* p = g_dropout_step;
+  return p ? seed + 0x632BE59BD9B4E019ull * (*p + 1) : seed;
+}
+
 // Counter-based dropout keep-mask: splitmix64 finaliser over (seed, element index).
 __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, float p_drop) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);

@@ -20,6 +20,7 @@ constexpr int kLnGroupThreads = 512;
 // NCH: 16-byte chunks per thread (M <= 512 * 8 * NCH); QONLY: GLU q-only saved state (z = Q only, h = x)
 template <int ACT, bool QONLY, int NCH>
 __global__ void __launch_bounds__(kLnGroupThreads, NCH <= 4 ? 2 : 1) ln_gate_bwd_group_kernel(LnGateArgs<bf16> a) {
+  a.seed = live_seed(a.seed);      // + the device-side step counter, if one is registered (common.cuh)
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   constexpr bool q_only = QONLY && ACT == STGCN_ACT_GLU;
   __shared__ float red[64];

@@ -36,47 +36,43 @@ struct Side {
   int next = 0;
   bool q_forked = false;     // q joined this call's work (a capturing stream must not wait on a never-forked one)
   cudaEvent_t event() { cudaEvent_t e = ev[next]; next = (next + 1) % kEvents; return e; }
-  static Side* get() {                     // one per host thread (forward and autograd-backward threads differ)
-    static thread_local Side* s = nullptr;
-    static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;      // A/B switch for profiling
-    // the per-kernel event profiler (stgcn_profile_begin/end) wants one kernel at a time: events on a helper stream would
-    // include the time that stream spent waiting for its dependencies
-    if (off || g_prof.on.load(std::memory_order_relaxed)) return nullptr;
-    if (!s) {
-      s = new Side();
-      STGCN_CUDA(cudaStreamCreateWithFlags(&s->p, cudaStreamNonBlocking));
-      STGCN_CUDA(cudaStreamCreateWithFlags(&s->q, cudaStreamNonBlocking));
-      for (int i = 0; i < kEvents; ++i) STGCN_CUDA(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
-    }
+  static constexpr int kMaxDevices = 16;
+  static int current_device() {
+    int dev = 0;
+    STGCN_CUDA(cudaGetDevice(&dev));
+    STGCN_CHECK(dev >= 0 && dev < kMaxDevices, STGCN_E_UNSUPPORTED, "device ordinal out of range for the helper-stream pool");
+    return dev;
+  }
+  static Side* make() {
+    Side* s = new Side();
+    STGCN_CUDA(cudaStreamCreateWithFlags(&s->p, cudaStreamNonBlocking));
+    STGCN_CUDA(cudaStreamCreateWithFlags(&s->q, cudaStreamNonBlocking));
+    for (int i = 0; i < kEvents; ++i) STGCN_CUDA(cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming));
     return s;
   }
-  // Opt-in (STGCN_SIDE_PER_STREAM=1, unmeasured): one pair of helper streams per CALLER stream, for hosts that run
-  // independent chains (e.g. two half-batches) on different streams of one thread -- with the single thread-local pair
-  // above, chain B's parameter preparation would queue behind chain A's forks.  All kPool pairs are created at the first
-  // call (a warm-up), none later, so a stream capture never sees a stream or event being created.
-  static constexpr int kPool = 4;
-  static bool per_stream() {
-    static const bool on = std::getenv("STGCN_SIDE_PER_STREAM") != nullptr;
-    return on;
+  static bool disabled() {
+    static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;      // everything on the caller's stream
+    // the per-kernel event profiler (stgcn_profile_begin/end) wants one kernel at a time: events on a helper stream would
+    // include the time that stream spent waiting for its dependencies
+    return off || g_prof.on.load(std::memory_order_relaxed);
   }
+  // One pair of helper streams per (host thread, device, CALLER stream): the forward and the autograd-backward threads
+  // differ, a process may drive several GPUs (streams and events belong to the device that was current when they were
+  // created), and independent chains on different caller streams (graph.GraphedStep(micro_streams=k)) must not queue
+  // behind each other's forks.  All kPool pairs of a device are created at the first call on it (a warm-up), none later,
+  // so a stream capture never sees a stream or event being created.
+  static constexpr int kPool = 8;
   static Side* get_for(cudaStream_t caller) {
-    static thread_local Side* pool[kPool] = {nullptr, nullptr, nullptr, nullptr};
-    static thread_local cudaStream_t owner[kPool];
-    static thread_local int used = 0;
-    static const bool off = std::getenv("STGCN_NO_SIDE_STREAMS") != nullptr;
-    if (off || g_prof.on.load(std::memory_order_relaxed)) return nullptr;
-    if (!pool[0]) {
-      for (int k = 0; k < kPool; ++k) {
-        pool[k] = new Side();
-        STGCN_CUDA(cudaStreamCreateWithFlags(&pool[k]->p, cudaStreamNonBlocking));
-        STGCN_CUDA(cudaStreamCreateWithFlags(&pool[k]->q, cudaStreamNonBlocking));
-        for (int i = 0; i < kEvents; ++i) STGCN_CUDA(cudaEventCreateWithFlags(&pool[k]->ev[i], cudaEventDisableTiming));
-      }
-    }
-    for (int k = 0; k < used; ++k)
-      if (owner[k] == caller) return pool[k];
-    if (used < kPool) { owner[used] = caller; return pool[used++]; }
-    return pool[0];        // more caller streams than pairs: share one (correct, merely more serialised)
+    struct PerDevice { Side* pool[kPool]; cudaStream_t owner[kPool]; int used; };
+    static thread_local PerDevice devs[kMaxDevices] = {};
+    if (disabled()) return nullptr;
+    PerDevice& d = devs[current_device()];
+    if (!d.pool[0])
+      for (int k = 0; k < kPool; ++k) d.pool[k] = make();
+    for (int k = 0; k < d.used; ++k)
+      if (d.owner[k] == caller) return d.pool[k];
+    if (d.used < kPool) { d.owner[d.used] = caller; return d.pool[d.used++]; }
+    return d.pool[0];        // more caller streams than pairs: share one (correct, merely more serialised)
   }
 };
 

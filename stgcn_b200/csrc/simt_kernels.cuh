@@ -1513,6 +1513,7 @@ __global__ void axpy_kernel(float alpha, const T* x, T* y, long long n) {
 // y = relu(x), with optional dropout; and its backward
 template <class T>
 __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int training, float p, uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float v = fmaxf(ldf(x + i), 0.f);
@@ -1522,6 +1523,7 @@ __global__ void relu_dropout_fwd_kernel(const T* x, T* y, long long n, int train
 template <class T>
 __global__ void relu_dropout_bwd_kernel(const T* dy, const T* x, T* dx, long long n, int training, float p,
                                         uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float g = ldf(x + i) > 0.f ? ldf(dy + i) : 0.f;
@@ -1553,6 +1555,7 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_fwd_kernel(const T* x, const float* w, const float* b, T* y,
                                                      float* mean, float* rstd, int M, float eps, int training,
                                                      float p, uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1603,6 +1606,7 @@ template <int NCH>
 __global__ void __launch_bounds__(512) ln_fwd_cached_kernel(const bf16* x, const float* w, const float* b, bf16* y,
                                                             float* mean, float* rstd, int M, float eps, int training,
                                                             float p, uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   __shared__ float red[32];
   const long long g = blockIdx.x;
   const bf16* xp = x + g * M;
@@ -1657,6 +1661,7 @@ template <class T, int VEC>
 __global__ void __launch_bounds__(512) ln_bwd_kernel(const T* x, const T* dy, const float* w, const float* mean,
                                                      const float* rstd, T* dx, int M, int training, float p,
                                                      uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   __shared__ float red[32];
   long long g = blockIdx.x;
   const T* xp = x + g * M;
@@ -1702,6 +1707,7 @@ template <class T, int VEC>
 __global__ void ln_param_grad_kernel(const T* x, const T* dy, const float* mean, const float* rstd, float* dw,
                                      float* db, int M, long long G, int groups_per_cta, int training, float p,
                                      uint64_t seed) {
+  seed = live_seed(seed);      // + the device-side step counter, if one is registered (common.cuh)
   int i = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
   if (i >= M) return;
   long long g0 = (long long)blockIdx.y * groups_per_cta;
@@ -1772,6 +1778,7 @@ __device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
 }
 template <class T>
 __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
+  a.seed = live_seed(a.seed);      // + the device-side step counter, if one is registered (common.cuh)
   __shared__ float red[64];
   const long long g = blockIdx.x;
   const T* xp = a.x + g * a.M;
@@ -1803,6 +1810,7 @@ __global__ void __launch_bounds__(256) ln_bwd_sums_kernel(LnGateArgs<T> a) {
 #endif
 template <class T, int ACT>
 __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnGateArgs<T> a) {
+  a.seed = live_seed(a.seed);      // + the device-side step counter, if one is registered (common.cuh)
   constexpr bool gated = ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU;
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch * 8 >= a.M) return;

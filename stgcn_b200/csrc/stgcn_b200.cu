@@ -46,7 +46,7 @@ inline void run_block(void* workspace, size_t workspace_bytes, cudaStream_t stre
   Arena keep(workspace, keep_bytes), ws(static_cast<char*>(workspace) + keep_bytes, workspace_bytes - keep_bytes);
   ops::Ctx c{ws, stream};
   c.keep = &keep;
-  c.side = ops::Side::per_stream() ? ops::Side::get_for(stream) : ops::Side::get();
+  c.side = ops::Side::get_for(stream);
   c.begin();
   try {
     body(c);
@@ -63,6 +63,13 @@ extern "C" {
 int stgcn_version(void) { return STGCN_ABI_VERSION; }
 const char* stgcn_last_error(void) { return g_last_error; }
 uint64_t stgcn_launch_count(void) { return g_launches.load(); }
+
+int stgcn_set_dropout_step(const uint64_t* device_counter) {
+  return guarded([&] {
+    const unsigned long long* p = reinterpret_cast<const unsigned long long*>(device_counter);
+    STGCN_CUDA(cudaMemcpyToSymbol(g_dropout_step, &p, sizeof(p)));
+  });
+}
 
 int stgcn_profile_begin(void) {
   return guarded([&] {

@@ -1,11 +1,20 @@
 """CUDA-graph capture of a whole training step body (forward + loss + backward [+ gradient all-reduce]).
 
-At B200 speeds the step of the default model is a few hundred small kernels lasting a few milliseconds in total, so
+At B200 speeds the step of the default model is a few dozen kernels lasting about a millisecond in total, so
 Python/autograd/ctypes launch overhead becomes visible; capturing the step once and replaying it removes the host from
 the loop (the reference's own loop syncs the host every step through ``l.item()``, main.py:170).
 
     step = GraphedStep(model, batch_shape=(B, 1, 12, N), target_shape=(B, N))
     loss = step(x, y)          # x, y: CUDA tensors (copied into the static buffers); gradients land in p.grad
+
+Dropout: the kernels take their seed by value, which a capture would freeze; the step therefore owns a device-side
+step counter, registered with the library (``stgcn_set_dropout_step``) and incremented by the last node of the graph,
+so every replay draws fresh masks and the forward and backward of one replay agree.
+
+Data parallelism: with ``reducer=FlatGradAllReducer(model)`` the gradients are views into one flat buffer and the
+all-reduce is part of the captured graph (``reduce_in_graph=True``): bucket 0 (output stage + all ST blocks but the
+first) is enqueued as soon as the backward of ``st_blocks[1]`` is, on NCCL's stream, and overlaps the backward of
+``st_blocks[0]``; bucket 1 follows at the end.
 """
 from __future__ import annotations
 
@@ -17,16 +26,21 @@ import torch
 from . import _lib as L
 
 
+def _has_active_dropout(model: torch.nn.Module) -> bool:
+    return any(isinstance(m, torch.nn.Dropout) and m.p > 0 and m.training for m in model.modules())
+
+
 class GraphedStep:
     def __init__(self, model: torch.nn.Module, batch_shape, target_shape, device=None,
-                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, micro_streams: int = 1):
-        """micro_streams > 1 (experimental, unmeasured at the end of round 1): the batch is cut into that many equal
-        chunks whose forward+backward chains run on separate streams inside the ONE captured graph, so the tails and
-        launch bubbles of one chain overlap the other's kernels; the chunk losses are scaled by 1/micro_streams, so
-        the accumulated gradients and ``loss`` equal the full-batch ones.  Set STGCN_SIDE_PER_STREAM=1 as well (one
-        pair of library helper streams per chain)."""
+                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, micro_streams: int = 1,
+                 reducer=None, reduce_in_graph: bool = True):
+        """micro_streams > 1: the batch is cut into that many equal chunks whose forward+backward chains run on separate
+        streams inside the ONE captured graph, so the tails and launch bubbles of one chain overlap the other's kernels;
+        the chunk losses are scaled by 1/micro_streams, so the accumulated gradients and ``loss`` equal the full-batch
+        ones.  reducer: a dist.FlatGradAllReducer; None = single process."""
         self.model = model
         dev = device or next(model.parameters()).device
+        self.device = dev
         self.x = torch.zeros(batch_shape, device=dev)
         self.y = torch.zeros(target_shape, device=dev)
         self.loss = torch.zeros(1, device=dev)
@@ -34,31 +48,68 @@ class GraphedStep:
         self.micro = int(micro_streams)
         if self.micro < 1 or batch_shape[0] % self.micro:
             raise ValueError(f"micro_streams={micro_streams} must divide the batch size {batch_shape[0]}")
+        self.reducer = reducer
+        if reducer is not None and self.micro > 1:
+            raise ValueError("micro_streams > 1 accumulates gradients across chains; not combined with a reducer")
         self._mstreams = [torch.cuda.Stream(device=dev) for _ in range(self.micro)] if self.micro > 1 else []
         self._mloss = [torch.zeros(1, device=dev) for _ in range(self.micro)] if self.micro > 1 else []
         self._lib = L.lib()
-        # warm up on a side stream (allocator pools, lazily sized workspaces, cuFuncSetAttribute calls)
+        self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        with torch.cuda.device(dev):
+            torch.cuda.synchronize(dev)
+            L.check(self._lib.stgcn_set_dropout_step(self.step_counter.data_ptr()))
+        self._hook_handle = None
+        self._in_graph_reduce = False
+        # warm up on a side stream (allocator pools, lazily sized workspaces, cuFuncSetAttribute calls, helper streams)
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(s):
-            for _ in range(warmup):
+            for i in range(max(warmup, 2 if reducer is not None else 1)):
                 self._body()
+                if reducer is not None:
+                    reducer()                   # first call binds the flat buffer; later warm-ups run NCCL once eagerly
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
+        self._in_graph_reduce = reducer is not None and reduce_in_graph and reducer._world() > 1
+        if self._in_graph_reduce:
+            self._install_overlap_hook()
         self.graph = torch.cuda.CUDAGraph()
         for p in model.parameters():
             p.grad = None
-        with torch.cuda.graph(self.graph):
+        # thread_local: NCCL's watchdog thread and the autograd worker may call into the runtime during the capture
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._body()
-        self.grads = [p.grad for p in model.parameters()]
+        self.params = list(model.parameters())
+        self.grads = [p.grad for p in self.params]
 
+    # ------------------------------------------------------------------ data-parallel overlap
+    def _install_overlap_hook(self):
+        """Issue bucket 0 of the gradient all-reduce when the backward of st_blocks[1] has been enqueued (its input
+        gradient exists), so it overlaps the backward of st_blocks[0]."""
+        blocks = getattr(self.model, "st_blocks", None)
+        if blocks is None or len(blocks) < 2 or self.reducer.n_buckets < 2:
+            return
+        step = self
+
+        def fwd_hook(module, inputs, output):
+            if step._in_graph_reduce and torch.is_grad_enabled() and output.requires_grad:
+                output.register_hook(lambda g: step.reducer.reduce_bucket(0, async_op=True))
+
+        # the OUTPUT of st_blocks[0] is the input of st_blocks[1]: its gradient is produced by st_blocks[1]'s backward
+        self._hook_handle = blocks[0].register_forward_hook(fwd_hook)
+
+    # ------------------------------------------------------------------ step body
     def _body_micro(self):
         model = self.model
-        for p in model.parameters():
-            p.grad = None
+        params = list(model.parameters())
         cur = torch.cuda.current_stream(self.x.device)
         k = self.micro
+        chain_grads = []
         for st, xc, yc, lc in zip(self._mstreams, self.x.chunk(k), self.y.chunk(k), self._mloss):
+            # every chain gets its OWN gradient tensors (p.grad is None when its backward runs): accumulating into a
+            # shared p.grad from two streams would race with the other chain's kernels that are still writing it
+            for p in params:
+                p.grad = None
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 Bc = xc.shape[0]
@@ -67,12 +118,22 @@ class GraphedStep:
                 L.check(self._lib.stgcn_mse_fwd_bwd(pred.data_ptr(), yc.data_ptr(), pred.numel(), C.c_float(1.0 / k),
                                                     lc.data_ptr(), dpred.data_ptr(), st.cuda_stream))
                 pred.backward(dpred)
+            chain_grads.append([p.grad for p in params])
         for st in self._mstreams:
             cur.wait_stream(st)
+        live = [i for i, g in enumerate(chain_grads[0]) if g is not None]
+        total = [chain_grads[0][i] for i in live]
+        for c in range(1, k):
+            torch._foreach_add_(total, [chain_grads[c][i] for i in live])
+        for p in params:
+            p.grad = None
+        for i, g in zip(live, total):
+            params[i].grad = g
         torch.stack(self._mloss).sum(0, out=self.loss)
         self.loss.mul_(1.0 / k)
         if self.post_backward is not None:
             self.post_backward()
+        self.step_counter.add_(1)
 
     def _body(self):
         if self.micro > 1:
@@ -87,16 +148,39 @@ class GraphedStep:
                                             self.loss.data_ptr(), dpred.data_ptr(),
                                             torch.cuda.current_stream(self.x.device).cuda_stream))
         pred.backward(dpred)
+        if self._in_graph_reduce:
+            self.reducer()                       # remaining buckets + join of the overlapped one
         if self.post_backward is not None:
             self.post_backward()
+        self.step_counter.add_(1)
+
+    # ------------------------------------------------------------------ replay
+    def _after_replay(self):
+        # a zero_grad(set_to_none=True) between steps detaches p.grad from the tensors the graph writes: re-point them
+        for p, g in zip(self.params, self.grads):
+            p.grad = g
+        if self.reducer is not None and not self._in_graph_reduce:
+            self.reducer()
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         self.x.copy_(x, non_blocking=True)
         self.y.copy_(y, non_blocking=True)
         self.graph.replay()
+        self._after_replay()
         return self.loss
 
     def replay(self) -> torch.Tensor:
         """Replay on whatever is already in the static buffers ``self.x`` / ``self.y``."""
         self.graph.replay()
+        self._after_replay()
         return self.loss
+
+    def close(self) -> None:
+        """Unregister the device step counter and the overlap hook (the object must not be replayed afterwards)."""
+        if self._hook_handle is not None:
+            self._hook_handle.remove()
+            self._hook_handle = None
+        self._in_graph_reduce = False
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)
+            L.check(self._lib.stgcn_set_dropout_step(None))

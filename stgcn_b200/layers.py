@@ -23,6 +23,7 @@ import math
 from typing import Dict, Optional, Tuple
 
 import torch
+import torch.distributed
 import torch.nn as nn
 import torch.nn.init as init
 
@@ -63,10 +64,25 @@ def _workspace(device: torch.device, nbytes: int) -> torch.Tensor:
     return buf
 
 
+def _mix64(z: int) -> int:
+    """splitmix64 finaliser (the same mixing the kernels apply per element)."""
+    z &= 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+    return z ^ (z >> 31)
+
+
 def _next_seed() -> int:
+    """Seed of one dropout call: (torch seed, data-parallel rank, call counter) hashed, so ranks that set the same manual
+    seed (as the reference's set_env does, main.py:27-36) still draw different masks for their shards and successive
+    layers / steps are decorrelated.  Under CUDA-graph replay the by-value seed is frozen at capture; graph.GraphedStep
+    registers a device-side step counter that the kernels add (stgcn_set_dropout_step)."""
     global _SEED_COUNTER
     _SEED_COUNTER += 1
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _SEED_COUNTER * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
+    rank = 0
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank = torch.distributed.get_rank()
+    return _mix64(_mix64(torch.initial_seed() + 0x9E3779B97F4A7C15 * (rank + 1)) + 0xD1B54A32D192ED03 * _SEED_COUNTER)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -116,7 +132,16 @@ def _sizes(fn, desc) -> Tuple[int, int]:
 
 
 def _grad_like(p: Optional[torch.Tensor], needed: bool) -> Optional[torch.Tensor]:
-    return torch.empty_like(p) if (p is not None and needed) else None
+    """Buffer the backward kernels write a parameter gradient into.  When the parameter is bound to a flat gradient
+    buffer (dist.FlatGradAllReducer.bind) and holds no gradient yet, that is a fresh view of its slot: autograd adopts
+    it as ``p.grad`` without a copy, so the data-parallel all-reduce runs on the flat buffer with no pack/unpack."""
+    if p is None or not needed:
+        return None
+    slot = getattr(p, "_stgcn_grad_slot", None)
+    if slot is not None and p.grad is None:
+        flat, off, n = slot
+        return flat.narrow(0, off, n).view_as(p)
+    return torch.empty_like(p)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -134,8 +159,9 @@ class _TconvFn(torch.autograd.Function):
         ws = _workspace(dev, ws_bytes)
         y = torch.empty((B, T - Kt + 1, N, c_out), dtype=x_cl.dtype, device=dev)
         params = L.TconvParams(_ptr(conv_w), _ptr(conv_b), _ptr(align_w), _ptr(align_b))
-        L.check(lib.stgcn_tconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
-                                    ws.data_ptr(), ws.numel(), _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_tconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream(dev)))
         ctx.desc = desc
         ctx.save_for_backward(x_cl, saved, conv_w, conv_b, align_w, align_b)
         return y
@@ -154,8 +180,9 @@ class _TconvFn(torch.autograd.Function):
         params = L.TconvParams(_ptr(conv_w), _ptr(conv_b), _ptr(align_w), _ptr(align_b))
         grads = L.TconvGrads(*[_ptr(t) for t in g])
         dy = dy.to(x_cl.dtype).contiguous()
-        L.check(lib.stgcn_tconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
-                                    C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_tconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
+                                        C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
         return (dx, None, *g)
 
 
@@ -171,8 +198,9 @@ class _GconvFn(torch.autograd.Function):
         ws = _workspace(dev, ws_bytes)
         y = torch.empty((B, T, N, c_out), dtype=x_cl.dtype, device=dev)
         params = L.GconvParams(_ptr(align_w), _ptr(align_b), _ptr(w), _ptr(b), _ptr(gso))
-        L.check(lib.stgcn_gconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
-                                    ws.data_ptr(), ws.numel(), _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_gconv_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(params), y.data_ptr(), saved.data_ptr(),
+                                        ws.data_ptr(), ws.numel(), _stream(dev)))
         ctx.desc = desc
         ctx.save_for_backward(x_cl, saved, gso, align_w, align_b, w, b)
         return y
@@ -190,8 +218,9 @@ class _GconvFn(torch.autograd.Function):
         params = L.GconvParams(_ptr(align_w), _ptr(align_b), _ptr(w), _ptr(b), _ptr(gso))
         grads = L.GconvGrads(*[_ptr(t) for t in g])
         dy = dy.to(x_cl.dtype).contiguous()
-        L.check(lib.stgcn_gconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
-                                    C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_gconv_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
+                                        C.byref(params), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), _stream(dev)))
         return (dx, None, None, *g)
 
 
@@ -206,8 +235,9 @@ class _LnormFn(torch.autograd.Function):
         saved = torch.empty(sv_bytes, dtype=torch.uint8, device=dev)
         y = torch.empty_like(x_cl)
         seed = _next_seed() if (training and p_drop > 0) else 0
-        L.check(lib.stgcn_lnorm_fwd(C.byref(desc), x_cl.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
-                                    saved.data_ptr(), seed, _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_lnorm_fwd(C.byref(desc), x_cl.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                        saved.data_ptr(), seed, _stream(dev)))
         ctx.desc, ctx.seed = desc, seed
         ctx.save_for_backward(x_cl, saved, w)
         return y
@@ -222,8 +252,9 @@ class _LnormFn(torch.autograd.Function):
         dw = torch.empty_like(w) if need[2] else None
         db = torch.empty_like(w) if need[3] else None
         dy = dy.to(x_cl.dtype).contiguous()
-        L.check(lib.stgcn_lnorm_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(), w.data_ptr(),
-                                    _ptr(dw), _ptr(db), _ptr(dx), None, 0, ctx.seed, _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_lnorm_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(), w.data_ptr(),
+                                        _ptr(dw), _ptr(db), _ptr(dx), None, 0, ctx.seed, _stream(dev)))
         return dx, None, dw, db
 
 
@@ -251,8 +282,9 @@ class _STBlockFn(torch.autograd.Function):
         y = torch.empty((B, T - 2 * (Kt - 1), N, c3), dtype=x_cl.dtype, device=dev)
         seed = _next_seed() if (training and p_drop > 0) else 0
         cparams = _STBlockFn._pack(params, gso)
-        L.check(lib.stgcn_stblock_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(cparams), y.data_ptr(), saved.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), seed, _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_stblock_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(cparams), y.data_ptr(), saved.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), seed, _stream(dev)))
         ctx.desc, ctx.seed, ctx.ws_bytes = desc, seed, ws_bytes
         ctx.save_for_backward(x_cl, saved, gso, *params)
         return y
@@ -277,9 +309,10 @@ class _STBlockFn(torch.autograd.Function):
         grads = L.StblockGrads(L.TconvGrads(*gp[0:4]), L.GconvGrads(*gp[4:8]), L.TconvGrads(*gp[8:12]), gp[12], gp[13])
         cparams = _STBlockFn._pack(params, gso)
         dy = dy.to(x_cl.dtype).contiguous()
-        L.check(lib.stgcn_stblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
-                                      C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
-                                      _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_stblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
+                                          C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
+                                          _stream(dev)))
         return (dx, None, None, *g)
 
 
@@ -299,8 +332,9 @@ class _OutBlockFn(torch.autograd.Function):
         y = torch.empty((B, T - Ko + 1, N, c_end), dtype=torch.float32, device=dev)
         seed = _next_seed() if (training and p_drop > 0) else 0
         cparams = _OutBlockFn._pack(params)
-        L.check(lib.stgcn_outblock_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(cparams), y.data_ptr(), saved.data_ptr(),
-                                       ws.data_ptr(), ws.numel(), seed, _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_outblock_fwd(C.byref(desc), x_cl.data_ptr(), C.byref(cparams), y.data_ptr(), saved.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), seed, _stream(dev)))
         ctx.desc, ctx.seed, ctx.ws_bytes = desc, seed, ws_bytes
         ctx.save_for_backward(x_cl, saved, *params)
         return y
@@ -324,9 +358,10 @@ class _OutBlockFn(torch.autograd.Function):
         grads = L.OutblockGrads(L.TconvGrads(*gp[0:4]), *gp[4:10])
         cparams = _OutBlockFn._pack(params)
         dy = dy.float().contiguous()
-        L.check(lib.stgcn_outblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
-                                       C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
-                                       _stream(dev)))
+        with torch.cuda.device(dev):      # kernels, helper streams and events follow the CUDA current device
+            L.check(lib.stgcn_outblock_bwd(C.byref(ctx.desc), x_cl.data_ptr(), saved.data_ptr(), dy.data_ptr(),
+                                           C.byref(cparams), C.byref(grads), _ptr(dx), ws.data_ptr(), ws.numel(), ctx.seed,
+                                           _stream(dev)))
         return (dx, None, *g)
 
 

@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(L):
     for name in declared:
         assert hasattr(handle, name), f"{name} declared in the header but not exported"
     assert sorted(L.EXPORTED_SYMBOLS) == declared          # the ctypes table covers exactly the header
-    assert L.lib().stgcn_version() == 1
+    assert L.lib().stgcn_version() == 2
 
 
 def test_ctypes_structs_match_header_layout(L):

@@ -41,11 +41,15 @@ def _worker(rank, world, init_file, out_file):
     net = _OracleNet(params, gso, cfg)
     red = FlatGradAllReducer(net)
     sl = shard_batch(B, rank, world)
-    for _ in range(2):   # two steps: the second exercises the cached flat buffer
+    for it in range(3):   # step 0 binds the flat buffer; step 1 reduces it in one go; step 2 bucket by bucket, bucket 0 early
         net.zero_grad(set_to_none=True)
         loss = torch.nn.functional.mse_loss(net(x[sl]).reshape(sl.stop - sl.start, -1), y[sl])
         loss.backward()
+        if it == 2:
+            red._check_bound()
+            red.reduce_bucket(0, async_op=True)         # what GraphedStep issues after st_blocks[1]'s backward
         red()
+    assert all(p.grad.data_ptr() == red.flat.data_ptr() + 4 * off for p, off in zip(red.live, red.offsets))
     if rank == 0:
         full = _OracleNet(params, gso, cfg)
         torch.nn.functional.mse_loss(full(x).reshape(B, -1), y).backward()
@@ -56,7 +60,8 @@ def _worker(rank, world, init_file, out_file):
             if b.grad is not None:
                 n_live += 1
                 worst = max(worst, float((a.grad - b.grad).norm() / b.grad.norm().clamp_min(1e-30)))
-        torch.save({"worst": worst, "n_live": n_live, "n_all": len(net.ps), "flat": red.numel}, out_file)
+        torch.save({"worst": worst, "n_live": n_live, "n_all": len(net.ps), "flat": red.numel,
+                    "buckets": red.bucket_bounds, "names": red.names}, out_file)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -69,6 +74,42 @@ def test_flat_allreduce_matches_full_batch():
     assert res["worst"] < 1e-5
     assert res["n_live"] == res["n_all"] - 10          # the 10 dead align-conv tensors are skipped
     assert res["flat"] > 0
+    # the oracle wrapper's parameters are an unnamed list (no st_blocks.* names): one bucket; the bucket split itself is
+    # covered by test_backward_order_and_buckets below
+    assert res["buckets"] == [(0, res["flat"])]
+
+
+def test_backward_order_and_buckets():
+    """Flat-buffer layout on the real module tree (CPU: construction and binding only, no kernels): output stage first,
+    then st_blocks.1, then st_blocks.0 in its own bucket; dead align convs are left out."""
+    sys.path.insert(0, ROOT)
+    from types import SimpleNamespace
+    from stgcn_b200 import models
+    from stgcn_b200.dist import FlatGradAllReducer
+    n = 9
+    blocks = [[1], [8, 4, 8], [8, 4, 8], [16, 16], [1]]
+    args = SimpleNamespace(Kt=3, Ks=3, act_func="glu", graph_conv_type="cheb_graph_conv", gso=torch.eye(n),
+                           enable_bias=True, droprate=0.0, n_his=12)
+    model = models.STGCNChebGraphConv(args, blocks, n)
+    dead = {k for k, _ in model.named_parameters() if ".align.align_conv." in k and "graph_conv" not in k}
+    for k, p in model.named_parameters():
+        if k not in dead:
+            p.grad = torch.full_like(p, 2.0)
+    red = FlatGradAllReducer(model)
+    red.bind()
+    assert red.names[0].startswith("output.")
+    first = [i for i, k in enumerate(red.names) if k.startswith("st_blocks.0.")]
+    second = [i for i, k in enumerate(red.names) if k.startswith("st_blocks.1.")]
+    assert max(second) < min(first) and max(first) == len(red.names) - 1
+    assert red.n_buckets == 2 and red.bucket_bounds[0][1] == red.offsets[first[0]] == red.bucket_bounds[1][0]
+    assert not (set(red.names) & dead)
+    assert float(red.flat.min()) == 2.0 and all(p.grad.data_ptr() == red.flat.data_ptr() + 4 * o
+                                                for p, o in zip(red.live, red.offsets))
+    from stgcn_b200.layers import _grad_like
+    p0 = red.live[0]
+    p0.grad = None
+    v = _grad_like(p0, True)                         # the buffer the backward kernels would write
+    assert v.data_ptr() == red.flat.data_ptr() + 4 * red.offsets[0] and v.shape == p0.shape
 
 
 def test_shard_batch():
