@@ -45,8 +45,8 @@ def load_operator(tag, kind):
     """Dense graph operator of a workload: the reference-derived matrices committed under tests/golden/, or the seeded
     synthetic operator of SURVEY.md §8(d) for the N=2048 sweep."""
     if tag.startswith("syn"):
-        from oracle import stgcn_oracle as O        # operator construction only (same helper the tests use)
-        return O.synthetic_gso(int(tag[3:]), seed=0)
+        from stgcn_b200.synthetic import synthetic_operator
+        return synthetic_operator(int(tag[3:]), seed=0)
     return torch.from_numpy(np.load(os.path.join(ROOT, "tests", "golden",
                                                  f"gso_{tag}_{'cheb' if kind == 'cheb_graph_conv' else 'gcn'}.npy")))
 
@@ -160,24 +160,56 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-# ---- CPU reference arm (oracle port; the Python reference itself cannot travel to the GPU box) --------------------
-def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, threads=0):
-    """Times the oracle's restatement of the reference step (same ATen ops as the reference: conv2d, einsum->bmm,
-    layer_norm, autograd) on all host cores.  Returns dict(samples_per_s, ms_per_step, cores, steps)."""
+# ---- CPU reference arm ---------------------------------------------------------------------------------------------
+CPU_THREADS = 16        # fixed: on the 128-thread GPU host the reference's step (many small ATen ops) is fastest around 16
+                        # threads (all 128 are ~100x slower, profiles/bench_r01_fp32_first.json); a per-run sweep made the
+                        # number wander 260-723 samples/s between driver runs
+
+
+def _reference_modules():
+    """The UNMODIFIED reference (model/layers.py, model/models.py) if a copy travels with the repo under baseline/_ref
+    (git-ignored; the reference is plain Python without a build, so `pip install --target` has nothing to install --
+    DESIGN.md §6); None otherwise.  /root/reference itself does not exist on the GPU box and is never read here."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref, "model", "layers.py")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        from model import models as ref_models       # noqa: the reference's own package name
+        return ref_models
+    except Exception:
+        return None
+
+
+def _make_cpu_step(workload, batch, droprate, device="cpu"):
+    """One training-step body (main.py:165-168 without the optimizer) of the reference's arithmetic on `device`:
+    the reference's own modules when present, else the oracle's restatement (same ATen ops: conv2d, einsum->bmm,
+    layer_norm, autograd).  Returns (step_fn, kind)."""
     from oracle import stgcn_oracle as O
     tag, kind, ks, _, _ = WORKLOADS[workload]
     blocks = workload_blocks(workload)
-    gso = load_operator(tag, kind)
+    gso = load_operator(tag, kind).to(device)
     n = gso.shape[0]
-    try:
-        avail = len(os.sched_getaffinity(0))
-    except AttributeError:
-        avail = os.cpu_count() or 1
-    params = {k: v.requires_grad_(True) for k, v in
-              O.init_params(blocks=blocks, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
     gen = torch.Generator().manual_seed(0)
-    x = torch.randn(batch, 1, 12, n, generator=gen)
-    y = torch.randn(batch, n, generator=gen)
+    x = torch.randn(batch, 1, 12, n, generator=gen).to(device)
+    y = torch.randn(batch, n, generator=gen).to(device)
+    ref_models = _reference_modules()
+    if ref_models is not None:
+        args = SimpleNamespace(Kt=3, Ks=ks, act_func="glu", graph_conv_type=kind, gso=gso, enable_bias=True,
+                               droprate=droprate, n_his=12)
+        cls = ref_models.STGCNChebGraphConv if kind == "cheb_graph_conv" else ref_models.STGCNGraphConv
+        model = cls(args, blocks, n).to(device)
+        model.train()
+
+        def step():
+            model.zero_grad(set_to_none=True)
+            loss = torch.nn.functional.mse_loss(model(x).view(batch, -1), y)
+            loss.backward()
+            return loss
+        return step, "reference"
+    params = {k: v.to(device).requires_grad_(True) for k, v in
+              O.init_params(blocks=blocks, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0).items()}
     cfg = dict(blocks=blocks, kt=3, n_his=12, act="glu", kind=kind, p_drop=droprate, training=True)
 
     def step():
@@ -186,24 +218,19 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, t
         loss = O.mse_step(x, y, params, gso, **cfg)
         loss.backward()
         return loss
+    return step, "port"
 
-    # Use the thread count that is FASTEST for the reference's step on this host (many small ATen ops: on the GPU box all 128
-    # hardware threads were far slower than a moderate count in the first measurement, profiles/bench_r01_fp32_first.json).
-    cores, best = avail, None
-    if threads:
-        cores = threads
-    else:
-        for cand in sorted({min(c, avail) for c in (4, 8, 16, 32, 64, avail)}):
-            torch.set_num_threads(cand)
-            step()
-            t0 = time.perf_counter()
-            step()
-            dt = time.perf_counter() - t0
-            if best is None or dt < best:
-                best, cores = dt, cand
-            elif dt > 1.5 * best:
-                break
+
+def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, threads=CPU_THREADS):
+    """Times the reference step on the host cores: median of the timed steps at a FIXED thread count.
+    Returns dict(samples_per_s, ms_per_step, cores, steps, kind)."""
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    cores = max(1, min(threads, avail))
     torch.set_num_threads(cores)
+    step, kind = _make_cpu_step(workload, batch, droprate)
     for _ in range(warmup):
         step()
     times = []
@@ -212,11 +239,30 @@ def cpu_reference_run(workload, batch, steps, warmup, droprate, budget_s=None, t
         t0 = time.perf_counter()
         step()
         times.append(time.perf_counter() - t0)
-        if budget_s is not None and time.perf_counter() - t_start > budget_s and i >= 2:
+        if budget_s is not None and time.perf_counter() - t_start > budget_s and i >= 9:
             break
-    total = sum(times)
-    return dict(samples_per_s=batch * len(times) / total, ms_per_step=1e3 * total / len(times), cores=cores,
-                steps=len(times), batch=batch, host_threads_available=avail)
+    med = float(np.median(times))
+    return dict(samples_per_s=batch / med, ms_per_step=1e3 * med, cores=cores, steps=len(times), batch=batch,
+                host_threads_available=avail, kind=kind)
+
+
+def cuda_eager_baseline(workload, batch, droprate, dev, steps=5, warmup=2):
+    """The incumbent on the same box: the reference's eager PyTorch path on the
+    GPU (cuDNN/cuBLAS kernels behind conv2d / einsum / layer_norm + autograd), same workload and batch, CUDA events.
+    A reported baseline: none of this repository's kernels run here."""
+    step, kind = _make_cpu_step(workload, batch, droprate, device=dev)
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "batch": batch, "steps": steps,
+            "kind": kind, "what": "reference arithmetic, eager PyTorch CUDA (fp32, TF32 off), same B200"}
 
 
 def _arm_watchdog(seconds, rank):
@@ -237,6 +283,128 @@ def _arm_watchdog(seconds, rank):
     t.start()
 
 
+class Runner:
+    """One workload on this rank's GPU through the public API: model on stgcn_b200.layers, the whole step (zero_grad +
+    forward + MSE + backward [+ gradient all-reduce]) captured in a CUDA graph (stgcn_b200.graph.GraphedStep)."""
+    POOL = 4      # distinct input batches cycled through, so no step re-reads a hot input
+
+    def __init__(self, workload, B, precision, dev, rank, world, droprate=0.0, graph=True, micro_streams=1,
+                 reduce_in_graph=True):
+        import stgcn_b200
+        from stgcn_b200 import _lib as L
+        from stgcn_b200.dist import FlatGradAllReducer
+        from stgcn_b200.synthetic import build_model
+        self.L, self.lib = L, L.lib()
+        self.workload, self.B, self.precision, self.dev, self.world = workload, B, precision, dev, world
+        tag, kind, ks, _, self.desc = WORKLOADS[workload]
+        self.kind, self.ks = kind, ks
+        self.blocks = workload_blocks(workload)
+        gso = load_operator(tag, kind)
+        self.n = n = gso.shape[0]
+        stgcn_b200.set_precision(precision)
+        self.model = build_model(gso, kind, ks, self.blocks, dev, droprate=droprate, seed=0)
+        self.model.train()
+        self.reducer = FlatGradAllReducer(self.model) if world > 1 else None
+        gen = torch.Generator().manual_seed(1234 + rank)
+        self.xs_host = [torch.randn(B, 1, 12, n, generator=gen).pin_memory() for _ in range(self.POOL)]
+        self.ys_host = [torch.randn(B, n, generator=gen).pin_memory() for _ in range(self.POOL)]
+        self.xs = [t.to(dev) for t in self.xs_host]
+        self.ys = [t.to(dev) for t in self.ys_host]
+        self.loss_buf = torch.zeros(1, device=dev)
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.graphed, self.launches_per_step, self.reduce_mode = None, None, "none" if world == 1 else "after-backward"
+        if graph:
+            from stgcn_b200.graph import GraphedStep
+            n_before = L.launch_count()
+            warm = 3
+            try:
+                self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
+                                           micro_streams=micro_streams, reducer=self.reducer,
+                                           reduce_in_graph=reduce_in_graph)
+            except Exception as e:                   # capture of the collective refused: reduce after the replay instead
+                if self.reducer is None or not reduce_in_graph:
+                    raise
+                sys.stderr.write(f"[bench] in-graph all-reduce not captured ({type(e).__name__}: {e}); reducing after replay\n")
+                torch.cuda.synchronize(dev)
+                self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
+                                           micro_streams=micro_streams, reducer=self.reducer, reduce_in_graph=False)
+            self.launches_per_step = (L.launch_count() - n_before) // (warm + 1)      # warm-up bodies + 1 capture
+            self.loss_buf = self.graphed.loss
+            if self.reducer is not None:
+                self.reduce_mode = "in-graph, bucket 0 overlaps st_blocks.0 backward" if self.graphed._in_graph_reduce \
+                    else "after-replay on the flat buffer"
+        self.x_dev, self.y_dev = torch.empty_like(self.xs[0]), torch.empty_like(self.ys[0])
+
+    def eager_step(self, x, y, reduce=True):
+        L, B = self.L, self.B
+        self.model.zero_grad(set_to_none=True)
+        pred = self.model(x).reshape(B, -1)                      # (B,1,1,N) view -> (B,N), main.py:166
+        dpred = torch.empty_like(pred)
+        L.check(self.lib.stgcn_mse_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), 1.0, self.loss_buf.data_ptr(),
+                                           dpred.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        pred.backward(dpred)
+        if reduce and self.reducer is not None:
+            self.reducer()
+
+    def step(self, i):
+        x, y = self.xs[i % self.POOL], self.ys[i % self.POOL]
+        if self.graphed is None:
+            self.eager_step(x, y)
+        else:
+            self.graphed(x, y)                   # device-to-device copy into the static buffers + replay (+ reduce)
+
+    def e2e_step(self, i):
+        """Host (pinned) buffers in, loss out, copies inside the timed region, through the public module API."""
+        if self.graphed is None:
+            self.x_dev.copy_(self.xs_host[i % self.POOL], non_blocking=True)
+            self.y_dev.copy_(self.ys_host[i % self.POOL], non_blocking=True)
+            self.eager_step(self.x_dev, self.y_dev)
+        else:
+            self.graphed(self.xs_host[i % self.POOL], self.ys_host[i % self.POOL])
+        self.loss_host.copy_(self.loss_buf, non_blocking=True)
+
+    def timed(self, fn, k):
+        import torch.distributed as dist
+        dev, world = self.dev, self.world
+
+        def sync_all():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        sync_all()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def measure(self, steps, warmup):
+        """(samples/s over all ranks, ms/step) of `steps` timed steps after `warmup` untimed ones; max over ranks."""
+        for i in range(warmup):
+            self.step(i)
+        ms = self.timed(self.step, steps)
+        return self.B * self.world * steps / (ms / 1e3), ms / steps
+
+    def close(self):
+        if self.graphed is not None:
+            self.graphed.close()
+        if self.reducer is not None:
+            self.reducer.unbind()
+
+
+def _short_line(r, value, ms_step, extra=None):
+    fwd_f, tot_f, _ = flops_per_sample(r.n, r.kind, r.ks, blocks=r.blocks)
+    d = {"workload": f"{r.desc} batch={r.B}/GPU x {r.world} GPU", "precision": r.precision, "value": value,
+         "unit": "samples/s", "ms_per_step": ms_step, "tflops_per_gpu": tot_f * value / r.world / 1e12}
+    d.update(extra or {})
+    return d
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -245,17 +413,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pemsd7m", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's BASELINE batch)")
-    ap.add_argument("--precision", default=os.environ.get("STGCN_PRECISION", "bf16"), choices=["fp32", "bf16"],
-                    help="bf16 = BASELINE.json configs[1] (tcgen05 path); fp32 = the 1e-3 parity path")
+    ap.add_argument("--precision", default=os.environ.get("STGCN_PRECISION", "bf16"), choices=["fp32", "bf16", "tf32x3"],
+                    help="bf16 = BASELINE.json configs[1] (fused tcgen05 path); tf32x3 = the 1e-3 parity gate on tensor "
+                         "cores; fp32 = the same gate on CUDA cores")
     ap.add_argument("--droprate", type=float, default=0.0,
                     help="dropout p for BOTH arms (0 = the stricter CPU comparison, BASELINE.md §2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra legs of the default line (parity_mode, cuda_baseline, other BASELINE configs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--micro-streams", type=int, default=1,
-                    help="experimental (unmeasured in round 1): run that many batch chunks as parallel chains on separate "
-                         "streams inside the captured step (stgcn_b200.graph.GraphedStep)")
-    ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "600")),
+                    help="run that many batch chunks as parallel chains on separate streams inside the captured step")
+    ap.add_argument("--reduce-after", action="store_true", help="N > 1: all-reduce after the graph replay, not inside it")
+    ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "900")),
                     help="watchdog: dump all Python stacks to stderr and exit 124 if the run has not finished by then")
     a = ap.parse_args()
 
@@ -263,17 +434,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     _arm_watchdog(a.max_seconds, rank)
-    # Multi-process runs keep every kernel of the library on the caller's stream.  The last round-1 attempt at N=2 did not
-    # finish; the likely cause is the rank-0-only profile pass issuing gradient all-reduces without partners (fixed below),
-    # but the GPU budget was exhausted before the helper streams could be exercised together with NCCL, so they stay off for
-    # N > 1 until that is measured (the step without them ran 165.6 k samples/s on 2 GPUs earlier in the round).
-    # STGCN_MULTI_GPU_STREAMS=1 overrides.
-    helper_streams = True
-    if a.micro_streams > 1:
-        os.environ.setdefault("STGCN_SIDE_PER_STREAM", "1")     # one pair of library helper streams per chain
-    if world > 1 and not os.environ.get("STGCN_MULTI_GPU_STREAMS"):
-        os.environ["STGCN_NO_SIDE_STREAMS"] = "1"          # read once by the library, before its first call
-        helper_streams = False
+    helper_streams = os.environ.get("STGCN_NO_SIDE_STREAMS") is None
     tag, kind, ks, default_b, desc = WORKLOADS[a.workload]
     B = a.batch or default_b
     steps, warmup = a.steps, max(a.warmup, 3)
@@ -286,16 +447,21 @@ def main():
         if rank != 0:
             return
         cpu_b = min(B, 32 if a.workload != "syn2048" else 2)       # ~1 GFLOP of conv/bmm per sample-step at N=2048
-        r = cpu_reference_run(a.workload, cpu_b, steps, warmup, a.droprate)
-        sample = (f"{r['steps']} steps of B={cpu_b} (a bounded sample of the B={B} workload), oracle port of the "
-                  f"reference step (same ATen ops), {r['cores']} host threads (fastest of a sweep; "
-                  f"{r['host_threads_available']} available)")
+        r = cpu_reference_run(a.workload, cpu_b, max(steps, 10), warmup, a.droprate)
+        what = "the unmodified reference (baseline/_ref)" if r["kind"] == "reference" else \
+            "oracle port of the reference step (same ATen ops)"
+        sample = (f"median of {r['steps']} steps of B={cpu_b} (a bounded sample of the B={B} workload: "
+                  f"BASELINE configs[0] batch), {what}, {r['cores']} host threads "
+                  f"(fixed; {r['host_threads_available']} available)")
+        cfg_ref = dict(cfg_common)
+        cfg_ref["workload"] = f"{desc} fwd+bwd+MSE, dropout {a.droprate}; CPU sample batch={cpu_b} (GPU arm: batch={B}/GPU)"
+        cfg_ref["cpu_sample_batch"] = cpu_b
         line = {"impl": "reference", "metric": "ST-block fwd+bwd samples/sec", "value": r["samples_per_s"],
                 "unit": "samples/s", "n_gpus": a.gpus, "steps": r["steps"], "warmup": warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": cfg_common,
+                "dtype": "f32", "data": "synthetic", "config": cfg_ref,
                 "cpu_baseline": {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"],
-                                 "kind": "port", "sample": sample},
+                                 "kind": r["kind"], "sample": sample},
                 "e2e": {"value": r["samples_per_s"], "unit": "samples/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -315,134 +481,52 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
-    import stgcn_b200
-    from stgcn_b200 import models, _lib as L
-    from stgcn_b200.dist import FlatGradAllReducer
-    from oracle import stgcn_oracle as O   # parameter init only (same shapes/keys as the reference)
-    stgcn_b200.set_precision(a.precision)
+    from stgcn_b200 import _lib as L
 
-    blocks = workload_blocks(a.workload)
-    gso = load_operator(tag, kind)
-    n = gso.shape[0]
-    args = SimpleNamespace(Kt=3, Ks=ks, act_func="glu", graph_conv_type=kind, gso=gso.to(dev), enable_bias=True,
-                           droprate=a.droprate, n_his=12)
-    cls = models.STGCNChebGraphConv if kind == "cheb_graph_conv" else models.STGCNGraphConv
-    model = cls(args, blocks, n).to(dev)
-    model.load_state_dict(O.init_params(blocks=blocks, kt=3, ks=ks, n_his=12, n_vertex=n, kind=kind, seed=0))
-    model.train()
-    reducer = FlatGradAllReducer(model)
-
-    # synthetic inputs: a pool of distinct batches cycled through so no step re-reads a hot input
-    POOL = 4
-    gen = torch.Generator().manual_seed(1234 + rank)
-    xs_host = [torch.randn(B, 1, 12, n, generator=gen).pin_memory() for _ in range(POOL)]
-    ys_host = [torch.randn(B, n, generator=gen).pin_memory() for _ in range(POOL)]
-    xs = [t.to(dev) for t in xs_host]
-    ys = [t.to(dev) for t in ys_host]
-    lib = L.lib()
-    loss_buf = torch.zeros(1, device=dev)
-    loss_host = torch.zeros(1).pin_memory()
-
-    def eager_step(x, y, reduce=True):
-        model.zero_grad(set_to_none=True)
-        pred = model(x).reshape(B, -1)                      # (B,1,1,N) view -> (B,N), main.py:166
-        dpred = torch.empty_like(pred)
-        L.check(lib.stgcn_mse_fwd_bwd(pred.data_ptr(), y.data_ptr(), pred.numel(), 1.0, loss_buf.data_ptr(),
-                                      dpred.data_ptr(), torch.cuda.current_stream().cuda_stream))
-        pred.backward(dpred)
-        if reduce:
-            reducer()
-
-    # The public API for a launch-free step: the whole forward + loss + backward captured once in a CUDA graph
-    # (stgcn_b200.graph.GraphedStep); the gradient all-reduce (N > 1) is issued right after the replay.
-    graphed = None
-    launches_per_step = None
-    if not a.no_graph:
-        from stgcn_b200.graph import GraphedStep
-        n_before = L.launch_count()
-        graphed = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=3, micro_streams=a.micro_streams)
-        launches_per_step = (L.launch_count() - n_before) // 4       # 3 warm-up bodies + 1 capture
-        loss_buf = graphed.loss
-
-    def step(x, y):
-        if graphed is None:
-            eager_step(x, y)
-        else:
-            graphed(x, y)                                   # device-to-device copy into the static buffers + replay
-            reducer()
-
-    def sync_all():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, k):
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for i in range(k):
-            fn(i)
-        e1.record()
-        sync_all()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+    run = Runner(a.workload, B, a.precision, dev, rank, world, droprate=a.droprate, graph=not a.no_graph,
+                 micro_streams=a.micro_streams, reduce_in_graph=not a.reduce_after)
+    n, blocks = run.n, run.blocks
 
     for i in range(warmup):
-        step(xs[i % POOL], ys[i % POOL])
+        run.step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     n0 = L.launch_count()
-    ms_total = timed(lambda i: step(xs[i % POOL], ys[i % POOL]), steps)
-    launches = (L.launch_count() - n0) if graphed is None else launches_per_step * steps
+    ms_total = run.timed(run.step, steps)
+    launches = (L.launch_count() - n0) if run.graphed is None else run.launches_per_step * steps
     value = B * world * steps / (ms_total / 1e3)
 
-    # e2e: host (pinned) buffers in, loss out, copies inside the timed region, through the public module API
-    x_dev, y_dev = torch.empty_like(xs[0]), torch.empty_like(ys[0])
-
-    def e2e_step(i):
-        if graphed is None:
-            x_dev.copy_(xs_host[i % POOL], non_blocking=True)
-            y_dev.copy_(ys_host[i % POOL], non_blocking=True)
-            eager_step(x_dev, y_dev)
-        else:
-            graphed(xs_host[i % POOL], ys_host[i % POOL])   # pinned host -> static device buffers, then replay
-            reducer()
-        loss_host.copy_(loss_buf, non_blocking=True)
-
     for i in range(2):
-        e2e_step(i)
-    ms_e2e = timed(e2e_step, steps)
+        run.e2e_step(i)
+    ms_e2e = run.timed(run.e2e_step, steps)
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = B * world * steps / (ms_e2e / 1e3)
-    h2d = xs_host[0].numel() * 4 + ys_host[0].numel() * 4
+    h2d = run.xs_host[0].numel() * 4 + run.ys_host[0].numel() * 4
 
     # live per-kernel CUDA-event profile of the same step (separate short pass so the timed loop is unperturbed)
-    roofline, top = None, []
+    roofline, roofline_tc, top = None, None, []
     fwd_f, tot_f, stages = flops_per_sample(n, kind, ks, blocks=blocks)
     peaks = {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
         peaks["source"] = "MEASURED_PEAKS.json"
+    esize = 2 if a.precision == "bf16" else 4
     if rank == 0 and not a.no_profile:
         psteps = 3
         L.profile_begin()
         for i in range(psteps):
-            # eager: the event profiler brackets individual launches.  NO collective here: this pass runs on rank 0 only,
-            # an all-reduce without its partners pairs up with the other ranks' final barrier and hangs the job (the N=2
-            # run of round 1 did exactly that)
-            eager_step(xs[i % POOL], ys[i % POOL], reduce=False)
+            # eager: the event profiler brackets individual launches.  NO collective here: this pass runs on rank 0 only
+            run.eager_step(run.xs[i % run.POOL], run.ys[i % run.POOL], reduce=False)
         prof = L.profile_end()
         tot_ms = sum(v[1] for v in prof.values())
         rows = sorted(prof.items(), key=lambda kv: -kv[1][1])
         top = [{"key": k, "launches_per_step": v[0] / psteps, "ms_per_step": v[1] / psteps,
                 "share": v[1] / tot_ms} for k, v in rows[:60]]
         # dominant kernel: algorithmic FLOPs / bytes of the stage it implements over its measured time, against the
-        # roof that bounds it (ridge = peak FLOP/s / peak B/s)
-        esize = 4 if a.precision == "fp32" else 2
+        # roof that bounds it (ridge = peak FLOP/s / peak B/s); plus the tcgen05 kernel with the largest share against
+        # the TENSOR roof whatever its arithmetic intensity (north_star quotes tensor-pipe utilisation)
         ridge = peaks["bf16_tflops_sustained"] * 1e12 / (peaks["hbm_gbs"] * 1e9)
         for k0, (c0, ms0) in rows:
             work = _kernel_work(k0, n, B, kind, ks, esize, blocks=blocks)
@@ -450,43 +534,99 @@ def main():
                 continue
             fl, by = work
             t_s = ms0 / psteps * 1e-3
-            if by > 0 and fl / by < ridge:
-                ach, peak, bound, unit = by / t_s / 1e9, peaks["hbm_gbs"], "hbm", "GB/s"
-            else:
-                ach, peak, bound, unit = fl / t_s / 1e12, peaks["bf16_tflops_sustained"], "tensor", "TFLOP/s"
-            roofline = {"kernel": k0, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                        "traffic": _ncu_traffic(k0, a.workload, B, a.precision), "peak_source": peaks["source"],
-                        "alg_flops_per_step": fl,
-                        "alg_bytes_per_step": by, "launches_per_step": c0 / psteps,
-                        "avg_launch_ms": ms0 / c0, "share_of_step": ms0 / tot_ms}
-            break
+            common = {"kernel": k0, "peak_source": peaks["source"], "alg_flops_per_step": fl, "alg_bytes_per_step": by,
+                      "launches_per_step": c0 / psteps, "avg_launch_ms": ms0 / c0, "share_of_step": ms0 / tot_ms}
+            if roofline is None:
+                if by > 0 and fl / by < ridge:
+                    ach, peak, bound, unit = by / t_s / 1e9, peaks["hbm_gbs"], "hbm", "GB/s"
+                else:
+                    ach, peak, bound, unit = fl / t_s / 1e12, peaks["bf16_tflops_sustained"], "tensor", "TFLOP/s"
+                roofline = {"bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                            "traffic": _ncu_traffic(k0, a.workload, B, a.precision), **common}
+            if roofline_tc is None and "umma" in k0 and fl > 0:
+                ach = fl / t_s / 1e12
+                roofline_tc = {"bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"],
+                               "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops_sustained"], **common}
+            if roofline is not None and roofline_tc is not None:
+                break
     step_tflops = tot_f * value / world / 1e12          # per GPU
     roofline_step = {"bound": "tensor", "achieved": step_tflops, "peak": peaks["bf16_tflops_sustained"],
                      "unit": "TFLOP/s", "frac": step_tflops / peaks["bf16_tflops_sustained"],
-                     "flops_per_sample": tot_f, "alg_bytes_per_sample": bytes_per_sample(n, 4 if a.precision == "fp32" else 2, blocks=blocks),
+                     "flops_per_sample": tot_f, "alg_bytes_per_sample": bytes_per_sample(n, esize, blocks=blocks),
                      "peak_source": peaks["source"]}
+    reduce_mode = run.reduce_mode
+    cuda_graph = run.graphed is not None
+    run.close()
+    del run
+    torch.cuda.empty_cache()
 
-    cpu_baseline = None
+    # ------------------------------------------------------------------ extra legs of the default line
+    extras = {}
+    default_line = a.workload == "pemsd7m" and not a.batch and a.precision == "bf16" and not a.no_extras and not a.no_graph
+    xsteps, xwarm = 10, 3
+    if default_line:
+        def leg(name, fn):
+            try:
+                extras[name] = fn()
+            except Exception as e:                       # an extra leg must never take the headline down with it
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+
+        def parity_leg():
+            r = Runner("pemsd7m", B, "tf32x3", dev, rank, world, droprate=a.droprate)
+            v, ms = r.measure(xsteps, xwarm)
+            out = _short_line(r, v, ms, {"what": "the 1e-3 parity gate on tensor cores: fp32 storage, every GEMM tcgen05 "
+                                                  "kind::tf32 with 3xTF32 operand splitting (tests/test_gpu_parity.py)"})
+            r.close()
+            return out
+
+        def config_leg(workload, batch, label):
+            r = Runner(workload, batch, "bf16", dev, rank, world, droprate=a.droprate)
+            v, ms = r.measure(xsteps, xwarm)
+            out = _short_line(r, v, ms, {"baseline_config": label, "global_batch": batch * world})
+            r.close()
+            return out
+
+        leg("parity_mode", parity_leg)
+        if world == 1:
+            leg("cfg3_metrla", lambda: config_leg("metrla", 512, "configs[2]: METR-LA N=207 GraphConv batch=512 on 1xB200"))
+        else:
+            # BASELINE configs[3]: PEMS-BAY, GLOBAL batch 1024 sharded over the ranks (strong scaling: 512/256/128 per GPU)
+            leg("cfg4_pemsbay", lambda: config_leg("pemsbay", 1024 // world,
+                                                   f"configs[3]: PEMS-BAY N=325 ChebGraphConv Ks=3 global batch=1024 over {world}xB200"))
+
+    cpu_baseline, cuda_baseline = None, None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        r = cpu_reference_run(a.workload, 32 if a.workload != "syn2048" else 2, 60, 3, a.droprate, budget_s=15.0)
-        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": "port",
-                        "sample": f"{r['steps']} steps of B={r['batch']} (BASELINE configs[0] batch), oracle port of the "
-                                  f"reference step on {r['cores']} host threads (fastest of a sweep; "
-                                  f"{r['host_threads_available']} available), dropout {a.droprate}"}
+        r = cpu_reference_run(a.workload, 32 if a.workload != "syn2048" else 2, 40, 3, a.droprate, budget_s=15.0)
+        what = "the unmodified reference (baseline/_ref)" if r["kind"] == "reference" else "oracle port of the reference step"
+        cpu_baseline = {"value": r["samples_per_s"], "unit": "samples/s", "cores": r["cores"], "kind": r["kind"],
+                        "sample": f"median of {r['steps']} steps of B={r['batch']} (BASELINE configs[0] batch), {what} on "
+                                  f"{r['cores']} host threads (fixed; {r['host_threads_available']} available), "
+                                  f"dropout {a.droprate}"}
+        if default_line:
+            try:
+                torch.backends.cuda.matmul.allow_tf32 = False
+                torch.backends.cudnn.allow_tf32 = False
+                cuda_baseline = cuda_eager_baseline(a.workload, B, a.droprate, dev)
+            except Exception as e:
+                cuda_baseline = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         line = {"metric": "ST-block fwd+bwd samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
                 "steps": steps, "warmup": warmup, "ms_per_step": ms_total / steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if a.precision == "fp32" else "bf16", "data": "synthetic",
+                "dtype": {"fp32": "f32", "bf16": "bf16", "tf32x3": "tf32x3"}[a.precision], "data": "synthetic",
                 "config": {**cfg_common, "precision": a.precision,
-                           "l2": f"{POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
-                           "parallelism": f"dp{world}", "cuda_graph": graphed is not None,
-                           "helper_streams": helper_streams, "micro_streams": a.micro_streams},
+                           "l2": f"{Runner.POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
+                           "parallelism": f"dp{world}", "cuda_graph": cuda_graph,
+                           "helper_streams": helper_streams, "micro_streams": a.micro_streams,
+                           "grad_allreduce": reduce_mode},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / steps},
-                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_step": roofline_step,
-                "cpu_baseline": cpu_baseline, "top_kernels": top}
+                "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "roofline_tensor": roofline_tc,
+                "roofline_step": roofline_step, "cpu_baseline": cpu_baseline, "cuda_baseline": cuda_baseline,
+                **extras, "top_kernels": top}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -22,9 +22,9 @@
  *     reference's own STConvBlock returns (a permuted view of a (B,T,N,C) buffer,
  *     layers.py:255), and for the first block's C=1 input it is the same bytes as (B,1,T,N).
  *   - Parameters are passed in the reference's own state_dict layouts, fp32.
- *   - dtype of activations: fp32 when precision == STGCN_PREC_FP32, bf16 when
- *     precision == STGCN_PREC_BF16 (inter-block activations only; the first block's
- *     input and all parameters/gradients stay fp32).
+ *   - dtype of activations: fp32 when precision == STGCN_PREC_FP32 or STGCN_PREC_TF32X3,
+ *     bf16 when precision == STGCN_PREC_BF16 (inter-block activations only; the first
+ *     block's input and all parameters/gradients stay fp32).
  */
 #ifndef STGCN_B200_H_
 #define STGCN_B200_H_
@@ -42,7 +42,10 @@ enum { STGCN_OK = 0, STGCN_E_INVALID = 10001, STGCN_E_WORKSPACE = 10002, STGCN_E
 enum { STGCN_ACT_GLU = 0, STGCN_ACT_GTU = 1, STGCN_ACT_RELU = 2, STGCN_ACT_SILU = 3,   /* layers.py:104-115 */
        STGCN_ACT_LINEAR = 4 };  /* bare (Kt,1) conv + bias, no residual: CausalConv2d.forward (layers.py:52-57) */
 enum { STGCN_GCONV_CHEB = 0, STGCN_GCONV_GCN = 1 };                                      /* layers.py:217-220 */
-enum { STGCN_PREC_FP32 = 0, STGCN_PREC_BF16 = 1 };
+enum { STGCN_PREC_FP32 = 0,     /* fp32 storage, CUDA-core kernels: the reference's arithmetic (parity gate 1e-3)        */
+       STGCN_PREC_BF16 = 1,     /* bf16 storage, tcgen05 kind::f16: throughput mode (BASELINE.json configs[1])           */
+       STGCN_PREC_TF32X3 = 2 }; /* fp32 storage, every GEMM on tcgen05 kind::tf32 with 3xTF32 operand splitting
+                                   (22 operand bits, fp32 accumulate): the parity gate on the tensor cores            */
 
 /* ---- gated temporal convolution (TemporalConvLayer, layers.py:59-120) ---------------- */
 typedef struct {

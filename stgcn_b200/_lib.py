@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("STGCN_B200_LIB") or os.path.join(_HERE, "lib", "libst
 
 ACT = {"glu": 0, "gtu": 1, "relu": 2, "silu": 3, "linear": 4}
 GCONV = {"cheb_graph_conv": 0, "graph_conv": 1}
-PREC = {"fp32": 0, "bf16": 1}
+PREC = {"fp32": 0, "bf16": 1, "tf32x3": 2}
 
 E_INVALID, E_WORKSPACE, E_UNSUPPORTED = 10001, 10002, 10003
 

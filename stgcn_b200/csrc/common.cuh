@@ -53,6 +53,14 @@ struct Profiler {
 };
 extern Profiler g_prof;
 extern thread_local const char* g_tag;     // current op label (set by the host-side op code)
+// STGCN_PREC_TF32X3: the fp32 chain's GEMM launchers (simt_kernels.cuh: launch_tapgemm / launch_gso / launch_wgrad) hand their
+// work to the 3xTF32 tcgen05 kernel (umma_x3.cuh) for the duration of the ABI call that set this
+extern thread_local bool g_x3;
+struct X3Scope {
+  bool prev;
+  explicit X3Scope(bool on) : prev(g_x3) { g_x3 = on; }
+  ~X3Scope() { g_x3 = prev; }
+};
 
 struct Tag {                               // RAII label for the launches of one logical op
   const char* prev;

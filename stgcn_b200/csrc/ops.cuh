@@ -15,6 +15,7 @@
 #include "umma_gso.cuh"
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
+#include "umma_x3.cuh"
 #include "ln_gate_group.cuh"
 
 namespace stgcn {

@@ -21,6 +21,17 @@
 
 namespace stgcn {
 namespace simt {
+struct RowMap;
+template <class TI, class TO = TI> struct TapArgs;
+template <class T> struct GsoArgs;
+template <class T> struct WgradArgs;
+}  // namespace simt
+namespace umma {      // umma_x3.cuh: the same three GEMMs on tcgen05 (3xTF32); false = shape not served
+inline bool x3_tapgemm(const simt::TapArgs<float, float>& a, cudaStream_t stream);
+inline bool x3_gso(const simt::GsoArgs<float>& a, cudaStream_t stream);
+inline bool x3_wgrad(const simt::WgradArgs<float>& a, cudaStream_t stream);
+}  // namespace umma
+namespace simt {
 
 constexpr int BK = 16;
 constexpr int NT = 256;
@@ -85,7 +96,7 @@ struct RowMap {
   long long tap_row_stride;
 };
 
-template <class TI, class TO = TI>
+template <class TI, class TO>
 struct TapArgs {
   const TI* in;        // [*, Cin]
   const float* wt;     // [ntaps*Cin, Co], Co contiguous
@@ -196,6 +207,9 @@ __global__ void __launch_bounds__(NT) tapgemm_kernel(TapArgs<TI, TO> a) {
 template <class TI, class TO>
 inline void launch_tapgemm(const TapArgs<TI, TO>& a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
+  if constexpr (std::is_same<TI, float>::value && std::is_same<TO, float>::value) {
+    if (g_x3 && umma::x3_tapgemm(a, s)) return;
+  }
   if (a.Co <= 16) {
     dim3 grid(ceil_div(a.rows, 128), ceil_div(a.Co, 16));
     STGCN_LAUNCH((tapgemm_kernel<TI, TO, 128, 16, 2, 4>), grid, NT, 0, s, a);
@@ -306,6 +320,9 @@ __global__ void __launch_bounds__(NT) gso_kernel(GsoArgs<T> a) {
 template <class T>
 inline void launch_gso(const GsoArgs<T>& a, cudaStream_t s) {
   if (a.G == 0) return;
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_x3 && umma::x3_gso(a, s)) return;
+  }
   dim3 grid(ceil_div(a.G * a.C, 64), ceil_div(a.N, 64));
   STGCN_LAUNCH((gso_kernel<T, 64, 64, 4, 4>), grid, NT, 0, s, a);
 }
@@ -584,6 +601,9 @@ inline size_t wgrad_partial_elems(long long rows, int Mtot, int Co) {
 template <class T>
 inline void launch_wgrad(WgradArgs<T> a, cudaStream_t s) {
   if (a.rows == 0 || a.Co == 0) return;
+  if constexpr (std::is_same<T, float>::value) {
+    if (g_x3 && umma::x3_wgrad(a, s)) return;
+  }
   const int Mtot = a.ntaps * a.Cin + (a.bias_row ? 1 : 0);
   const WgradPlanSimt pl = plan_wgrad_simt(a.rows, Mtot, a.Co);
   a.rows_per_cta = (int)pl.rpc;

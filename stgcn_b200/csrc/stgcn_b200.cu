@@ -8,6 +8,7 @@ thread_local char g_last_error[512] = "";
 std::atomic<uint64_t> g_launches{0};
 Profiler g_prof;
 thread_local const char* g_tag = nullptr;
+thread_local bool g_x3 = false;
 }  // namespace stgcn
 
 using namespace stgcn;
@@ -15,17 +16,22 @@ using namespace stgcn;
 namespace {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline void need_prec(int precision) {
-  STGCN_CHECK(precision == STGCN_PREC_FP32 || precision == STGCN_PREC_BF16, STGCN_E_UNSUPPORTED, "unknown precision mode");
+  STGCN_CHECK(precision == STGCN_PREC_FP32 || precision == STGCN_PREC_BF16 || precision == STGCN_PREC_TF32X3,
+              STGCN_E_UNSUPPORTED, "unknown precision mode");
 }
 using bf16 = __nv_bfloat16;
 // run `body` with T bound to the activation storage type of this precision mode
 #define STGCN_DISPATCH(precision, ...)                                         \
   do {                                                                         \
     need_prec(precision);                                                      \
-    if ((precision) == STGCN_PREC_FP32) { using T = float; __VA_ARGS__; }      \
-    else { using T = bf16; __VA_ARGS__; }                                      \
+    if ((precision) == STGCN_PREC_BF16) { using T = bf16; __VA_ARGS__; }       \
+    else {                                                                     \
+      using T = float;                                                         \
+      ::stgcn::X3Scope _x3((precision) == STGCN_PREC_TF32X3);                  \
+      __VA_ARGS__;                                                             \
+    }                                                                          \
   } while (0)
-inline size_t elem_size(int precision) { return precision == STGCN_PREC_FP32 ? sizeof(float) : sizeof(bf16); }
+inline size_t elem_size(int precision) { return precision == STGCN_PREC_BF16 ? sizeof(bf16) : sizeof(float); }
 inline size_t max2(size_t a, size_t b) { return a > b ? a : b; }
 
 // Block-level calls (stblock / outblock).  The workspace is split into a "keep" region -- prepared weights and gradient

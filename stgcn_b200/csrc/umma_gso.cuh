@@ -141,9 +141,9 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ------------------------------------------------------------------------------------------------
 // K-tiled variant for operators that do not fit shared memory (N > ~1500; BASELINE configs[4], N = 2048): the A tile
 // [128 x 64] of every K block travels through the ring next to its B block instead of staying resident.  Lhat (8 MB
-// in bf16 at N = 2048) stays in the 126 MB L2, so the re-reads per group set are L2 traffic.  Opt-in
-// (STGCN_GSO_KTILED=1; also forces this kernel for small N so the existing graph-conv tests can exercise it); written
-// after the GPU budget of round 1 was spent: NOT yet run on a GPU.  Same roles / accumulator handling as umma_gso_kernel.
+// in bf16 at N = 2048) stays in the 126 MB L2, so the re-reads per group set are L2 traffic.  Serves the shapes the
+// resident-operator kernel cannot (STGCN_GSO_KTILED=1 forces it for every shape: test knob).  Same roles / accumulator
+// handling as umma_gso_kernel.
 // Next step for the roofline at N = 2048: cta_group::2 (M = 256) with TMA multicast of the B block across the pair.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTapThreads, 1)
@@ -285,8 +285,10 @@ inline GsoPlan plan_gso(int N, int C) {
   pl.ok = true;
   return pl;
 }
-inline bool gso_ktiled_enabled() {
-  static const bool on = std::getenv("STGCN_GSO_KTILED") != nullptr;      // opt-in: not yet validated on a GPU
+// test knob: route EVERY shape through the K-tiled kernel (the small-N graph-conv tests then exercise it); by default it
+// serves only the shapes the resident-operator kernel cannot take
+inline bool gso_ktiled_forced() {
+  static const bool on = std::getenv("STGCN_GSO_KTILED") != nullptr;
   return on;
 }
 // K-tiled plan: stages of (16 KB A block + B block); nothing resident
@@ -309,15 +311,15 @@ inline GsoPlan plan_gso_ktiled(int N, int C) {
 }
 inline bool gso_supported(int N, int C, long long G) {
   if (G <= 0) return false;
-  if (gso_ktiled_enabled()) return plan_gso_ktiled(N, C).ok;
-  return plan_gso(N, C).ok;
+  if (gso_ktiled_forced()) return plan_gso_ktiled(N, C).ok;
+  return plan_gso(N, C).ok || plan_gso_ktiled(N, C).ok;
 }
 inline size_t gso_prep_elems(int N) { return (size_t)N * ((N + 63) / 64 * 64); }
 
 // mbf: bf16 [N][Kp] prepared operator (gso_prep_kernel)
 inline void launch_gso_umma(const bf16* mbf, const bf16* in, const bf16* aux, bf16* out, int N, int C, long long G,
                             float alpha, float beta, cudaStream_t stream) {
-  const bool ktiled = gso_ktiled_enabled();
+  const bool ktiled = gso_ktiled_forced() || !plan_gso(N, C).ok;
   GsoPlan pl = ktiled ? plan_gso_ktiled(N, C) : plan_gso(N, C);
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma gso: unsupported shape");
   uint64_t ad[2] = {(uint64_t)pl.Kp, (uint64_t)N};

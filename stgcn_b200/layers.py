@@ -36,7 +36,9 @@ _PRECISION = "fp32"
 
 
 def set_precision(mode: str) -> None:
-    """'fp32': CUDA-core fp32 parity path (<=1e-3 rel of the reference).  'bf16': tcgen05 path."""
+    """'fp32': CUDA-core fp32 parity path (<=1e-3 rel of the reference).  'tf32x3': the same fp32 chain with every GEMM
+    on tcgen05 (3xTF32 operand splitting, fp32 accumulate) -- the parity gate on the tensor cores.  'bf16': bf16 storage,
+    fused tcgen05 kernels (throughput mode)."""
     global _PRECISION
     if mode not in L.PREC:
         raise ValueError(f"precision must be one of {sorted(L.PREC)}")
@@ -95,7 +97,7 @@ def _stream(device) -> int:
 
 def _act_dtype() -> torch.dtype:
     """Storage type of activations crossing the C ABI in the current precision mode."""
-    return torch.float32 if _PRECISION == "fp32" else torch.bfloat16
+    return torch.bfloat16 if _PRECISION == "bf16" else torch.float32
 
 
 def _require_cuda(x: torch.Tensor, what: str) -> None:

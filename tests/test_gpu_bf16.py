@@ -193,6 +193,43 @@ def test_bf16_fused_graph_conv_layer(kind, ks, c_in, N, B, T, relu, cuda_device)
             assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < tol, k
 
 
+@pytest.mark.parametrize("kind,ks,c_in,N,B,T", [("cheb_graph_conv", 3, 64, 325, 2, 6), ("cheb_graph_conv", 3, 16, 325, 3, 4),
+                                                  ("graph_conv", 3, 64, 325, 2, 3), ("cheb_graph_conv", 5, 64, 2048, 1, 2),
+                                                  ("cheb_graph_conv", 2, 64, 1100, 1, 3)])
+@pytest.mark.parametrize("c", [16, 64])
+def test_bf16_graph_conv_large_n(kind, ks, c_in, N, B, T, c, cuda_device):
+    """Graph sizes the fused TMEM-resident kernel does not take (N = 325: PEMS-BAY, BASELINE configs[3]) and the K-tiled
+    node contraction for operators that do not fit shared memory (N = 2048, 64 channels: BASELINE configs[4]).
+    Oracle evaluated on the same bf16-rounded operands."""
+    from stgcn_b200 import layers
+    if c_in < c:
+        pytest.skip("the reference never widens in the graph-conv layer")
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(ks * 7 + c + N)
+    torch.manual_seed(ks * 7 + c + N)
+    a = torch.randn(N, N, generator=gen)
+    gso = (a / torch.linalg.matrix_norm(a, ord=2)).float()
+    layer = layers.GraphConvLayer(kind, c_in, c, ks, gso.to(dev), True).to(dev)
+    p = {"g." + k: v.detach().cpu().clone() for k, v in layer.state_dict().items()}
+    x = torch.randn(B, c_in, T, N, generator=gen)
+    xg = x.to(dev).requires_grad_(True)
+    y = layer(xg, _relu=0)
+    assert y.dtype == torch.bfloat16
+    rb = lambda t: t.bfloat16().float()
+    pr = {k: (rb(v) if v.dim() > 1 else v.clone()).requires_grad_(True) for k, v in p.items()}
+    xr = rb(x).requires_grad_(True)
+    yr = O.graph_conv_layer(xr, pr, "g.", rb(gso), c, kind)
+    assert rel_l2(y.float().cpu(), yr) < 1.5e-2
+    dy = torch.randn(yr.shape, generator=gen)
+    y.backward(dy.to(dev).bfloat16())
+    yr.backward(rb(dy))
+    assert rel_l2(xg.grad.cpu(), xr.grad) < 4e-2
+    named = dict(layer.named_parameters())
+    for k, v in pr.items():
+        if v.grad is not None:
+            assert rel_l2(named[k[2:]].grad.cpu(), v.grad) < 4e-2, k
+
+
 @pytest.mark.parametrize("dataset,kind,B", [("pemsd7m", "cheb_graph_conv", 8), ("metrla", "graph_conv", 4)])
 def test_bf16_graphed_step_matches_eager(dataset, kind, B, cuda_device):
     """The whole step (forward + MSE + backward) is captured in ONE CUDA graph although the block-level calls fork helper
@@ -238,3 +275,92 @@ def test_bf16_graphed_step_matches_eager(dataset, kind, B, cuda_device):
             assert set(got) == set(grads_ref)
             for k, g_ref in grads_ref.items():
                 assert rel_l2(got[k].cpu(), g_ref.cpu()) <= 1e-4, (rep, k, rel_l2(got[k].cpu(), g_ref.cpu()))
+
+
+def _pems_model(dev, droprate, B, seed=5):
+    from stgcn_b200.synthetic import build_model
+    gso = load_gso("pemsd7m", "cheb")
+    blocks = [[1], [64, 16, 64], [64, 16, 64], [128, 128], [1]]
+    model = build_model(gso, "cheb_graph_conv", 3, blocks, dev, droprate=droprate, seed=seed)
+    model.train()
+    gen = torch.Generator().manual_seed(11)
+    n = gso.shape[0]
+    return model, torch.randn(B, 1, 12, n, generator=gen).to(dev), torch.randn(B, n, generator=gen).to(dev), n
+
+
+def test_graphed_step_dropout_masks_change_per_replay(cuda_device):
+    """A captured step bakes the by-value dropout seeds in; the device-side step counter (stgcn_set_dropout_step) must
+    give every replay fresh masks, and the forward and backward of one replay the SAME mask."""
+    from stgcn_b200.graph import GraphedStep
+    dev = cuda_device
+    B = 1          # 8 (b, t) groups: ~2^-8 of the (n, c) positions are dropped in every group, which the last check needs
+    model, x, y, n = _pems_model(dev, 0.5, B)
+    # the mask of the last dropout (output block, after fc1+ReLU) decides which fc2 inputs are zero: observe it through
+    # a forward hook on the first ST block's output instead (LayerNorm output has no exact zeros without dropout)
+    seen = []
+    h = model.st_blocks[0].register_forward_hook(lambda m, i, o: seen.append(o))
+    step = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2)
+    h.remove()
+    static_out = seen[-1]                     # the tensor the captured graph writes block 0's output into
+    masks, losses, grads = [], [], []
+    for rep in range(3):
+        loss = step(x, y)
+        torch.cuda.synchronize()
+        masks.append((static_out != 0).clone())
+        losses.append(loss.item())
+        grads.append(model.st_blocks[0].tc2_ln.weight.grad.clone())
+    for m in masks:
+        assert abs(m.float().mean().item() - 0.5) < 0.02
+    assert not torch.equal(masks[0], masks[1]) and not torch.equal(masks[1], masks[2])
+    assert len({round(l, 6) for l in losses}) == 3
+    # forward/backward agreement: dropped positions of block 0's output receive no gradient through the LayerNorm
+    # affine, so d(ln.weight) equals the sum over kept positions only -- recompute it from an eager pass with the same
+    # counter value is not possible from outside; instead check the necessary condition that a (n, c) column that was
+    # dropped in every (b, t) of a replay has an exactly zero weight gradient
+    for m, g in zip(masks, grads):
+        kept_any = m.permute(0, 2, 3, 1).reshape(-1, m.shape[3], m.shape[1]).any(0)      # (N, C)
+        assert torch.count_nonzero(g[~kept_any]) == 0
+    step.close()
+
+
+def test_graphed_step_regrads_after_zero_grad(cuda_device):
+    """optimizer.zero_grad(set_to_none=True) between replays must not disconnect p.grad from the graph's buffers."""
+    from stgcn_b200.graph import GraphedStep
+    dev = cuda_device
+    B = 4
+    model, x, y, n = _pems_model(dev, 0.0, B)
+    step = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2)
+    step(x, y)
+    torch.cuda.synchronize()
+    ref = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    model.zero_grad(set_to_none=True)
+    assert all(p.grad is None for p in model.parameters())
+    step(x, y)
+    torch.cuda.synchronize()
+    for k, p in model.named_parameters():
+        if k in ref:
+            assert p.grad is not None and rel_l2(p.grad.cpu(), ref[k].cpu()) <= 1e-4, k
+    step.close()
+
+
+def test_graphed_step_micro_streams_match_single_chain(cuda_device):
+    """Two half-batch chains on two streams inside one captured graph give the full-batch loss and gradients."""
+    from stgcn_b200.graph import GraphedStep
+    dev = cuda_device
+    B = 8
+    model, x, y, n = _pems_model(dev, 0.0, B)
+    one = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2)
+    l1 = one(x, y).item()
+    torch.cuda.synchronize()
+    g1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    one.close()
+    two = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2, micro_streams=2)
+    for rep in range(2):
+        l2 = two(x, y).item()
+        torch.cuda.synchronize()
+        assert abs(l1 - l2) <= 2e-3 * abs(l1)
+        g2 = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        assert set(g1) == set(g2)
+        for k in g1:      # bf16 activations: the two chains round differently from the single one
+            assert rel_l2(g2[k].cpu(), g1[k].cpu()) <= 5e-2, (k, rel_l2(g2[k].cpu(), g1[k].cpu()))
+    two.close()

@@ -1,5 +1,8 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the oracle and the reference-generated
-golden vectors.  Tolerance: north_star's 1e-3 relative (per-tensor rel-L2) for fp32; exact for index work."""
+golden vectors.  Tolerance: north_star's 1e-3 relative (per-tensor rel-L2); exact for index work.
+
+Every test runs in BOTH parity modes: ``fp32`` (CUDA-core kernels) and ``tf32x3`` (the same fp32 chain with every GEMM
+on tcgen05 tensor cores, 3xTF32 operand splitting -- csrc/umma_x3.cuh).  Same tolerances for both."""
 import math
 from types import SimpleNamespace
 
@@ -11,8 +14,16 @@ from oracle import stgcn_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-TOL = 1e-3          # the parity gate of BASELINE.json's north_star (fp32 path)
-TIGHT = 2e-4        # what the fp32 path is expected to achieve on outputs
+TOL = 1e-3          # the parity gate of BASELINE.json's north_star
+TIGHT = 2e-4        # what both parity modes are expected to achieve on outputs
+
+
+@pytest.fixture(autouse=True, params=["fp32", "tf32x3"])
+def parity_mode(request):
+    import stgcn_b200
+    stgcn_b200.set_precision(request.param)
+    yield request.param
+    stgcn_b200.set_precision("fp32")
 
 
 def _model_from_cfg(cfg, gso, dev, droprate=0.0):
