@@ -232,6 +232,27 @@ int stgcn_umma_microbench(const int32_t* cfg17, unsigned long long* out3_dev, vo
 int stgcn_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float loss_scale,
                       float* loss, float* dpred, void* stream);
 
+/* ---- the callers either side of the path (SURVEY.md §8f "next" rows) --------------------- */
+/* N2: optimizer step fused over ONE flat fp32 buffer of all live parameters (and its flat gradient buffer, the one
+ * the backward kernels and the all-reduce already work on).  Replaces optimizer.step() of torch.optim.AdamW
+ * (main.py:147-148,169; decoupled weight decay, bias-corrected moments) -- one launch instead of one per tensor.
+ * grad_scale multiplies every gradient first (1/world when the all-reduce summed).  step = 1-based step number; when
+ * step_dev != NULL the kernel uses *step_dev + 1 instead (a captured graph cannot change a by-value argument; pass the
+ * counter registered with stgcn_set_dropout_step, or any device int64 the caller increments).  lr_dev: optional
+ * device-side learning rate overriding lr (StepLR, main.py:158).                                                   */
+int stgcn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                     float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                     int64_t step, const int64_t* step_dev, const float* lr_dev, void* stream);
+/* same for the reference's Lion optimizer (script/opt.py:34-76)                                                 */
+int stgcn_lion_step(float* params, const float* grads, float* exp_avg, int64_t n, float lr, float beta1,
+                    float beta2, float weight_decay, float grad_scale, const float* lr_dev, void* stream);
+/* N3: the windows of ONE batch built on the device from the resident (z-scored) series [len, N]:
+ * x[i,0,t,:] = series[s_i + t,:] for t < n_his, y[i,:] = series[s_i + n_his + n_pred - 1,:], s_i = starts[i] (device
+ * int64 [B]) or start0 + i when starts == NULL.  Replaces data_transform (script/dataloader.py:32-48), which
+ * materialises every window of the split (12x the series) up front; pure index work, bit exact.                  */
+int stgcn_windows(const float* series, int64_t len, int32_t N, int32_t n_his, int32_t n_pred,
+                  const int64_t* starts, int64_t start0, int32_t B, float* x, float* y, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

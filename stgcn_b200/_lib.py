@@ -123,6 +123,12 @@ _SIGNATURES = [
     ("stgcn_debug_timeline", C.c_int, [_fp]),
     ("stgcn_umma_microbench", C.c_int, [C.POINTER(C.c_int32), _fp, _fp]),
     ("stgcn_mse_fwd_bwd", C.c_int, [_fp, _fp, C.c_int64, C.c_float, _fp, _fp, _fp]),
+    ("stgcn_adamw_step", C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_float, C.c_int64, _fp, _fp, _fp]),
+    ("stgcn_lion_step", C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _fp,
+                                  _fp]),
+    ("stgcn_windows", C.c_int, [_fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_int64, C.c_int32, _fp, _fp,
+                                _fp]),
 ]
 EXPORTED_SYMBOLS = [s[0] for s in _SIGNATURES]
 

@@ -2,6 +2,7 @@
 #include "ops.cuh"
 #include "umma_selftest.cuh"
 #include "umma_bench.cuh"
+#include "train_ops.cuh"
 
 namespace stgcn {
 thread_local char g_last_error[512] = "";
@@ -333,6 +334,43 @@ int stgcn_mse_fwd_bwd(const float* pred, const float* target, int64_t n, float l
     int blocks = ceil_div(n, 256 * 8);
     if (blocks > 148 * 4) blocks = 148 * 4;
     STGCN_LAUNCH(simt::mse_kernel, blocks, 256, 0, s, pred, target, (long long)n, loss_scale, loss, dpred);
+  });
+}
+
+// ---------------------------------------------------------------- optimizer / windows
+int stgcn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, float grad_scale, int64_t step,
+                     const int64_t* step_dev, const float* lr_dev, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(params && grads && exp_avg && exp_avg_sq && n >= 0, STGCN_E_INVALID, "null argument");
+    STGCN_CHECK(step >= 1 || step_dev, STGCN_E_INVALID, "AdamW step numbers start at 1");
+    if (n == 0) return;
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    STGCN_CHECK(al16(params) && al16(grads) && al16(exp_avg) && al16(exp_avg_sq), STGCN_E_INVALID,
+                "flat optimizer buffers must be 16-byte aligned");
+    train::AdamWArgs a{params, grads, exp_avg, exp_avg_sq, (long long)n, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                       (long long)step, reinterpret_cast<const long long*>(step_dev), lr_dev};
+    STGCN_LAUNCH(train::adamw_kernel, train::elementwise_grid((n + 3) / 4), 256, 0, as_stream(stream), a);
+  });
+}
+int stgcn_lion_step(float* params, const float* grads, float* exp_avg, int64_t n, float lr, float beta1, float beta2,
+                    float weight_decay, float grad_scale, const float* lr_dev, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(params && grads && exp_avg && n >= 0, STGCN_E_INVALID, "null argument");
+    if (n == 0) return;
+    STGCN_LAUNCH(train::lion_kernel, train::elementwise_grid(n), 256, 0, as_stream(stream), params, grads, exp_avg,
+                 (long long)n, lr, lr_dev, beta1, beta2, weight_decay, grad_scale);
+  });
+}
+int stgcn_windows(const float* series, int64_t len, int32_t N, int32_t n_his, int32_t n_pred, const int64_t* starts,
+                  int64_t start0, int32_t B, float* x, float* y, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(series && x && y, STGCN_E_INVALID, "null argument");
+    STGCN_CHECK(len > 0 && N > 0 && n_his > 0 && n_pred > 0 && B >= 0, STGCN_E_INVALID, "bad window geometry");
+    if (B == 0) return;
+    STGCN_LAUNCH(train::windows_kernel, train::elementwise_grid((long long)B * (n_his + 1) * N), 256, 0, as_stream(stream),
+                 series, (long long)len, (int)N, (int)n_his, (int)n_pred, reinterpret_cast<const long long*>(starts),
+                 (long long)start0, (int)B, x, y);
   });
 }
 

@@ -57,6 +57,8 @@ class FlatGradAllReducer:
     ``None`` (``zero_grad(set_to_none=True)``) before every backward once the buffer is bound: autograd then adopts the
     view the kernels filled; with a stale ``p.grad`` it would add the new gradient to itself."""
 
+    ALIGN = 64          # floats
+
     def __init__(self, module: torch.nn.Module, group: Optional[dist.ProcessGroup] = None, split_first_block: bool = True):
         self.module = module
         self.group = group
@@ -79,10 +81,12 @@ class FlatGradAllReducer:
         self.names = [n for n, _ in order]
         self.live = [p for _, p in order]
         self.sizes = [p.numel() for p in self.live]
-        self.offsets = [0]
-        for s in self.sizes[:-1]:
-            self.offsets.append(self.offsets[-1] + s)
-        total = self.offsets[-1] + self.sizes[-1]
+        # every slot starts on a 256-byte boundary (64 floats), like a tensor of its own would: the kernels take their
+        # 16-byte vector paths only on aligned parameter / gradient pointers.  The padding stays zero.
+        self.offsets, total = [], 0
+        for s in self.sizes:
+            self.offsets.append(total)
+            total += (s + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         dev = self.live[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         cut = total

@@ -103,7 +103,12 @@ def test_backward_order_and_buckets():
     assert max(second) < min(first) and max(first) == len(red.names) - 1
     assert red.n_buckets == 2 and red.bucket_bounds[0][1] == red.offsets[first[0]] == red.bucket_bounds[1][0]
     assert not (set(red.names) & dead)
-    assert float(red.flat.min()) == 2.0 and all(p.grad.data_ptr() == red.flat.data_ptr() + 4 * o
+    used = torch.zeros_like(red.flat, dtype=torch.bool)
+    for o, sz in zip(red.offsets, red.sizes):
+        assert o % 64 == 0                                # slots are 256-byte aligned; the padding between them is zero
+        used[o:o + sz] = True
+    assert float(red.flat[used].min()) == 2.0 and float(red.flat[~used].abs().max() if (~used).any() else 0.0) == 0.0
+    assert all(p.grad.data_ptr() == red.flat.data_ptr() + 4 * o
                                                 for p, o in zip(red.live, red.offsets))
     from stgcn_b200.layers import _grad_like
     p0 = red.live[0]
