@@ -16,7 +16,6 @@
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
 #include "umma_x3.cuh"
-#include "ln_gate_group.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -838,24 +837,8 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   if (dw) zero(dw, M, c.ps());       // parameter-gradient accumulators: zeroed on the helper stream (Ctx)
   if (db) zero(db, M, c.ps());
   c.prep_ready();
-  if constexpr (std::is_same<T, simt::bf16>::value) {
-    // opt-in (STGCN_LN_GROUP=1, ln_gate_group.cuh): one CTA per group produces dz in a single pass on the caller's stream;
-    // the parameter gradients, which nothing on that stream waits for, go to helper stream q
-    static const bool group_on = std::getenv("STGCN_LN_GROUP") != nullptr;
-    if (group_on && ln_gate_group_supported(a)) {
-      launch_ln_gate_bwd_group(tc.act, a, s);
-      if (dw || db) {
-        c.post_after();                  // q sees the zeroed accumulators (joined into the caller's stream above)
-        const int xb = ceil_div(M, 128 * 8);
-        int ychunks = (int)std::min<long long>(G, std::max<long long>(1, (148 * 16) / xb));
-        const int gpc = ceil_div(G, ychunks);
-        ychunks = ceil_div(G, gpc);
-        STGCN_LAUNCH((ln_param_grad_kernel<T, 8>), dim3(xb, ychunks), 128, 0, c.qs(), x, dy, stats, stats + G, dw, db, M, G, gpc,
-                     d.training, d.p_drop, seed);
-      }
-      return true;
-    }
-  }
+  // (a one-CTA-per-group variant that drops the read-only sums pass measured 0.7 % slower on the whole step and was
+  // removed: profiles/r02_ab_batch_a.md)
   launch_ln_gate_bwd(tc.act, a, umma::sm_count(), s);
   return true;
 }

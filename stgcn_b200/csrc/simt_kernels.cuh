@@ -1026,9 +1026,7 @@ __global__ void __launch_bounds__(256) smallc_conv_gate_fwd_kernel(SmallCArgs<T>
 // Cin == 1 specialisation: the K = Kt weights of this thread's 8 (+8 gate) channels live in registers; each thread
 // walks rows with a grid stride (its channel group never changes), so the loop body is K loads of x, K*16 FMAs, the
 // gate, and three 16-byte stores.
-// PF (opt-in with STGCN_SMALLC1_PREFETCH=1, unmeasured): the next row's taps are requested one iteration ahead (ncu: long
-// scoreboard 49 % on the x loads).  PF = false is the validated round-1 kernel, unchanged.
-template <class T, int K, int ACT, bool PF = false>
+template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T> a) {
   const int groups = a.Cout / 8;
   const bool gated = a.W == 2 * a.Cout;
@@ -1045,43 +1043,6 @@ __global__ void __launch_bounds__(256) smallc1_conv_gate_fwd_kernel(SmallCArgs<T
       wq[k][i] = gated ? a.wt[k * a.W + a.Cout + j0 + i] : 0.f;
     }
   }
-  if constexpr (PF) {
-    const long long stride = (long long)gridDim.x * lanes;
-    long long r = (long long)blockIdx.x * lanes + rl;
-    float xn[K];
-#pragma unroll
-    for (int k = 0; k < K; ++k) xn[k] = 0.f;
-    auto fetch = [&](long long rr) {
-      long long in0; int t_unused;
-      row_decode(rr, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
-#pragma unroll
-      for (int k = 0; k < K; ++k) xn[k] = ldf(a.x + in0 + (long long)k * a.N);
-    };
-    if (r < a.rows) fetch(r);
-    for (; r < a.rows; r += stride) {
-      float xv[K], zp[8], zq[8], hv[8];
-#pragma unroll
-      for (int k = 0; k < K; ++k) xv[k] = xn[k];
-      if (r + stride < a.rows) fetch(r + stride);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        float p = bp[i], q = bq[i];
-#pragma unroll
-        for (int k = 0; k < K; ++k) { p = fmaf(xv[k], wp[k][i], p); q = fmaf(xv[k], wq[k][i], q); }
-        zp[i] = p; zq[i] = q;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float res = (a.explicit_res && j0 + i == 0) ? xv[K - 1] : 0.f;
-        hv[i] = act_fwd<kFastAct<T>>(ACT, zp[i] + res, zq[i]);
-      }
-      if (!a.skip_z) {
-        store8(a.z + r * a.W + j0, zp);
-        if (gated) store8(a.z + r * a.W + a.Cout + j0, zq);
-      }
-      store8(a.h + r * a.Cout + j0, hv);
-    }
-  } else
   for (long long r = (long long)blockIdx.x * lanes + rl; r < a.rows; r += (long long)gridDim.x * lanes) {
     long long in0; int t_unused;
     row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
@@ -1112,11 +1073,6 @@ template <class T>
 inline void launch_smallc1_conv_gate_fwd(const SmallCArgs<T>& a, cudaStream_t s) {
   const int lanes = 256 / (a.Cout / 8);
   const int blocks = (int)std::min<long long>(ceil_div(a.rows, lanes), 148 * 8);
-  static const bool pf_on = std::getenv("STGCN_SMALLC1_PREFETCH") != nullptr;      // opt-in variant (see the kernel)
-  if (pf_on && a.Kt == 3 && a.act == STGCN_ACT_GLU) {
-    STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 3, STGCN_ACT_GLU, true>), blocks, 256, 0, s, a);
-    return;
-  }
   // the activation is a template parameter: a runtime switch inside the 8-wide unrolled gate cost a branch chain per element
 #define STGCN_SC1F(ACTV) do { \
     if (a.Kt == 2) STGCN_LAUNCH((smallc1_conv_gate_fwd_kernel<T, 2, ACTV>), blocks, 256, 0, s, a); \
@@ -1200,11 +1156,9 @@ __global__ void __launch_bounds__(256) smallc_gate_wgrad_kernel(SmallCArgs<T> a)
 
 // Cin == 1 specialisation of the above (the model input): 8 channels per thread with 16-byte loads, K = Kt taps known
 // at compile time, shuffle + shared-memory reduction, per-CTA partials.
-// PF (opt-in, STGCN_SMALLC1_PREFETCH=1; bf16, z recomputed, no dz output): the next row's x taps and dh chunk are
-// requested one iteration ahead and the weights are read from shared memory as float4 -- ncu showed the loop waiting on
-// the x loads (long scoreboard 33 %) and on scalar LDS (short scoreboard 14 %, MIO 7 %).  PF = false is the validated
-// round-1 kernel, unchanged.
-template <class T, int K, int ACT, bool PF = false>
+// (A variant that requested the next row's operands one iteration ahead measured 2.5 % slower on the whole step --
+// profiles/r02_ab_batch_a.md -- and was removed.)
+template <class T, int K, int ACT>
 __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a) {
   __shared__ float red[8][2 * (K + 1) * 64];       // [warp][half][k][<=64 channels per pass]
   const bool gated = a.W == 2 * a.Cout;
@@ -1226,61 +1180,6 @@ __global__ void __launch_bounds__(256) smallc1_gate_wgrad_kernel(SmallCArgs<T> a
   }
   const long long r0 = (long long)blockIdx.x * a.rows_per_cta;
   const long long r1 = min(a.rows, r0 + a.rows_per_cta);
-  if constexpr (PF && std::is_same<T, bf16>::value) {
-    long long r = r0 + rl;
-    float xn[K];
-    uint4 dhn = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int k = 0; k < K; ++k) xn[k] = 0.f;
-    auto fetch = [&](long long rr) {
-      long long in0; int t_unused;
-      row_decode(rr, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
-#pragma unroll
-      for (int k = 0; k < K; ++k) xn[k] = ldf(a.x + in0 + (long long)k * a.N);
-      dhn = *reinterpret_cast<const uint4*>(a.dh + rr * a.Cout + j0);
-    };
-    if (r < r1) fetch(r);
-    for (; r < r1; r += lanes) {
-      float xv[K], zp[8], zq[8], dh[8], du[8], dq[8];
-#pragma unroll
-      for (int k = 0; k < K; ++k) xv[k] = xn[k];
-      unpack8(dhn, dh);
-      if (r + lanes < r1) fetch(r + lanes);
-      {
-        const float4 b0 = *reinterpret_cast<const float4*>(w_s + K * a.W + j0), b1 = *reinterpret_cast<const float4*>(w_s + K * a.W + j0 + 4);
-        zp[0] = b0.x; zp[1] = b0.y; zp[2] = b0.z; zp[3] = b0.w; zp[4] = b1.x; zp[5] = b1.y; zp[6] = b1.z; zp[7] = b1.w;
-        if (gated) {
-          const float4 c0 = *reinterpret_cast<const float4*>(w_s + K * a.W + a.Cout + j0), c1 = *reinterpret_cast<const float4*>(w_s + K * a.W + a.Cout + j0 + 4);
-          zq[0] = c0.x; zq[1] = c0.y; zq[2] = c0.z; zq[3] = c0.w; zq[4] = c1.x; zq[5] = c1.y; zq[6] = c1.z; zq[7] = c1.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) zq[i] = 0.f;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < K; ++k) {
-        const float4 p0 = *reinterpret_cast<const float4*>(w_s + k * a.W + j0), p1 = *reinterpret_cast<const float4*>(w_s + k * a.W + j0 + 4);
-        const float wp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) zp[i] = fmaf(xv[k], wp[i], zp[i]);
-        if (gated) {
-          const float4 q0 = *reinterpret_cast<const float4*>(w_s + k * a.W + a.Cout + j0), q1 = *reinterpret_cast<const float4*>(w_s + k * a.W + a.Cout + j0 + 4);
-          const float wq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) zq[i] = fmaf(xv[k], wq[i], zq[i]);
-        }
-      }
-      if (a.explicit_res && j0 == 0) zp[0] += xv[K - 1];        // residual = zero-padded input: channel 0 only
-#pragma unroll
-      for (int i = 0; i < 8; ++i) act_bwd<true>(ACT, zp[i], gated ? zq[i] : 0.f, dh[i], du[i], dq[i]);
-#pragma unroll
-      for (int k = 0; k < K; ++k)
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { accp[k][i] = fmaf(xv[k], du[i], accp[k][i]); accq[k][i] = fmaf(xv[k], dq[i], accq[k][i]); }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { accp[K][i] += du[i]; accq[K][i] += dq[i]; }
-    }
-  } else
   for (long long r = r0 + rl; r < r1; r += lanes) {
     long long in0; int t_unused;
     row_decode(r, a.T_out * a.N, a.N, (long long)a.T_in * a.N, in0, t_unused);
@@ -1355,11 +1254,6 @@ inline bool smallc1_supported(int Cin, int Cout, int Kt) {
 }
 template <class T>
 inline void launch_smallc1_gate_wgrad(const SmallCArgs<T>& a, int ctas, cudaStream_t s) {
-  static const bool pf_on = std::getenv("STGCN_SMALLC1_PREFETCH") != nullptr;      // opt-in variant (see the kernel)
-  if (pf_on && std::is_same<T, bf16>::value && a.skip_z && a.dz == nullptr && a.Kt == 3 && a.act == STGCN_ACT_GLU) {
-    STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3, STGCN_ACT_GLU, true>), ctas, 256, 0, s, a);
-    return;
-  }
 #define STGCN_SC1B(ACTV) do { \
     if (a.Kt == 2) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 2, ACTV>), ctas, 256, 0, s, a); \
     else if (a.Kt == 3) STGCN_LAUNCH((smallc1_gate_wgrad_kernel<T, 3, ACTV>), ctas, 256, 0, s, a); \

@@ -129,7 +129,7 @@ class GraphedStep:
             p.grad = None
         for i, g in zip(live, total):
             params[i].grad = g
-        torch.stack(self._mloss).sum(0, out=self.loss)
+        self.loss.copy_(torch.stack(self._mloss).sum(0))
         self.loss.mul_(1.0 / k)
         if self.post_backward is not None:
             self.post_backward()
