@@ -111,19 +111,23 @@ def bytes_per_sample(n, dtype_bytes, blocks=BLOCKS, kt=3, n_his=12):
 
 # ---- clocks sampler ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms in the background; `stop()` summarises the samples that
+    arrived between `mark_load_begin()` and `mark_load_end()` (the timed regions plus, when those are shorter than a few
+    sampling periods, an extra observation window of the same step)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows = []
+        self.rows = []          # (arrival time, line)
         self.proc = None
         self.index = index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -131,7 +135,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.time(), line.strip()))
+
+    def wait_first_sample(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end:
+            time.sleep(0.05)
+
+    def mark_load_begin(self):
+        self.t0 = time.time()
+
+    def mark_load_end(self):
+        self.t1 = time.time()
+
+    def samples_under_load(self):
+        lo = self.t0 if self.t0 is not None else 0.0
+        hi = self.t1 if self.t1 is not None else float("inf")
+        return sum(1 for t, _ in self.rows if lo <= t <= hi)
 
     def stop(self):
         if self.proc is None:
@@ -143,7 +163,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        lo = self.t0 if self.t0 is not None else 0.0
+        hi = self.t1 if self.t1 is not None else float("inf")
+        for t, r in self.rows:
+            if not (lo <= t <= hi):
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -155,7 +179,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(nm)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"], "rows_total": len(self.rows)}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
                 "samples": len(sm)}
 
@@ -262,7 +286,7 @@ def cuda_eager_baseline(workload, batch, droprate, dev, steps=5, warmup=2):
     torch.cuda.synchronize(dev)
     ms = e0.elapsed_time(e1) / steps
     return {"value": batch / (ms / 1e3), "unit": "samples/s", "ms_per_step": ms, "batch": batch, "steps": steps,
-            "kind": kind, "what": "reference arithmetic, eager PyTorch CUDA (fp32, TF32 off), same B200"}
+            "kind": kind, "what": "reference arithmetic, eager PyTorch CUDA, same B200"}
 
 
 def _arm_watchdog(seconds, rank):
@@ -487,11 +511,13 @@ def main():
                  micro_streams=a.micro_streams, reduce_in_graph=not a.reduce_after)
     n, blocks = run.n, run.blocks
 
-    for i in range(warmup):
-        run.step(i)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    for i in range(warmup):
+        run.step(i)
+    sampler.mark_load_begin()
     n0 = L.launch_count()
     ms_total = run.timed(run.step, steps)
     launches = (L.launch_count() - n0) if run.graphed is None else run.launches_per_step * steps
@@ -500,6 +526,21 @@ def main():
     for i in range(2):
         run.e2e_step(i)
     ms_e2e = run.timed(run.e2e_step, steps)
+    # the timed regions last tens of milliseconds, nvidia-smi samples every 100 ms: keep the same step running (untimed,
+    # all ranks: it contains the collective) until at least 5 samples have been taken under this load
+    obs_rounds = 0
+    while obs_rounds < 40:
+        need_more = torch.tensor([1 if (rank == 0 and sampler.samples_under_load() < 5 and sampler.proc is not None) else 0],
+                                 device=dev)
+        if world > 1:
+            dist.broadcast(need_more, src=0)
+        if int(need_more.item()) == 0:
+            break
+        for i in range(50):
+            run.step(i)
+        torch.cuda.synchronize()
+        obs_rounds += 1
+    sampler.mark_load_end()
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = B * world * steps / (ms_e2e / 1e3)
     h2d = run.xs_host[0].numel() * 4 + run.ys_host[0].numel() * 4
@@ -606,9 +647,14 @@ def main():
                                   f"dropout {a.droprate}"}
         if default_line:
             try:
+                # PyTorch's defaults (what the reference's main.py runs with: TF32 allowed in cuDNN convolutions, fp32
+                # matmuls) and the strict-fp32 variant
+                cuda_baseline = cuda_eager_baseline(a.workload, B, a.droprate, dev)
+                cuda_baseline["what"] = "reference arithmetic, eager PyTorch CUDA with PyTorch's default math modes, same B200"
                 torch.backends.cuda.matmul.allow_tf32 = False
                 torch.backends.cudnn.allow_tf32 = False
-                cuda_baseline = cuda_eager_baseline(a.workload, B, a.droprate, dev)
+                strict = cuda_eager_baseline(a.workload, B, a.droprate, dev)
+                cuda_baseline["strict_fp32"] = {"value": strict["value"], "ms_per_step": strict["ms_per_step"]}
             except Exception as e:
                 cuda_baseline = {"error": f"{type(e).__name__}: {e}"[:300]}
 

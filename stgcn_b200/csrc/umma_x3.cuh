@@ -18,7 +18,8 @@
 // Operands come straight from the fp32 tensors: 8 producer warps load them (coalesced along whichever axis is contiguous
 // in memory), split every value and write the hi / lo tiles K-major with the 128-byte swizzle -- the operand layout the
 // bf16 tap kernel uses for 64-channel inputs (validated there; only the instruction kind and element size differ).
-// Warp roles: 0-3 epilogue (TMEM lane quarter = warp index), 4 MMA issuer + TMEM allocation, 5-12 producers.
+// Warp roles: 0-3 epilogue (TMEM lane quarter = warp index), 4 MMA issuer + TMEM allocation, 5-12 producers (two groups
+// of four warps on alternate pipeline stages).
 #pragma once
 #include "umma.cuh"
 #include "simt_kernels.cuh"
@@ -30,6 +31,7 @@ namespace umma {
 enum { X3_TAP = 0, X3_GSO = 1, X3_WGRAD = 2 };
 constexpr int kX3EpiWarps = 4, kX3ProdWarps = 8;
 constexpr int kX3ProdThreads = 32 * kX3ProdWarps;
+constexpr int kX3GroupThreads = kX3ProdThreads / 2;      // producers work as two groups on alternate stages
 constexpr int kX3Threads = 32 * (kX3EpiWarps + 1) + kX3ProdThreads;      // 416
 constexpr int kX3KC = 32;               // K elements per stage
 constexpr int kX3MaxStages = 4;
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
   uint32_t ncols = 32;
   while ((int)ncols < 2 * p.BN) ncols <<= 1;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], kX3ProdWarps); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], kX3ProdWarps / 2); mbar_init(&empty[s], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], kX3EpiWarps); }
     fence_barrier_init();
   }
@@ -130,135 +132,170 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
 
   if (warp > kX3EpiWarps) {
     // =========================== producers ================================
+    // Two groups of 4 warps take alternate stages, so two stages' global loads are always in flight (one group alone
+    // exposed a full HBM round trip per stage: 3 us per 128x128x32 stage, profiles/r02_ab_batch_a.md).  Within a stage a
+    // thread issues ALL its loads first, then splits and stores.
     const int tp = threadIdx.x - 32 * (kX3EpiWarps + 1);
+    const int grp = tp >> 7, tq = tp & 127;
     const long long TN_out = (long long)p.map.T_out * p.map.N, TN_in = (long long)p.map.T_in * p.map.N;
     const long long tap_step = (long long)p.map.t_shift * p.map.N + p.map.tap_row_stride;
-    const int brow = tp % p.BN, bchunk0 = tp / p.BN, bstep = kX3ProdThreads / p.BN;      // this thread's B row and chunks
+    const bool wide = p.BN == 256;                       // two B rows per thread
+    const int NB = p.BN / 16;                            // B tasks (16-byte chunks) per thread and stage
+    const int brow0 = wide ? tq : tq % p.BN, bchunk0 = wide ? 0 : tq / p.BN, bstep = wide ? 1 : kX3GroupThreads / p.BN;
     uint32_t g = 0;
     for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const X3Tile t = x3_tile(p, tile);
       const int m0 = t.mt * 128, n0 = t.nt * p.BN;
       // ---- per-tile row contexts
-      long long a_base[4] = {0, 0, 0, 0};
-      int a_t[4] = {0, 0, 0, 0};
-      long long b_base = -1;              // GSO: offset of column J in x;  WGRAD: unused
-      int b_tap = -2, b_c = 0;            // WGRAD: (tap, c) of row mm; -1 = bias row; -2 = padding
+      long long a_base[8];
+      int a_t[8];
+      long long b_base[2] = {-1, -1};     // GSO: offset of column J in x
+      int b_tap[2] = {-2, -2}, b_c[2] = {0, 0};            // WGRAD: (tap, c) of row mm; -1 = bias row; -2 = padding
       if (MODE == X3_TAP) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const long long r = (long long)m0 + (tp >> 3) + 32 * j;
+        for (int j = 0; j < 8; ++j) {
+          const long long r = (long long)m0 + (tq >> 3) + 16 * j;
+          a_base[j] = 0;
           if (r < p.rows) simt::row_decode(r, (int)TN_out, p.map.N, TN_in, a_base[j], a_t[j]);
           else a_t[j] = -(1 << 24);
         }
       } else if (MODE == X3_GSO) {
-        const long long J = (long long)n0 + brow;
-        if (J < p.G * p.C) { const long long gg = J / p.C; b_base = gg * p.N * p.C + (J - gg * p.C); }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const long long J = (long long)n0 + brow0 + 128 * q;
+          if ((q == 0 || wide) && J < p.G * p.C) { const long long gg = J / p.C; b_base[q] = gg * p.N * p.C + (J - gg * p.C); }
+        }
       } else {
-        const int mm = n0 + brow;
-        if (mm < p.Kw) { b_tap = mm / p.Cin; b_c = mm - b_tap * p.Cin; }
-        else if (mm == p.Kw && p.bias_row) b_tap = -1;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int mm = n0 + brow0 + 128 * q;
+          if (q == 0 || wide) {
+            if (mm < p.Kw) { b_tap[q] = mm / p.Cin; b_c[q] = mm - b_tap[q] * p.Cin; }
+            else if (mm == p.Kw && p.bias_row) b_tap[q] = -1;
+          }
+        }
       }
       for (int kc = 0; kc < t.nkc; ++kc, ++g) {
+        if ((int)(g & 1) != grp) continue;
         const uint32_t s = g % p.S, ph = (g / p.S) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t a_hi = st, a_lo = st + kX3ATile, b_hi = st + b_off, b_lo = st + b_off + b_tile;
         const long long k0 = t.kbeg + (long long)kc * kX3KC;
         if (MODE == X3_WGRAD) {
-          if (tp < kX3KC) {
-            const long long r = k0 + tp;
+          if (tq < kX3KC) {
+            const long long r = k0 + tq;
             long long base = -1; int tt = 0;
             if (r < t.kend) simt::row_decode(r, (int)TN_out, p.map.N, TN_in, base, tt);
-            dec_base[s][tp] = base; dec_t[s][tp] = tt;
+            dec_base[s][tq] = base; dec_t[s][tq] = tt;
           }
-          named_bar_sync(3, kX3ProdThreads);
+          named_bar_sync(3 + grp, kX3GroupThreads);
         }
-        // ---- A tile
-        if (MODE == X3_TAP || (MODE == X3_GSO && !p.trans)) {
-          // source contiguous along K: lane quad-of-8 covers one row's 128 bytes
-          const int chunk = tp & 7;
-          const long long gk = k0 + 4 * chunk;
-          int tap = 0, c = 0;
-          if (MODE == X3_TAP && gk < p.Ktot) { tap = (int)(gk / p.Cin); c = (int)(gk - (long long)tap * p.Cin); }
+        const bool a_kcontig = MODE == X3_TAP || (MODE == X3_GSO && !p.trans);
+        // ---- loads: A tile (8 chunks per thread)
+        float va[8][4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int row = (tp >> 3) + 32 * j;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < 8; ++j) {
+          va[j][0] = va[j][1] = va[j][2] = va[j][3] = 0.f;
+          if (a_kcontig) {          // source contiguous along K: 8 lanes cover one row's 128 bytes
+            const int chunk = tq & 7, row = (tq >> 3) + 16 * j;
+            const long long gk = k0 + 4 * chunk;
             if (MODE == X3_TAP) {
-              const int ti = a_t[j] + p.map.t_shift * tap;
-              if (gk < p.Ktot && ti >= 0 && ti < p.map.T_in) {
-                const float4 q = __ldg(reinterpret_cast<const float4*>(p.in + (a_base[j] + tap * tap_step) * p.Cin + c));
-                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+              if (gk < p.Ktot) {
+                const int tap = (int)(gk / p.Cin), c = (int)(gk - (long long)tap * p.Cin);
+                const int ti = a_t[j] + p.map.t_shift * tap;
+                if (ti >= 0 && ti < p.map.T_in) {
+                  const float4 q = __ldg(reinterpret_cast<const float4*>(p.in + (a_base[j] + tap * tap_step) * p.Cin + c));
+                  va[j][0] = q.x; va[j][1] = q.y; va[j][2] = q.z; va[j][3] = q.w;
+                }
               }
             } else {
               const int h = m0 + row;
               if (h < p.N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < p.N) v[i] = __ldg(p.L + (long long)h * p.N + gk + i);
+                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (long long)h * p.N + gk + i);
               }
             }
-            x3_store_chunk(a_hi, a_lo, row, chunk, v);
-          }
-        } else {
-          // source contiguous along M: one lane per row, four K steps gathered by four coalesced loads
-          const int row = tp & 127;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int chunk = (tp >> 7) + 2 * j;
+          } else {                  // source contiguous along M: one lane per row, four K steps by four coalesced loads
+            const int row = tq, chunk = j;
             const long long gk = k0 + 4 * chunk;
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
             if (MODE == X3_GSO) {
               const int h = m0 + row;
               if (h < p.N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < p.N) v[i] = __ldg(p.L + (gk + i) * p.N + h);
+                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (gk + i) * p.N + h);
               }
-            } else {      // X3_WGRAD: A(o, r) = dz[r, o]
+            } else {                // X3_WGRAD: A(o, r) = dz[r, o]
               const int o = m0 + row;
               if (o < p.Co) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < t.kend) v[i] = __ldg(p.dz + (gk + i) * p.ldz + o);
+                  if (gk + i < t.kend) va[j][i] = __ldg(p.dz + (gk + i) * p.ldz + o);
               }
             }
-            x3_store_chunk(a_hi, a_lo, row, chunk, v);
           }
         }
-        // ---- B tile (always contiguous along N in memory)
-        for (int chunk = bchunk0; chunk < 8; chunk += bstep) {
+        // ---- loads: B tile (always contiguous along N in memory), in halves of up to 8 chunks per thread
+        auto load_b = [&](int u, float* v) {
+          v[0] = v[1] = v[2] = v[3] = 0.f;
+          const int q = wide ? (u & 1) : 0;
+          const int chunk = wide ? (u >> 1) : bchunk0 + u * bstep;
+          if (chunk >= 8) return;
           const long long gk = k0 + 4 * chunk;
-          float v[4] = {0.f, 0.f, 0.f, 0.f};
           if (MODE == X3_TAP) {
-            const int o = n0 + brow;
+            const int o = n0 + brow0 + 128 * q;
             if (o < p.Co) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
                 if (gk + i < p.Ktot) v[i] = __ldg(p.wt + (gk + i) * p.Co + o);
             }
           } else if (MODE == X3_GSO) {
-            if (b_base >= 0) {
+            if (b_base[q] >= 0) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (gk + i < p.N) v[i] = __ldg(p.in + b_base + (gk + i) * p.C);
+                if (gk + i < p.N) v[i] = __ldg(p.in + b_base[q] + (gk + i) * p.C);
             }
           } else {
-            if (b_tap >= -1) {
+            if (b_tap[q] >= -1) {
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const long long rb = dec_base[s][4 * chunk + i];
                 if (rb >= 0) {
-                  if (b_tap < 0) v[i] = 1.f;
+                  if (b_tap[q] < 0) v[i] = 1.f;
                   else {
-                    const int ti = dec_t[s][4 * chunk + i] + p.map.t_shift * b_tap;
-                    if (ti >= 0 && ti < p.map.T_in) v[i] = __ldg(p.in + (rb + b_tap * tap_step) * p.Cin + b_c);
+                    const int ti = dec_t[s][4 * chunk + i] + p.map.t_shift * b_tap[q];
+                    if (ti >= 0 && ti < p.map.T_in) v[i] = __ldg(p.in + (rb + b_tap[q] * tap_step) * p.Cin + b_c[q]);
                   }
                 }
               }
             }
           }
-          x3_store_chunk(b_hi, b_lo, brow, chunk, v);
+        };
+        auto store_b = [&](int u, const float* v) {
+          const int q = wide ? (u & 1) : 0;
+          const int chunk = wide ? (u >> 1) : bchunk0 + u * bstep;
+          if (chunk < 8) x3_store_chunk(b_hi, b_lo, brow0 + 128 * q, chunk, v);
+        };
+        float vb[8][4];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < NB) load_b(u, vb[u]);
+        // ---- split + store
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (a_kcontig) x3_store_chunk(a_hi, a_lo, (tq >> 3) + 16 * j, tq & 7, va[j]);
+          else x3_store_chunk(a_hi, a_lo, tq, j, va[j]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (u < NB) store_b(u, vb[u]);
+        if (NB > 8) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) load_b(8 + u, vb[u]);
+#pragma unroll
+          for (int u = 0; u < 8; ++u) store_b(8 + u, vb[u]);
         }
         fence_proxy_async();              // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncwarp();
