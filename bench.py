@@ -312,8 +312,7 @@ class Runner:
     forward + MSE + backward [+ gradient all-reduce]) captured in a CUDA graph (stgcn_b200.graph.GraphedStep)."""
     POOL = 4      # distinct input batches cycled through, so no step re-reads a hot input
 
-    def __init__(self, workload, B, precision, dev, rank, world, droprate=0.0, graph=True, micro_streams=1,
-                 reduce_in_graph=True):
+    def __init__(self, workload, B, precision, dev, rank, world, droprate=0.0, graph=True, reduce_in_graph=True):
         import stgcn_b200
         from stgcn_b200 import _lib as L
         from stgcn_b200.dist import FlatGradAllReducer
@@ -343,15 +342,14 @@ class Runner:
             warm = 3
             try:
                 self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
-                                           micro_streams=micro_streams, reducer=self.reducer,
-                                           reduce_in_graph=reduce_in_graph)
+                                           reducer=self.reducer, reduce_in_graph=reduce_in_graph)
             except Exception as e:                   # capture of the collective refused: reduce after the replay instead
                 if self.reducer is None or not reduce_in_graph:
                     raise
                 sys.stderr.write(f"[bench] in-graph all-reduce not captured ({type(e).__name__}: {e}); reducing after replay\n")
                 torch.cuda.synchronize(dev)
                 self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
-                                           micro_streams=micro_streams, reducer=self.reducer, reduce_in_graph=False)
+                                           reducer=self.reducer, reduce_in_graph=False)
             self.launches_per_step = (L.launch_count() - n_before) // (warm + 1)      # warm-up bodies + 1 capture
             self.loss_buf = self.graphed.loss
             if self.reducer is not None:
@@ -447,8 +445,6 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra legs of the default line (parity_mode, cuda_baseline, other BASELINE configs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--micro-streams", type=int, default=1,
-                    help="run that many batch chunks as parallel chains on separate streams inside the captured step")
     ap.add_argument("--reduce-after", action="store_true", help="N > 1: all-reduce after the graph replay, not inside it")
     ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "900")),
                     help="watchdog: dump all Python stacks to stderr and exit 124 if the run has not finished by then")
@@ -508,7 +504,7 @@ def main():
     from stgcn_b200 import _lib as L
 
     run = Runner(a.workload, B, a.precision, dev, rank, world, droprate=a.droprate, graph=not a.no_graph,
-                 micro_streams=a.micro_streams, reduce_in_graph=not a.reduce_after)
+                 reduce_in_graph=not a.reduce_after)
     n, blocks = run.n, run.blocks
 
     sampler = ClockSampler(local_rank)
@@ -666,7 +662,7 @@ def main():
                 "config": {**cfg_common, "precision": a.precision,
                            "l2": f"{Runner.POOL} input batches cycled; per-step activation working set exceeds the 126 MB L2",
                            "parallelism": f"dp{world}", "cuda_graph": cuda_graph,
-                           "helper_streams": helper_streams, "micro_streams": a.micro_streams,
+                           "helper_streams": helper_streams,
                            "grad_allreduce": reduce_mode},
                 "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / steps},

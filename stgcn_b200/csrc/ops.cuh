@@ -16,6 +16,7 @@
 #include "umma_wgrad.cuh"
 #include "umma_cheb.cuh"
 #include "umma_x3.cuh"
+#include "umma_fb0.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -565,7 +566,10 @@ inline void gconv_fwd(const stgcn_gconv_desc& d, const T* x, const stgcn_gconv_p
 
 template <class T>
 inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, const T* y, const T* dy,
-                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c) {
+                      const stgcn_gconv_params& p, const stgcn_gconv_grads& gr, T* dx, Ctx c, T* dst_ext = nullptr) {
+  // dst_ext: optional caller-owned [depth][rows, c_out] buffer for the stack gradients; plane 0 (the gradient w.r.t. the
+  // aligned input) then outlives this call, and with dx == nullptr the caller applies the align conv's data gradient
+  // itself (stblock_bwd: fused into the first temporal conv's backward, umma_fb0.cuh)
   gconv_check(d);
   ScopedMark sm(c.ws);
   const long long rows = (long long)d.B * d.T * d.N;
@@ -574,7 +578,7 @@ inline void gconv_bwd(const stgcn_gconv_desc& d, const T* x, const T* stack, con
   const int depth = gconv_stack_depth(d);
   const int ntw = d.gconv == STGCN_GCONV_CHEB ? d.Ks : 1;
   T* dg = c.KW().take<T>(plane);
-  T* dst = c.KW().take<T>((size_t)depth * plane);
+  T* dst = dst_ext ? dst_ext : c.KW().take<T>((size_t)depth * plane);
   float* wT = c.K().take<float>((size_t)ntw * C * C);
   float* dwt = c.K().take<float>((size_t)(ntw * C + 1) * C);
   float* dwa = c.K().take<float>(d.c_in > C ? (size_t)(d.c_in + 1) * C : 0);
@@ -843,6 +847,40 @@ inline bool lnorm_gate_bwd(const stgcn_lnorm_desc& d, const stgcn_tconv_desc& tc
   return true;
 }
 
+// ============================ first temporal conv: fused backward ============================
+// Block 0 of the default architecture (c_in = 1 -> 64 GLU channels, then the 64 -> 16 align conv of the graph-conv layer):
+// one tcgen05 kernel forms dH1 = dX0 . Wa in tensor memory, applies the GLU backward with z recomputed from x, and
+// contracts dZ with the x window into the conv weight / bias gradients (umma_fb0.cuh).  Only when no data gradient is
+// wanted (the block input is the model input).  Shapes only -- the sizing pass and the live pass must agree.
+template <class T>
+inline bool first_bwd_shape_ok(const stgcn_stblock_desc& d, long long rows1) {
+  if constexpr (std::is_same<T, simt::bf16>::value) return umma::fb0_supported(d.c_in, d.c1, d.c2, d.Kt, d.act, rows1);
+  return false;
+}
+inline void first_tconv_bwd_fused(const stgcn_tconv_desc& d, const simt::bf16* x, const simt::bf16* dst0, simt::bf16* wa_bf,
+                                  const float* align_w, const stgcn_tconv_params& p, const stgcn_tconv_grads& gr, Ctx c) {
+  TconvGeom g = tconv_geom(d);
+  ScopedMark sm(c.ws);
+  const int Kw = d.Kt * d.c_in;
+  float* dwt = c.K().take<float>((size_t)(Kw + 1) * g.W);
+  float* wfw = c.K().take<float>((size_t)d.Kt * g.W * d.c_in);
+  float* bias_f = c.K().take<float>(g.W);
+  if (c.dry()) return;
+  STGCN_CHECK(p.conv_w && p.conv_b && align_w, STGCN_E_INVALID, "first temporal conv backward: missing parameters");
+  const cudaStream_t ps = c.ps();
+  zero(dwt, (size_t)(Kw + 1) * g.W, ps);
+  launch_gather3(p.conv_w, wfw, d.Kt, d.c_in, g.W, 0, 1, d.Kt, (long long)d.c_in * d.Kt, 0, ps);     // wfw[k*W + o] = conv_w[o][0][k]
+  launch_gather3(p.conv_b, bias_f, 1, 1, g.W, 0, 0, 0, 1, 0, ps);
+  launch_gather3(align_w, wa_bf, 1, d.c_out, 16, 0, 0, 1, d.c_out, 0, ps);                            // wa[j*16 + o] = align_w[o][j]
+  c.prep_ready();
+  umma::launch_fb0(dst0, wa_bf, x, wfw, bias_f, dwt, g.rows_out, d.Kt, g.T_out, d.T, d.N, 1, c.stream);
+  c.post_after();
+  GatherBatch gb(c.qs());
+  if (gr.conv_w) gb.add(dwt, gr.conv_w, g.W, d.c_in, d.Kt, 0, 1, g.W, (long long)d.c_in * g.W);
+  if (gr.conv_b) gb.add(dwt, gr.conv_b, 1, 1, g.W, (long long)Kw * g.W, 0, 0, 1);
+  gb.flush();
+}
+
 // ============================ ST-conv block ==================================================
 struct StGeom {
   int T1, T2;
@@ -908,9 +946,22 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
   { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr,
                                                                   (!ln_fused && tconv_qonly<T>(g.tc2)) ? s.h3 : nullptr); }
-  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, dh1, c); }
-  { Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd"); tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr,
-                                                                  tconv_qonly<T>(g.tc1) ? s.h1 : nullptr); }
+  // first block, no data gradient wanted: align data gradient + GLU backward + weight gradient in one tcgen05 kernel
+  const bool fb0_shape = first_bwd_shape_ok<T>(d, g.rows1);
+  T* dst_ext = c.KW().take<T>(fb0_shape ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
+  simt::bf16* wa_bf = c.K().take<simt::bf16>(fb0_shape ? (size_t)d.c1 * d.c2 : 0);
+  const bool fb0 = fb0_shape && !c.dry() && dx == nullptr && (gr.tc1.conv_w || gr.tc1.conv_b);
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, fb0 ? nullptr : dh1, c,
+                                                               fb0_shape ? dst_ext : nullptr); }
+  if (fb0) {
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      Tag t("st0.tc1.bwd");
+      first_tconv_bwd_fused(g.tc1, x, dst_ext, wa_bf, p.gc.align_w, p.tc1, gr.tc1, c);
+    }
+  } else {
+    Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd");
+    tconv_bwd<T>(g.tc1, x, s.z1, dh1, p.tc1, gr.tc1, dx, c, nullptr, tconv_qonly<T>(g.tc1) ? s.h1 : nullptr);
+  }
 }
 
 // ============================ output block ===================================================

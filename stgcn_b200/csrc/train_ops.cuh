@@ -23,7 +23,7 @@ struct AdamWArgs {
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, float lr, float b1, float b2, float eps,
                                           float wd, float step_size, float inv_bc2_sqrt) {
   p *= 1.f - lr * wd;
-  m = b1 * m + (1.f - b1) * g;            // torch: exp_avg.lerp_(grad, 1 - beta1)
+  m = fmaf(1.f - b1, g - m, m);            // torch: exp_avg.lerp_(grad, 1 - beta1) = m + (1 - beta1) (g - m)
   v = b2 * v + (1.f - b2) * g * g;        // torch: exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
   const float denom = sqrtf(v) * inv_bc2_sqrt + eps;
   p -= step_size * (m / denom);

@@ -1,0 +1,241 @@
+// umma_fb0.cuh -- backward of the FIRST temporal convolution of the model (Cin = 1: layers.py:87-105 on the raw
+// (B,1,T,N) window) fused with the data gradient of the graph-conv layer's 1x1 align conv (layers.py:16,225) that
+// feeds it, on tcgen05 (bf16 throughput mode).  One persistent kernel replaces
+//     lowrank_expand_kernel   dH1[r, 0:64] = dX0[r, 0:16] . Wa            (wrote 75 MB, 68 us at B = 256)
+//   + smallc1_gate_wgrad      dZ = GLU'(dH1; z recomputed from x), dW = dZ^T . x-window   (read them back, 110 us; the
+//                             384 fp32 weight-gradient accumulators per thread made it issue bound at 10.6 % of HBM)
+// and reads only the 16-channel gradient dX0 (19 MB) and the 3 MB input:
+//
+//   per tile of 128 flat rows r = (b, t, n):
+//     MMA 1   D1[128 r x 64]   = dX0 tile [128 x 16] (K-major, cp.async producer)  x  Wa^T [64 x 16] (resident)
+//     epilogue (16 warps)      dH1 = D1 (TMEM -> registers);  P, Q recomputed from the Kt taps of x (Kt FMAs each);
+//                              dU = dH1 * s,  dQ = dH1 * (P + res) * s (1 - s),  s = sigmoid(Q)
+//                              -> bf16 dZ tile [128 r][128 o] in shared memory (MN-major A operand, 128B swizzle),
+//                                 x-window tile [128 r][16] = (x_t .. x_{t+Kt-1}, 1, 0 ...) (MN-major B operand)
+//     MMA 2   D2[128 o x 16]  += dZ^T . x-window          (K = 128 rows; accumulates over ALL tiles of the CTA in TMEM)
+//   end:      D2 columns 0..Kt-1 = dW taps, column Kt = bias gradient -> fp32 atomics into dwt[(k) * 128 + o].
+//
+// The block-0 input needs no data gradient (it is the model input), so dZ never reaches HBM.
+// Serves the default architecture's first block: c_in = 1, 64 GLU channels, 16 graph-conv channels, Kt in {2, 3}.
+#pragma once
+#include "umma_tap.cuh"
+
+namespace stgcn {
+namespace umma {
+
+constexpr int kFb0EpiWarps = 16;
+constexpr int kFb0Threads = 64 + 32 * kFb0EpiWarps;      // warp 0 producer, warp 1 MMA issuer, 16 epilogue warps
+constexpr int kFb0Stages = 8;                            // dX0 tiles in flight (4 KB each)
+
+struct Fb0Params {
+  const bf16* dst0;        // [rows, 16] gradient w.r.t. the aligned (16-channel) graph-conv input
+  const bf16* wa;          // [64][16] K-major: wa[j * 16 + o] = align_w[o][j]
+  const bf16* x;           // [B, T_in, N] model input (Cin = 1)
+  const float* wt;         // [Kt][128] forward-layout conv weights: wt[k * 128 + o] = conv_w[o][0][k]
+  const float* bias;       // [128]
+  float* dwt;              // [(Kt + 1)][128], pre-zeroed: taps then bias row
+  long long rows;
+  int n_tiles, Kt, T_out, T_in, N, explicit_res;
+};
+
+// shared-memory map (offsets from the 1024-aligned base)
+constexpr uint32_t kFb0ARing = 0;                                   // kFb0Stages x 4096
+constexpr uint32_t kFb0Wa = kFb0ARing + kFb0Stages * 4096;          // 2048
+constexpr uint32_t kFb0Wpq = kFb0Wa + 2048;                         // float4 [2][64] = 2048
+constexpr uint32_t kFb0X3 = kFb0Wpq + 2048;                         // 2 x 4096
+constexpr uint32_t kFb0Dz = kFb0X3 + 2 * 4096;                      // 2 x 32768 (1024-aligned: 32768+2048+2048+8192 = 45056)
+constexpr uint32_t kFb0Smem = kFb0Dz + 2 * 32768 + 1024;
+
+__global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[2], d1_empty[2], dz_full[2], dz_empty[2], done;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time staging: Wa^T (K-major, 32-byte rows, 32B swizzle) and the per-channel (w_0..w_2, bias) quads
+  if (threadIdx.x < 128) {
+    const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
+    const uint4 v = *reinterpret_cast<const uint4*>(p.wa + j * 16 + h * 8);
+    *reinterpret_cast<uint4*>(smem + kFb0Wa + j * 32 + ((h ^ ((j >> 2) & 1)) << 4)) = v;
+  } else if (threadIdx.x < 256) {
+    const int o = threadIdx.x - 128;                    // pre-activation channel: 0..63 = P half, 64..127 = Q half
+    float4 w;
+    w.x = p.wt[o];
+    w.y = p.wt[128 + o];
+    w.z = p.Kt > 2 ? p.wt[256 + o] : 0.f;
+    w.w = p.bias[o];
+    reinterpret_cast<float4*>(smem + kFb0Wpq)[o] = w;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kFb0Stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kFb0EpiWarps);
+      mbar_init(&dz_full[i], kFb0EpiWarps); mbar_init(&dz_empty[i], 1);
+    }
+    mbar_init(&done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);          // D1: 2 x 64 columns, D2: 16 columns
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+  const int n_my = p.n_tiles > (int)blockIdx.x ? (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (warp == 0) {
+    // =========================== producer: dX0 tiles by cp.async ================================
+    int pending = -1;
+    for (int i = 0; i < n_my; ++i) {
+      const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
+      const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1;
+      mbar_wait(&a_empty[s], ph ^ 1);
+      uint8_t* dst = smem + kFb0ARing + s * 4096;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int q = lane + 32 * c, row = q >> 1, h = q & 1;
+        const bool ok = r0 + row < p.rows;
+        const bf16* src = p.dst0 + (ok ? (r0 + row) : 0) * 16 + h * 8;
+        cp_async16(dst + row * 32 + ((h ^ ((row >> 2) & 1)) << 4), src, ok ? 16u : 0u);
+      }
+      cp_async_commit();
+      if (pending >= 0) {                                 // the previous tile has landed after this wait
+        cp_async_wait<1>();
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[pending]);
+      }
+      pending = (int)s;
+    }
+    if (pending >= 0) {
+      cp_async_wait<0>();
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_full[pending]);
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer =============================
+    if (elect_one()) {
+      const uint32_t idesc1 = make_idesc_bf16(128, 64, 0, 0);            // K-major x K-major
+      const uint32_t idesc2 = make_idesc_bf16(128, 16, 1, 1);            // MN-major x MN-major (contraction over rows)
+      const uint64_t pk32 = make_smem_desc(0, 16, 256, SWZ_32B);         // K-major, 32-byte rows
+      const uint64_t pdz = make_smem_desc(0, 16384, 1024, SWZ_128B);     // MN-major: 64-channel chunks 16 KB apart
+      const uint64_t px3 = make_smem_desc(0, 4096, 256, SWZ_32B);        // MN-major: [rows][16]
+      const uint32_t wa_s = smem_u32(smem + kFb0Wa);
+      auto mma1 = [&](int i) {
+        const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1, ab = i & 1, aph = (i >> 1) & 1;
+        mbar_wait(&a_full[s], ph);
+        mbar_wait(&d1_empty[ab], aph ^ 1);
+        tc_fence_after();
+        mma_bf16_ss(tmem_base + ab * 64, desc_at(pk32, smem_u32(smem + kFb0ARing + s * 4096)), desc_at(pk32, wa_s), idesc1, 0);
+        mma_commit(&d1_full[ab]);
+        mma_commit(&a_empty[s]);
+      };
+      if (n_my > 0) mma1(0);
+      for (int i = 0; i < n_my; ++i) {
+        if (i + 1 < n_my) mma1(i + 1);
+        const uint32_t zb = i & 1, zph = (i >> 1) & 1;
+        mbar_wait(&dz_full[zb], zph);
+        tc_fence_after();
+        uint64_t da = desc_at(pdz, smem_u32(smem + kFb0Dz + zb * 32768)), db = desc_at(px3, smem_u32(smem + kFb0X3 + zb * 4096));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {                     // 16 rows per instruction
+          mma_bf16_ss(tmem_base + 128, da, db, idesc2, (i != 0 || k != 0) ? 1u : 0u);
+          da += 2048 >> 4; db += 512 >> 4;
+        }
+        mma_commit(&dz_empty[zb]);
+      }
+      mma_commit(&done);
+    }
+  } else {
+    // =========================== epilogue warps ==========================
+    const int q = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter; 16-channel group
+    const int row = q * 32 + lane, c0 = grp * 16;
+    const float4* wpq = reinterpret_cast<const float4*>(smem + kFb0Wpq);
+    for (int i = 0; i < n_my; ++i) {
+      const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
+      const bool valid = r < p.rows;
+      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
+      if (valid) {
+        long long in0; int t_unused;
+        simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
+        x0 = simt::ldf(p.x + in0);
+        x1 = simt::ldf(p.x + in0 + p.N);
+        if (p.Kt > 2) x2 = simt::ldf(p.x + in0 + 2LL * p.N);
+      }
+      const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
+      const uint32_t ab = i & 1, aph = (i >> 1) & 1;
+      mbar_wait(&d1_full[ab], aph);
+      tc_fence_after();
+      uint32_t rr[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * 64 + c0, rr);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d1_empty[ab]);
+      float du[16], dq[16];
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float4 wp = wpq[c0 + e], wq = wpq[64 + c0 + e];
+        float u = fmaf(x0, wp.x, fmaf(x1, wp.y, fmaf(x2, wp.z, wp.w)));
+        const float g = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, wq.w)));
+        if (c0 + e == 0) u += xres;
+        const float s = sigmoid_tanh_(g);
+        const float dh = valid ? __uint_as_float(rr[e]) : 0.f;
+        du[e] = dh * s;
+        dq[e] = dh * u * s * (1.f - s);
+      }
+      const uint32_t zb = i & 1, zph = (i >> 1) & 1;
+      mbar_wait(&dz_empty[zb], zph ^ 1);
+      const uint32_t dzs = smem_u32(smem + kFb0Dz + zb * 32768);
+      stage_store8_s(dzs, row, c0, pack8_bf16(du));
+      stage_store8_s(dzs, row, c0 + 8, pack8_bf16(du + 8));
+      stage_store8_s(dzs + 16384u, row, c0, pack8_bf16(dq));
+      stage_store8_s(dzs + 16384u, row, c0 + 8, pack8_bf16(dq + 8));
+      if (grp == 0) {
+        float xw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (valid) { xw[0] = x0; xw[1] = x1; if (p.Kt > 2) xw[2] = x2; xw[p.Kt > 2 ? 3 : 2] = 1.f; }
+        uint8_t* x3 = smem + kFb0X3 + zb * 4096 + row * 32;
+        const int sw = (row >> 2) & 1;
+        *reinterpret_cast<uint4*>(x3 + ((0 ^ sw) << 4)) = pack8_bf16(xw);
+        *reinterpret_cast<uint4*>(x3 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dz_full[zb]);
+    }
+    // ---- flush: D2[o][k] -> dwt[k * 128 + o]
+    if (grp == 0 && n_my > 0) {
+      mbar_wait(&done, 0);
+      tc_fence_after();
+      uint32_t rr[16];
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128, rr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k <= p.Kt) atomicAdd(p.dwt + k * 128 + row, __uint_as_float(rr[k]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
+// shapes this kernel serves (all three datasets' first block in the default architecture)
+inline bool fb0_supported(int c_in, int c1, int c2, int Kt, int act, long long rows) {
+  return c_in == 1 && c1 == 64 && c2 == 16 && (Kt == 2 || Kt == 3) && act == STGCN_ACT_GLU && rows > 0 && rows < (1LL << 31);
+}
+
+inline void launch_fb0(const bf16* dst0, const bf16* wa, const bf16* x, const float* wt, const float* bias, float* dwt,
+                       long long rows, int Kt, int T_out, int T_in, int N, int explicit_res, cudaStream_t stream) {
+  Fb0Params p{};
+  p.dst0 = dst0; p.wa = wa; p.x = x; p.wt = wt; p.bias = bias; p.dwt = dwt; p.rows = rows;
+  p.n_tiles = (int)((rows + 127) / 128); p.Kt = Kt; p.T_out = T_out; p.T_in = T_in; p.N = N; p.explicit_res = explicit_res;
+  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
+  STGCN_LAUNCH(umma_fb0_kernel, grid, kFb0Threads, kFb0Smem, stream, p);
+}
+
+}  // namespace umma
+}  // namespace stgcn

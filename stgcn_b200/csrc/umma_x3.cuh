@@ -92,16 +92,20 @@ __device__ __forceinline__ void x3_store_chunk(uint32_t hi_tile, uint32_t lo_til
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(lo_tile + off), "r"(l[0]), "r"(l[1]), "r"(l[2]), "r"(l[3]) : "memory");
 }
 
-struct X3Tile { int mt, nt, ks; long long kbeg, kend; int nkc; };
-__device__ __forceinline__ X3Tile x3_tile(const X3Params& p, long long tile) {
+// All index arithmetic of the pipeline is 32-bit: the host guarantees tiles, rows and K below 2^31, and 64-bit integer
+// division is a ~150-instruction subroutine on the GPU -- with it in the producers' per-chunk path the first version of
+// this kernel was instruction bound at 3 us per stage (profiles/r02_ab_batch_b.md).
+struct X3Tile { int mt, nt, ks, kbeg, kend, nkc; };
+__device__ __forceinline__ X3Tile x3_tile(const X3Params& p, unsigned tile) {
   X3Tile t;
-  t.ks = (int)(tile % p.k_splits);
-  const long long rest = tile / p.k_splits;
-  t.nt = (int)(rest % p.n_tiles);
-  t.mt = (int)(rest / p.n_tiles);
-  t.kbeg = (long long)t.ks * p.k_per_split;
-  t.kend = t.kbeg + p.k_per_split < p.Ktot ? t.kbeg + p.k_per_split : p.Ktot;
-  t.nkc = (int)((t.kend - t.kbeg + kX3KC - 1) / kX3KC);
+  const unsigned rest = tile / (unsigned)p.k_splits;
+  t.ks = (int)(tile - rest * (unsigned)p.k_splits);
+  t.mt = (int)(rest / (unsigned)p.n_tiles);
+  t.nt = (int)(rest - (unsigned)t.mt * (unsigned)p.n_tiles);
+  t.kbeg = t.ks * (int)p.k_per_split;
+  const long long ke = (long long)t.kbeg + p.k_per_split;
+  t.kend = (int)(ke < p.Ktot ? ke : p.Ktot);
+  t.nkc = (t.kend - t.kbeg + kX3KC - 1) / kX3KC;
   return t;
 }
 
@@ -127,7 +131,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
-  const long long n_tiles = (long long)p.m_tiles * p.n_tiles * p.k_splits;
+  const unsigned n_tiles = (unsigned)p.m_tiles * (unsigned)p.n_tiles * (unsigned)p.k_splits;
   const uint32_t b_off = 2u * kX3ATile, b_tile = (uint32_t)p.BN * 128u;
 
   if (warp > kX3EpiWarps) {
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
     const int NB = p.BN / 16;                            // B tasks (16-byte chunks) per thread and stage
     const int brow0 = wide ? tq : tq % p.BN, bchunk0 = wide ? 0 : tq / p.BN, bstep = wide ? 1 : kX3GroupThreads / p.BN;
     uint32_t g = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const X3Tile t = x3_tile(p, tile);
       const int m0 = t.mt * 128, n0 = t.nt * p.BN;
       // ---- per-tile row contexts
@@ -181,10 +185,10 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
         mbar_wait(&empty[s], ph ^ 1);
         const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
         const uint32_t a_hi = st, a_lo = st + kX3ATile, b_hi = st + b_off, b_lo = st + b_off + b_tile;
-        const long long k0 = t.kbeg + (long long)kc * kX3KC;
+        const int k0 = t.kbeg + kc * kX3KC;
         if (MODE == X3_WGRAD) {
           if (tq < kX3KC) {
-            const long long r = k0 + tq;
+            const int r = k0 + tq;
             long long base = -1; int tt = 0;
             if (r < t.kend) simt::row_decode(r, (int)TN_out, p.map.N, TN_in, base, tt);
             dec_base[s][tq] = base; dec_t[s][tq] = tt;
@@ -194,15 +198,19 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
         const bool a_kcontig = MODE == X3_TAP || (MODE == X3_GSO && !p.trans);
         // ---- loads: A tile (8 chunks per thread)
         float va[8][4];
+        const int ka = k0 + 4 * (tq & 7);                  // K-contiguous sources: this thread's chunk of every row
+        int a_tap = 0, a_c = 0;
+        if (MODE == X3_TAP) { a_tap = (int)((unsigned)ka / (unsigned)p.Cin); a_c = ka - a_tap * p.Cin; }
+        const int Kend = (int)p.Ktot;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           va[j][0] = va[j][1] = va[j][2] = va[j][3] = 0.f;
           if (a_kcontig) {          // source contiguous along K: 8 lanes cover one row's 128 bytes
-            const int chunk = tq & 7, row = (tq >> 3) + 16 * j;
-            const long long gk = k0 + 4 * chunk;
+            const int row = (tq >> 3) + 16 * j;
+            const int gk = ka;
             if (MODE == X3_TAP) {
-              if (gk < p.Ktot) {
-                const int tap = (int)(gk / p.Cin), c = (int)(gk - (long long)tap * p.Cin);
+              if (gk < Kend) {
+                const int tap = a_tap, c = a_c;
                 const int ti = a_t[j] + p.map.t_shift * tap;
                 if (ti >= 0 && ti < p.map.T_in) {
                   const float4 q = __ldg(reinterpret_cast<const float4*>(p.in + (a_base[j] + tap * tap_step) * p.Cin + c));
@@ -214,25 +222,25 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
               if (h < p.N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (long long)h * p.N + gk + i);
+                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (long long)h * p.N + (gk + i));
               }
             }
           } else {                  // source contiguous along M: one lane per row, four K steps by four coalesced loads
             const int row = tq, chunk = j;
-            const long long gk = k0 + 4 * chunk;
+            const int gk = k0 + 4 * chunk;
             if (MODE == X3_GSO) {
               const int h = m0 + row;
               if (h < p.N) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (gk + i) * p.N + h);
+                  if (gk + i < p.N) va[j][i] = __ldg(p.L + (long long)(gk + i) * p.N + h);
               }
             } else {                // X3_WGRAD: A(o, r) = dz[r, o]
               const int o = m0 + row;
               if (o < p.Co) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                  if (gk + i < t.kend) va[j][i] = __ldg(p.dz + (gk + i) * p.ldz + o);
+                  if (gk + i < t.kend) va[j][i] = __ldg(p.dz + (long long)(gk + i) * p.ldz + o);
               }
             }
           }
@@ -243,19 +251,19 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
           const int q = wide ? (u & 1) : 0;
           const int chunk = wide ? (u >> 1) : bchunk0 + u * bstep;
           if (chunk >= 8) return;
-          const long long gk = k0 + 4 * chunk;
+          const int gk = k0 + 4 * chunk;
           if (MODE == X3_TAP) {
             const int o = n0 + brow0 + 128 * q;
             if (o < p.Co) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (gk + i < p.Ktot) v[i] = __ldg(p.wt + (gk + i) * p.Co + o);
+                if (gk + i < Kend) v[i] = __ldg(p.wt + (long long)(gk + i) * p.Co + o);
             }
           } else if (MODE == X3_GSO) {
             if (b_base[q] >= 0) {
 #pragma unroll
               for (int i = 0; i < 4; ++i)
-                if (gk + i < p.N) v[i] = __ldg(p.in + b_base[q] + (gk + i) * p.C);
+                if (gk + i < p.N) v[i] = __ldg(p.in + b_base[q] + (long long)(gk + i) * p.C);
             }
           } else {
             if (b_tap[q] >= -1) {
@@ -308,7 +316,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
       const uint32_t idesc = make_idesc_tf32(128, p.BN);
       const uint64_t dproto = make_smem_desc(0, 16, 1024, SWZ_128B);
       uint32_t g = 0, acc_cnt = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++acc_cnt) {
+      for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++acc_cnt) {
         const X3Tile t = x3_tile(p, tile);
         const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
         mbar_wait(&tempty[ab], aph ^ 1);
@@ -339,7 +347,7 @@ __global__ void __launch_bounds__(kX3Threads, 1) umma_x3_kernel(X3Params p) {
     // =========================== epilogue warps ==========================
     const int row = warp * 32 + lane;           // TMEM lane = tile row
     uint32_t acc_cnt = 0;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++acc_cnt) {
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++acc_cnt) {
       const X3Tile t = x3_tile(p, tile);
       const int m0 = t.mt * 128, n0 = t.nt * p.BN;
       const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
@@ -454,6 +462,7 @@ inline void x3_plan_tiles(X3Params& p, long long Mrows, long long Ncols) {
 template <int MODE>
 inline void x3_launch(const X3Params& p, const char* name, cudaStream_t stream) {
   const long long tiles = (long long)p.m_tiles * p.n_tiles * p.k_splits;
+  STGCN_CHECK(tiles < (1LL << 31) && p.Ktot < (1LL << 31) && p.k_per_split < (1LL << 31), STGCN_E_UNSUPPORTED, "x3 GEMM: index range");
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   const size_t smem = (size_t)p.S * p.stage_bytes + 1024;
   STGCN_CUDA(cudaFuncSetAttribute(umma_x3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -32,12 +32,13 @@ def _has_active_dropout(model: torch.nn.Module) -> bool:
 
 class GraphedStep:
     def __init__(self, model: torch.nn.Module, batch_shape, target_shape, device=None,
-                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, micro_streams: int = 1,
-                 reducer=None, reduce_in_graph: bool = True):
-        """micro_streams > 1: the batch is cut into that many equal chunks whose forward+backward chains run on separate
-        streams inside the ONE captured graph, so the tails and launch bubbles of one chain overlap the other's kernels;
-        the chunk losses are scaled by 1/micro_streams, so the accumulated gradients and ``loss`` equal the full-batch
-        ones.  reducer: a dist.FlatGradAllReducer; None = single process."""
+                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, reducer=None,
+                 reduce_in_graph: bool = True):
+        """reducer: a dist.FlatGradAllReducer; None = single process.  post_backward: called at the end of the captured
+        body (e.g. a fused optimizer step, optim.FlatAdamW.step).
+        (Splitting the batch into chains on parallel streams inside the graph was measured and removed: 2 chains -8 %,
+        4 chains -30 % on PeMSD7-M B=256 -- the persistent kernels of the chains compete for the same SMs,
+        profiles/r02_ab_batch_b.md.)"""
         self.model = model
         dev = device or next(model.parameters()).device
         self.device = dev
@@ -45,14 +46,7 @@ class GraphedStep:
         self.y = torch.zeros(target_shape, device=dev)
         self.loss = torch.zeros(1, device=dev)
         self.post_backward = post_backward
-        self.micro = int(micro_streams)
-        if self.micro < 1 or batch_shape[0] % self.micro:
-            raise ValueError(f"micro_streams={micro_streams} must divide the batch size {batch_shape[0]}")
         self.reducer = reducer
-        if reducer is not None and self.micro > 1:
-            raise ValueError("micro_streams > 1 accumulates gradients across chains; not combined with a reducer")
-        self._mstreams = [torch.cuda.Stream(device=dev) for _ in range(self.micro)] if self.micro > 1 else []
-        self._mloss = [torch.zeros(1, device=dev) for _ in range(self.micro)] if self.micro > 1 else []
         self._lib = L.lib()
         self.step_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         with torch.cuda.device(dev):
@@ -99,45 +93,7 @@ class GraphedStep:
         self._hook_handle = blocks[0].register_forward_hook(fwd_hook)
 
     # ------------------------------------------------------------------ step body
-    def _body_micro(self):
-        model = self.model
-        params = list(model.parameters())
-        cur = torch.cuda.current_stream(self.x.device)
-        k = self.micro
-        chain_grads = []
-        for st, xc, yc, lc in zip(self._mstreams, self.x.chunk(k), self.y.chunk(k), self._mloss):
-            # every chain gets its OWN gradient tensors (p.grad is None when its backward runs): accumulating into a
-            # shared p.grad from two streams would race with the other chain's kernels that are still writing it
-            for p in params:
-                p.grad = None
-            st.wait_stream(cur)
-            with torch.cuda.stream(st):
-                Bc = xc.shape[0]
-                pred = model(xc).reshape(Bc, -1).float()
-                dpred = torch.empty_like(pred)
-                L.check(self._lib.stgcn_mse_fwd_bwd(pred.data_ptr(), yc.data_ptr(), pred.numel(), C.c_float(1.0 / k),
-                                                    lc.data_ptr(), dpred.data_ptr(), st.cuda_stream))
-                pred.backward(dpred)
-            chain_grads.append([p.grad for p in params])
-        for st in self._mstreams:
-            cur.wait_stream(st)
-        live = [i for i, g in enumerate(chain_grads[0]) if g is not None]
-        total = [chain_grads[0][i] for i in live]
-        for c in range(1, k):
-            torch._foreach_add_(total, [chain_grads[c][i] for i in live])
-        for p in params:
-            p.grad = None
-        for i, g in zip(live, total):
-            params[i].grad = g
-        self.loss.copy_(torch.stack(self._mloss).sum(0))
-        self.loss.mul_(1.0 / k)
-        if self.post_backward is not None:
-            self.post_backward()
-        self.step_counter.add_(1)
-
     def _body(self):
-        if self.micro > 1:
-            return self._body_micro()
         model = self.model
         for p in model.parameters():
             p.grad = None

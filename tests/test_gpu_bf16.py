@@ -343,24 +343,44 @@ def test_graphed_step_regrads_after_zero_grad(cuda_device):
     step.close()
 
 
-def test_graphed_step_micro_streams_match_single_chain(cuda_device):
-    """Two half-batch chains on two streams inside one captured graph give the full-batch loss and gradients."""
-    from stgcn_b200.graph import GraphedStep
+@pytest.mark.parametrize("N,B,kt,kind", [(228, 5, 3, "cheb_graph_conv"), (41, 3, 3, "cheb_graph_conv"), (207, 2, 2, "graph_conv"),
+                                          (325, 3, 3, "cheb_graph_conv")])
+def test_bf16_first_block_fused_backward(N, B, kt, kind, cuda_device):
+    """Block 0 of the default architecture without a data gradient (the model input needs none): the align conv's data
+    gradient, the GLU backward (z recomputed from x) and the first conv's weight gradient run as ONE tcgen05 kernel
+    (csrc/umma_fb0.cuh).  Checked against (a) the unfused path -- same block with x.requires_grad -- and (b) the fp64
+    oracle; ragged last row tile (rows not a multiple of 128), Kt = 2 and 3."""
+    from stgcn_b200 import layers, _lib as L
     dev = cuda_device
-    B = 8
-    model, x, y, n = _pems_model(dev, 0.0, B)
-    one = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2)
-    l1 = one(x, y).item()
-    torch.cuda.synchronize()
-    g1 = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
-    one.close()
-    two = GraphedStep(model, (B, 1, 12, n), (B, n), device=dev, warmup=2, micro_streams=2)
-    for rep in range(2):
-        l2 = two(x, y).item()
-        torch.cuda.synchronize()
-        assert abs(l1 - l2) <= 2e-3 * abs(l1)
-        g2 = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
-        assert set(g1) == set(g2)
-        for k in g1:      # bf16 activations: the two chains round differently from the single one
-            assert rel_l2(g2[k].cpu(), g1[k].cpu()) <= 5e-2, (k, rel_l2(g2[k].cpu(), g1[k].cpu()))
-    two.close()
+    gen = torch.Generator().manual_seed(N + B)
+    torch.manual_seed(N + B)
+    gso = O.synthetic_gso(N, seed=N)
+    T = 12 if kt == 3 else 8
+    blk = layers.STConvBlock(kt, 3, N, 1, [64, 16, 64], "glu", kind, gso.to(dev), True, 0.0).to(dev)
+    blk.train()
+    x = torch.randn(B, 1, T, N, generator=gen)
+    dy = torch.randn(B, 64, T - 2 * (kt - 1), N, generator=gen)
+
+    def run(requires_grad):
+        blk.zero_grad(set_to_none=True)
+        xg = x.to(dev).requires_grad_(requires_grad)
+        L.profile_begin()
+        blk(xg).backward(dy.to(dev).bfloat16())
+        prof = L.profile_end()
+        return {k: p.grad.detach().float().cpu().clone() for k, p in blk.named_parameters() if p.grad is not None}, prof
+
+    fused, prof_f = run(False)
+    plain, prof_p = run(True)
+    assert any("umma_fb0_kernel" in k for k in prof_f), sorted(prof_f)
+    assert not any("umma_fb0_kernel" in k for k in prof_p)
+    assert not any("lowrank_expand" in k or "smallc1_gate_wgrad" in k for k in prof_f)
+    assert set(fused) == set(plain)
+    for k in fused:
+        tol = 3e-2 if k.startswith("tmp_conv1.causal_conv") else 1e-6        # everything else runs the same kernels
+        assert rel_l2(fused[k], plain[k]) <= tol, (k, rel_l2(fused[k], plain[k]))
+    # fp64 oracle of the block
+    p64 = {"b." + k: v.detach().double().cpu().requires_grad_(True) for k, v in blk.state_dict().items()}
+    y64 = O.st_conv_block(x.double(), p64, "b.", gso.double(), kt, [64, 16, 64], "glu", kind)
+    y64.backward(dy.double())
+    for k in ("tmp_conv1.causal_conv.weight", "tmp_conv1.causal_conv.bias"):
+        assert rel_l2(fused[k], p64["b." + k].grad) < 6e-2, (k, rel_l2(fused[k], p64["b." + k].grad))
