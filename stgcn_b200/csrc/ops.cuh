@@ -951,12 +951,29 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   T* dst_ext = c.KW().take<T>(fb0_shape ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
   simt::bf16* wa_bf = c.K().take<simt::bf16>(fb0_shape ? (size_t)d.c1 * d.c2 : 0);
   const bool fb0 = fb0_shape && !c.dry() && dx == nullptr && (gr.tc1.conv_w || gr.tc1.conv_b);
-  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, fb0 ? nullptr : dh1, c,
-                                                               fb0_shape ? dst_ext : nullptr); }
+  // later blocks (q-only GLU state): the align data gradient + gate backward in one tcgen05 kernel that writes dZ
+  bool fbg_shape = false;
+  if constexpr (std::is_same<T, simt::bf16>::value)
+    fbg_shape = !fb0_shape && tconv_qonly<T>(g.tc1) && umma::fb_gate_supported(d.c1, d.c2, d.act, g.rows1);
+  T* dst_ext2 = c.KW().take<T>(fbg_shape ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);
+  simt::bf16* wa_bf2 = c.K().take<simt::bf16>(fbg_shape ? (size_t)d.c1 * d.c2 : 0);
+  T* dz1 = c.KW().take<T>(fbg_shape ? (size_t)g.rows1 * 2 * d.c1 : 0);
+  const bool fbg = fbg_shape && !c.dry();
+  { Tag t(first ? "st0.gc.bwd" : "st1.gc.bwd"); gconv_bwd<T>(g.gc, s.h1, s.stack, s.h2, dh2, p.gc, gr.gc, (fb0 || fbg) ? nullptr : dh1, c,
+                                                               fb0_shape ? dst_ext : (fbg_shape ? dst_ext2 : nullptr)); }
   if (fb0) {
     if constexpr (std::is_same<T, simt::bf16>::value) {
       Tag t("st0.tc1.bwd");
       first_tconv_bwd_fused(g.tc1, x, dst_ext, wa_bf, p.gc.align_w, p.tc1, gr.tc1, c);
+    }
+  } else if (fbg) {
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd");
+      STGCN_CHECK(p.gc.align_w, STGCN_E_INVALID, "stblock_bwd: missing align conv weight");
+      launch_gather3(p.gc.align_w, wa_bf2, 1, d.c1, d.c2, 0, 0, 1, d.c1, 0, c.ps());      // wa[j*16 + o] = align_w[o][j]
+      c.prep_ready();
+      umma::launch_fb_gate(dst_ext2, wa_bf2, s.z1, s.h1, dz1, g.rows1, c.stream);
+      tconv_bwd<T>(g.tc1, x, s.z1, nullptr, p.tc1, gr.tc1, dx, c, dz1);
     }
   } else {
     Tag t(first ? "st0.tc1.bwd" : "st1.tc1.bwd");

@@ -17,6 +17,12 @@
 //
 // The block-0 input needs no data gradient (it is the model input), so dZ never reaches HBM.
 // Serves the default architecture's first block: c_in = 1, 64 GLU channels, 16 graph-conv channels, Kt in {2, 3}.
+//
+// MODE 1 (FB_GATE) -- the same front end for the temporal convs of the LATER blocks (c_in >= 16, GLU with the q-only saved
+// state): MMA 1 as above, then the epilogue reads the saved gate half Q and the layer output H1 (16-byte loads),
+// dU = dH1 * s, dQ = dH1 * H1 * (1 - s), and writes dZ = (dU | dQ) [rows, 128] to HBM for the data-gradient and
+// weight-gradient kernels.  Replaces lowrank_expand_kernel + gate_vec_kernel (33 + 51 us at B = 256: dH1 written and read
+// back at 64 channels).
 #pragma once
 #include "umma_tap.cuh"
 
@@ -27,6 +33,7 @@ constexpr int kFb0EpiWarps = 16;
 constexpr int kFb0Threads = 64 + 32 * kFb0EpiWarps;      // warp 0 producer, warp 1 MMA issuer, 16 epilogue warps
 constexpr int kFb0Stages = 8;                            // dX0 tiles in flight (4 KB each)
 
+enum { FB_FIRST = 0, FB_GATE = 1 };
 struct Fb0Params {
   const bf16* dst0;        // [rows, 16] gradient w.r.t. the aligned (16-channel) graph-conv input
   const bf16* wa;          // [64][16] K-major: wa[j * 16 + o] = align_w[o][j]
@@ -36,6 +43,10 @@ struct Fb0Params {
   float* dwt;              // [(Kt + 1)][128], pre-zeroed: taps then bias row
   long long rows;
   int n_tiles, Kt, T_out, T_in, N, explicit_res;
+  // FB_GATE
+  const bf16* q;           // [rows, 64] saved gate half of the pre-activation
+  const bf16* h;           // [rows, 64] layer output
+  bf16* dz;                // [rows, 128] out: (dU | dQ)
 };
 
 // shared-memory map (offsets from the 1024-aligned base)
@@ -46,6 +57,7 @@ constexpr uint32_t kFb0X3 = kFb0Wpq + 2048;                         // 2 x 4096
 constexpr uint32_t kFb0Dz = kFb0X3 + 2 * 4096;                      // 2 x 32768 (1024-aligned: 32768+2048+2048+8192 = 45056)
 constexpr uint32_t kFb0Smem = kFb0Dz + 2 * 32768 + 1024;
 
+template <int MODE>
 __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -58,7 +70,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
     const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
     const uint4 v = *reinterpret_cast<const uint4*>(p.wa + j * 16 + h * 8);
     *reinterpret_cast<uint4*>(smem + kFb0Wa + j * 32 + ((h ^ ((j >> 2) & 1)) << 4)) = v;
-  } else if (threadIdx.x < 256) {
+  } else if (MODE == FB_FIRST && threadIdx.x < 256) {
     const int o = threadIdx.x - 128;                    // pre-activation channel: 0..63 = P half, 64..127 = Q half
     float4 w;
     w.x = p.wt[o];
@@ -135,6 +147,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       if (n_my > 0) mma1(0);
       for (int i = 0; i < n_my; ++i) {
         if (i + 1 < n_my) mma1(i + 1);
+        if (MODE != FB_FIRST) continue;
         const uint32_t zb = i & 1, zph = (i >> 1) & 1;
         mbar_wait(&dz_full[zb], zph);
         tc_fence_after();
@@ -157,12 +170,19 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
       const bool valid = r < p.rows;
       float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-      if (valid) {
-        long long in0; int t_unused;
-        simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
-        x0 = simt::ldf(p.x + in0);
-        x1 = simt::ldf(p.x + in0 + p.N);
-        if (p.Kt > 2) x2 = simt::ldf(p.x + in0 + 2LL * p.N);
+      uint4 qv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, hv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (MODE == FB_FIRST) {
+        if (valid) {
+          long long in0; int t_unused;
+          simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
+          x0 = simt::ldf(p.x + in0);
+          x1 = simt::ldf(p.x + in0 + p.N);
+          if (p.Kt > 2) x2 = simt::ldf(p.x + in0 + 2LL * p.N);
+        }
+      } else if (valid) {               // requested before the accumulator wait: the loads fly while MMA 1 completes
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + r * 64 + c0);
+        const uint4* hp = reinterpret_cast<const uint4*>(p.h + r * 64 + c0);
+        qv[0] = qp[0]; qv[1] = qp[1]; hv[0] = hp[0]; hv[1] = hp[1];
       }
       const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
       const uint32_t ab = i & 1, aph = (i >> 1) & 1;
@@ -175,16 +195,35 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&d1_empty[ab]);
       float du[16], dq[16];
+      if (MODE == FB_FIRST) {
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const float4 wp = wpq[c0 + e], wq = wpq[64 + c0 + e];
-        float u = fmaf(x0, wp.x, fmaf(x1, wp.y, fmaf(x2, wp.z, wp.w)));
-        const float g = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, wq.w)));
-        if (c0 + e == 0) u += xres;
-        const float s = sigmoid_tanh_(g);
-        const float dh = valid ? __uint_as_float(rr[e]) : 0.f;
-        du[e] = dh * s;
-        dq[e] = dh * u * s * (1.f - s);
+        for (int e = 0; e < 16; ++e) {
+          const float4 wp = wpq[c0 + e], wq = wpq[64 + c0 + e];
+          float u = fmaf(x0, wp.x, fmaf(x1, wp.y, fmaf(x2, wp.z, wp.w)));
+          const float g = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, wq.w)));
+          if (c0 + e == 0) u += xres;
+          const float s = sigmoid_tanh_(g);
+          const float dh = valid ? __uint_as_float(rr[e]) : 0.f;
+          du[e] = dh * s;
+          dq[e] = dh * u * s * (1.f - s);
+        }
+      } else {
+        float qf[16], hf[16];
+        unpack8_bf16(qv[0], qf); unpack8_bf16(qv[1], qf + 8);
+        unpack8_bf16(hv[0], hf); unpack8_bf16(hv[1], hf + 8);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float s = sigmoid_tanh_(qf[e]);
+          const float dh = __uint_as_float(rr[e]);
+          du[e] = dh * s;
+          dq[e] = dh * hf[e] * (1.f - s);
+        }
+        if (valid) {
+          uint4* dp = reinterpret_cast<uint4*>(p.dz + r * 128 + c0);
+          dp[0] = pack8_bf16(du); dp[1] = pack8_bf16(du + 8);
+          dp[8] = pack8_bf16(dq); dp[9] = pack8_bf16(dq + 8);          // + 64 channels = 8 x 16 bytes
+        }
+        continue;
       }
       const uint32_t zb = i & 1, zph = (i >> 1) & 1;
       mbar_wait(&dz_empty[zb], zph ^ 1);
@@ -206,7 +245,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       if (lane == 0) mbar_arrive(&dz_full[zb]);
     }
     // ---- flush: D2[o][k] -> dwt[k * 128 + o]
-    if (grp == 0 && n_my > 0) {
+    if (MODE == FB_FIRST && grp == 0 && n_my > 0) {
       mbar_wait(&done, 0);
       tc_fence_after();
       uint32_t rr[16];
@@ -233,8 +272,22 @@ inline void launch_fb0(const bf16* dst0, const bf16* wa, const bf16* x, const fl
   p.dst0 = dst0; p.wa = wa; p.x = x; p.wt = wt; p.bias = bias; p.dwt = dwt; p.rows = rows;
   p.n_tiles = (int)((rows + 127) / 128); p.Kt = Kt; p.T_out = T_out; p.T_in = T_in; p.N = N; p.explicit_res = explicit_res;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
-  STGCN_LAUNCH(umma_fb0_kernel, grid, kFb0Threads, kFb0Smem, stream, p);
+  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
+  STGCN_LAUNCH_NAMED("umma_fb0_kernel<FIRST>", umma_fb0_kernel<FB_FIRST>, grid, kFb0Threads, kFb0Smem, stream, p);
+}
+
+// later blocks: dZ = GLU'(dX0 . Wa; Q, H1) for a 64-channel GLU conv in front of a 64 -> 16 align conv (q-only saved state)
+inline bool fb_gate_supported(int c1, int c2, int act, long long rows) {
+  return c1 == 64 && c2 == 16 && act == STGCN_ACT_GLU && rows > 0 && rows < (1LL << 31);
+}
+inline void launch_fb_gate(const bf16* dst0, const bf16* wa, const bf16* q, const bf16* h, bf16* dz, long long rows,
+                           cudaStream_t stream) {
+  Fb0Params p{};
+  p.dst0 = dst0; p.wa = wa; p.q = q; p.h = h; p.dz = dz; p.rows = rows; p.n_tiles = (int)((rows + 127) / 128);
+  p.Kt = 2; p.T_out = 1; p.T_in = 1; p.N = 1;
+  const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
+  STGCN_LAUNCH_NAMED("umma_fb0_kernel<GATE>", umma_fb0_kernel<FB_GATE>, grid, kFb0Threads, kFb0Smem, stream, p);
 }
 
 }  // namespace umma

@@ -101,7 +101,7 @@ def test_adamw_kernel_matches_oracle(cuda_device):
                                          1, steps.data_ptr(), None, torch.cuda.current_stream().cuda_stream))
         steps.add_(1)
         assert np.allclose(pd.cpu().numpy(), pn, rtol=3e-6, atol=1e-7), t
-    assert np.allclose(md.cpu().numpy(), m, rtol=1e-5, atol=1e-7) and np.allclose(vd.cpu().numpy(), v, rtol=1e-5, atol=1e-9)
+    assert np.allclose(md.cpu().numpy(), m, rtol=1e-5, atol=1e-7) and np.allclose(vd.cpu().numpy(), v, rtol=1e-4, atol=1e-9)
 
 
 def test_device_windows_bit_exact(cuda_device):
