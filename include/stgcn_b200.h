@@ -253,6 +253,19 @@ int stgcn_lion_step(float* params, const float* grads, float* exp_avg, int64_t n
 int stgcn_windows(const float* series, int64_t len, int32_t N, int32_t n_his, int32_t n_pred,
                   const int64_t* starts, int64_t start0, int32_t B, float* x, float* y, void* stream);
 
+/* N4: graph-shift-operator preprocessing on the device, dense (N, N) fp32 in and out; replaces calc_gso
+ * (script/utility.py:6-57) and calc_chebynet_gso (:59-76) for dense operators.  gso_type: STGCN_GSO_* below (the
+ * reference's eight strings).  chebynet != 0 additionally rescales to 2 L / lambda_max - I with lambda_max = ||L||_2 from
+ * a device-side power iteration (the reference calls scipy.sparse.linalg.norm(gso, 2)); eig_out (device, 2 floats,
+ * optional) receives lambda_max and the iteration count.  workspace: (N*N + 3*N + 8) floats.  N <= 2048.           */
+enum { STGCN_GSO_SYM_NORM_ADJ = 0, STGCN_GSO_SYM_RENORM_ADJ = 1, STGCN_GSO_SYM_NORM_LAP = 2, STGCN_GSO_SYM_RENORM_LAP = 3,
+       STGCN_GSO_RW_NORM_ADJ = 4, STGCN_GSO_RW_RENORM_ADJ = 5, STGCN_GSO_RW_NORM_LAP = 6, STGCN_GSO_RW_RENORM_LAP = 7 };
+int stgcn_gso_build(const float* adj, int32_t N, int32_t gso_type, int32_t chebynet, float* out, float* eig_out,
+                    float* workspace, size_t workspace_floats, void* stream);
+/* calc_chebynet_gso alone (utility.py:59-76) on an already normalised dense operator; same workspace and eig_out.   */
+int stgcn_gso_rescale(const float* gso, int32_t N, float* out, float* eig_out, float* workspace,
+                      size_t workspace_floats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,3 +49,39 @@ def data_transform(data, n_his, n_pred):
         x[i, 0] = data[i: i + n_his]
         y[i] = data[i + n_his + n_pred - 1]
     return x, y
+
+
+# ---- graph shift operator -------------------------------------------------------------------------
+def calc_gso_dense(dir_adj, gso_type):
+    """Dense restatement of calc_gso (script/utility.py:6-57) in float64: symmetrise by elementwise max (:18),
+    + I for the *_renorm_* types (:20-22), D^-1/2 A D^-1/2 (:24-32) or D^-1 A (:40-47), Laplacian I - (.) (:33-36, :48-51)."""
+    a = np.asarray(dir_adj, dtype=np.float64)
+    n = a.shape[0]
+    a = np.maximum(a, a.T)
+    if "renorm" in gso_type:
+        a = a + np.eye(n)
+    d = a.sum(axis=1)
+    if gso_type.startswith("sym_"):
+        with np.errstate(divide="ignore"):
+            dis = np.power(d, -0.5)
+        dis[np.isinf(dis)] = 0.0
+        g = dis[:, None] * a * dis[None, :]
+    elif gso_type.startswith("rw_"):
+        with np.errstate(divide="ignore"):
+            di = np.power(d, -1.0)
+        di[np.isinf(di)] = 0.0
+        g = di[:, None] * a
+    else:
+        raise ValueError(f"{gso_type} is not defined.")
+    if gso_type.endswith("_lap"):
+        g = np.eye(n) - g
+    return g
+
+
+def calc_chebynet_gso_dense(gso):
+    """calc_chebynet_gso (script/utility.py:59-76): lambda_max = ||gso||_2 (scipy.sparse.linalg.norm(gso, 2) there);
+    gso - I when lambda_max >= 2, else 2 gso / lambda_max - I."""
+    g = np.asarray(gso, dtype=np.float64)
+    lam = np.linalg.norm(g, 2)
+    eye = np.eye(g.shape[0])
+    return (g - eye if lam >= 2 else 2 * g / lam - eye), lam

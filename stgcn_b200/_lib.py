@@ -127,6 +127,8 @@ _SIGNATURES = [
                                    C.c_float, C.c_int64, _fp, _fp, _fp]),
     ("stgcn_lion_step", C.c_int, [_fp, _fp, _fp, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _fp,
                                   _fp]),
+    ("stgcn_gso_build", C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, _sz, _fp]),
+    ("stgcn_gso_rescale", C.c_int, [_fp, C.c_int32, _fp, _fp, _fp, _sz, _fp]),
     ("stgcn_windows", C.c_int, [_fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _fp, C.c_int64, C.c_int32, _fp, _fp,
                                 _fp]),
 ]

@@ -3,6 +3,7 @@
 #include "umma_selftest.cuh"
 #include "umma_bench.cuh"
 #include "train_ops.cuh"
+#include "gso_ops.cuh"
 
 namespace stgcn {
 thread_local char g_last_error[512] = "";
@@ -371,6 +372,45 @@ int stgcn_windows(const float* series, int64_t len, int32_t N, int32_t n_his, in
     STGCN_LAUNCH(train::windows_kernel, train::elementwise_grid((long long)B * (n_his + 1) * N), 256, 0, as_stream(stream),
                  series, (long long)len, (int)N, (int)n_his, (int)n_pred, reinterpret_cast<const long long*>(starts),
                  (long long)start0, (int)B, x, y);
+  });
+}
+
+// ---------------------------------------------------------------- graph shift operator
+int stgcn_gso_build(const float* adj, int32_t N, int32_t gso_type, int32_t chebynet, float* out, float* eig_out,
+                    float* workspace, size_t workspace_floats, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(adj && out && workspace, STGCN_E_INVALID, "null argument");
+    STGCN_CHECK(N > 0 && N <= 2048, STGCN_E_UNSUPPORTED, "gso_build: 1 <= N <= 2048");
+    STGCN_CHECK(gso_type >= STGCN_GSO_SYM_NORM_ADJ && gso_type <= STGCN_GSO_RW_RENORM_LAP, STGCN_E_INVALID,
+                "gso_type is not defined.");
+    STGCN_CHECK(workspace_floats >= (size_t)N * N + 3 * (size_t)N + 8, STGCN_E_WORKSPACE, "workspace/saved buffer too small");
+    cudaStream_t s = as_stream(stream);
+    float* a = workspace; float* d = a + (size_t)N * N; float* v = d + N; float* u = v + N; float* eig = u + N;
+    const int renorm = gso_type & 1, lap = (gso_type >> 1) & 1, rw = (gso_type >> 2) & 1;
+    const int nb = ceil_div((long long)N * N, 256);
+    STGCN_LAUNCH(gso::symmetrize_kernel, nb, 256, 0, s, adj, a, (int)N, renorm);
+    STGCN_LAUNCH(gso::rowsum_kernel, ceil_div(N, 8), 256, 0, s, (const float*)a, d, (int)N);
+    STGCN_LAUNCH(gso::normalize_kernel, nb, 256, 0, s, (const float*)a, (const float*)d, out, (int)N, rw, lap);
+    if (chebynet) {
+      STGCN_LAUNCH(gso::spectral_norm_kernel, 1, 1024, 0, s, (const float*)out, (int)N, v, u, eig, 30000, 1e-7f);
+      STGCN_LAUNCH(gso::cheb_rescale_kernel, nb, 256, 0, s, (const float*)out, out, (int)N, (const float*)eig);
+      if (eig_out) STGCN_CUDA(cudaMemcpyAsync(eig_out, eig, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+  });
+}
+
+int stgcn_gso_rescale(const float* gso_in, int32_t N, float* out, float* eig_out, float* workspace,
+                      size_t workspace_floats, void* stream) {
+  return guarded([&] {
+    STGCN_CHECK(gso_in && out && workspace, STGCN_E_INVALID, "null argument");
+    STGCN_CHECK(N > 0 && N <= 2048, STGCN_E_UNSUPPORTED, "gso_rescale: 1 <= N <= 2048");
+    STGCN_CHECK(workspace_floats >= (size_t)N * N + 3 * (size_t)N + 8, STGCN_E_WORKSPACE, "workspace/saved buffer too small");
+    cudaStream_t s = as_stream(stream);
+    float* d = workspace + (size_t)N * N; float* v = d + N; float* u = v + N; float* eig = u + N;
+    const int nb = ceil_div((long long)N * N, 256);
+    STGCN_LAUNCH(gso::spectral_norm_kernel, 1, 1024, 0, s, gso_in, (int)N, v, u, eig, 30000, 1e-7f);
+    STGCN_LAUNCH(gso::cheb_rescale_kernel, nb, 256, 0, s, gso_in, out, (int)N, (const float*)eig);
+    if (eig_out) STGCN_CUDA(cudaMemcpyAsync(eig_out, eig, 2 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   });
 }
 

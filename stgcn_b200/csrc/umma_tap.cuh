@@ -82,6 +82,14 @@ struct TapParams {
   // the shared-memory address, zero fill past N)
   int narrow_cp;
   const bf16* in_ptr; long long sn, st, sb;   // element strides of `in` (vertex, time, batch)
+  // Bias and residual on the TENSOR pipe instead of the epilogue (the epilogue warps bound this kernel: per 8 output
+  // columns the bias cost 4 LDS + 16 FADD and the residual a 16-byte load, 16 unpack ops, 8 FADD and 8 selects):
+  //   bias_mma: one extra K = 16 instruction per tile, A = an all-ones tile, B = [bias_hi, bias_lo, 0 ...] per channel
+  //             (bias split into two bf16 so the sum is exact to 2^-17);
+  //   res_mma : the residual operand is a time slice of `in` that is in the ring anyway (aux == in); Cin/16 extra
+  //             instructions multiply it by an identity block (exact: 1.0 x bf16 into the fp32 accumulator).
+  int bias_mma, res_mma, res_dt;
+  uint32_t x_bytes;           // shared memory of the extra operands (ones 4 KB | bias tile | identity tap), after the weights
   unsigned long long* dbg;    // optional [16] timeline stamps (globaltimer ns) written by CTA (0,0); diagnostics only
 };
 
@@ -191,14 +199,16 @@ __device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
   return it;
 }
 
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool AUX>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                 const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmZ, TapParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* w_s = smem;
-  uint8_t* ring = smem + p.w_bytes;       // w_bytes is a multiple of 1024
+  uint8_t* x_s = smem + p.w_bytes;        // extra operands: ones tile | bias tile | identity tap (each 1024-aligned)
+  uint8_t* ring = x_s + p.x_bytes;        // w_bytes, x_bytes are multiples of 1024
+  const uint32_t bias_tile_off = 4096, id_off = 4096 + (((uint32_t)p.CoT * 32 + 1023) & ~1023u);
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[8], tempty[8];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
@@ -208,6 +218,33 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
   if (threadIdx.x == 0) STGCN_STAMP(0);
   for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
+  if (p.bias_mma) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<uint4*>(x_s)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    for (int i = threadIdx.x; i < 2 * p.CoT; i += blockDim.x) {            // K-major [CoT][16], 32-byte rows, 32B swizzle
+      const int o = i >> 1, c = i & 1;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (c == 0 && p.bias) {
+        const float b = p.bias[co0 + o];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+        v.x = pack_bf16x2(__bfloat162float(hi), b - __bfloat162float(hi));
+      }
+      *reinterpret_cast<uint4*>(x_s + bias_tile_off + o * 32 + ((c ^ ((o >> 2) & 1)) << 4)) = v;
+    }
+  }
+  if (p.res_mma) {
+    // identity tap in the weights' own block layout: block kb = [CoT rows][KB columns], row pitch KB*2 bytes, swizzled
+    const int cpr = p.KB / 8, n_chunks = p.nKB * p.CoT * cpr;            // 16-byte chunks per row / in total
+    for (int i = threadIdx.x; i < n_chunks; i += blockDim.x) {
+      const int c8 = i % cpr, o = (i / cpr) % p.CoT, kb = i / (cpr * p.CoT);
+      const int c_first = kb * p.KB + c8 * 8, og = co0 + o;             // channels [c_first, +8) of input; output channel og
+      uint32_t w[4] = {0, 0, 0, 0};
+      const int d = og - c_first;
+      if (d >= 0 && d < 8 && og < p.aux_cols) w[d >> 1] = (d & 1) ? 0x3F800000u : 0x00003F80u;
+      const int sw = p.KB == 64 ? (o & 7) : (p.KB == 32 ? ((o >> 1) & 3) : ((o >> 2) & 1));
+      *reinterpret_cast<uint4*>(x_s + id_off + (size_t)kb * p.CoT * p.KB * 2 + o * p.KB * 2 + ((c8 ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  fence_proxy_async();
   uint32_t ncols = 32;
   while ((int)ncols < p.NB * p.CoT) ncols <<= 1;
   const int epi_arrivals = 4 * p.col_parts;
@@ -343,6 +380,26 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               }
             }
           }
+          if (p.res_mma) {
+            const int ti = t_o + p.res_dt;
+            if (ti >= 0 && ti < p.T_src) {                 // the slice was waited for by its tap above
+              const uint32_t g = g_base + (ti - wi.s_lo), s = g % p.S;
+              const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes), b_base = smem_u32(x_s + id_off);
+              for (int kb = 0; kb < p.nKB; ++kb) {
+                uint64_t da = desc_at(dproto, a_base + kb * ablk), db = desc_at(dproto, b_base + kb * wblk);
+                for (int k = 0; k < nk16; ++k) {
+                  mma_bf16_ss(d_tmem, da, db, idesc, accumulate);
+                  accumulate = 1;
+                  da += 2; db += 2;
+                }
+              }
+            }
+          }
+          if (p.bias_mma) {
+            const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
+            mma_bf16_ss(d_tmem, desc_at(p32, smem_u32(x_s)), desc_at(p32, smem_u32(x_s + bias_tile_off)), idesc, accumulate);
+            accumulate = 1;
+          }
           if (acc_cnt == 8) STGCN_STAMP(22);
           mma_commit(&tfull[ab]);
           if (acc_cnt == 8) STGCN_STAMP(23);
@@ -378,7 +435,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
         const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
         const int t_aux = t_o + p.aux_dt;
-        const bool aux_ok = p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
+        const bool aux_ok = AUX && p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
+        const bool bias_epi = p.bias != nullptr && !p.bias_mma;
         const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
         const int cfirst = cpart * 16;
         const int cstep = p.col_parts * 16;
@@ -416,8 +474,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           tmem_ld_32x32b_x8(t_addr + cc, rp);
           if (gated) tmem_ld_32x32b_x8(t_addr + p.Cout + cc, rq);
           const uint4 rcur = rnext;
-          const bool has_aux = cc < n_aux;
-          {   // prefetch the next group's aux
+          const bool has_aux = AUX && cc < n_aux;
+          if (AUX) {   // prefetch the next group's aux
             const int gn = gi + 1;
             const int cn = cfirst + (gn >> 1) * cstep + (gn & 1) * 8;
             if (gn < n_grp && cn < n_aux) rnext = *reinterpret_cast<const uint4*>(aux_row + cbase + cn);
@@ -426,11 +484,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           float zp[8], zq[8], av[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) { zp[i] = __uint_as_float(rp[i]); zq[i] = gated ? __uint_as_float(rq[i]) : 0.f; }
-          add_bias8(zp, bias_s + cc);
-          if (gated) add_bias8(zq, bias_s + p.Cout + cc);
-          if (has_aux) unpack8_bf16(rcur, av);
+          if (bias_epi) {
+            add_bias8(zp, bias_s + cc);
+            if (gated) add_bias8(zq, bias_s + p.Cout + cc);
+          }
+          if (AUX && has_aux) unpack8_bf16(rcur, av);
           if (EPI == EPI_LINEAR) {
-            if (has_aux) {
+            if (AUX && has_aux) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) zp[i] += av[i];
             }
@@ -444,13 +504,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           } else {
             float h[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>(has_aux ? zp[i] + av[i] : zp[i], zq[i]);
-            const uint4 op = pack8_bf16(zp), oh = pack8_bf16(h);
+            for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>((AUX && has_aux) ? zp[i] + av[i] : zp[i], zq[i]);
+            const uint4 oh = pack8_bf16(h);
             if (stg) {
               if (gated && p.q_only) {
                 stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
               } else {
-                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, op);
+                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, pack8_bf16(zp));
                 if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + cc) >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
               }
               stage_store8_s(stg_s + (uint32_t)(p.nZ + (cc >> 6)) * 16384u, row, cc & 63, oh);
@@ -458,7 +518,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
               if (gated && p.q_only) {
                 *reinterpret_cast<uint4*>(p.out_z + orow * p.Cout + cc) = pack8_bf16(zq);
               } else {
-                *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = op;
+                *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = pack8_bf16(zp);
                 if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
               }
               *reinterpret_cast<uint4*>(p.out + orow * p.Cout + cc) = oh;
@@ -467,7 +527,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         }
         if (warp == 2 && acc_cnt == 8) STGCN_STAMP(14);
 #ifndef STGCN_TAP_NO_AUX_PREFETCH
-        if (p.tile_parts == 1 && p.aux != nullptr && cfirst < p.aux_cols - cbase) {
+        if (AUX && p.tile_parts == 1 && p.aux != nullptr && cfirst < p.aux_cols - cbase) {
           int nt = t_o + 1, nb = b, nn = n;
           bool more = true;
           if (nt >= wi.t_end) {
@@ -534,10 +594,22 @@ constexpr size_t kSmemBudget = 225 * 1024;
 struct TapPlan {
   bool ok; int KB, nKB, CoT, nCoT, S; uint32_t swz, sbo, tile_bytes, w_bytes; size_t smem;
   int store_tma, nbuf, nZ, nO; uint32_t stage_off, stage_bytes;
+  uint32_t x_bytes; int bias_mma, res_mma;      // extra operands for bias / residual on the tensor pipe (TapParams)
 };
 
 // gate: the epilogue needs the whole pre-activation width W = Co in one CTA; Cout = its output channels.
-inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout = 0, bool q_only = false) {
+inline TapPlan plan_tap_x(int Cin, int Co, int Kt, int T_src, bool gate, int Cout, bool q_only, bool want_bias, bool want_res);
+// want_bias / want_res: the call has a bias / a residual that could ride on the tensor pipe.  The extra operands cost
+// shared memory (4 KB ones + CoT*32 B bias tile + one more weight tap for the identity); when that does not fit next to the
+// ring the plan falls back to the epilogue for the residual, then for both.
+inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout = 0, bool q_only = false,
+                        bool want_bias = false, bool want_res = false) {
+  TapPlan pl = plan_tap_x(Cin, Co, Kt, T_src, gate, Cout, q_only, want_bias, want_res);
+  if (!pl.ok && want_res) pl = plan_tap_x(Cin, Co, Kt, T_src, gate, Cout, q_only, want_bias, false);
+  if (!pl.ok && want_bias) pl = plan_tap_x(Cin, Co, Kt, T_src, gate, Cout, q_only, false, false);
+  return pl;
+}
+inline TapPlan plan_tap_x(int Cin, int Co, int Kt, int T_src, bool gate, int Cout, bool q_only, bool want_bias, bool want_res) {
   TapPlan pl{};
   pl.ok = false;
   if (Cin % 16 || Co % 16 || Cin < 16 || Co < 16) return pl;
@@ -554,6 +626,11 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout 
     if (gate && CoT != Co) break;
     size_t wb = (size_t)Kt * CoT * Cin * 2;
     wb = (wb + 1023) & ~size_t(1023);
+    size_t xb = 0;
+    if (want_bias || want_res) xb = 4096 + (((size_t)CoT * 32 + 1023) & ~size_t(1023));
+    if (want_res) xb += ((size_t)CoT * Cin * 2 + 1023) & ~size_t(1023);
+    const size_t wb_only = wb;
+    wb += xb;                                     // the planner treats the extra operands like weights: resident
     if (wb + (size_t)live * pl.tile_bytes > kSmemBudget) continue;
     // output staging for TMA stores (64-column sub-tiles of 16 KB); two buffers if they fit next to >= live+1 stages
     int nZ = 0, nO = 0;
@@ -567,7 +644,8 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout 
     int S = (int)((kSmemBudget - wb - stage_total) / pl.tile_bytes);
     if (S > kMaxStages) S = kMaxStages;
     if (S < live) continue;
-    pl.CoT = CoT; pl.nCoT = Co / CoT; pl.S = S; pl.w_bytes = (uint32_t)wb;
+    pl.CoT = CoT; pl.nCoT = Co / CoT; pl.S = S; pl.w_bytes = (uint32_t)wb_only; pl.x_bytes = (uint32_t)xb;
+    pl.bias_mma = (want_bias || want_res) ? 1 : 0; pl.res_mma = want_res ? 1 : 0;
     pl.store_tma = nbuf > 0; pl.nbuf = nbuf; pl.nZ = nZ; pl.nO = nO;
     pl.stage_off = (uint32_t)(wb + (size_t)S * pl.tile_bytes);
     pl.stage_bytes = (uint32_t)per_buf;
@@ -578,11 +656,19 @@ inline TapPlan plan_tap(int Cin, int Co, int Kt, int T_src, bool gate, int Cout 
   return pl;
 }
 
+// shapes only (the sizing passes probe with placeholder pointers): a bias rides on the tensor pipe whenever there is one;
+// a residual when it has the input's channel count and time extent and sits at one of the taps' time offsets -- whether
+// it really IS the input tensor is checked at launch (otherwise the reserved identity tap stays unused)
+inline bool tap_want_bias(const TapProblem& q) { return q.bias != nullptr; }
+inline bool tap_want_res(const TapProblem& q) {
+  return q.aux != nullptr && q.C_aux == q.Cin && q.T_aux == q.T_src && q.aux_dt - q.t0 >= 0 && q.aux_dt - q.t0 < q.Kt &&
+         q.in_stride_n == 0 && q.in_stride_t == 0 && q.in_stride_b == 0 && q.aux_cols > 0;
+}
 inline bool tap_supported(const TapProblem& q) {
   if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
   if (q.aux && (q.aux_cols % 16 != 0 || q.C_aux % 16 != 0)) return false;      // vector residual loads
   if (q.T_out < 1 || q.T_src < 1 || q.N < 1 || q.B < 1) return false;
-  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0).ok;
+  return plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0, tap_want_bias(q), tap_want_res(q)).ok;
 }
 
 inline int sm_count() {
@@ -596,7 +682,7 @@ inline int sm_count() {
 }
 
 inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
-  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0);
+  TapPlan pl = plan_tap(q.Cin, q.Co, q.Kt, q.T_src, q.epi == EPI_GATE, q.Cout, q.q_only != 0, tap_want_bias(q), tap_want_res(q));
   STGCN_CHECK(pl.ok, STGCN_E_UNSUPPORTED, "umma tap GEMM: unsupported shape");
   const CUtensorMapSwizzle tsw = pl.KB == 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                : (pl.KB == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -632,9 +718,13 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.stage_bytes = pl.stage_bytes;
   p.B = q.B; p.N = q.N; p.T_src = q.T_src; p.T_out = q.T_out; p.Kt = q.Kt; p.t0 = q.t0;
   p.Cin = q.Cin; p.KB = pl.KB; p.nKB = pl.nKB; p.CoT = pl.CoT; p.S = pl.S; p.swz = pl.swz; p.sbo = pl.sbo;
-  p.tile_bytes = pl.tile_bytes; p.w_bytes = pl.w_bytes;
+  p.tile_bytes = pl.tile_bytes; p.w_bytes = pl.w_bytes; p.x_bytes = pl.x_bytes;
+  p.bias_mma = (pl.bias_mma && q.bias != nullptr) ? 1 : 0;
+  p.res_mma = (pl.res_mma && q.aux == q.in) ? 1 : 0;
+  p.res_dt = q.aux_dt;
   p.act = q.act; p.Cout = q.Cout; p.W = q.Co; p.bias = q.bias;
-  p.aux = q.aux; p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
+  p.aux = p.res_mma ? nullptr : q.aux;      // the epilogue handles only what the tensor pipe does not
+  p.aux_dt = q.aux_dt; p.T_aux = q.T_aux; p.C_aux = q.C_aux; p.aux_cols = q.aux_cols;
   p.out = q.out; p.ld_out = q.ld_out; p.co_valid = q.Co; p.out_z = q.out_z; p.relu = q.relu;
   p.q_only = (q.epi == EPI_GATE && q.act == STGCN_ACT_GLU && q.q_only) ? 1 : 0;
   p.dbg = g_tap_dbg;
@@ -686,17 +776,20 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     STGCN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     STGCN_LAUNCH_NAMED(kname, kern, grid, kTapThreadsWide, pl.smem, stream, tmX, tmW, tmO, tmZ, p);
   };
+  const bool aux_epi = p.aux != nullptr;
+#define STGCN_TAP_GO(EPIV, ACTV) do { if (aux_epi) go(umma_tap_kernel<EPIV, ACTV, true>); else go(umma_tap_kernel<EPIV, ACTV, false>); } while (0)
   if (q.epi == EPI_GATE) {
     switch (q.act) {
-      case STGCN_ACT_GLU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_GLU>); break;
-      case STGCN_ACT_GTU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_GTU>); break;
-      case STGCN_ACT_RELU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_RELU>); break;
-      case STGCN_ACT_SILU: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_SILU>); break;
-      default: go(umma_tap_kernel<EPI_GATE, STGCN_ACT_LINEAR>); break;
+      case STGCN_ACT_GLU: STGCN_TAP_GO(EPI_GATE, STGCN_ACT_GLU); break;
+      case STGCN_ACT_GTU: STGCN_TAP_GO(EPI_GATE, STGCN_ACT_GTU); break;
+      case STGCN_ACT_RELU: STGCN_TAP_GO(EPI_GATE, STGCN_ACT_RELU); break;
+      case STGCN_ACT_SILU: STGCN_TAP_GO(EPI_GATE, STGCN_ACT_SILU); break;
+      default: STGCN_TAP_GO(EPI_GATE, STGCN_ACT_LINEAR); break;
     }
   } else {
-    go(umma_tap_kernel<EPI_LINEAR, STGCN_ACT_LINEAR>);
+    STGCN_TAP_GO(EPI_LINEAR, STGCN_ACT_LINEAR);
   }
+#undef STGCN_TAP_GO
 }
 
 }  // namespace umma

@@ -38,3 +38,36 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def make_gso_golden():
+    """Adjacency inputs for the device-side operator preprocessing with the operators the UNMODIFIED
+    reference derives from them (utility.calc_gso / calc_chebynet_gso, sym_* types: the rw_* types crash in the reference
+    under the installed scipy).  PeMSD7-M's real adjacency (the dense form of data/pemsd7-m/adj.npz) and a
+    small random directed weighted graph with an isolated vertex."""
+    import scipy.sparse as sp
+    from script import utility
+    os.chdir("/root/reference")
+    adj, n = ref_dl.load_adj("pemsd7-m")
+    dense = np.asarray(adj.todense(), dtype=np.float32)
+    out = {"adj_pemsd7m": dense}
+    for t in ("sym_norm_lap", "sym_renorm_adj"):
+        g = utility.calc_gso(sp.csc_matrix(dense.astype(np.float64)), t)
+        out[f"pemsd7m_{t}"] = np.asarray(g.todense(), dtype=np.float32)
+        out[f"pemsd7m_{t}_cheb"] = np.asarray(utility.calc_chebynet_gso(g).todense(), dtype=np.float32)
+    rng = np.random.default_rng(3)
+    a = rng.random((40, 40)) * (rng.random((40, 40)) < 0.2)
+    np.fill_diagonal(a, 0.0)
+    a[7, :] = 0.0
+    a[:, 7] = 0.0                                   # isolated vertex: degree 0 -> 1/0 must become 0
+    out["adj_rand"] = a.astype(np.float32)
+    for t in ("sym_norm_adj", "sym_renorm_adj", "sym_norm_lap", "sym_renorm_lap"):
+        g = utility.calc_gso(sp.csc_matrix(a.astype(np.float32).astype(np.float64)), t)
+        out[f"rand_{t}"] = np.asarray(g.todense(), dtype=np.float32)
+        out[f"rand_{t}_cheb"] = np.asarray(utility.calc_chebynet_gso(g).todense(), dtype=np.float32)
+    np.savez_compressed(os.path.join(HERE, "train_gso.npz"), **out)
+    print("written train_gso.npz", {k: v.shape for k, v in out.items() if k.startswith("adj")})
+
+
+if __name__ == "__main__" and "--gso" in sys.argv:
+    make_gso_golden()

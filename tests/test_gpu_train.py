@@ -145,3 +145,30 @@ def test_graphed_step_with_fused_optimizer_trains(cuda_device):
         step.close()
     finally:
         stgcn_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("name,types", [("pemsd7m", ("sym_norm_lap", "sym_renorm_adj")),
+                                         ("rand", ("sym_norm_adj", "sym_renorm_adj", "sym_norm_lap", "sym_renorm_lap",
+                                                   "rw_norm_adj", "rw_renorm_lap"))])
+def test_device_gso_matches_reference(name, types, cuda_device):
+    """Operator preprocessing on the device vs the reference-derived golden operators (sym_* types)
+    and the oracle (rw_* types, which crash in the reference under the installed scipy): calc_gso to fp32 rounding,
+    the Chebyshev rescale to the accuracy of the power iteration's lambda_max (<= 1e-5 relative)."""
+    from stgcn_b200 import gso as G
+    dev = cuda_device
+    z = np.load(os.path.join(GOLDEN, "train_gso.npz"))
+    adj = torch.from_numpy(z[f"adj_{name}"]).to(dev)
+    for t in types:
+        ref = T.calc_gso_dense(z[f"adj_{name}"].astype(np.float64), t)
+        if f"{name}_{t}" in z.files:
+            assert np.allclose(ref, z[f"{name}_{t}"], rtol=1e-6, atol=1e-7)
+        got = G.calc_gso(adj, t)
+        assert rel_l2(got.cpu(), torch.from_numpy(ref)) < 2e-6, t
+        cheb_ref, lam = T.calc_chebynet_gso_dense(ref)
+        cheb, eig = G.calc_chebynet_gso(got, return_eigval=True)
+        assert abs(eig[0].item() - lam) <= 1e-5 * lam, (t, eig.tolist(), lam)
+        assert rel_l2(cheb.cpu(), torch.from_numpy(cheb_ref)) < 3e-5, t
+        one = G.build_operator(adj, t, True)
+        assert rel_l2(one.cpu(), torch.from_numpy(cheb_ref)) < 3e-5, t
+    with pytest.raises(ValueError):
+        G.calc_gso(adj, "sym_lap")

@@ -53,3 +53,20 @@ def test_oracles_live_against_reference_when_mounted():
     x, y = ref_dl.data_transform(data, 6, 2, "cpu")
     xo, yo = T.data_transform(data, 6, 2)
     assert np.array_equal(xo, x.numpy()) and np.array_equal(yo, y.numpy())
+
+
+def test_gso_oracle_matches_reference_golden():
+    """Dense calc_gso / calc_chebynet_gso restatement against the operators the unmodified reference derived
+    (tests/golden/make_train_golden.py --gso); also the committed gso_pemsd7m_*.npy the models are benchmarked on."""
+    z = np.load(os.path.join(GOLDEN, "train_gso.npz"))
+    for name, types in (("pemsd7m", ("sym_norm_lap", "sym_renorm_adj")),
+                        ("rand", ("sym_norm_adj", "sym_renorm_adj", "sym_norm_lap", "sym_renorm_lap"))):
+        adj = z[f"adj_{name}"].astype(np.float64)
+        for t in types:
+            g = T.calc_gso_dense(adj, t)
+            assert np.allclose(g, z[f"{name}_{t}"], rtol=1e-6, atol=1e-7), (name, t)
+            c, lam = T.calc_chebynet_gso_dense(g)
+            assert np.allclose(c, z[f"{name}_{t}_cheb"], rtol=1e-5, atol=2e-6), (name, t, lam)
+    cheb = np.load(os.path.join(GOLDEN, "gso_pemsd7m_cheb.npy"))
+    c, _ = T.calc_chebynet_gso_dense(T.calc_gso_dense(z["adj_pemsd7m"].astype(np.float64), "sym_norm_lap"))
+    assert np.allclose(c, cheb, rtol=1e-5, atol=2e-6)
