@@ -312,7 +312,7 @@ class Runner:
     forward + MSE + backward [+ gradient all-reduce]) captured in a CUDA graph (stgcn_b200.graph.GraphedStep)."""
     POOL = 4      # distinct input batches cycled through, so no step re-reads a hot input
 
-    def __init__(self, workload, B, precision, dev, rank, world, droprate=0.0, graph=True, reduce_in_graph=True):
+    def __init__(self, workload, B, precision, dev, rank, world, droprate=0.0, graph=True):
         import stgcn_b200
         from stgcn_b200 import _lib as L
         from stgcn_b200.dist import FlatGradAllReducer
@@ -340,21 +340,11 @@ class Runner:
             from stgcn_b200.graph import GraphedStep
             n_before = L.launch_count()
             warm = 3
-            try:
-                self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
-                                           reducer=self.reducer, reduce_in_graph=reduce_in_graph)
-            except Exception as e:                   # capture of the collective refused: reduce after the replay instead
-                if self.reducer is None or not reduce_in_graph:
-                    raise
-                sys.stderr.write(f"[bench] in-graph all-reduce not captured ({type(e).__name__}: {e}); reducing after replay\n")
-                torch.cuda.synchronize(dev)
-                self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm,
-                                           reducer=self.reducer, reduce_in_graph=False)
+            self.graphed = GraphedStep(self.model, (B, 1, 12, n), (B, n), device=dev, warmup=warm, reducer=self.reducer)
             self.launches_per_step = (L.launch_count() - n_before) // (warm + 1)      # warm-up bodies + 1 capture
             self.loss_buf = self.graphed.loss
             if self.reducer is not None:
-                self.reduce_mode = "in-graph, bucket 0 overlaps st_blocks.0 backward" if self.graphed._in_graph_reduce \
-                    else "after-replay on the flat buffer"
+                self.reduce_mode = "ncclAvg on the flat gradient buffer the backward kernels write, right behind the graph replay"
         self.x_dev, self.y_dev = torch.empty_like(self.xs[0]), torch.empty_like(self.ys[0])
 
     def eager_step(self, x, y, reduce=True):
@@ -445,7 +435,6 @@ def main():
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra legs of the default line (parity_mode, cuda_baseline, other BASELINE configs)")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
-    ap.add_argument("--reduce-after", action="store_true", help="N > 1: all-reduce after the graph replay, not inside it")
     ap.add_argument("--max-seconds", type=int, default=int(os.environ.get("STGCN_BENCH_MAX_SECONDS", "900")),
                     help="watchdog: dump all Python stacks to stderr and exit 124 if the run has not finished by then")
     a = ap.parse_args()
@@ -503,8 +492,7 @@ def main():
         dist.barrier()
     from stgcn_b200 import _lib as L
 
-    run = Runner(a.workload, B, a.precision, dev, rank, world, droprate=a.droprate, graph=not a.no_graph,
-                 reduce_in_graph=not a.reduce_after)
+    run = Runner(a.workload, B, a.precision, dev, rank, world, droprate=a.droprate, graph=not a.no_graph)
     n, blocks = run.n, run.blocks
 
     sampler = ClockSampler(local_rank)

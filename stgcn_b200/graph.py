@@ -1,4 +1,4 @@
-"""CUDA-graph capture of a whole training step body (forward + loss + backward [+ gradient all-reduce]).
+"""CUDA-graph capture of a whole training step body (forward + loss + backward [+ fused optimizer]).
 
 At B200 speeds the step of the default model is a few dozen kernels lasting about a millisecond in total, so
 Python/autograd/ctypes launch overhead becomes visible; capturing the step once and replaying it removes the host from
@@ -11,10 +11,13 @@ Dropout: the kernels take their seed by value, which a capture would freeze; the
 step counter, registered with the library (``stgcn_set_dropout_step``) and incremented by the last node of the graph,
 so every replay draws fresh masks and the forward and backward of one replay agree.
 
-Data parallelism: with ``reducer=FlatGradAllReducer(model)`` the gradients are views into one flat buffer and the
-all-reduce is part of the captured graph (``reduce_in_graph=True``): bucket 0 (output stage + all ST blocks but the
-first) is enqueued as soon as the backward of ``st_blocks[1]`` is, on NCCL's stream, and overlaps the backward of
-``st_blocks[0]``; bucket 1 follows at the end.
+Data parallelism: with ``reducer=FlatGradAllReducer(model)`` the gradients are views into one flat buffer that the
+captured backward kernels write directly, and the ``ncclAvg`` all-reduce of that buffer is enqueued right behind every
+replay (no pack/unpack copies, no scaling kernel).  Capturing the collective INSIDE the graph (bucket 0 issued from an
+autograd hook behind ``st_blocks[1]``'s backward so that it overlaps ``st_blocks[0]``'s) was built and tried on 2 B200s
+in round 2: both users of it (the 2-GPU test and bench.py) dead-locked at the first replays
+(profiles/r02_ab_batch_d.md), so the collective stays outside the graph; measured 96 % weak-scaling efficiency at
+2 GPUs with it there.
 """
 from __future__ import annotations
 
@@ -26,16 +29,12 @@ import torch
 from . import _lib as L
 
 
-def _has_active_dropout(model: torch.nn.Module) -> bool:
-    return any(isinstance(m, torch.nn.Dropout) and m.p > 0 and m.training for m in model.modules())
-
-
 class GraphedStep:
     def __init__(self, model: torch.nn.Module, batch_shape, target_shape, device=None,
-                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, reducer=None,
-                 reduce_in_graph: bool = True):
-        """reducer: a dist.FlatGradAllReducer; None = single process.  post_backward: called at the end of the captured
-        body (e.g. a fused optimizer step, optim.FlatAdamW.step).
+                 post_backward: Optional[Callable[[], None]] = None, warmup: int = 3, reducer=None):
+        """reducer: a dist.FlatGradAllReducer (None = single process); it runs after every replay.
+        post_backward: called at the end of the captured body (e.g. a fused optimizer step, optim.FlatAdamW.step; with a
+        reducer the optimizer must run after the all-reduce, i.e. outside: call it after ``step(x, y)``).
         (Splitting the batch into chains on parallel streams inside the graph was measured and removed: 2 chains -8 %,
         4 chains -30 % on PeMSD7-M B=256 -- the persistent kernels of the chains compete for the same SMs,
         profiles/r02_ab_batch_b.md.)"""
@@ -52,8 +51,6 @@ class GraphedStep:
         with torch.cuda.device(dev):
             torch.cuda.synchronize(dev)
             L.check(self._lib.stgcn_set_dropout_step(self.step_counter.data_ptr()))
-        self._hook_handle = None
-        self._in_graph_reduce = False
         # warm up on a side stream (allocator pools, lazily sized workspaces, cuFuncSetAttribute calls, helper streams)
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream(dev))
@@ -61,38 +58,18 @@ class GraphedStep:
             for i in range(max(warmup, 2 if reducer is not None else 1)):
                 self._body()
                 if reducer is not None:
-                    reducer()                   # first call binds the flat buffer; later warm-ups run NCCL once eagerly
+                    reducer()                   # first call binds the flat buffer; later warm-ups run NCCL eagerly
         torch.cuda.current_stream(dev).wait_stream(s)
         torch.cuda.synchronize(dev)
-        self._in_graph_reduce = reducer is not None and reduce_in_graph and reducer._world() > 1
-        if self._in_graph_reduce:
-            self._install_overlap_hook()
         self.graph = torch.cuda.CUDAGraph()
         for p in model.parameters():
             p.grad = None
-        # thread_local: NCCL's watchdog thread and the autograd worker may call into the runtime during the capture
+        # thread_local: other threads (NCCL's watchdog, when a process group exists) may call into the runtime meanwhile
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self._body()
         self.params = list(model.parameters())
         self.grads = [p.grad for p in self.params]
 
-    # ------------------------------------------------------------------ data-parallel overlap
-    def _install_overlap_hook(self):
-        """Issue bucket 0 of the gradient all-reduce when the backward of st_blocks[1] has been enqueued (its input
-        gradient exists), so it overlaps the backward of st_blocks[0]."""
-        blocks = getattr(self.model, "st_blocks", None)
-        if blocks is None or len(blocks) < 2 or self.reducer.n_buckets < 2:
-            return
-        step = self
-
-        def fwd_hook(module, inputs, output):
-            if step._in_graph_reduce and torch.is_grad_enabled() and output.requires_grad:
-                output.register_hook(lambda g: step.reducer.reduce_bucket(0, async_op=True))
-
-        # the OUTPUT of st_blocks[0] is the input of st_blocks[1]: its gradient is produced by st_blocks[1]'s backward
-        self._hook_handle = blocks[0].register_forward_hook(fwd_hook)
-
-    # ------------------------------------------------------------------ step body
     def _body(self):
         model = self.model
         for p in model.parameters():
@@ -104,18 +81,15 @@ class GraphedStep:
                                             self.loss.data_ptr(), dpred.data_ptr(),
                                             torch.cuda.current_stream(self.x.device).cuda_stream))
         pred.backward(dpred)
-        if self._in_graph_reduce:
-            self.reducer()                       # remaining buckets + join of the overlapped one
         if self.post_backward is not None:
             self.post_backward()
         self.step_counter.add_(1)
 
-    # ------------------------------------------------------------------ replay
     def _after_replay(self):
         # a zero_grad(set_to_none=True) between steps detaches p.grad from the tensors the graph writes: re-point them
         for p, g in zip(self.params, self.grads):
             p.grad = g
-        if self.reducer is not None and not self._in_graph_reduce:
+        if self.reducer is not None:
             self.reducer()
 
     def __call__(self, x: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
@@ -132,11 +106,7 @@ class GraphedStep:
         return self.loss
 
     def close(self) -> None:
-        """Unregister the device step counter and the overlap hook (the object must not be replayed afterwards)."""
-        if self._hook_handle is not None:
-            self._hook_handle.remove()
-            self._hook_handle = None
-        self._in_graph_reduce = False
+        """Unregister the device step counter (the object must not be replayed afterwards)."""
         with torch.cuda.device(self.device):
             torch.cuda.synchronize(self.device)
             L.check(self._lib.stgcn_set_dropout_step(None))

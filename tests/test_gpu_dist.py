@@ -1,8 +1,7 @@
 """2-GPU NCCL test of the data-parallel step on the PRODUCT layers (skipped with fewer than 2 GPUs): every rank runs its
 batch shard through the captured step (stgcn_b200.graph.GraphedStep) with the flat-buffer reducer -- gradients written by
-the backward kernels straight into the flat buffer, all-reduce (ncclAvg) inside the graph, bucket 0 overlapping the first
-block's backward -- and the averaged gradients must equal the full-batch gradients (MSE is a mean over equal shards,
-LayerNorm is per sample: SURVEY.md §8e)."""
+the backward kernels straight into the flat buffer, ncclAvg all-reduce of it behind every replay -- and the averaged
+gradients must equal the full-batch gradients (MSE is a mean over equal shards, LayerNorm is per sample: SURVEY.md §8e)."""
 import os
 import sys
 import tempfile
@@ -14,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, init_file, out_file, precision, in_graph):
+def _worker(rank, world, init_file, out_file, precision):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -39,8 +38,8 @@ def _worker(rank, world, init_file, out_file, precision, in_graph):
     sl = shard_batch(B, rank, world)
     Bs = sl.stop - sl.start
     red = FlatGradAllReducer(model)
-    step = GraphedStep(model, (Bs, 1, 12, n), (Bs, n), device=dev, warmup=2, reducer=red, reduce_in_graph=in_graph)
-    assert step._in_graph_reduce == in_graph and red.n_buckets == 2
+    step = GraphedStep(model, (Bs, 1, 12, n), (Bs, n), device=dev, warmup=2, reducer=red)
+    assert red.n_buckets == 2
     for _ in range(2):                       # replays are repeatable
         step(x[sl].to(dev), y[sl].to(dev))
     torch.cuda.synchronize()
@@ -58,14 +57,14 @@ def _worker(rank, world, init_file, out_file, precision, in_graph):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("precision,in_graph,tol", [("fp32", True, 1e-4), ("bf16", True, 5e-2), ("fp32", False, 1e-4)])
-def test_nccl_averaged_shard_grads_equal_full_batch(precision, in_graph, tol, cuda_device):
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-2)])
+def test_nccl_averaged_shard_grads_equal_full_batch(precision, tol, cuda_device):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     with tempfile.TemporaryDirectory() as td:
         init_file, out_file = os.path.join(td, "init"), os.path.join(td, "out.pt")
-        mp.spawn(_worker, args=(2, init_file, out_file, precision, in_graph), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, init_file, out_file, precision), nprocs=2, join=True)
         res = torch.load(out_file)
     assert res["n_live"] == 28
     assert res["worst"] < tol, res
