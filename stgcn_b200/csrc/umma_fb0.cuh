@@ -53,15 +53,21 @@ struct Fb0Params {
 constexpr uint32_t kFb0ARing = 0;                                   // kFb0Stages x 4096
 constexpr uint32_t kFb0Wa = kFb0ARing + kFb0Stages * 4096;          // 2048
 constexpr uint32_t kFb0Wpq = kFb0Wa + 2048;                         // float4 [2][64] = 2048
-constexpr uint32_t kFb0X3 = kFb0Wpq + 2048;                         // 2 x 4096
-constexpr uint32_t kFb0Dz = kFb0X3 + 2 * 4096;                      // 2 x 32768 (1024-aligned: 32768+2048+2048+8192 = 45056)
-constexpr uint32_t kFb0Smem = kFb0Dz + 2 * 32768 + 1024;
+constexpr int kFb0ND1 = 3;                                          // dH1 accumulators in TMEM (64 columns each); 3 x 64 + 16 fit a 256-column
+                                                                    // allocation, which leaves room for a weight-gradient kernel of the helper stream on the same SM
+constexpr int kFb0NZ = 3;                                           // dZ / x-window tile pairs in shared memory
+constexpr uint32_t kFb0X3 = kFb0Wpq + 2048;                         // kFb0NZ x 4096
+constexpr uint32_t kFb0Dz = kFb0X3 + kFb0NZ * 4096;                 // kFb0NZ x 32768 (1024-aligned: 36864 + 12288 = 49152)
+constexpr uint32_t kFb0Smem = kFb0Dz + kFb0NZ * 32768 + 1024;
+constexpr uint32_t kFb0D2Col = kFb0ND1 * 64;                        // TMEM column of the weight-gradient accumulator
+// (the first version double-buffered both: 2.4 us per 128-row tile against ~0.9 us of epilogue issue time -- every tile
+// waited for the previous tile's MMA 2 and the next tile's MMA 1 in turn; profiles/r02_ab_batch_c.md)
 
 template <int MODE>
 __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[2], d1_empty[2], dz_full[2], dz_empty[2], done;
+  __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[kFb0ND1], d1_empty[kFb0ND1], dz_full[kFb0NZ], dz_empty[kFb0NZ], done;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -81,14 +87,12 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFb0Stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kFb0EpiWarps);
-      mbar_init(&dz_full[i], kFb0EpiWarps); mbar_init(&dz_empty[i], 1);
-    }
+    for (int i = 0; i < kFb0ND1; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kFb0EpiWarps); }
+    for (int i = 0; i < kFb0NZ; ++i) { mbar_init(&dz_full[i], kFb0EpiWarps); mbar_init(&dz_empty[i], 1); }
     mbar_init(&done, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 256);          // D1: 2 x 64 columns, D2: 16 columns
+  if (warp == 1) tmem_alloc(&tmem_base_s, 256);          // D1: kFb0ND1 x 64 columns, D2: 16 columns
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       const uint64_t px3 = make_smem_desc(0, 4096, 256, SWZ_32B);        // MN-major: [rows][16]
       const uint32_t wa_s = smem_u32(smem + kFb0Wa);
       auto mma1 = [&](int i) {
-        const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1, ab = i & 1, aph = (i >> 1) & 1;
+        const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1, ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
         mbar_wait(&a_full[s], ph);
         mbar_wait(&d1_empty[ab], aph ^ 1);
         tc_fence_after();
@@ -144,17 +148,17 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
         mma_commit(&d1_full[ab]);
         mma_commit(&a_empty[s]);
       };
-      if (n_my > 0) mma1(0);
+      int next1 = 0;                                      // MMA 1 runs up to kFb0ND1 - 1 tiles ahead of MMA 2
       for (int i = 0; i < n_my; ++i) {
-        if (i + 1 < n_my) mma1(i + 1);
+        for (; next1 < n_my && next1 < i + kFb0ND1; ++next1) mma1(next1);
         if (MODE != FB_FIRST) continue;
-        const uint32_t zb = i & 1, zph = (i >> 1) & 1;
+        const uint32_t zb = i % kFb0NZ, zph = (i / kFb0NZ) & 1;
         mbar_wait(&dz_full[zb], zph);
         tc_fence_after();
         uint64_t da = desc_at(pdz, smem_u32(smem + kFb0Dz + zb * 32768)), db = desc_at(px3, smem_u32(smem + kFb0X3 + zb * 4096));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                     // 16 rows per instruction
-          mma_bf16_ss(tmem_base + 128, da, db, idesc2, (i != 0 || k != 0) ? 1u : 0u);
+          mma_bf16_ss(tmem_base + kFb0D2Col, da, db, idesc2, (i != 0 || k != 0) ? 1u : 0u);
           da += 2048 >> 4; db += 512 >> 4;
         }
         mma_commit(&dz_empty[zb]);
@@ -185,7 +189,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
         qv[0] = qp[0]; qv[1] = qp[1]; hv[0] = hp[0]; hv[1] = hp[1];
       }
       const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
-      const uint32_t ab = i & 1, aph = (i >> 1) & 1;
+      const uint32_t ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
       mbar_wait(&d1_full[ab], aph);
       tc_fence_after();
       uint32_t rr[16];
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
         }
         continue;
       }
-      const uint32_t zb = i & 1, zph = (i >> 1) & 1;
+      const uint32_t zb = i % kFb0NZ, zph = (i / kFb0NZ) & 1;
       mbar_wait(&dz_empty[zb], zph ^ 1);
       const uint32_t dzs = smem_u32(smem + kFb0Dz + zb * 32768);
       stage_store8_s(dzs, row, c0, pack8_bf16(du));
@@ -249,7 +253,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       mbar_wait(&done, 0);
       tc_fence_after();
       uint32_t rr[16];
-      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + 128, rr);
+      tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + kFb0D2Col, rr);
       tmem_ld_wait();
 #pragma unroll
       for (int k = 0; k < 4; ++k)

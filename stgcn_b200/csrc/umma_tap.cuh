@@ -660,9 +660,13 @@ inline TapPlan plan_tap_x(int Cin, int Co, int Kt, int T_src, bool gate, int Cou
 // a residual when it has the input's channel count and time extent and sits at one of the taps' time offsets -- whether
 // it really IS the input tensor is checked at launch (otherwise the reserved identity tap stays unused)
 inline bool tap_want_bias(const TapProblem& q) { return q.bias != nullptr; }
+// Not when the epilogue stores the pre-activation P itself (EPI_GATE without the q-only state: the backward adds the
+// residual to the saved P again), and not for narrow outputs (Co < 32: the Cin/16 extra N = 16 instructions cost the
+// issuer as much as a main tap each -- st0.tc2's data gradient got 16 % slower with them, profiles/r02_ab_batch_e.md).
 inline bool tap_want_res(const TapProblem& q) {
   return q.aux != nullptr && q.C_aux == q.Cin && q.T_aux == q.T_src && q.aux_dt - q.t0 >= 0 && q.aux_dt - q.t0 < q.Kt &&
-         q.in_stride_n == 0 && q.in_stride_t == 0 && q.in_stride_b == 0 && q.aux_cols > 0;
+         q.in_stride_n == 0 && q.in_stride_t == 0 && q.in_stride_b == 0 && q.aux_cols > 0 && q.Co >= 32 &&
+         (q.epi == EPI_LINEAR || (q.act == STGCN_ACT_GLU && q.q_only != 0));
 }
 inline bool tap_supported(const TapProblem& q) {
   if (q.epi == EPI_GATE && (q.Cout % 16 != 0)) return false;
