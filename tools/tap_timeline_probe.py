@@ -1,6 +1,6 @@
 # NOTE: the in-kernel globaltimer stamps are compiled in only with -DSTGCN_TIMELINE:
 #   tools/build_variants.sh tl="-DSTGCN_TIMELINE" && STGCN_B200_LIB=$PWD/build/variants/tl.so python <this script>
-import sys; sys.path.insert(0,'/root/repo')
+import os, sys; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, stgcn_b200
 from stgcn_b200 import layers, _lib as L
 stgcn_b200.set_precision("bf16")
