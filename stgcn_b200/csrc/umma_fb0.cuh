@@ -170,24 +170,36 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
     const int q = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter; 16-channel group
     const int row = q * 32 + lane, c0 = grp * 16;
     const float4* wpq = reinterpret_cast<const float4*>(smem + kFb0Wpq);
+    // The per-row operands of tile i + 1 (x taps, or the Q / H1 chunks) are requested while tile i is being computed:
+    // issued at the top of their own tile their L2 / HBM round trip (~1 us) sat in front of every tile's arithmetic
+    // (2.4 us per tile against ~0.9 us of epilogue issue time, profiles/r02_ab_batch_f.md).
+    float xn0 = 0.f, xn1 = 0.f, xn2 = 0.f;
+    uint4 qn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, hn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+    auto fetch = [&](int i) {
+      xn0 = xn1 = xn2 = 0.f;
+      qn[0] = qn[1] = hn[0] = hn[1] = make_uint4(0, 0, 0, 0);
+      if (i >= n_my) return;
+      const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
+      if (r >= p.rows) return;
+      if (MODE == FB_FIRST) {
+        long long in0; int t_unused;
+        simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
+        xn0 = simt::ldf(p.x + in0);
+        xn1 = simt::ldf(p.x + in0 + p.N);
+        if (p.Kt > 2) xn2 = simt::ldf(p.x + in0 + 2LL * p.N);
+      } else {
+        const uint4* qp = reinterpret_cast<const uint4*>(p.q + r * 64 + c0);
+        const uint4* hp = reinterpret_cast<const uint4*>(p.h + r * 64 + c0);
+        qn[0] = qp[0]; qn[1] = qp[1]; hn[0] = hp[0]; hn[1] = hp[1];
+      }
+    };
+    fetch(0);
     for (int i = 0; i < n_my; ++i) {
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
       const bool valid = r < p.rows;
-      float x0 = 0.f, x1 = 0.f, x2 = 0.f;
-      uint4 qv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, hv[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (MODE == FB_FIRST) {
-        if (valid) {
-          long long in0; int t_unused;
-          simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
-          x0 = simt::ldf(p.x + in0);
-          x1 = simt::ldf(p.x + in0 + p.N);
-          if (p.Kt > 2) x2 = simt::ldf(p.x + in0 + 2LL * p.N);
-        }
-      } else if (valid) {               // requested before the accumulator wait: the loads fly while MMA 1 completes
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q + r * 64 + c0);
-        const uint4* hp = reinterpret_cast<const uint4*>(p.h + r * 64 + c0);
-        qv[0] = qp[0]; qv[1] = qp[1]; hv[0] = hp[0]; hv[1] = hp[1];
-      }
+      const float x0 = xn0, x1 = xn1, x2 = xn2;
+      const uint4 qv[2] = {qn[0], qn[1]}, hv[2] = {hn[0], hn[1]};
+      fetch(i + 1);
       const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
       const uint32_t ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
       mbar_wait(&d1_full[ab], aph);

@@ -46,7 +46,8 @@ static_assert(kTapEpiWarps % 4 == 0 && kTapEpiGroups >= 1 && kTapEpiGroups <= 4,
 #define STGCN_TAP_PRODUCERS 4
 #endif
 constexpr int kTapProducers = STGCN_TAP_PRODUCERS;  // cp.async producer warps for narrow inputs: warp 0 and the warps after the epilogue
-constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps + 32 * (kTapProducers - 1);
+constexpr int kTapThreadsWide = 64 + 32 * kTapEpiWarps + 32 * (kTapProducers - 1) + 32;      // last warp: TMA-store warp
+constexpr int kTapStoreWarp = 2 + kTapEpiWarps + (kTapProducers - 1);
 
 struct TapParams {
   int B, N, T_src, T_out, Kt, t0;
@@ -210,6 +211,10 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint8_t* ring = x_s + p.x_bytes;        // w_bytes, x_bytes are multiples of 1024
   const uint32_t bias_tile_off = 4096, id_off = 4096 + (((uint32_t)p.CoT * 32 + 1023) & ~1023u);
   __shared__ __align__(8) uint64_t full[kMaxStages], empty[kMaxStages], wfull, tfull[8], tempty[8];
+  // output staging hand-off: epilogue warps -> store warp (sfull: one arrival per epilogue warp) and back (sempty: the TMA
+  // store has read the buffer).  The first version synchronised all 16 epilogue warps with two named barriers per tile and
+  // had one of them issue the stores: ~1 us of a 2.35 us tile period was that hand-off (timeline, profiles/r02_ab_batch_f.md)
+  __shared__ __align__(8) uint64_t sfull[2], sempty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float bias_s[256];
 
@@ -253,6 +258,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&wfull, 1);
     for (int i = 0; i < p.NB; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_arrivals); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], kTapEpiWarps); mbar_init(&sempty[i], 1); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
@@ -262,9 +268,32 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) STGCN_STAMP(1);
 
-  const bool is_producer = warp == 0 || warp >= 2 + kTapEpiWarps;
+  const bool is_producer = warp == 0 || (warp >= 2 + kTapEpiWarps && warp < kTapStoreWarp);
   const int prod_idx = warp == 0 ? 0 : warp - (2 + kTapEpiWarps) + 1;
-  if (is_producer) {
+  if (warp == kTapStoreWarp) {
+    // =========================== TMA-store warp ==========================
+    if (p.store_tma && lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const TapItem wi = tap_item(p, item);
+        for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++cnt) {
+          const uint32_t buf = p.nbuf == 2 ? (cnt & 1) : 0, ph = p.nbuf == 2 ? ((cnt >> 1) & 1) : (cnt & 1);
+          mbar_wait(&sfull[buf], ph);
+          const uint8_t* stg = smem + p.stage_off + (size_t)buf * p.stage_bytes;
+          for (int z = 0; z < p.nZ; ++z) tma_store_4d(&tmZ, stg + (size_t)z * 16384, z * 64, wi.n0, t_o, wi.b);
+          for (int o = 0; o < p.nO; ++o) tma_store_4d(&tmO, stg + (size_t)(p.nZ + o) * 16384, co0 + o * 64, wi.n0, t_o, wi.b);
+          tma_store_commit();
+          if (p.nbuf == 2) {
+            if (cnt > 0) { tma_store_wait_read<1>(); mbar_arrive(&sempty[(cnt - 1) & 1]); }     // previous tile's buffer is free
+          } else {
+            tma_store_wait_read<0>();
+            mbar_arrive(&sempty[0]);
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+    }
+  } else if (is_producer) {
     // =========================== producer ================================
     if (warp == 0 && lane == 0) {
       tma_prefetch_desc(&tmX);
@@ -451,11 +480,11 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         have_pre = false;
         uint8_t* stg = nullptr;
         uint32_t stg_s = 0;
+        const uint32_t sbuf = p.nbuf == 2 ? (acc_cnt & 1) : 0, sph = p.nbuf == 2 ? ((acc_cnt >> 1) & 1) : (acc_cnt & 1);
         if (p.store_tma) {
-          // the staging buffer used nbuf tiles ago must have been read out by its TMA store
-          if (threadIdx.x == 64) { if (p.nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-          named_bar_sync(1, 32 * kTapEpiWarps);
-          stg = smem + p.stage_off + (size_t)(p.nbuf == 2 ? (acc_cnt & 1) : 0) * p.stage_bytes;      // nbuf is 1 or 2
+          // the staging buffer used nbuf tiles ago must have been read out by its TMA store (store warp -> sempty)
+          mbar_wait(&sempty[sbuf], sph ^ 1);
+          stg = smem + p.stage_off + (size_t)sbuf * p.stage_bytes;      // nbuf is 1 or 2
           stg_s = smem_u32(stg);
         }
         mbar_wait(&tfull[ab], aph);
@@ -547,18 +576,13 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         if (lane == 0) mbar_arrive(&tempty[ab]);
         if (stg) {
           fence_proxy_async();                       // staged tile -> visible to the TMA (async proxy)
-          named_bar_sync(2, 32 * kTapEpiWarps);
-          if (threadIdx.x == 64) {
-            for (int z = 0; z < p.nZ; ++z) tma_store_4d(&tmZ, stg + (size_t)z * 16384, z * 64, n0, t_o, b);
-            for (int o = 0; o < p.nO; ++o) tma_store_4d(&tmO, stg + (size_t)(p.nZ + o) * 16384, co0 + o * 64, n0, t_o, b);
-            tma_store_commit();
-          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sfull[sbuf]);  // the store warp issues the TMA stores once all epilogue warps arrived
         }
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(5);
         if (warp == 2 && acc_cnt == 8) STGCN_STAMP(15);
       }
     }
-    if (p.store_tma && threadIdx.x == 64) tma_store_wait_all<0>();
     if (warp == 2) STGCN_STAMP(6);
   }
   tc_fence_before();
