@@ -55,6 +55,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Position in an S-deep mbarrier ring (stage index + phase bit), advanced incrementally.  The single-thread roles
+// (TMA producer, MMA issuer) used to compute `g % S, (g / S) & 1` per slice: every runtime integer division is ~150
+// dependent cycles for a lone thread, 5-8 of them per tile were ~1 us of a 2.4 us tile period -- with loads, MMAs, epilogue
+// math and stores all knocked out the tap kernel still took 55 % of its time (profiles/r02_ab_batch_h.md).
+struct RingPos {
+  uint32_t s, ph;
+  __device__ __forceinline__ void advance(uint32_t S) { if (++s == S) { s = 0; ph ^= 1; } }
+  __device__ __forceinline__ void advance_by(uint32_t n, uint32_t S) {
+    s += n;
+    while (s >= S) { s -= S; ph ^= 1; }
+  }
+};
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

@@ -59,10 +59,10 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tma_prefetch_desc(&tmB);
       mbar_arrive_expect_tx(&afull, p.a_bytes);
       for (int kb = 0; kb < p.nKB; ++kb) tma_load_2d(a_s + (size_t)kb * 16384, &tmA, &afull, kb * 64, h0);
-      uint32_t g = 0;
+      RingPos rp{0, 0};                               // no integer division in the single-thread roles (umma.cuh)
       for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x) {
-        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
-          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        for (int kb = 0; kb < p.nKB; ++kb, rp.advance(p.S)) {
+          const uint32_t s = rp.s, ph = rp.ph;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], p.stage_bytes);
           tma_load_3d(ring + (size_t)s * p.stage_bytes, &tmB, &full[s], 0, kb * 64, set * p.Gb);
@@ -73,14 +73,15 @@ umma_gso_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, NC, 0, 1);
       mbar_wait(&afull, 0);
-      uint32_t g = 0, acc_cnt = 0;
+      uint32_t acc_cnt = 0;
+      RingPos rp{0, 0};
       for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x, ++acc_cnt) {
         const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
         mbar_wait(&tempty[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * NC;
-        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
-          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        for (int kb = 0; kb < p.nKB; ++kb, rp.advance(p.S)) {
+          const uint32_t s = rp.s, ph = rp.ph;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_s + (size_t)kb * 16384);
@@ -176,10 +177,10 @@ umma_gso_ktiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (lane == 0) {
       tma_prefetch_desc(&tmA);
       tma_prefetch_desc(&tmB);
-      uint32_t g = 0;
+      RingPos rp{0, 0};                               // no integer division in the single-thread roles (umma.cuh)
       for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x) {
-        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
-          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        for (int kb = 0; kb < p.nKB; ++kb, rp.advance(p.S)) {
+          const uint32_t s = rp.s, ph = rp.ph;
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], stage_total);
           uint8_t* st = ring + (size_t)s * stage_total;
@@ -191,14 +192,15 @@ umma_gso_ktiled_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   } else if (warp == 1) {
     if (elect_one()) {
       const uint32_t idesc = make_idesc_bf16(128, NC, 0, 1);
-      uint32_t g = 0, acc_cnt = 0;
+      uint32_t acc_cnt = 0;
+      RingPos rp{0, 0};
       for (int set = blockIdx.x; set < p.n_sets; set += gridDim.x, ++acc_cnt) {
         const uint32_t ab = acc_cnt & 1, aph = (acc_cnt >> 1) & 1;
         mbar_wait(&tempty[ab], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + ab * NC;
-        for (int kb = 0; kb < p.nKB; ++kb, ++g) {
-          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+        for (int kb = 0; kb < p.nKB; ++kb, rp.advance(p.S)) {
+          const uint32_t s = rp.s, ph = rp.ph;
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t a_base = smem_u32(ring + (size_t)s * stage_total);

@@ -200,6 +200,11 @@ __device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
   return it;
 }
 
+#ifdef STGCN_KO_MMA
+#define STGCN_TAP_MMA(...) do { } while (0)
+#else
+#define STGCN_TAP_MMA(...) mma_bf16_ss(__VA_ARGS__)
+#endif
 template <int EPI, int ACT, bool AUX>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -280,15 +285,16 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t buf = p.nbuf == 2 ? (cnt & 1) : 0, ph = p.nbuf == 2 ? ((cnt >> 1) & 1) : (cnt & 1);
           mbar_wait(&sfull[buf], ph);
           const uint8_t* stg = smem + p.stage_off + (size_t)buf * p.stage_bytes;
+#ifndef STGCN_KO_STORE      // knock-out builds (tools/ko_probe.py): which resource bounds the tile period
           for (int z = 0; z < p.nZ; ++z) tma_store_4d(&tmZ, stg + (size_t)z * 16384, z * 64, wi.n0, t_o, wi.b);
           for (int o = 0; o < p.nO; ++o) tma_store_4d(&tmO, stg + (size_t)(p.nZ + o) * 16384, co0 + o * 64, wi.n0, t_o, wi.b);
+#endif
           tma_store_commit();
-          if (p.nbuf == 2) {
-            if (cnt > 0) { tma_store_wait_read<1>(); mbar_arrive(&sempty[(cnt - 1) & 1]); }     // previous tile's buffer is free
-          } else {
-            tma_store_wait_read<0>();
-            mbar_arrive(&sempty[0]);
-          }
+          // Release the buffer as soon as THIS tile's stores have read it.  (Releasing tile i-1's buffer only after tile i's
+          // stores were issued made every epilogue warp wait for all 16 warps to finish tile i before it could start tile
+          // i+1 in the other buffer: the double buffer behaved like a CTA-wide barrier per tile.)
+          tma_store_wait_read<0>();
+          mbar_arrive(&sempty[buf]);
         }
       }
       tma_store_wait_all<0>();
@@ -306,18 +312,23 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     if (!p.narrow_cp) {
       if (warp == 0 && lane == 0) {
         uint32_t g = 0;
+        RingPos rp{0, 0};
         const uint32_t ablk = 128u * p.KB * 2;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
           const TapItem wi = tap_item(p, item);
           const int b = wi.b, n0 = wi.n0;
-          for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g) {
-            const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
+            const uint32_t s = rp.s;
             if (g == 24) STGCN_STAMP(25);
-            mbar_wait(&empty[s], ph ^ 1);
+            mbar_wait(&empty[s], rp.ph ^ 1);
             if (g == 24) STGCN_STAMP(26);
+#ifdef STGCN_KO_LOAD
+            mbar_arrive(&full[s]); (void)ablk; (void)b; (void)n0;
+#else
             mbar_arrive_expect_tx(&full[s], p.tile_bytes);
             uint8_t* dst = ring + (size_t)s * p.tile_bytes;
             for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
+#endif
             if (g == 24) STGCN_STAMP(27);
             if (g == 25) STGCN_STAMP(28);
             if (g == 32) STGCN_STAMP(29);
@@ -330,13 +341,14 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // warps take alternate slices (one warp's per-slice bookkeeping latency, ~0.4 us, was the limiter); each
       // publishes a slice when it has issued its next one, so one copy group per warp is always in flight.
       uint32_t g = 0;
+      RingPos rp{0, 0};
       int pending = -1;                                  // this warp's issued-but-unpublished slice (stage index)
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const TapItem wi = tap_item(p, item);
         const int b = wi.b, n0 = wi.n0;
-        for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g) {
+        for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
           if ((int)(g % kTapProducers) != prod_idx) continue;
-          const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+          const uint32_t s = rp.s, ph = rp.ph;
           if (g == 24) STGCN_STAMP(25);
           mbar_wait(&empty[s], ph ^ 1);
           if (g == 24) STGCN_STAMP(26);
@@ -347,7 +359,11 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             const int q = lane + 32 * i, row = q >> 1, h = q & 1;
             const bool ok = n0 + row < p.N;
             const bf16* src = src0 + (long long)(ok ? n0 + row : 0) * p.sn + h * 8;
+#ifndef STGCN_KO_LOAD
             cp_async16(dst + row * 32 + ((h ^ ((row >> 2) & 1)) << 4), src, ok ? 16u : 0u);
+#else
+            (void)dst; (void)src;
+#endif
           }
           cp_async_commit();
           if (g == 24) STGCN_STAMP(27);
@@ -378,69 +394,84 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int nk16 = p.KB / 16;
       mbar_wait(&wfull, 0);
       STGCN_STAMP(2);
-      uint32_t g_base = 0, acc_cnt = 0;
+      // Ring bookkeeping without integer division (RingPos, umma.cuh).  `base` = ring position of the item's first slice
+      // s_lo; `win` = position of slice max(t_o + t0, s_lo), the first one the current output step can touch; `skip` = taps
+      // whose slice lies before s_lo (data-gradient launches: t0 < 0).  The window slides by one slice per output step, so
+      // only slices past `n_waited` (offset from s_lo) need a full-barrier wait: one per step instead of Kt.
+      uint32_t acc_cnt = 0, ab = 0, aph = 0;
+      RingPos base{0, 0};
+      const uint32_t id_base = smem_u32(x_s + id_off);
+      const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
+      const uint64_t d_ones = desc_at(p32, smem_u32(x_s)), d_bias = desc_at(p32, smem_u32(x_s + bias_tile_off));
+      const uint32_t ring_s = smem_u32(ring), w_base = smem_u32(w_s);
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const TapItem wi = tap_item(p, item);
+        RingPos win = base;
+        int skip = wi.s_lo - (wi.t_begin + p.t0);          // > 0 only when t_begin + t0 < 0
+        int n_waited = 0;
         for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
-          const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
           if (acc_cnt == 8) STGCN_STAMP(16);
           mbar_wait(&tempty[ab], aph ^ 1);
           if (acc_cnt == 8) STGCN_STAMP(17);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + ab * p.CoT;
           uint32_t accumulate = 0;
-          for (int j = 0; j < p.Kt; ++j) {
+          RingPos pos = win;
+          const int d_win = skip > 0 ? 0 : t_o + p.t0 - wi.s_lo;     // offset of `win` from s_lo
+          uint32_t res_a = 0;                                        // ring address of the residual slice (res_mma)
+          for (int j = skip > 0 ? skip : 0; j < p.Kt; ++j, pos.advance(p.S)) {
             const int ti = t_o + j + p.t0;
-            if (ti < 0 || ti >= p.T_src) continue;
-            const uint32_t g = g_base + (ti - wi.s_lo), s = g % p.S, ph = (g / p.S) & 1;
-            mbar_wait(&full[s], ph);
+            if (ti >= wi.s_hi) break;
+            const int d = d_win + j - (skip > 0 ? skip : 0);
+            if (d >= n_waited) {
+              mbar_wait(&full[pos.s], pos.ph);
+              tc_fence_after();
+              n_waited = d + 1;
+            }
             if (acc_cnt == 0) STGCN_STAMP(3);
             if (acc_cnt == 8) STGCN_STAMP(8);
             if (acc_cnt == 8) STGCN_STAMP(18 + j);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes);
-            const uint32_t b_base = smem_u32(w_s + (size_t)j * p.nKB * wblk);
+            const uint32_t a_base = ring_s + pos.s * p.tile_bytes;
+            const uint32_t b_base = w_base + (uint32_t)j * p.nKB * wblk;
+            if (j == p.res_dt - p.t0) res_a = a_base;
             for (int kb = 0; kb < p.nKB; ++kb) {
               uint64_t da = desc_at(dproto, a_base + kb * ablk), db = desc_at(dproto, b_base + kb * wblk);
               for (int k = 0; k < nk16; ++k) {
-                mma_bf16_ss(d_tmem, da, db, idesc, accumulate);
+                STGCN_TAP_MMA(d_tmem, da, db, idesc, accumulate);
                 accumulate = 1;
                 da += 2; db += 2;         // 32 bytes = one K = 16 step
               }
             }
           }
-          if (p.res_mma) {
-            const int ti = t_o + p.res_dt;
-            if (ti >= 0 && ti < p.T_src) {                 // the slice was waited for by its tap above
-              const uint32_t g = g_base + (ti - wi.s_lo), s = g % p.S;
-              const uint32_t a_base = smem_u32(ring + (size_t)s * p.tile_bytes), b_base = smem_u32(x_s + id_off);
-              for (int kb = 0; kb < p.nKB; ++kb) {
-                uint64_t da = desc_at(dproto, a_base + kb * ablk), db = desc_at(dproto, b_base + kb * wblk);
-                for (int k = 0; k < nk16; ++k) {
-                  mma_bf16_ss(d_tmem, da, db, idesc, accumulate);
-                  accumulate = 1;
-                  da += 2; db += 2;
-                }
+          if (p.res_mma && res_a != 0) {                   // the slice was waited for by its tap above
+            for (int kb = 0; kb < p.nKB; ++kb) {
+              uint64_t da = desc_at(dproto, res_a + kb * ablk), db = desc_at(dproto, id_base + kb * wblk);
+              for (int k = 0; k < nk16; ++k) {
+                STGCN_TAP_MMA(d_tmem, da, db, idesc, accumulate);
+                accumulate = 1;
+                da += 2; db += 2;
               }
             }
           }
           if (p.bias_mma) {
-            const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
-            mma_bf16_ss(d_tmem, desc_at(p32, smem_u32(x_s)), desc_at(p32, smem_u32(x_s + bias_tile_off)), idesc, accumulate);
+            STGCN_TAP_MMA(d_tmem, d_ones, d_bias, idesc, accumulate);
             accumulate = 1;
           }
           if (acc_cnt == 8) STGCN_STAMP(22);
           mma_commit(&tfull[ab]);
           if (acc_cnt == 8) STGCN_STAMP(23);
           // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
-          const int t_rel = t_o + p.t0;                      // t_rel >= 0 implies t_rel >= s_lo; t_rel < s_hi always
-          if (t_rel >= 0 && t_rel < p.T_src) mma_commit(&empty[(g_base + (t_rel - wi.s_lo)) % p.S]);
-          if (t_o == wi.t_end - 1)
-            for (int ti = (t_rel + 1 > wi.s_lo ? t_rel + 1 : wi.s_lo); ti < wi.s_hi; ++ti)
-              mma_commit(&empty[(g_base + (ti - wi.s_lo)) % p.S]);
+          if (t_o == wi.t_end - 1) {
+            RingPos r = win;
+            for (int ti = wi.s_lo + d_win; ti < wi.s_hi; ++ti, r.advance(p.S)) mma_commit(&empty[r.s]);
+          } else if (skip <= 0 && t_o + p.t0 < wi.s_hi) {
+            mma_commit(&empty[win.s]);
+          }
+          if (skip > 0) --skip; else win.advance(p.S);
+          if (++ab == (uint32_t)p.NB) { ab = 0; aph ^= 1; }
           if (acc_cnt == 8) STGCN_STAMP(24);
         }
-        g_base += wi.s_hi - wi.s_lo;
+        base.advance_by((uint32_t)(wi.s_hi - wi.s_lo), p.S);
       }
     }
   } else {
@@ -460,7 +491,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int n = n0 + row;
       const bool valid = n < p.N;
       for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
-        if (p.tile_parts > 1 && (int)(acc_cnt % p.tile_parts) != tpart) continue;   // warp groups alternate tiles
+        if ((int)(acc_cnt & (uint32_t)(p.tile_parts - 1)) != tpart) continue;       // tile_parts is 1, 2 or 4   // warp groups alternate tiles
         const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
         const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
         const int t_aux = t_o + p.aux_dt;
@@ -494,7 +525,11 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         tc_fence_after();
         const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
         constexpr bool gated = EPI == EPI_GATE && (ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU);
+#ifdef STGCN_KO_EPI
+        const int n_grp = 0;
+#else
         const int n_grp = ((width - cfirst + cstep - 1) / cstep) * 2;      // 8-column groups this warp handles
+#endif
 #pragma unroll 1
         for (int gi = 0; gi < n_grp; ++gi) {
           const int cc = cfirst + (gi >> 1) * cstep + (gi & 1) * 8;       // local column of this group

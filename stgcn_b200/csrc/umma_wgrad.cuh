@@ -77,23 +77,23 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
     if (lane == 0) {
       tma_prefetch_desc(&tmZ);
       tma_prefetch_desc(&tmX);
-      uint32_t gx = 0, gz = 0;
+      RingPos rx{0, 0}, rz{0, 0};                   // ring positions advance incrementally: no integer division (umma.cuh)
       const uint32_t z_tx = (uint32_t)p.a_real * p.a_chunk_bytes;
       auto load_x = [&](int ti, int bi, int n0) {
-        const uint32_t s = gx % p.Sx, ph = (gx / p.Sx) & 1;
+        const uint32_t s = rx.s, ph = rx.ph;
         mbar_wait(&xempty[s], ph ^ 1);
         mbar_arrive_expect_tx(&xfull[s], p.x_bytes);
         uint8_t* dst = xring + (size_t)s * p.x_bytes;
         for (int c = 0; c < nxc; ++c) tma_load_4d(dst + (size_t)c * p.KR * xcw * 2, &tmX, &xfull[s], c * xcw, n0, ti, bi);
-        ++gx;
+        rx.advance(p.Sx);
       };
       auto load_z = [&](int t_o, int b, int n0) {
-        const uint32_t s = gz % p.Sz, ph = (gz / p.Sz) & 1;
+        const uint32_t s = rz.s, ph = rz.ph;
         mbar_wait(&zempty[s], ph ^ 1);
         mbar_arrive_expect_tx(&zfull[s], z_tx);
         uint8_t* dst = zring + (size_t)s * p.z_bytes;
         for (int c = 0; c < p.a_real; ++c) tma_load_4d(dst + (size_t)c * p.a_chunk_bytes, &tmZ, &zfull[s], o0 + c * p.a_cw, n0, t_o, b);
-        ++gz;
+        rz.advance(p.Sz);
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int ts = item % p.n_tsplit, rest = item / p.n_tsplit;
@@ -122,24 +122,31 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
       const uint64_t pb = make_smem_desc(0, (uint32_t)p.KR * xcw * 2, p.b_sbo, p.b_swz);
       const uint64_t pones = make_smem_desc(0, 2048, 256, SWZ_32B);
       const uint64_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
-      uint32_t gx_base = 0, gz = 0, started = 0;
+      uint32_t started = 0;
+      RingPos rz{0, 0}, xwin{0, 0};                 // xwin: ring position of the first X slice of the current output step
+      const uint32_t zring_s = smem_u32(zring), xring_s = smem_u32(xring);
+      const int nk = p.KR / 16;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int ts = item % p.n_tsplit;
         const int t_begin = ts * p.t_chunk, t_end = t_begin + p.t_chunk < p.T_out ? t_begin + p.t_chunk : p.T_out;
         const int t_len = t_end - t_begin;
-        for (int t_r = 0; t_r < t_len; ++t_r, ++gz) {                 // t_r: output step relative to the item's first
-          const uint32_t sz = gz % p.Sz, phz = (gz / p.Sz) & 1;
-          mbar_wait(&zfull[sz], phz);
+        int n_waited = 0;                           // X slices of this item already waited for (the window slides by one)
+        for (int t_r = 0; t_r < t_len; ++t_r, rz.advance(p.Sz)) {     // t_r: output step relative to the item's first
+          mbar_wait(&zfull[rz.s], rz.ph);
           tc_fence_after();
-          const uint32_t a_base = smem_u32(zring + (size_t)sz * p.z_bytes);
-          for (int j = 0; j < p.Kt; ++j) {
-            const uint32_t gx = gx_base + (p.plane_mode ? t_r * p.Kt + j : t_r + j), sx = gx % p.Sx, phx = (gx / p.Sx) & 1;
-            mbar_wait(&xfull[sx], phx);
-            tc_fence_after();
-            const uint32_t b_base = smem_u32(xring + (size_t)sx * p.x_bytes);
+          const uint32_t a_base = zring_s + rz.s * p.z_bytes;
+          RingPos px = xwin;
+          for (int j = 0; j < p.Kt; ++j, px.advance(p.Sx)) {
+            const int d = p.plane_mode ? t_r * p.Kt + j : t_r + j;
+            if (d >= n_waited) {
+              mbar_wait(&xfull[px.s], px.ph);
+              tc_fence_after();
+              n_waited = d + 1;
+            }
+            const uint32_t b_base = xring_s + px.s * p.x_bytes;
             const uint32_t acc = (started >> j) & 1;
             uint64_t da = desc_at(pa, a_base), db = desc_at(pb, b_base);
-            for (int k = 0; k < p.KR / 16; ++k) {
+            for (int k = 0; k < nk; ++k) {
               mma_bf16_ss(tmem_base + j * p.Cin, da, db, idesc, acc | (k != 0));
               da += a_step; db += b_step;
             }
@@ -148,22 +155,22 @@ umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_constant
           if (p.want_bias) {
             const uint32_t acc = (started >> 31) & 1;
             uint64_t da = desc_at(pa, a_base);
-            for (int k = 0; k < p.KR / 16; ++k) {
+            for (int k = 0; k < nk; ++k) {
               mma_bf16_ss(tmem_base + p.Kt * p.Cin, da, desc_at(pones, ones_a + (k & 3) * 512), idesc_b, acc | (k != 0));
               da += a_step;
             }
             started |= 1u << 31;
           }
-          mma_commit(&zempty[sz]);
+          mma_commit(&zempty[rz.s]);
           if (p.plane_mode) {
-            for (int j = 0; j < p.Kt; ++j) mma_commit(&xempty[(gx_base + t_r * p.Kt + j) % p.Sx]);
+            for (int j = 0; j < p.Kt; ++j, xwin.advance(p.Sx)) mma_commit(&xempty[xwin.s]);
           } else {
-            mma_commit(&xempty[(gx_base + t_r) % p.Sx]);
+            mma_commit(&xempty[xwin.s]);
+            xwin.advance(p.Sx);
             if (t_r == t_len - 1)
-              for (int ti = t_len; ti < t_len + p.Kt - 1; ++ti) mma_commit(&xempty[(gx_base + ti) % p.Sx]);
+              for (int j = 0; j < p.Kt - 1; ++j, xwin.advance(p.Sx)) mma_commit(&xempty[xwin.s]);
           }
         }
-        gx_base += p.plane_mode ? t_len * p.Kt : t_len + p.Kt - 1;
       }
       mma_commit(&done);
     }
@@ -251,9 +258,9 @@ umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
     if (lane == 0) {
       tma_prefetch_desc(&tmZ);
       tma_prefetch_desc(&tmX);
-      uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
-        const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+      RingPos rp{0, 0};
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, rp.advance(p.S)) {
+        const uint32_t s = rp.s, ph = rp.ph;
         const int r0 = tile * kFlatRows;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], p.stage_bytes);
@@ -274,8 +281,9 @@ umma_wgrad_flat_kernel(const __grid_constant__ CUtensorMap tmZ, const __grid_con
       const uint64_t pones = make_smem_desc(0, 2048, 256, SWZ_32B);
       const uint64_t a_step = p.a_kadv >> 4, b_step = p.b_kadv >> 4;
       uint32_t g = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g) {
-        const uint32_t s = g % p.S, ph = (g / p.S) & 1;
+      RingPos rp{0, 0};
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++g, rp.advance(p.S)) {
+        const uint32_t s = rp.s, ph = rp.ph;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t a_base = smem_u32(ring + (size_t)s * p.stage_bytes);
