@@ -30,29 +30,44 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~kMbarHintNs elapsed.
+// Without the hint a waiting warp came back every ~150 cycles and re-issued a 6-instruction spin iteration: 11 of them
+// per tile in the tap kernel's epilogue warps, 15 % of that kernel's issue slots (ncu source page, profiles/r02_ab_batch_l.md).
+constexpr uint32_t kMbarHintNs = 20000;
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_saddr, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(bar_saddr), "r"(parity), "r"(kMbarHintNs)
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU.
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return mbar_try_wait_a(smem_u32(bar), parity); }
+// Bounded wait: a protocol bug traps (-> launch error) instead of hanging the GPU (2^17 x 20 us = 2.6 s).
 #ifndef STGCN_MBAR_SPIN_LIMIT
-#define STGCN_MBAR_SPIN_LIMIT (1u << 26)
+#define STGCN_MBAR_SPIN_LIMIT (1u << 17)
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __noinline__ void mbar_timeout_trap() {
+  printf("stgcn: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+  __trap();
+}
+// by shared-window address (kernels keep the barrier arrays' base addresses in registers: the generic-pointer form
+// re-derives the address with a 4-instruction S2UR / ULEA sequence at every use)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_saddr, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > STGCN_MBAR_SPIN_LIMIT) {
-      printf("stgcn: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
-    }
+  while (!mbar_try_wait_a(bar_saddr, parity)) {
+    if (++spins > STGCN_MBAR_SPIN_LIMIT) mbar_timeout_trap();
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_a(smem_u32(bar), parity); }
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_a(uint32_t bar_saddr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_saddr), "r"(bytes) : "memory");
 }
 
 // Position in an S-deep mbarrier ring (stage index + phase bit), advanced incrementally.  The single-thread roles
@@ -228,6 +243,10 @@ __device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+__device__ __forceinline__ void mma_commit_a(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
 }
 
 // ------------------------------------------------------------------------------------------------

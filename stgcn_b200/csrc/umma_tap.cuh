@@ -146,8 +146,11 @@ __device__ __forceinline__ unsigned long long gtime() {
 // ~15 instructions per tile per warp in the issue-bound epilogue.
 #ifdef STGCN_TIMELINE
 #define STGCN_STAMP(i) do { if (dbg_on) p.dbg[i] = gtime(); } while (0)
+// SM-cycle stamps (clock64: ~20 cycles, where a %globaltimer read costs the lone issuer thread several hundred)
+#define STGCN_CSTAMP(cond, i) do { if (dbg_on && (cond)) p.dbg[i] = (unsigned long long)clock64(); } while (0)
 #else
 #define STGCN_STAMP(i) do { (void)dbg_on; } while (0)
+#define STGCN_CSTAMP(cond, i) do { (void)dbg_on; } while (0)
 #endif
 
 __device__ __forceinline__ uint4 pack8_bf16(const float* v) {
@@ -205,6 +208,22 @@ __device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
 #else
 #define STGCN_TAP_MMA(...) mma_bf16_ss(__VA_ARGS__)
 #endif
+// All K = 16 steps of one tap for a compile-time block shape: straight-line UTCHMMA with immediate descriptor offsets.
+// (The runtime kb / k loops cost the lone issuer thread ~10 dependent instructions and a branch per instruction; the
+// issuer needed ~3500 cycles per 17-instruction tile, profiles/r02_ab_batch_j.md.)  a16 / w16: bytes >> 4 between
+// 64-channel blocks of the slice / of the weight tap.
+template <int NKB, int NK16>
+__device__ __forceinline__ void tap_issue(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t a16, uint32_t w16, uint32_t idesc,
+                                          uint32_t& accumulate) {
+#pragma unroll
+  for (int kb = 0; kb < NKB; ++kb) {
+#pragma unroll
+    for (int k = 0; k < NK16; ++k) {
+      STGCN_TAP_MMA(d_tmem, da + (uint64_t)(kb * a16 + 2 * k), db + (uint64_t)(kb * w16 + 2 * k), idesc, accumulate);
+      accumulate = 1;
+    }
+  }
+}
 template <int EPI, int ACT, bool AUX>
 __global__ void __launch_bounds__(kTapThreadsWide, 1)
 umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
@@ -263,7 +282,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     for (int s = 0; s < p.S; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&wfull, 1);
     for (int i = 0; i < p.NB; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], epi_arrivals); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], kTapEpiWarps); mbar_init(&sempty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sfull[i], epi_arrivals); mbar_init(&sempty[i], 1); }     // one arrival per epilogue warp of the tile
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, ncols);
@@ -272,6 +291,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_s;
   if (threadIdx.x == 0) STGCN_STAMP(1);
+  // barrier arrays by shared-window address (umma.cuh: the generic-pointer forms re-derive it at every use)
+  const uint32_t full_a = smem_u32(full), empty_a = smem_u32(empty), tfull_a = smem_u32(tfull), tempty_a = smem_u32(tempty),
+                 sfull_a = smem_u32(sfull), sempty_a = smem_u32(sempty);
 
   const bool is_producer = warp == 0 || (warp >= 2 + kTapEpiWarps && warp < kTapStoreWarp);
   const int prod_idx = warp == 0 ? 0 : warp - (2 + kTapEpiWarps) + 1;
@@ -283,7 +305,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const TapItem wi = tap_item(p, item);
         for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++cnt) {
           const uint32_t buf = p.nbuf == 2 ? (cnt & 1) : 0, ph = p.nbuf == 2 ? ((cnt >> 1) & 1) : (cnt & 1);
-          mbar_wait(&sfull[buf], ph);
+          STGCN_CSTAMP(cnt >= 8 && cnt < 10, 70 + (cnt - 8) * 4);
+          mbar_wait_a(sfull_a + buf * 8, ph);
+          STGCN_CSTAMP(cnt >= 8 && cnt < 10, 71 + (cnt - 8) * 4);
           const uint8_t* stg = smem + p.stage_off + (size_t)buf * p.stage_bytes;
 #ifndef STGCN_KO_STORE      // knock-out builds (tools/ko_probe.py): which resource bounds the tile period
           for (int z = 0; z < p.nZ; ++z) tma_store_4d(&tmZ, stg + (size_t)z * 16384, z * 64, wi.n0, t_o, wi.b);
@@ -293,8 +317,10 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           // Release the buffer as soon as THIS tile's stores have read it.  (Releasing tile i-1's buffer only after tile i's
           // stores were issued made every epilogue warp wait for all 16 warps to finish tile i before it could start tile
           // i+1 in the other buffer: the double buffer behaved like a CTA-wide barrier per tile.)
+          STGCN_CSTAMP(cnt >= 8 && cnt < 10, 72 + (cnt - 8) * 4);
           tma_store_wait_read<0>();
-          mbar_arrive(&sempty[buf]);
+          mbar_arrive_a(sempty_a + buf * 8);
+          STGCN_CSTAMP(cnt >= 8 && cnt < 10, 73 + (cnt - 8) * 4);
         }
       }
       tma_store_wait_all<0>();
@@ -319,19 +345,17 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const int b = wi.b, n0 = wi.n0;
           for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
             const uint32_t s = rp.s;
-            if (g == 24) STGCN_STAMP(25);
-            mbar_wait(&empty[s], rp.ph ^ 1);
-            if (g == 24) STGCN_STAMP(26);
+            STGCN_CSTAMP(g >= 24 && g < 27, 40 + (g - 24) * 3);
+            mbar_wait_a(empty_a + s * 8, rp.ph ^ 1);
+            STGCN_CSTAMP(g >= 24 && g < 27, 41 + (g - 24) * 3);
 #ifdef STGCN_KO_LOAD
             mbar_arrive(&full[s]); (void)ablk; (void)b; (void)n0;
 #else
-            mbar_arrive_expect_tx(&full[s], p.tile_bytes);
+            mbar_arrive_expect_tx_a(full_a + s * 8, p.tile_bytes);
             uint8_t* dst = ring + (size_t)s * p.tile_bytes;
             for (int kb = 0; kb < p.nKB; ++kb) tma_load_4d(dst + (size_t)kb * ablk, &tmX, &full[s], kb * p.KB, n0, ti, b);
 #endif
-            if (g == 24) STGCN_STAMP(27);
-            if (g == 25) STGCN_STAMP(28);
-            if (g == 32) STGCN_STAMP(29);
+            STGCN_CSTAMP(g >= 24 && g < 27, 42 + (g - 24) * 3);
           }
         }
       }
@@ -349,9 +373,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
           if ((int)(g % kTapProducers) != prod_idx) continue;
           const uint32_t s = rp.s, ph = rp.ph;
-          if (g == 24) STGCN_STAMP(25);
-          mbar_wait(&empty[s], ph ^ 1);
-          if (g == 24) STGCN_STAMP(26);
+          STGCN_CSTAMP(warp == 0 && g >= 24 && g <= 32, 90 + (g - 24));
+          mbar_wait_a(empty_a + s * 8, ph ^ 1);
+          STGCN_CSTAMP(warp == 0 && g >= 24 && g <= 32, 91 + (g - 24));
           uint8_t* dst = ring + (size_t)s * p.tile_bytes;
           const bf16* src0 = p.in_ptr + (long long)b * p.sb + (long long)ti * p.st;
 #pragma unroll
@@ -366,7 +390,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 #endif
           }
           cp_async_commit();
-          if (g == 24) STGCN_STAMP(27);
+          STGCN_CSTAMP(warp == 0 && g >= 24 && g <= 32, 92 + (g - 24));
           if (pending >= 0) {                            // the previous slice of this warp has landed after this wait
             cp_async_wait<1>();
             fence_proxy_async();
@@ -374,8 +398,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             if (lane == 0) mbar_arrive(&full[pending]);
           }
           pending = (int)s;
-          if (g == 24) STGCN_STAMP(28);
-          if (g == 32) STGCN_STAMP(29);
+          STGCN_CSTAMP(warp == 0 && g >= 24 && g <= 32, 93 + (g - 24));
         }
       }
       if (pending >= 0) {
@@ -401,89 +424,185 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t acc_cnt = 0, ab = 0, aph = 0;
       RingPos base{0, 0};
       const uint32_t id_base = smem_u32(x_s + id_off);
+      const uint32_t a16 = ablk >> 4, w16 = wblk >> 4;
+      const int shape = p.nKB * 8 + nk16, Kt = p.Kt, t0 = p.t0, S = p.S, NB = p.NB, res_j = p.res_dt - p.t0;
+      const bool res_mma = p.res_mma != 0, bias_mma = p.bias_mma != 0;
+      const uint32_t tile_bytes = p.tile_bytes, CoT = p.CoT, tap_bytes = (uint32_t)p.nKB * wblk;
+      auto issue = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t& accumulate) {
+        const uint64_t da = desc_at(dproto, a_base), db = desc_at(dproto, b_base);
+        switch (shape) {
+          case 1 * 8 + 1: tap_issue<1, 1>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
+          case 1 * 8 + 2: tap_issue<1, 2>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
+          case 1 * 8 + 4: tap_issue<1, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
+          case 2 * 8 + 4: tap_issue<2, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
+          case 4 * 8 + 4: tap_issue<4, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
+          default:
+            for (int kb = 0; kb < p.nKB; ++kb)
+              for (int k = 0; k < nk16; ++k) {
+                STGCN_TAP_MMA(d_tmem, da + (uint64_t)(kb * a16 + 2 * k), db + (uint64_t)(kb * w16 + 2 * k), idesc, accumulate);
+                accumulate = 1;
+              }
+        }
+      };
       const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
       const uint64_t d_ones = desc_at(p32, smem_u32(x_s)), d_bias = desc_at(p32, smem_u32(x_s + bias_tile_off));
       const uint32_t ring_s = smem_u32(ring), w_base = smem_u32(w_s);
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const TapItem wi = tap_item(p, item);
         RingPos win = base;
-        int skip = wi.s_lo - (wi.t_begin + p.t0);          // > 0 only when t_begin + t0 < 0
+        int skip = wi.s_lo - (wi.t_begin + t0);          // > 0 only when t_begin + t0 < 0
         int n_waited = 0;
         for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
-          if (acc_cnt == 8) STGCN_STAMP(16);
-          mbar_wait(&tempty[ab], aph ^ 1);
-          if (acc_cnt == 8) STGCN_STAMP(17);
+          STGCN_CSTAMP(acc_cnt >= 8 && acc_cnt < 12, 32 + (acc_cnt - 8));
+          mbar_wait_a(tempty_a + ab * 8, aph ^ 1);
+          STGCN_CSTAMP(acc_cnt == 8, 36);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ab * p.CoT;
+          const uint32_t d_tmem = tmem_base + ab * CoT;
           uint32_t accumulate = 0;
           RingPos pos = win;
-          const int d_win = skip > 0 ? 0 : t_o + p.t0 - wi.s_lo;     // offset of `win` from s_lo
+          const int d_win = skip > 0 ? 0 : t_o + t0 - wi.s_lo;     // offset of `win` from s_lo
           uint32_t res_a = 0;                                        // ring address of the residual slice (res_mma)
-          for (int j = skip > 0 ? skip : 0; j < p.Kt; ++j, pos.advance(p.S)) {
-            const int ti = t_o + j + p.t0;
+          for (int j = skip > 0 ? skip : 0; j < Kt; ++j, pos.advance(S)) {
+            const int ti = t_o + j + t0;
             if (ti >= wi.s_hi) break;
             const int d = d_win + j - (skip > 0 ? skip : 0);
             if (d >= n_waited) {
-              mbar_wait(&full[pos.s], pos.ph);
+              mbar_wait_a(full_a + pos.s * 8, pos.ph);
               tc_fence_after();
               n_waited = d + 1;
             }
             if (acc_cnt == 0) STGCN_STAMP(3);
-            if (acc_cnt == 8) STGCN_STAMP(8);
-            if (acc_cnt == 8) STGCN_STAMP(18 + j);
-            const uint32_t a_base = ring_s + pos.s * p.tile_bytes;
-            const uint32_t b_base = w_base + (uint32_t)j * p.nKB * wblk;
-            if (j == p.res_dt - p.t0) res_a = a_base;
-            for (int kb = 0; kb < p.nKB; ++kb) {
-              uint64_t da = desc_at(dproto, a_base + kb * ablk), db = desc_at(dproto, b_base + kb * wblk);
-              for (int k = 0; k < nk16; ++k) {
-                STGCN_TAP_MMA(d_tmem, da, db, idesc, accumulate);
-                accumulate = 1;
-                da += 2; db += 2;         // 32 bytes = one K = 16 step
-              }
-            }
+            STGCN_CSTAMP(acc_cnt == 8 && j < 4, 80 + 2 * j);
+            const uint32_t a_base = ring_s + pos.s * tile_bytes;
+            const uint32_t b_base = w_base + (uint32_t)j * tap_bytes;
+            if (j == res_j) res_a = a_base;
+            issue(d_tmem, a_base, b_base, accumulate);
+            STGCN_CSTAMP(acc_cnt == 8 && j < 4, 81 + 2 * j);
           }
-          if (p.res_mma && res_a != 0) {                   // the slice was waited for by its tap above
-            for (int kb = 0; kb < p.nKB; ++kb) {
-              uint64_t da = desc_at(dproto, res_a + kb * ablk), db = desc_at(dproto, id_base + kb * wblk);
-              for (int k = 0; k < nk16; ++k) {
-                STGCN_TAP_MMA(d_tmem, da, db, idesc, accumulate);
-                accumulate = 1;
-                da += 2; db += 2;
-              }
-            }
-          }
-          if (p.bias_mma) {
+          if (res_mma && res_a != 0) issue(d_tmem, res_a, id_base, accumulate);   // the slice was waited for by its tap above
+          STGCN_CSTAMP(acc_cnt == 8, 88);
+          if (bias_mma) {
             STGCN_TAP_MMA(d_tmem, d_ones, d_bias, idesc, accumulate);
             accumulate = 1;
           }
-          if (acc_cnt == 8) STGCN_STAMP(22);
-          mma_commit(&tfull[ab]);
-          if (acc_cnt == 8) STGCN_STAMP(23);
+          STGCN_CSTAMP(acc_cnt == 8, 37);
+          mma_commit_a(tfull_a + ab * 8);
+          STGCN_CSTAMP(acc_cnt == 8, 38);
           // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
           if (t_o == wi.t_end - 1) {
             RingPos r = win;
-            for (int ti = wi.s_lo + d_win; ti < wi.s_hi; ++ti, r.advance(p.S)) mma_commit(&empty[r.s]);
-          } else if (skip <= 0 && t_o + p.t0 < wi.s_hi) {
-            mma_commit(&empty[win.s]);
+            for (int ti = wi.s_lo + d_win; ti < wi.s_hi; ++ti, r.advance(S)) mma_commit_a(empty_a + r.s * 8);
+          } else if (skip <= 0 && t_o + t0 < wi.s_hi) {
+            mma_commit_a(empty_a + win.s * 8);
           }
-          if (skip > 0) --skip; else win.advance(p.S);
-          if (++ab == (uint32_t)p.NB) { ab = 0; aph ^= 1; }
-          if (acc_cnt == 8) STGCN_STAMP(24);
+          if (skip > 0) --skip; else win.advance(S);
+          if (++ab == (uint32_t)NB) { ab = 0; aph ^= 1; }
+          STGCN_CSTAMP(acc_cnt == 8, 39);
         }
-        base.advance_by((uint32_t)(wi.s_hi - wi.s_lo), p.S);
+        base.advance_by((uint32_t)(wi.s_hi - wi.s_lo), (uint32_t)S);
       }
     }
   } else {
     // =========================== epilogue warps ==========================
+    // Per 128-row tile and warp the FIXED costs (barrier waits, proxy fence, arrivals, address set-up) were ~2900 cycles
+    // against ~1700 for the column arithmetic (SM-cycle timeline, profiles/r02_ab_batch_j.md), so: 16-column chunks (one
+    // TMEM round trip per chunk, both halves' loads in flight together), ONE fence + warp sync + the two arrivals at the
+    // end, and nothing per tile that a per-item or per-kernel value can replace.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
     const int grp = (warp - 2) >> 2;            // warp group (4 warps = 128 TMEM lanes)
     const int cpart = grp % p.col_parts, tpart = grp / p.col_parts;
     const int row = q * 32 + lane;
+    const uint32_t tile_mask = (uint32_t)(p.tile_parts - 1);              // tile_parts is 1, 2 or 4
+    constexpr bool gated = EPI == EPI_GATE && (ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU);
+    const int cfirst = cpart * 16, cstep = p.col_parts * 16;
+    const int cbase = EPI == EPI_LINEAR ? co0 : 0;                        // column offset of aux / output tensors
+    const int width = EPI == EPI_LINEAR ? p.CoT : p.Cout;
+    const bool bias_epi = p.bias != nullptr && !p.bias_mma;
+    const bool have_aux = AUX && p.aux != nullptr;
+    const int n_aux_all = have_aux ? p.aux_cols - cbase : 0;              // aux covers local columns [0, n_aux)
+    const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t stage0 = smem_u32(smem + p.stage_off);
+    // ---- fast path (the shapes the model's large layers use): staged output, no aux operand, bias on the tensor pipe;
+    // EPI_LINEAR, or the GLU gate with the q-only saved state.  ~130 instructions per warp and tile instead of ~590: the
+    // epilogue warps' instruction stream was what bounded the kernel (57 % issue-active, 80 % of it epilogue code).
+    constexpr bool kFastKind = !AUX && (EPI == EPI_LINEAR || (EPI == EPI_GATE && ACT == STGCN_ACT_GLU));
+    const bool fast = kFastKind && p.store_tma && !bias_epi && (EPI == EPI_LINEAR || p.q_only);
+    if (kFastKind && fast) {
+      const uint32_t rs = (uint32_t)row & 7u, rowoff = (uint32_t)row * 128u;
+      const uint32_t h_off = (uint32_t)p.nZ * 16384u;                    // gate: H sub-tiles follow the Q sub-tiles
+      const int relu = p.relu, NBm = p.NB - 1, nb_shift = p.nb_shift, nbuf2 = p.nbuf == 2;
+      const uint32_t CoT = p.CoT, Cout = p.Cout, stage_bytes = p.stage_bytes;
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        int nt = p.T_out;
+        if (p.n_tsplit != 1) { const TapItem wi = tap_item(p, item); nt = wi.t_end - wi.t_begin; }
+        for (int i = 0; i < nt; ++i, ++cnt) {
+          if ((cnt & tile_mask) != (uint32_t)tpart) continue;
+          const uint32_t ab = cnt & NBm, aph = (cnt >> nb_shift) & 1;
+          const uint32_t sbuf = nbuf2 ? (cnt & 1) : 0, sph = nbuf2 ? ((cnt >> 1) & 1) : (cnt & 1);
+          STGCN_CSTAMP(warp == 2 && cnt >= 8 && cnt < 11, 49 + (cnt - 8) * 6);
+          STGCN_CSTAMP(warp == 1 + kTapEpiWarps && cnt >= 8 && cnt < 10, 67 + (cnt - 8));
+          mbar_wait_a(sempty_a + sbuf * 8, sph ^ 1);
+          STGCN_CSTAMP(warp == 2 && cnt >= 8 && cnt < 11, 50 + (cnt - 8) * 6);
+          mbar_wait_a(tfull_a + ab * 8, aph);
+          STGCN_CSTAMP(warp == 2 && cnt >= 8 && cnt < 11, 51 + (cnt - 8) * 6);
+          tc_fence_after();
+          const uint32_t t_addr = t_lane + ab * CoT;
+          const uint32_t srow = stage0 + sbuf * stage_bytes + rowoff;
+#ifdef STGCN_KO_EPI
+          const int width_t = 0;
+#else
+          const int width_t = width;
+#endif
+#pragma unroll 1
+          for (int cc = cfirst; cc < width_t; cc += cstep) {
+            uint32_t rp[16], rq[16];
+            tmem_ld_32x32b_x16(t_addr + cc, rp);
+            if (EPI == EPI_GATE) tmem_ld_32x32b_x16(t_addr + Cout + cc, rq);
+            const uint32_t sub = srow + ((uint32_t)cc >> 6) * 16384u, ch = ((uint32_t)cc >> 3) & 7u;
+            const uint32_t o0 = sub + ((ch ^ rs) << 4), o1 = sub + (((ch + 1) ^ rs) << 4);
+            tmem_ld_wait();
+            if (EPI == EPI_LINEAR) {
+              uint32_t w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float a = __uint_as_float(rp[2 * k]), c = __uint_as_float(rp[2 * k + 1]);
+                if (relu) { a = fmaxf(a, 0.f); c = fmaxf(c, 0.f); }
+                w[k] = pack_bf16x2(a, c);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o0), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o1), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+            } else {
+              uint32_t wq[8], wh[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float q0 = __uint_as_float(rq[2 * k]), q1 = __uint_as_float(rq[2 * k + 1]);
+                const float h0 = __uint_as_float(rp[2 * k]) * sigmoid_tanh_(q0), h1 = __uint_as_float(rp[2 * k + 1]) * sigmoid_tanh_(q1);
+                wq[k] = pack_bf16x2(q0, q1);
+                wh[k] = pack_bf16x2(h0, h1);
+              }
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o0), "r"(wq[0]), "r"(wq[1]), "r"(wq[2]), "r"(wq[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o1), "r"(wq[4]), "r"(wq[5]), "r"(wq[6]), "r"(wq[7]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o0 + h_off), "r"(wh[0]), "r"(wh[1]), "r"(wh[2]), "r"(wh[3]) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(o1 + h_off), "r"(wh[4]), "r"(wh[5]), "r"(wh[6]), "r"(wh[7]) : "memory");
+            }
+          }
+          STGCN_CSTAMP(warp == 2 && cnt >= 8 && cnt < 11, 52 + (cnt - 8) * 6);
+          tc_fence_before();
+          fence_proxy_async();                           // staged tile -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive_a(tempty_a + ab * 8);
+            mbar_arrive_a(sfull_a + sbuf * 8);           // the store warp issues the TMA stores once all warps of the tile arrived
+          }
+          STGCN_CSTAMP(warp == 2 && cnt >= 8 && cnt < 11, 53 + (cnt - 8) * 6);
+        }
+      }
+    } else {
     uint32_t acc_cnt = 0;
     // first aux chunk of the NEXT tile, requested while the current tile is still being finished: loaded at the top of
     // its own tile the L2 round trip (~0.3 us of a ~2 us tile) sat exposed in front of every tile's column loop
-    uint4 rpre = make_uint4(0, 0, 0, 0);
+    uint4 rpre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     bool have_pre = false;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const TapItem wi = tap_item(p, item);
@@ -491,107 +610,104 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int n = n0 + row;
       const bool valid = n < p.N;
       for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
-        if ((int)(acc_cnt & (uint32_t)(p.tile_parts - 1)) != tpart) continue;       // tile_parts is 1, 2 or 4   // warp groups alternate tiles
+        if ((acc_cnt & tile_mask) != (uint32_t)tpart) continue;             // warp groups alternate tiles
         const uint32_t ab = acc_cnt & (p.NB - 1), aph = (acc_cnt >> p.nb_shift) & 1;
-        const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
         const int t_aux = t_o + p.aux_dt;
-        const bool aux_ok = AUX && p.aux != nullptr && t_aux >= 0 && t_aux < p.T_aux && valid;
-        const bool bias_epi = p.bias != nullptr && !p.bias_mma;
-        const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux : nullptr;
-        const int cfirst = cpart * 16;
-        const int cstep = p.col_parts * 16;
-        // Columns are processed in 8-wide groups by a ROLLED loop: the fully unrolled 16-wide version was ~60 KB of
-        // SASS and thrashed the instruction caches (144 cycles per element, profiles/r01_bf16_summary.md).  The
-        // residual / aux operand of the next group is fetched one iteration ahead.
-        const int cbase = EPI == EPI_LINEAR ? co0 : 0;              // column offset of aux / output tensors
-        const int width = EPI == EPI_LINEAR ? p.CoT : p.Cout;
-        const int n_aux = aux_row ? p.aux_cols - cbase : 0;         // aux covers local columns [0, n_aux)
-        uint4 rnext = make_uint4(0, 0, 0, 0);
-        if (cfirst < n_aux) rnext = have_pre ? rpre : *reinterpret_cast<const uint4*>(aux_row + cbase + cfirst);
-        have_pre = false;
-        uint8_t* stg = nullptr;
-        uint32_t stg_s = 0;
-        const uint32_t sbuf = p.nbuf == 2 ? (acc_cnt & 1) : 0, sph = p.nbuf == 2 ? ((acc_cnt >> 1) & 1) : (acc_cnt & 1);
-        if (p.store_tma) {
-          // the staging buffer used nbuf tiles ago must have been read out by its TMA store (store warp -> sempty)
-          mbar_wait(&sempty[sbuf], sph ^ 1);
-          stg = smem + p.stage_off + (size_t)sbuf * p.stage_bytes;      // nbuf is 1 or 2
-          stg_s = smem_u32(stg);
+        const bool aux_ok = have_aux && t_aux >= 0 && t_aux < p.T_aux && valid;
+        const bf16* aux_row = aux_ok ? p.aux + (((long long)b * p.T_aux + t_aux) * p.N + n) * p.C_aux + cbase : nullptr;
+        const int n_aux = aux_ok ? n_aux_all : 0;
+        uint4 rnext[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (AUX && cfirst < n_aux) {
+          if (have_pre) { rnext[0] = rpre[0]; rnext[1] = rpre[1]; }
+          else { rnext[0] = reinterpret_cast<const uint4*>(aux_row + cfirst)[0]; rnext[1] = reinterpret_cast<const uint4*>(aux_row + cfirst)[1]; }
         }
-        mbar_wait(&tfull[ab], aph);
+        have_pre = false;
+        const uint32_t sbuf = p.nbuf == 2 ? (acc_cnt & 1) : 0, sph = p.nbuf == 2 ? ((acc_cnt >> 1) & 1) : (acc_cnt & 1);
+        const bool stg = p.store_tma != 0;
+        const uint32_t stg_s = stage0 + sbuf * p.stage_bytes;
+        STGCN_CSTAMP(warp == 2 && acc_cnt >= 8 && acc_cnt < 11, 49 + (acc_cnt - 8) * 6);
+        STGCN_CSTAMP(warp == 1 + kTapEpiWarps && acc_cnt >= 8 && acc_cnt < 10, 67 + (acc_cnt - 8));
+        // the staging buffer used nbuf tiles ago must have been read out by its TMA store (store warp -> sempty)
+        if (stg) mbar_wait_a(sempty_a + sbuf * 8, sph ^ 1);
+        STGCN_CSTAMP(warp == 2 && acc_cnt >= 8 && acc_cnt < 11, 50 + (acc_cnt - 8) * 6);
+        mbar_wait_a(tfull_a + ab * 8, aph);
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(4);
         if (warp == 2 && acc_cnt == 8) STGCN_STAMP(9);
         if (warp == 2 && acc_cnt == 16) STGCN_STAMP(10);
+        STGCN_CSTAMP(warp == 2 && acc_cnt >= 8 && acc_cnt < 11, 51 + (acc_cnt - 8) * 6);
         tc_fence_after();
-        const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + ab * p.CoT;
-        constexpr bool gated = EPI == EPI_GATE && (ACT == STGCN_ACT_GLU || ACT == STGCN_ACT_GTU);
+        const uint32_t t_addr = t_lane + ab * p.CoT;
 #ifdef STGCN_KO_EPI
-        const int n_grp = 0;
+        const int width_t = 0;
 #else
-        const int n_grp = ((width - cfirst + cstep - 1) / cstep) * 2;      // 8-column groups this warp handles
+        const int width_t = width;
 #endif
 #pragma unroll 1
-        for (int gi = 0; gi < n_grp; ++gi) {
-          const int cc = cfirst + (gi >> 1) * cstep + (gi & 1) * 8;       // local column of this group
-          if (cc >= width) break;
-          uint32_t rp[8], rq[8];
-          tmem_ld_32x32b_x8(t_addr + cc, rp);
-          if (gated) tmem_ld_32x32b_x8(t_addr + p.Cout + cc, rq);
-          const uint4 rcur = rnext;
+        for (int cc = cfirst; cc < width_t; cc += cstep) {                 // one 16-column chunk per iteration
+          uint32_t rp[16], rq[16];
+          tmem_ld_32x32b_x16(t_addr + cc, rp);
+          if (gated) tmem_ld_32x32b_x16(t_addr + p.Cout + cc, rq);
+          const uint4 rcur[2] = {rnext[0], rnext[1]};
           const bool has_aux = AUX && cc < n_aux;
-          if (AUX) {   // prefetch the next group's aux
-            const int gn = gi + 1;
-            const int cn = cfirst + (gn >> 1) * cstep + (gn & 1) * 8;
-            if (gn < n_grp && cn < n_aux) rnext = *reinterpret_cast<const uint4*>(aux_row + cbase + cn);
+          if (AUX && cc + cstep < width_t && cc + cstep < n_aux) {           // prefetch the next chunk's aux
+            rnext[0] = reinterpret_cast<const uint4*>(aux_row + cc + cstep)[0];
+            rnext[1] = reinterpret_cast<const uint4*>(aux_row + cc + cstep)[1];
           }
           tmem_ld_wait();
-          float zp[8], zq[8], av[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) { zp[i] = __uint_as_float(rp[i]); zq[i] = gated ? __uint_as_float(rq[i]) : 0.f; }
-          if (bias_epi) {
-            add_bias8(zp, bias_s + cc);
-            if (gated) add_bias8(zq, bias_s + p.Cout + cc);
-          }
-          if (AUX && has_aux) unpack8_bf16(rcur, av);
-          if (EPI == EPI_LINEAR) {
-            if (AUX && has_aux) {
+          for (int hf = 0; hf < 2; ++hf) {
+            const int c8 = cc + hf * 8;
+            float zp[8], zq[8], av[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) zp[i] += av[i];
+            for (int i = 0; i < 8; ++i) { zp[i] = __uint_as_float(rp[hf * 8 + i]); zq[i] = gated ? __uint_as_float(rq[hf * 8 + i]) : 0.f; }
+            if (bias_epi) {
+              add_bias8(zp, bias_s + c8);
+              if (gated) add_bias8(zq, bias_s + p.Cout + c8);
             }
-            if (p.relu) {
+            if (AUX && has_aux) unpack8_bf16(rcur[hf], av);
+            const uint32_t sub = stg_s + (uint32_t)(c8 >> 6) * 16384u;
+            if (EPI == EPI_LINEAR) {
+              if (AUX && has_aux) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) zp[i] = fmaxf(zp[i], 0.f);
-            }
-            const uint4 o = pack8_bf16(zp);
-            if (stg) stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, o);
-            else if (valid && co0 + cc < p.co_valid) *reinterpret_cast<uint4*>(p.out + orow * p.ld_out + co0 + cc) = o;
-          } else {
-            float h[8];
+                for (int i = 0; i < 8; ++i) zp[i] += av[i];
+              }
+              if (p.relu) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>((AUX && has_aux) ? zp[i] + av[i] : zp[i], zq[i]);
-            const uint4 oh = pack8_bf16(h);
-            if (stg) {
-              if (gated && p.q_only) {
-                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
-              } else {
-                stage_store8_s(stg_s + (uint32_t)(cc >> 6) * 16384u, row, cc & 63, pack8_bf16(zp));
-                if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + cc) >> 6) * 16384u, row, cc & 63, pack8_bf16(zq));
+                for (int i = 0; i < 8; ++i) zp[i] = fmaxf(zp[i], 0.f);
               }
-              stage_store8_s(stg_s + (uint32_t)(p.nZ + (cc >> 6)) * 16384u, row, cc & 63, oh);
-            } else if (valid) {
-              if (gated && p.q_only) {
-                *reinterpret_cast<uint4*>(p.out_z + orow * p.Cout + cc) = pack8_bf16(zq);
-              } else {
-                *reinterpret_cast<uint4*>(p.out_z + orow * p.W + cc) = pack8_bf16(zp);
-                if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + cc) = pack8_bf16(zq);
+              const uint4 o = pack8_bf16(zp);
+              if (stg) stage_store8_s(sub, row, c8 & 63, o);
+              else if (valid && co0 + c8 < p.co_valid)
+                *reinterpret_cast<uint4*>(p.out + (((long long)b * p.T_out + t_o) * p.N + n) * p.ld_out + co0 + c8) = o;
+            } else {
+              float h[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) h[i] = epi_act<ACT>((AUX && has_aux) ? zp[i] + av[i] : zp[i], zq[i]);
+              const uint4 oh = pack8_bf16(h);
+              if (stg) {
+                if (gated && p.q_only) {
+                  stage_store8_s(sub, row, c8 & 63, pack8_bf16(zq));
+                } else {
+                  stage_store8_s(sub, row, c8 & 63, pack8_bf16(zp));
+                  if (gated) stage_store8_s(stg_s + (uint32_t)((p.Cout + c8) >> 6) * 16384u, row, c8 & 63, pack8_bf16(zq));
+                }
+                stage_store8_s(stg_s + (uint32_t)(p.nZ + (c8 >> 6)) * 16384u, row, c8 & 63, oh);
+              } else if (valid) {
+                const long long orow = ((long long)b * p.T_out + t_o) * p.N + n;
+                if (gated && p.q_only) {
+                  *reinterpret_cast<uint4*>(p.out_z + orow * p.Cout + c8) = pack8_bf16(zq);
+                } else {
+                  *reinterpret_cast<uint4*>(p.out_z + orow * p.W + c8) = pack8_bf16(zp);
+                  if (gated) *reinterpret_cast<uint4*>(p.out_z + orow * p.W + p.Cout + c8) = pack8_bf16(zq);
+                }
+                *reinterpret_cast<uint4*>(p.out + orow * p.Cout + c8) = oh;
               }
-              *reinterpret_cast<uint4*>(p.out + orow * p.Cout + cc) = oh;
             }
           }
         }
-        if (warp == 2 && acc_cnt == 8) STGCN_STAMP(14);
+        STGCN_CSTAMP(warp == 2 && acc_cnt >= 8 && acc_cnt < 11, 52 + (acc_cnt - 8) * 6);
 #ifndef STGCN_TAP_NO_AUX_PREFETCH
-        if (AUX && p.tile_parts == 1 && p.aux != nullptr && cfirst < p.aux_cols - cbase) {
+        if (AUX && p.tile_parts == 1 && have_aux && cfirst < n_aux_all) {
           int nt = t_o + 1, nb = b, nn = n;
           bool more = true;
           if (nt >= wi.t_end) {
@@ -601,23 +717,24 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           const int ta = nt + p.aux_dt;
           if (more && ta >= 0 && ta < p.T_aux && nn < p.N) {
-            rpre = *reinterpret_cast<const uint4*>(p.aux + (((long long)nb * p.T_aux + ta) * p.N + nn) * p.C_aux + cbase + cfirst);
+            const uint4* pa = reinterpret_cast<const uint4*>(p.aux + (((long long)nb * p.T_aux + ta) * p.N + nn) * p.C_aux + cbase + cfirst);
+            rpre[0] = pa[0]; rpre[1] = pa[1];
             have_pre = true;
           }
         }
 #endif
         tc_fence_before();
+        if (stg) fence_proxy_async();                  // staged tile -> visible to the TMA (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[ab]);
-        if (stg) {
-          fence_proxy_async();                       // staged tile -> visible to the TMA (async proxy)
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sfull[sbuf]);  // the store warp issues the TMA stores once all epilogue warps arrived
+        if (lane == 0) {
+          mbar_arrive_a(tempty_a + ab * 8);
+          if (stg) mbar_arrive_a(sfull_a + sbuf * 8);    // the store warp issues the TMA stores once all warps of the tile arrived
         }
+        STGCN_CSTAMP(warp == 2 && acc_cnt >= 8 && acc_cnt < 11, 53 + (acc_cnt - 8) * 6);
         if (warp == 2 && acc_cnt == 0) STGCN_STAMP(5);
-        if (warp == 2 && acc_cnt == 8) STGCN_STAMP(15);
       }
     }
+    }   // generic epilogue
     if (warp == 2) STGCN_STAMP(6);
   }
   tc_fence_before();
@@ -808,7 +925,11 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     int cp = 1;
     for (int d = 1; d <= kTapEpiGroups; ++d)
       if (kTapEpiGroups % d == 0 && d * 16 <= width) cp = d;
-    if (p.store_tma && cp != kTapEpiGroups) p.store_tma = 0;
+    // STGCN_TAP_TP2=1 (A/B knob): staged tiles alternate between two 8-warp groups, each with its own staging buffer and
+    // 32 columns per warp -- the per-tile fixed costs of a warp are then paid every other tile
+    static const bool tp2 = [] { const char* e = std::getenv("STGCN_TAP_TP2"); return e && e[0] == '1'; }();
+    if (p.store_tma && cp == kTapEpiGroups && tp2 && p.nbuf == 2 && kTapEpiGroups == 4) cp = 2;
+    if (p.store_tma && cp != kTapEpiGroups && !(tp2 && cp == 2 && p.nbuf == 2 && kTapEpiGroups == 4)) p.store_tma = 0;
     p.col_parts = cp; p.tile_parts = kTapEpiGroups / cp;
   }
   p.n_node_tiles = (q.N + 127) / 128;
