@@ -24,6 +24,7 @@
 //   EPI_GATE  : z = acc + bias stored (saved for backward); h = act(z, residual) stored
 #pragma once
 #include <cstdlib>
+#include <type_traits>
 
 #include "umma.cuh"
 #include "simt_kernels.cuh"
@@ -67,6 +68,7 @@ struct TapParams {
   // 512 (sample, tile) items over 148 CTAs quantise to 4 rounds for 3.46 rounds of work; halving the items'
   // length costs Kt-1 re-loaded slices per cut and gets 7 rounds of half the length (13% fewer tiles per CTA).
   int n_tsplit, t_chunk;
+  int d_ts, d_nt, d_b;         // decomposition of the item stride gridDim.x (TapIter)
   int relu;                   // linear epilogue: clamp at 0 after bias/aux
   int NB, nb_shift;           // TMEM accumulator ring depth (power of two) and its log2
   // epilogue work split: the kTapEpiGroups warp groups form col_parts x tile_parts; group g handles the 16-column
@@ -203,6 +205,37 @@ __device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
   return it;
 }
 
+// Division-free walk over a CTA's items item0, item0 + G, item0 + 2 G ... (G = gridDim.x).  The first decomposition is
+// computed once at kernel start by all threads and broadcast with a shuffle, the stride's decomposition comes from the
+// host: every later value is derived from warp-uniform integers with compare / subtract only.  (tap_item()'s runtime
+// divisions run on the vector pipe; their results -- and everything derived from them: ring positions, descriptors,
+// TMEM addresses -- then lived in vector registers and reached the uniform-register operands of UTCHMMA / UTCBAR through
+// R2UR moves, ~60 instructions per tap in the issuer thread; profiles/r02_ab_batch_m.md.)
+struct TapIter {
+  int item, ts, nt, b;
+  __device__ __forceinline__ bool valid(const TapParams& p) const { return item < p.n_items; }
+  __device__ __forceinline__ void next(const TapParams& p) {
+    item += (int)gridDim.x;
+    ts += p.d_ts;
+    int c = 0;
+    if (ts >= p.n_tsplit) { ts -= p.n_tsplit; c = 1; }
+    nt += p.d_nt + c;
+    c = 0;
+    if (nt >= p.n_node_tiles) { nt -= p.n_node_tiles; c = 1; }
+    b += p.d_b + c;
+  }
+  __device__ __forceinline__ TapItem get(const TapParams& p) const {
+    TapItem it;
+    it.b = b; it.n0 = nt * 128;
+    it.t_begin = ts * p.t_chunk;
+    it.t_end = it.t_begin + p.t_chunk < p.T_out ? it.t_begin + p.t_chunk : p.T_out;
+    const int lo = it.t_begin + p.t0, hi = it.t_end + p.t0 + p.Kt - 1;     // slices [lo, hi) are touched
+    it.s_lo = lo > 0 ? lo : 0;
+    it.s_hi = hi < p.T_src ? hi : p.T_src;
+    return it;
+  }
+};
+
 #ifdef STGCN_KO_MMA
 #define STGCN_TAP_MMA(...) do { } while (0)
 #else
@@ -245,6 +278,14 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int co0 = blockIdx.y * p.CoT;
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && lane == 0;
+  TapIter it0;            // this CTA's first item, warp-uniform by construction (shuffle)
+  {
+    const int item = (int)blockIdx.x, ts = item % p.n_tsplit, rest = item / p.n_tsplit, b = rest / p.n_node_tiles;
+    it0.item = item;
+    it0.ts = __shfl_sync(0xffffffffu, ts, 0);
+    it0.nt = __shfl_sync(0xffffffffu, rest - b * p.n_node_tiles, 0);
+    it0.b = __shfl_sync(0xffffffffu, b, 0);
+  }
   if (threadIdx.x == 0) STGCN_STAMP(0);
   for (int i = threadIdx.x; i < p.CoT; i += blockDim.x) bias_s[i] = p.bias ? p.bias[co0 + i] : 0.f;
   if (p.bias_mma) {
@@ -301,8 +342,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // =========================== TMA-store warp ==========================
     if (p.store_tma && lane == 0) {
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const TapItem wi = tap_item(p, item);
+      for (TapIter it = it0; it.valid(p); it.next(p)) {
+        const TapItem wi = it.get(p);
         for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++cnt) {
           const uint32_t buf = p.nbuf == 2 ? (cnt & 1) : 0, ph = p.nbuf == 2 ? ((cnt >> 1) & 1) : (cnt & 1);
           STGCN_CSTAMP(cnt >= 8 && cnt < 10, 70 + (cnt - 8) * 4);
@@ -340,8 +381,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         uint32_t g = 0;
         RingPos rp{0, 0};
         const uint32_t ablk = 128u * p.KB * 2;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-          const TapItem wi = tap_item(p, item);
+        for (TapIter it = it0; it.valid(p); it.next(p)) {
+          const TapItem wi = it.get(p);
           const int b = wi.b, n0 = wi.n0;
           for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
             const uint32_t s = rp.s;
@@ -367,8 +408,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       uint32_t g = 0;
       RingPos rp{0, 0};
       int pending = -1;                                  // this warp's issued-but-unpublished slice (stage index)
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const TapItem wi = tap_item(p, item);
+      for (TapIter it = it0; it.valid(p); it.next(p)) {
+        const TapItem wi = it.get(p);
         const int b = wi.b, n0 = wi.n0;
         for (int ti = wi.s_lo; ti < wi.s_hi; ++ti, ++g, rp.advance(p.S)) {
           if ((int)(g % kTapProducers) != prod_idx) continue;
@@ -410,12 +451,17 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
   } else if (warp == 1) {
     // =========================== MMA issuer =============================
+    // shared-memory / tensor-memory bases as shuffled (provably warp-uniform, not rematerialisable) values: the compiler
+    // otherwise re-derives them from SR_CgaCtaId inside the loops and moves them to uniform registers per instruction
+    const uint32_t u_ring = uniform_u32(smem_u32(ring)), u_w = uniform_u32(smem_u32(w_s)), u_x = uniform_u32(smem_u32(x_s));
+    const uint32_t u_full = uniform_u32(full_a), u_empty = uniform_u32(empty_a), u_tfull = uniform_u32(tfull_a),
+                   u_tempty = uniform_u32(tempty_a), u_tmem = uniform_u32(tmem_base), u_wfull = uniform_u32(smem_u32(&wfull));
     if (elect_one()) {      // one elected lane, known to the compiler as such (issue cost: see umma.cuh)
       const uint32_t idesc = make_idesc_bf16(128, p.CoT, 0, 0);
       const uint64_t dproto = make_smem_desc(0, 16, p.sbo, p.swz);
       const uint32_t wblk = (uint32_t)p.CoT * p.KB * 2, ablk = 128u * p.KB * 2;
       const int nk16 = p.KB / 16;
-      mbar_wait(&wfull, 0);
+      mbar_wait_a(u_wfull, 0);
       STGCN_STAMP(2);
       // Ring bookkeeping without integer division (RingPos, umma.cuh).  `base` = ring position of the item's first slice
       // s_lo; `win` = position of slice max(t_o + t0, s_lo), the first one the current output step can touch; `skip` = taps
@@ -423,83 +469,92 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // only slices past `n_waited` (offset from s_lo) need a full-barrier wait: one per step instead of Kt.
       uint32_t acc_cnt = 0, ab = 0, aph = 0;
       RingPos base{0, 0};
-      const uint32_t id_base = smem_u32(x_s + id_off);
+      const uint32_t id_base = u_x + id_off;
       const uint32_t a16 = ablk >> 4, w16 = wblk >> 4;
       const int shape = p.nKB * 8 + nk16, Kt = p.Kt, t0 = p.t0, S = p.S, NB = p.NB, res_j = p.res_dt - p.t0;
       const bool res_mma = p.res_mma != 0, bias_mma = p.bias_mma != 0;
       const uint32_t tile_bytes = p.tile_bytes, CoT = p.CoT, tap_bytes = (uint32_t)p.nKB * wblk;
-      auto issue = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t& accumulate) {
-        const uint64_t da = desc_at(dproto, a_base), db = desc_at(dproto, b_base);
-        switch (shape) {
-          case 1 * 8 + 1: tap_issue<1, 1>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
-          case 1 * 8 + 2: tap_issue<1, 2>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
-          case 1 * 8 + 4: tap_issue<1, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
-          case 2 * 8 + 4: tap_issue<2, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
-          case 4 * 8 + 4: tap_issue<4, 4>(d_tmem, da, db, a16, w16, idesc, accumulate); break;
-          default:
+      const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
+      const uint64_t d_ones = desc_at(p32, u_x), d_bias = desc_at(p32, u_x + bias_tile_off);
+      const uint32_t ring_s = u_ring, w_base = u_w;
+      // the item / tile loops, instantiated per block shape (NKB x NK16 K-steps per tap; 0 = runtime loops): the dispatch
+      // happens once per kernel instead of an indirect branch per tap
+      auto run = [&](auto nkb_c, auto nk16_c) {
+        constexpr int NKB = decltype(nkb_c)::value, NK16 = decltype(nk16_c)::value;
+        auto issue = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t& accumulate) {
+          const uint64_t da = desc_at(dproto, a_base), db = desc_at(dproto, b_base);
+          if constexpr (NKB > 0) {
+            tap_issue<NKB, NK16>(d_tmem, da, db, a16, w16, idesc, accumulate);
+          } else {
             for (int kb = 0; kb < p.nKB; ++kb)
               for (int k = 0; k < nk16; ++k) {
                 STGCN_TAP_MMA(d_tmem, da + (uint64_t)(kb * a16 + 2 * k), db + (uint64_t)(kb * w16 + 2 * k), idesc, accumulate);
                 accumulate = 1;
               }
+          }
+        };
+        for (TapIter it = it0; it.valid(p); it.next(p)) {
+          const TapItem wi = it.get(p);
+          RingPos win = base;
+          int skip = wi.s_lo - (wi.t_begin + t0);          // > 0 only when t_begin + t0 < 0
+          int n_waited = 0;
+          for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
+            STGCN_CSTAMP(acc_cnt >= 8 && acc_cnt < 12, 32 + (acc_cnt - 8));
+            mbar_wait_a(u_tempty + ab * 8, aph ^ 1);
+            STGCN_CSTAMP(acc_cnt == 8, 36);
+            tc_fence_after();
+            const uint32_t d_tmem = u_tmem + ab * CoT;
+            uint32_t accumulate = 0;
+            RingPos pos = win;
+            const int d_win = skip > 0 ? 0 : t_o + t0 - wi.s_lo;     // offset of `win` from s_lo
+            uint32_t res_a = 0;                                        // ring address of the residual slice (res_mma)
+            for (int j = skip > 0 ? skip : 0; j < Kt; ++j, pos.advance(S)) {
+              const int ti = t_o + j + t0;
+              if (ti >= wi.s_hi) break;
+              const int d = d_win + j - (skip > 0 ? skip : 0);
+              if (d >= n_waited) {
+                mbar_wait_a(u_full + pos.s * 8, pos.ph);
+                tc_fence_after();
+                n_waited = d + 1;
+              }
+              if (acc_cnt == 0) STGCN_STAMP(3);
+              STGCN_CSTAMP(acc_cnt == 8 && j < 4, 80 + 2 * j);
+              const uint32_t a_base = ring_s + pos.s * tile_bytes;
+              const uint32_t b_base = w_base + (uint32_t)j * tap_bytes;
+              if (j == res_j) res_a = a_base;
+              issue(d_tmem, a_base, b_base, accumulate);
+              STGCN_CSTAMP(acc_cnt == 8 && j < 4, 81 + 2 * j);
+            }
+            if (res_mma && res_a != 0) issue(d_tmem, res_a, id_base, accumulate);   // the slice was waited for by its tap above
+            STGCN_CSTAMP(acc_cnt == 8, 88);
+            if (bias_mma) {
+              STGCN_TAP_MMA(d_tmem, d_ones, d_bias, idesc, accumulate);
+              accumulate = 1;
+            }
+            STGCN_CSTAMP(acc_cnt == 8, 37);
+            mma_commit_a(u_tfull + ab * 8);
+            STGCN_CSTAMP(acc_cnt == 8, 38);
+            // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
+            if (t_o == wi.t_end - 1) {
+              RingPos r = win;
+              for (int ti = wi.s_lo + d_win; ti < wi.s_hi; ++ti, r.advance(S)) mma_commit_a(u_empty + r.s * 8);
+            } else if (skip <= 0 && t_o + t0 < wi.s_hi) {
+              mma_commit_a(u_empty + win.s * 8);
+            }
+            if (skip > 0) --skip; else win.advance(S);
+            if (++ab == (uint32_t)NB) { ab = 0; aph ^= 1; }
+            STGCN_CSTAMP(acc_cnt == 8, 39);
+          }
+          base.advance_by((uint32_t)(wi.s_hi - wi.s_lo), (uint32_t)S);
         }
       };
-      const uint64_t p32 = make_smem_desc(0, 16, 256, SWZ_32B);
-      const uint64_t d_ones = desc_at(p32, smem_u32(x_s)), d_bias = desc_at(p32, smem_u32(x_s + bias_tile_off));
-      const uint32_t ring_s = smem_u32(ring), w_base = smem_u32(w_s);
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const TapItem wi = tap_item(p, item);
-        RingPos win = base;
-        int skip = wi.s_lo - (wi.t_begin + t0);          // > 0 only when t_begin + t0 < 0
-        int n_waited = 0;
-        for (int t_o = wi.t_begin; t_o < wi.t_end; ++t_o, ++acc_cnt) {
-          STGCN_CSTAMP(acc_cnt >= 8 && acc_cnt < 12, 32 + (acc_cnt - 8));
-          mbar_wait_a(tempty_a + ab * 8, aph ^ 1);
-          STGCN_CSTAMP(acc_cnt == 8, 36);
-          tc_fence_after();
-          const uint32_t d_tmem = tmem_base + ab * CoT;
-          uint32_t accumulate = 0;
-          RingPos pos = win;
-          const int d_win = skip > 0 ? 0 : t_o + t0 - wi.s_lo;     // offset of `win` from s_lo
-          uint32_t res_a = 0;                                        // ring address of the residual slice (res_mma)
-          for (int j = skip > 0 ? skip : 0; j < Kt; ++j, pos.advance(S)) {
-            const int ti = t_o + j + t0;
-            if (ti >= wi.s_hi) break;
-            const int d = d_win + j - (skip > 0 ? skip : 0);
-            if (d >= n_waited) {
-              mbar_wait_a(full_a + pos.s * 8, pos.ph);
-              tc_fence_after();
-              n_waited = d + 1;
-            }
-            if (acc_cnt == 0) STGCN_STAMP(3);
-            STGCN_CSTAMP(acc_cnt == 8 && j < 4, 80 + 2 * j);
-            const uint32_t a_base = ring_s + pos.s * tile_bytes;
-            const uint32_t b_base = w_base + (uint32_t)j * tap_bytes;
-            if (j == res_j) res_a = a_base;
-            issue(d_tmem, a_base, b_base, accumulate);
-            STGCN_CSTAMP(acc_cnt == 8 && j < 4, 81 + 2 * j);
-          }
-          if (res_mma && res_a != 0) issue(d_tmem, res_a, id_base, accumulate);   // the slice was waited for by its tap above
-          STGCN_CSTAMP(acc_cnt == 8, 88);
-          if (bias_mma) {
-            STGCN_TAP_MMA(d_tmem, d_ones, d_bias, idesc, accumulate);
-            accumulate = 1;
-          }
-          STGCN_CSTAMP(acc_cnt == 8, 37);
-          mma_commit_a(tfull_a + ab * 8);
-          STGCN_CSTAMP(acc_cnt == 8, 38);
-          // release the slices no later output step needs: ti = t_o + t0, plus the tail after the last step
-          if (t_o == wi.t_end - 1) {
-            RingPos r = win;
-            for (int ti = wi.s_lo + d_win; ti < wi.s_hi; ++ti, r.advance(S)) mma_commit_a(empty_a + r.s * 8);
-          } else if (skip <= 0 && t_o + t0 < wi.s_hi) {
-            mma_commit_a(empty_a + win.s * 8);
-          }
-          if (skip > 0) --skip; else win.advance(S);
-          if (++ab == (uint32_t)NB) { ab = 0; aph ^= 1; }
-          STGCN_CSTAMP(acc_cnt == 8, 39);
-        }
-        base.advance_by((uint32_t)(wi.s_hi - wi.s_lo), (uint32_t)S);
+      using std::integral_constant;
+      switch (shape) {
+        case 1 * 8 + 1: run(integral_constant<int, 1>{}, integral_constant<int, 1>{}); break;
+        case 1 * 8 + 4: run(integral_constant<int, 1>{}, integral_constant<int, 4>{}); break;
+        case 2 * 8 + 4: run(integral_constant<int, 2>{}, integral_constant<int, 4>{}); break;
+        case 4 * 8 + 4: run(integral_constant<int, 4>{}, integral_constant<int, 4>{}); break;
+        default: run(integral_constant<int, 0>{}, integral_constant<int, 0>{}); break;
       }
     }
   } else {
@@ -533,9 +588,9 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const int relu = p.relu, NBm = p.NB - 1, nb_shift = p.nb_shift, nbuf2 = p.nbuf == 2;
       const uint32_t CoT = p.CoT, Cout = p.Cout, stage_bytes = p.stage_bytes;
       uint32_t cnt = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      for (TapIter it = it0; it.valid(p); it.next(p)) {
         int nt = p.T_out;
-        if (p.n_tsplit != 1) { const TapItem wi = tap_item(p, item); nt = wi.t_end - wi.t_begin; }
+        if (p.n_tsplit != 1) { const TapItem wi = it.get(p); nt = wi.t_end - wi.t_begin; }
         for (int i = 0; i < nt; ++i, ++cnt) {
           if ((cnt & tile_mask) != (uint32_t)tpart) continue;
           const uint32_t ab = cnt & NBm, aph = (cnt >> nb_shift) & 1;
@@ -604,8 +659,8 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     // its own tile the L2 round trip (~0.3 us of a ~2 us tile) sat exposed in front of every tile's column loop
     uint4 rpre[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     bool have_pre = false;
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const TapItem wi = tap_item(p, item);
+    for (TapIter it = it0; it.valid(p); it.next(p)) {
+      const TapItem wi = it.get(p);
       const int b = wi.b, n0 = wi.n0;
       const int n = n0 + row;
       const bool valid = n < p.N;
@@ -711,9 +766,10 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           int nt = t_o + 1, nb = b, nn = n;
           bool more = true;
           if (nt >= wi.t_end) {
-            const int nitem = item + (int)gridDim.x;
-            more = nitem < p.n_items;
-            if (more) { const TapItem w2 = tap_item(p, nitem); nb = w2.b; nn = w2.n0 + row; nt = w2.t_begin; }
+            TapIter i2 = it;
+            i2.next(p);
+            more = i2.valid(p);
+            if (more) { const TapItem w2 = i2.get(p); nb = w2.b; nn = w2.n0 + row; nt = w2.t_begin; }
           }
           const int ta = nt + p.aux_dt;
           if (more && ta >= 0 && ta < p.T_aux && nn < p.N) {
@@ -954,6 +1010,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
   p.n_items = q.B * p.n_node_tiles * p.n_tsplit;
   int gx = p.n_items < ctas ? p.n_items : ctas;
   if (gx < 1) gx = 1;
+  p.d_ts = gx % p.n_tsplit; p.d_nt = (gx / p.n_tsplit) % p.n_node_tiles; p.d_b = gx / (p.n_tsplit * p.n_node_tiles);
   dim3 grid(gx, pl.nCoT);
   const char* kname = q.epi == EPI_GATE ? "umma_tap_kernel<EPI_GATE>" : "umma_tap_kernel<EPI_LINEAR>";
   auto go = [&](auto kern) {
