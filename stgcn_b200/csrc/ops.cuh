@@ -17,6 +17,7 @@
 #include "umma_cheb.cuh"
 #include "umma_x3.cuh"
 #include "umma_fb0.cuh"
+#include "umma_fb2.cuh"
 
 namespace stgcn {
 namespace ops {
@@ -939,13 +940,54 @@ inline void stblock_bwd(const stgcn_stblock_desc& d, const T* x, Arena& sv, cons
   T* dh1 = c.ws.take<T>((size_t)g.rows1 * d.c1);
   const bool first = d.c_in == 1;
   T* dz2 = c.KW().take<T>(tconv_saved_elems(g.tc2));
-  float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2);
-  bool ln_fused;
+  float* lnsums = c.ws.take<float>((size_t)2 * d.B * g.T2 * kLnPgMaxParts);      // per column part (ln_bwd_sums_pg_kernel)
+  // LayerNorm backward + gate backward + data gradient + weight gradient of the second temporal conv in ONE tcgen05 kernel
+  // (umma_fb2.cuh; dZ never reaches HBM): shapes of the default architecture, q-only GLU state, no dropout mask to apply
+  bool fb2_shape = false;
+  if constexpr (std::is_same<T, simt::bf16>::value)
+    fb2_shape = tconv_qonly<T>(g.tc2) && umma::fb2_supported(d.c2, d.c3, d.Kt, d.act, g.T1, g.rows2, d.N) && d.N * d.c3 % 8 == 0 &&
+                ln_pg_parts(d.N * d.c3) <= kLnPgMaxParts;
+  float* dwt2 = c.K().take<float>(fb2_shape ? (size_t)(d.Kt * d.c2 + 1) * 2 * d.c3 : 0);
+  static const bool no_fb2 = std::getenv("STGCN_NO_FB2") != nullptr;        // A/B knob
+  const bool fb2 = fb2_shape && !no_fb2 && !(d.training && d.p_drop > 0.f);
+  bool ln_fused = false;
+  if (fb2) {
+    if constexpr (std::is_same<T, simt::bf16>::value) {
+      if (!c.dry()) {
+        Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd");
+        STGCN_CHECK(p.tc2.conv_w && p.ln_w, STGCN_E_INVALID, "stblock_bwd: missing parameters");
+        const int M = d.N * d.c3;
+        const long long G = (long long)d.B * g.T2;
+        zero(dwt2, (size_t)(d.Kt * d.c2 + 1) * 2 * d.c3, c.ps());
+        if (gr.ln_w) zero(gr.ln_w, M, c.ps());
+        if (gr.ln_b) zero(gr.ln_b, M, c.ps());
+        c.prep_ready();
+        // group sums (deterministic, per column part) + LayerNorm parameter gradients in one pass over (dY, H3)
+        LnGateArgs<T> a{};
+        a.x = s.h3; a.dy = dy; a.w = p.ln_w; a.mean = s.stats; a.rstd = s.stats + G; a.sums = lnsums; a.M = M; a.G = G;
+        a.dw = gr.ln_w; a.db = gr.ln_b;
+        launch_ln_bwd_sums_pg(a, umma::sm_count(), c.stream);
+        umma::Fb2Params q{};
+        q.dy = dy; q.h3 = s.h3; q.q = s.z2; q.h2 = s.h2; q.mean = s.stats; q.rstd = s.stats + G; q.sums = lnsums;
+        q.gamma = p.ln_w; q.conv_w = p.tc2.conv_w; q.dh2 = dh2; q.dwt = dwt2;
+        q.n_parts = ln_pg_parts(M); q.part_stride = 2 * G;
+        q.B = d.B; q.T2 = g.T2; q.T1 = g.T1; q.N = d.N;
+        umma::launch_fb2(q, c.stream);
+        c.post_after();
+        GatherBatch gb(c.qs());
+        const int W2 = 2 * d.c3, Kw2 = d.Kt * d.c2;
+        if (gr.tc2.conv_w) gb.add(dwt2, gr.tc2.conv_w, W2, d.c2, d.Kt, 0, 1, W2, (long long)d.c2 * W2);
+        if (gr.tc2.conv_b) gb.add(dwt2, gr.tc2.conv_b, 1, 1, W2, (long long)Kw2 * W2, 0, 0, 1);
+        gb.flush();
+      }
+    }
+  } else {
   { Tag t(first ? "st0.ln.bwd" : "st1.ln.bwd");
     ln_fused = lnorm_gate_bwd<T>(g.ln, g.tc2, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, s.z2, s.h2, dz2, lnsums, seed, c, tconv_qonly<T>(g.tc2));
     if (!ln_fused) lnorm_bwd<T>(g.ln, s.h3, s.stats, dy, p.ln_w, gr.ln_w, gr.ln_b, dh3, seed, c.stream, c.dry()); }
   { Tag t(first ? "st0.tc2.bwd" : "st1.tc2.bwd"); tconv_bwd<T>(g.tc2, s.h2, s.z2, dh3, p.tc2, gr.tc2, dh2, c, ln_fused ? dz2 : nullptr,
                                                                   (!ln_fused && tconv_qonly<T>(g.tc2)) ? s.h3 : nullptr); }
+  }
   // first block, no data gradient wanted: align data gradient + GLU backward + weight gradient in one tcgen05 kernel
   const bool fb0_shape = first_bwd_shape_ok<T>(d, g.rows1);
   T* dst_ext = c.KW().take<T>(fb0_shape ? (size_t)gconv_stack_depth(g.gc) * g.rows1 * d.c2 : 0);

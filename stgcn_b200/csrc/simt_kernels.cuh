@@ -1788,6 +1788,98 @@ __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnG
     if (a.db) atomicAdd(a.db + i + k, ab[k]);
   }
 }
+// One pass over (dY, x) for BOTH reductions of the LayerNorm backward, in front of umma_fb2_kernel (no dropout):
+//   * the two sums of every (b, t) group, deterministic: CTA (part, range) covers the columns [part * 8192, +8192) of
+//     the groups of its range and writes sums[part][g][2] (already / M) after a block reduction; the consumer adds the
+//     parts in a fixed order (atomics would perturb dZ's bf16 rounding from run to run);
+//   * the parameter gradients dw / db: thread = two fixed 8-column chunks, accumulated in registers over the CTA's groups,
+//     one atomic per element per CTA at the end.
+// The next group's operands are requested before the current group is reduced.  (ln_bwd_sums_kernel + a separate
+// parameter-gradient pass read the two tensors twice: 26 + 62 us for block 0 at B = 256.)
+constexpr int kLnPgThreads = 256, kLnPgCols = kLnPgThreads * 8, kLnPgMaxParts = 8;
+constexpr int kLnPgBatch = 4;      // groups per iteration: 4 x 8 KB requested per CTA before anything is consumed
+template <class T>
+__global__ void __launch_bounds__(kLnPgThreads, 3) ln_bwd_sums_pg_kernel(LnGateArgs<T> a) {
+  // (one group per iteration -- 8 KB per CTA in flight, then a block reduction -- was latency bound: 63 us for 120 MB)
+  __shared__ float red[kLnPgThreads / 32][2 * kLnPgBatch];
+  const int part = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = part * kLnPgCols + tid * 8;
+  const bool act = i0 < a.M;
+  float wv[8], aw[8], ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { wv[k] = 0.f; aw[k] = 0.f; ab[k] = 0.f; }
+  if (act) load8(a.w + i0, wv);
+  const long long g0 = (long long)blockIdx.y * a.groups_per_cta;
+  const long long g1 = min(a.G, g0 + a.groups_per_cta);
+  const float inv_m = 1.f / (float)a.M;
+  for (long long gb = g0; gb < g1; gb += kLnPgBatch) {
+    uint4 xr[kLnPgBatch], dr[kLnPgBatch];
+    float mu[kLnPgBatch], rs[kLnPgBatch];
+#pragma unroll
+    for (int j = 0; j < kLnPgBatch; ++j) {
+      xr[j] = dr[j] = make_uint4(0, 0, 0, 0);
+      mu[j] = 0.f; rs[j] = 0.f;
+      if (gb + j < g1) {
+        mu[j] = a.mean[gb + j]; rs[j] = a.rstd[gb + j];
+        if (act) { xr[j] = *reinterpret_cast<const uint4*>(a.x + (gb + j) * a.M + i0); dr[j] = *reinterpret_cast<const uint4*>(a.dy + (gb + j) * a.M + i0); }
+      }
+    }
+    float sv[2 * kLnPgBatch];
+#pragma unroll
+    for (int j = 0; j < kLnPgBatch; ++j) {
+      const uint32_t xw[4] = {xr[j].x, xr[j].y, xr[j].z, xr[j].w}, dw4[4] = {dr[j].x, dr[j].y, dr[j].z, dr[j].w};
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xv = __uint_as_float((k & 1) ? (xw[k >> 1] & 0xffff0000u) : (xw[k >> 1] << 16));
+        const float dv = __uint_as_float((k & 1) ? (dw4[k >> 1] & 0xffff0000u) : (dw4[k >> 1] << 16));
+        const float xh = (xv - mu[j]) * rs[j], gi = dv * wv[k];      // inactive threads / groups: dv = 0
+        s1 += gi; s2 = fmaf(gi, xh, s2);
+        aw[k] = fmaf(dv, xh, aw[k]);
+        ab[k] += dv;
+      }
+      sv[2 * j] = s1; sv[2 * j + 1] = s2;
+    }
+    // deterministic block reduction of the 2 x kLnPgBatch sums
+#pragma unroll
+    for (int v = 0; v < 2 * kLnPgBatch; ++v) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sv[v] += __shfl_xor_sync(0xffffffffu, sv[v], o);
+    }
+    __syncthreads();                                        // red[] of the previous batch has been read
+    if (lane == 0) {
+#pragma unroll
+      for (int v = 0; v < 2 * kLnPgBatch; ++v) red[warp][v] = sv[v];
+    }
+    __syncthreads();
+    if (tid < 2 * kLnPgBatch) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnPgThreads / 32; ++w) t += red[w][tid];
+      const long long g = gb + (tid >> 1);
+      if (g < g1) a.sums[((long long)part * a.G + g) * 2 + (tid & 1)] = t * inv_m;
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (a.dw) atomicAdd(a.dw + i0 + k, aw[k]);
+      if (a.db) atomicAdd(a.db + i0 + k, ab[k]);
+    }
+  }
+}
+inline int ln_pg_parts(int M) { return ceil_div(M, kLnPgCols); }
+template <class T>
+inline void launch_ln_bwd_sums_pg(LnGateArgs<T> a, int sms, cudaStream_t s) {
+  static_assert(std::is_same<T, bf16>::value, "bf16 activations only (the kernel unpacks bf16 pairs)");
+  const int parts = ln_pg_parts(a.M);
+  int ranges = std::max(1, (3 * sms) / parts);
+  if (ranges > a.G) ranges = (int)a.G;
+  a.groups_per_cta = ceil_div(a.G, ranges);
+  ranges = ceil_div(a.G, a.groups_per_cta);
+  STGCN_LAUNCH(ln_bwd_sums_pg_kernel<T>, dim3(parts, ranges), kLnPgThreads, 0, s, a);
+}
+
 template <class T>
 inline bool ln_gate_bwd_supported(const LnGateArgs<T>& a) {
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };

@@ -33,7 +33,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~kMbarHintNs elapsed.
 // Without the hint a waiting warp came back every ~150 cycles and re-issued a 6-instruction spin iteration: 11 of them
 // per tile in the tap kernel's epilogue warps, 15 % of that kernel's issue slots (ncu source page, profiles/r02_ab_batch_l.md).
-constexpr uint32_t kMbarHintNs = 20000;
+#ifndef STGCN_MBAR_HINT_NS
+#define STGCN_MBAR_HINT_NS 20000
+#endif
+constexpr uint32_t kMbarHintNs = STGCN_MBAR_HINT_NS;
 __device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar_saddr, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -981,9 +981,10 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
     int cp = 1;
     for (int d = 1; d <= kTapEpiGroups; ++d)
       if (kTapEpiGroups % d == 0 && d * 16 <= width) cp = d;
-    // STGCN_TAP_TP2=1 (A/B knob): staged tiles alternate between two 8-warp groups, each with its own staging buffer and
-    // 32 columns per warp -- the per-tile fixed costs of a warp are then paid every other tile
-    static const bool tp2 = [] { const char* e = std::getenv("STGCN_TAP_TP2"); return e && e[0] == '1'; }();
+    // staged tiles alternate between two 8-warp groups, each with its own staging buffer and 32 columns per warp: the
+    // per-tile fixed costs of a warp (barrier waits, fence, arrivals) are paid every other tile (+1.6 % on the step,
+    // profiles/r02_ab_batch_n.md)
+    constexpr bool tp2 = true;
     if (p.store_tma && cp == kTapEpiGroups && tp2 && p.nbuf == 2 && kTapEpiGroups == 4) cp = 2;
     if (p.store_tma && cp != kTapEpiGroups && !(tp2 && cp == 2 && p.nbuf == 2 && kTapEpiGroups == 4)) p.store_tma = 0;
     p.col_parts = cp; p.tile_parts = kTapEpiGroups / cp;
