@@ -713,6 +713,10 @@ def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
         if "umma_fb0_kernel<GATE>" in kern:     # align data gradient + q-only GLU backward: dX0, Q, H in; dZ out
             c2 = d["c2"]
             return 2.0 * c2 * cout * rows(tout), rows(tout) * (c2 + 2 * cout + W) * e
+        if "umma_fb2_kernel" in kern:           # LayerNorm bwd + GLU bwd + data gradient + weight gradient of the second conv:
+            return 2.0 * gemm, (3 * rows(tout) * cout + 2 * rows(tin) * cin) * e    # dY, H3, Q, H2 in; dH2 out
+        if "ln_bwd_sums_pg" in kern:            # group sums + LayerNorm parameter gradients: one pass over dY and H3
+            return 0.0, 2 * rows(tout) * cout * e
         if "umma_tap" in kern or "tapgemm" in kern:
             if direction == "fwd":
                 return gemm, (rows(tin) * cin + rows(tout) * (W + cout)) * e

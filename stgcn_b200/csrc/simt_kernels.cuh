@@ -1796,7 +1796,7 @@ __global__ void __launch_bounds__(128, STGCN_LNGATE_MINB) ln_gate_bwd_kernel(LnG
 //     one atomic per element per CTA at the end.
 // The next group's operands are requested before the current group is reduced.  (ln_bwd_sums_kernel + a separate
 // parameter-gradient pass read the two tensors twice: 26 + 62 us for block 0 at B = 256.)
-constexpr int kLnPgThreads = 256, kLnPgCols = kLnPgThreads * 8, kLnPgMaxParts = 8;
+constexpr int kLnPgThreads = 256, kLnPgCols = kLnPgThreads * 8, kLnPgMaxParts = 16;
 constexpr int kLnPgBatch = 4;      // groups per iteration: 4 x 8 KB requested per CTA before anything is consumed
 template <class T>
 __global__ void __launch_bounds__(kLnPgThreads, 3) ln_bwd_sums_pg_kernel(LnGateArgs<T> a) {

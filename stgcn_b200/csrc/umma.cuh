@@ -32,7 +32,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes or ~kMbarHintNs elapsed.
 // Without the hint a waiting warp came back every ~150 cycles and re-issued a 6-instruction spin iteration: 11 of them
-// per tile in the tap kernel's epilogue warps, 15 % of that kernel's issue slots (ncu source page, profiles/r02_ab_batch_l.md).
+// per tile in the tap kernel's epilogue warps, 15 % of that kernel's issue slots (ncu source page, profiles/r02_ab_batch_h.md).
 #ifndef STGCN_MBAR_HINT_NS
 #define STGCN_MBAR_HINT_NS 20000
 #endif
@@ -138,6 +138,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(m)),
                "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }

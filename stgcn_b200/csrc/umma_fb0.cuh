@@ -59,15 +59,22 @@ constexpr int kFb0NZ = 3;                                           // dZ / x-wi
 constexpr uint32_t kFb0X3 = kFb0Wpq + 2048;                         // kFb0NZ x 4096
 constexpr uint32_t kFb0Dz = kFb0X3 + kFb0NZ * 4096;                 // kFb0NZ x 32768 (1024-aligned: 36864 + 12288 = 49152)
 constexpr uint32_t kFb0Smem = kFb0Dz + kFb0NZ * 32768 + 1024;
+// FB_GATE only: the saved Q and H1 tiles [128 rows][64 ch] arrive by TMA (128B swizzle), two stages of 2 x 16 KB
+constexpr int kFb0NQH = 2;
+constexpr uint32_t kFb0QH = kFb0Dz + kFb0NZ * 32768;
+constexpr uint32_t kFb0SmemGate = kFb0QH + kFb0NQH * 32768 + 1024;
 constexpr uint32_t kFb0D2Col = kFb0ND1 * 64;                        // TMEM column of the weight-gradient accumulator
 // (the first version double-buffered both: 2.4 us per 128-row tile against ~0.9 us of epilogue issue time -- every tile
 // waited for the previous tile's MMA 2 and the next tile's MMA 1 in turn; profiles/r02_ab_batch_c.md)
 
 template <int MODE>
-__global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
+__global__ void __launch_bounds__(kFb0Threads, 1)
+umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmH,
+                const __grid_constant__ CUtensorMap tmZ, Fb0Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[kFb0ND1], d1_empty[kFb0ND1], dz_full[kFb0NZ], dz_empty[kFb0NZ], done;
+  __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[kFb0ND1], d1_empty[kFb0ND1], dz_full[kFb0NZ], dz_empty[kFb0NZ], done,
+      qh_full[kFb0NQH], qh_empty[kFb0NQH];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -90,6 +97,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
     for (int i = 0; i < kFb0ND1; ++i) { mbar_init(&d1_full[i], 1); mbar_init(&d1_empty[i], kFb0EpiWarps); }
     for (int i = 0; i < kFb0NZ; ++i) { mbar_init(&dz_full[i], kFb0EpiWarps); mbar_init(&dz_empty[i], 1); }
     mbar_init(&done, 1);
+    for (int i = 0; i < kFb0NQH; ++i) { mbar_init(&qh_full[i], 1); mbar_init(&qh_empty[i], kFb0EpiWarps); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 256);          // D1: kFb0ND1 x 64 columns, D2: 16 columns
@@ -106,6 +114,15 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
     for (int i = 0; i < n_my; ++i) {
       const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
       const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1;
+      if (MODE == FB_GATE && lane == 0) {
+        // saved gate half Q and layer output H1 of this tile: two [128 rows x 64 ch] boxes, rows past the end read as zeros
+        const uint32_t s2 = i % kFb0NQH, ph2 = (i / kFb0NQH) & 1;
+        mbar_wait(&qh_empty[s2], ph2 ^ 1);
+        mbar_arrive_expect_tx(&qh_full[s2], 32768);
+        tma_load_2d(smem + kFb0QH + s2 * 32768, &tmQ, &qh_full[s2], 0, (int)r0);
+        tma_load_2d(smem + kFb0QH + s2 * 32768 + 16384, &tmH, &qh_full[s2], 0, (int)r0);
+      }
+      __syncwarp();
       mbar_wait(&a_empty[s], ph ^ 1);
       uint8_t* dst = smem + kFb0ARing + s * 4096;
 #pragma unroll
@@ -151,8 +168,18 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       int next1 = 0;                                      // MMA 1 runs up to kFb0ND1 - 1 tiles ahead of MMA 2
       for (int i = 0; i < n_my; ++i) {
         for (; next1 < n_my && next1 < i + kFb0ND1; ++next1) mma1(next1);
-        if (MODE != FB_FIRST) continue;
         const uint32_t zb = i % kFb0NZ, zph = (i / kFb0NZ) & 1;
+        if (MODE != FB_FIRST) {
+          // FB_GATE: the finished dZ tile leaves through two TMA stores (P half | Q half); the buffer is free once read
+          mbar_wait(&dz_full[zb], zph);
+          const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
+          tma_store_2d(&tmZ, smem + kFb0Dz + zb * 32768, 0, (int)r0);
+          tma_store_2d(&tmZ, smem + kFb0Dz + zb * 32768 + 16384, 64, (int)r0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&dz_empty[zb]);
+          continue;
+        }
         mbar_wait(&dz_full[zb], zph);
         tc_fence_after();
         uint64_t da = desc_at(pdz, smem_u32(smem + kFb0Dz + zb * 32768)), db = desc_at(px3, smem_u32(smem + kFb0X3 + zb * 4096));
@@ -163,6 +190,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
         }
         mma_commit(&dz_empty[zb]);
       }
+      if (MODE != FB_FIRST) tma_store_wait_all<0>();
       mma_commit(&done);
     }
   } else {
@@ -187,10 +215,6 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
         xn0 = simt::ldf(p.x + in0);
         xn1 = simt::ldf(p.x + in0 + p.N);
         if (p.Kt > 2) xn2 = simt::ldf(p.x + in0 + 2LL * p.N);
-      } else {
-        const uint4* qp = reinterpret_cast<const uint4*>(p.q + r * 64 + c0);
-        const uint4* hp = reinterpret_cast<const uint4*>(p.h + r * 64 + c0);
-        qn[0] = qp[0]; qn[1] = qp[1]; hn[0] = hp[0]; hn[1] = hp[1];
       }
     };
     fetch(0);
@@ -198,8 +222,23 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
       const bool valid = r < p.rows;
       const float x0 = xn0, x1 = xn1, x2 = xn2;
-      const uint4 qv[2] = {qn[0], qn[1]}, hv[2] = {hn[0], hn[1]};
+      uint4 qv[2] = {qn[0], qn[1]}, hv[2] = {hn[0], hn[1]};
       fetch(i + 1);
+      if (MODE == FB_GATE) {
+        // Q / H1 chunks of this thread's row from the TMA-staged tiles (one row per thread straight from global memory
+        // touched 32 different 128-byte lines per warp-wide load: ~4000 L1 wavefront cycles per tile with the dZ stores,
+        // profiles/r02_ab_batch_h.md); the 128B swizzle makes the row-per-thread reads conflict free
+        const uint32_t s2 = i % kFb0NQH, ph2 = (i / kFb0NQH) & 1;
+        mbar_wait(&qh_full[s2], ph2);
+        const uint8_t* qs_ = smem + kFb0QH + s2 * 32768 + row * 128;
+        const int ch = c0 >> 3, sw = row & 7;
+        qv[0] = *reinterpret_cast<const uint4*>(qs_ + ((ch ^ sw) << 4));
+        qv[1] = *reinterpret_cast<const uint4*>(qs_ + (((ch + 1) ^ sw) << 4));
+        hv[0] = *reinterpret_cast<const uint4*>(qs_ + 16384 + ((ch ^ sw) << 4));
+        hv[1] = *reinterpret_cast<const uint4*>(qs_ + 16384 + (((ch + 1) ^ sw) << 4));
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&qh_empty[s2]);
+      }
       const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
       const uint32_t ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
       mbar_wait(&d1_full[ab], aph);
@@ -234,12 +273,6 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
           du[e] = dh * s;
           dq[e] = dh * hf[e] * (1.f - s);
         }
-        if (valid) {
-          uint4* dp = reinterpret_cast<uint4*>(p.dz + r * 128 + c0);
-          dp[0] = pack8_bf16(du); dp[1] = pack8_bf16(du + 8);
-          dp[8] = pack8_bf16(dq); dp[9] = pack8_bf16(dq + 8);          // + 64 channels = 8 x 16 bytes
-        }
-        continue;
       }
       const uint32_t zb = i % kFb0NZ, zph = (i / kFb0NZ) & 1;
       mbar_wait(&dz_empty[zb], zph ^ 1);
@@ -248,7 +281,7 @@ __global__ void __launch_bounds__(kFb0Threads, 1) umma_fb0_kernel(Fb0Params p) {
       stage_store8_s(dzs, row, c0 + 8, pack8_bf16(du + 8));
       stage_store8_s(dzs + 16384u, row, c0, pack8_bf16(dq));
       stage_store8_s(dzs + 16384u, row, c0 + 8, pack8_bf16(dq + 8));
-      if (grp == 0) {
+      if (MODE == FB_FIRST && grp == 0) {
         float xw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (valid) { xw[0] = x0; xw[1] = x1; if (p.Kt > 2) xw[2] = x2; xw[p.Kt > 2 ? 3 : 2] = 1.f; }
         uint8_t* x3 = smem + kFb0X3 + zb * 4096 + row * 32;
@@ -288,8 +321,9 @@ inline void launch_fb0(const bf16* dst0, const bf16* wa, const bf16* x, const fl
   p.dst0 = dst0; p.wa = wa; p.x = x; p.wt = wt; p.bias = bias; p.dwt = dwt; p.rows = rows;
   p.n_tiles = (int)((rows + 127) / 128); p.Kt = Kt; p.T_out = T_out; p.T_in = T_in; p.N = N; p.explicit_res = explicit_res;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
+  CUtensorMap none{};                                     // FB_FIRST touches no tensor map
   STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
-  STGCN_LAUNCH_NAMED("umma_fb0_kernel<FIRST>", umma_fb0_kernel<FB_FIRST>, grid, kFb0Threads, kFb0Smem, stream, p);
+  STGCN_LAUNCH_NAMED("umma_fb0_kernel<FIRST>", umma_fb0_kernel<FB_FIRST>, grid, kFb0Threads, kFb0Smem, stream, none, none, none, p);
 }
 
 // later blocks: dZ = GLU'(dX0 . Wa; Q, H1) for a 64-channel GLU conv in front of a 64 -> 16 align conv (q-only saved state)
@@ -302,8 +336,14 @@ inline void launch_fb_gate(const bf16* dst0, const bf16* wa, const bf16* q, cons
   p.dst0 = dst0; p.wa = wa; p.q = q; p.h = h; p.dz = dz; p.rows = rows; p.n_tiles = (int)((rows + 127) / 128);
   p.Kt = 2; p.T_out = 1; p.T_in = 1; p.N = 1;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
-  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
-  STGCN_LAUNCH_NAMED("umma_fb0_kernel<GATE>", umma_fb0_kernel<FB_GATE>, grid, kFb0Threads, kFb0Smem, stream, p);
+  // flat-row tensor maps: Q, H1 [rows][64] and dZ [rows][128]; boxes of 64 channels x 128 rows, 128B swizzle
+  const uint64_t qd[2] = {64, (uint64_t)rows}, qs[1] = {128}, zd[2] = {128, (uint64_t)rows}, zs[1] = {256};
+  const uint32_t box[2] = {64, 128};
+  const CUtensorMap tmQ = make_tmap_bf16(q, 2, qd, qs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap tmH = make_tmap_bf16(h, 2, qd, qs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  const CUtensorMap tmZ = make_tmap_bf16(dz, 2, zd, zs, box, CU_TENSOR_MAP_SWIZZLE_128B);
+  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0SmemGate));
+  STGCN_LAUNCH_NAMED("umma_fb0_kernel<GATE>", umma_fb0_kernel<FB_GATE>, grid, kFb0Threads, kFb0SmemGate, stream, tmQ, tmH, tmZ, p);
 }
 
 }  // namespace umma

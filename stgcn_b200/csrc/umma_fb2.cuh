@@ -17,7 +17,7 @@
 //         accumulators in tensor memory, X_tau complete after tile tau) + one identity instruction for the zero-padded
 //         residual into X_{t+2}.  (A scatter form -- one N = 48 accumulator per tile, summed over three tiles by the
 //         epilogue -- needs a third of the instructions but three readers per accumulator; its epilogue step took 1700
-//         cycles, profiles/r02_ab_batch_q.md.)
+//         cycles, profiles/r02_ab_batch_h.md.)
 //   MMA weight gradient:  G_j[128 channels x 16] += dZ_t^T . H2_{t+j},  G_b += dZ_t^T . 1    (K = 128 rows; accumulators
 //         persistent in tensor memory over all tiles of the CTA, flushed once with fp32 atomics)
 //   E2  dH2_tau = X_tau -> bf16, 32 bytes per row to HBM.
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kFb2Threads, 1) umma_fb2_kernel(Fb2Params p) {
     // w*8 .. w*8+7 and lane l the 16-byte chunk (l & 7) of rows w*8 + (l >> 3) and + 4: every LDG.128 of a warp reads 512
     // contiguous bytes.  (With the TMEM-style mapping -- one row per thread -- every warp-wide load touched 32 different
     // 128-byte lines: 16 loads x 32 L1 wavefronts x 16 warps ~ 8000 cycles per tile, 5 us per tile measured,
-    // profiles/r02_ab_batch_p.md.)  E1 never reads tensor memory, so nothing ties it to the lane = row layout.
+    // profiles/r02_ab_batch_h.md.)  E1 never reads tensor memory, so nothing ties it to the lane = row layout.
     const int ew = warp - 2, c8 = lane & 7;
     const int er[2] = {ew * 8 + (lane >> 3), ew * 8 + 4 + (lane >> 3)};       // tile rows of this thread
     const bool ev[2] = {n0 + er[0] < p.N, n0 + er[1] < p.N};

@@ -210,7 +210,7 @@ __device__ __forceinline__ TapItem tap_item(const TapParams& p, int item) {
 // host: every later value is derived from warp-uniform integers with compare / subtract only.  (tap_item()'s runtime
 // divisions run on the vector pipe; their results -- and everything derived from them: ring positions, descriptors,
 // TMEM addresses -- then lived in vector registers and reached the uniform-register operands of UTCHMMA / UTCBAR through
-// R2UR moves, ~60 instructions per tap in the issuer thread; profiles/r02_ab_batch_m.md.)
+// R2UR moves, ~60 instructions per tap in the issuer thread; profiles/r02_ab_batch_h.md.)
 struct TapIter {
   int item, ts, nt, b;
   __device__ __forceinline__ bool valid(const TapParams& p) const { return item < p.n_items; }
@@ -243,7 +243,7 @@ struct TapIter {
 #endif
 // All K = 16 steps of one tap for a compile-time block shape: straight-line UTCHMMA with immediate descriptor offsets.
 // (The runtime kb / k loops cost the lone issuer thread ~10 dependent instructions and a branch per instruction; the
-// issuer needed ~3500 cycles per 17-instruction tile, profiles/r02_ab_batch_j.md.)  a16 / w16: bytes >> 4 between
+// issuer needed ~3500 cycles per 17-instruction tile, profiles/r02_ab_batch_h.md.)  a16 / w16: bytes >> 4 between
 // 64-channel blocks of the slice / of the weight tap.
 template <int NKB, int NK16>
 __device__ __forceinline__ void tap_issue(uint32_t d_tmem, uint64_t da, uint64_t db, uint32_t a16, uint32_t w16, uint32_t idesc,
@@ -560,7 +560,7 @@ umma_tap_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   } else {
     // =========================== epilogue warps ==========================
     // Per 128-row tile and warp the FIXED costs (barrier waits, proxy fence, arrivals, address set-up) were ~2900 cycles
-    // against ~1700 for the column arithmetic (SM-cycle timeline, profiles/r02_ab_batch_j.md), so: 16-column chunks (one
+    // against ~1700 for the column arithmetic (SM-cycle timeline, profiles/r02_ab_batch_h.md), so: 16-column chunks (one
     // TMEM round trip per chunk, both halves' loads in flight together), ONE fence + warp sync + the two arrivals at the
     // end, and nothing per tile that a per-item or per-kernel value can replace.
     const int q = warp & 3;                     // TMEM lane quarter this warp may access
@@ -983,7 +983,7 @@ inline void launch_tap(const TapProblem& q, cudaStream_t stream) {
       if (kTapEpiGroups % d == 0 && d * 16 <= width) cp = d;
     // staged tiles alternate between two 8-warp groups, each with its own staging buffer and 32 columns per warp: the
     // per-tile fixed costs of a warp (barrier waits, fence, arrivals) are paid every other tile (+1.6 % on the step,
-    // profiles/r02_ab_batch_n.md)
+    // profiles/r02_ab_batch_h.md)
     constexpr bool tp2 = true;
     if (p.store_tma && cp == kTapEpiGroups && tp2 && p.nbuf == 2 && kTapEpiGroups == 4) cp = 2;
     if (p.store_tma && cp != kTapEpiGroups && !(tp2 && cp == 2 && p.nbuf == 2 && kTapEpiGroups == 4)) p.store_tma = 0;
