@@ -665,17 +665,20 @@ def main():
 
 def _ncu_traffic(key, workload, B, precision):
     """DRAM bytes (read + write) per launch of this kernel from the committed `ncu --set full` captures
-    (profiles/r01_traffic.json; PeMSD7-M, B=256, bf16 only), or None when that kernel was not captured."""
+    (profiles/r02_traffic.json, then r01_traffic.json; PeMSD7-M, B=256, bf16 only), or None when that kernel was not captured."""
     import re
     if workload != "pemsd7m" or B != 256 or precision != "bf16":
         return None
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(path):
-        return None
     tag, kern = key.split(":", 1)
     m = re.search(r"[A-Za-z_][A-Za-z0-9_]*", kern)
-    row = json.load(open(path))["kernels"].get(f"{tag}:{m.group(0) if m else kern}")
-    return None if row is None else row["dram_read_bytes"] + row["dram_write_bytes"]
+    for name in ("r02_traffic.json", "r01_traffic.json"):          # newest capture that has the kernel
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        row = json.load(open(path))["kernels"].get(f"{tag}:{m.group(0) if m else kern}")
+        if row is not None:
+            return row["dram_read_bytes"] + row["dram_write_bytes"]
+    return None
 
 
 def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):

@@ -383,7 +383,7 @@ __global__ void __launch_bounds__(kFb2Threads, 1) umma_fb2_kernel(Fb2Params p) {
 // shapes this kernel serves
 inline bool fb2_supported(int c_in, int c_out, int Kt, int act, int T_in, long long rows_out, int N) {
   return c_in == kFb2Ci && c_out == kFb2Co && Kt == kFb2Kt && act == STGCN_ACT_GLU && T_in >= Kt && rows_out > 0 &&
-         rows_out < (1LL << 31) && N >= 1 && (N + 127) / 128 <= sm_count();
+         rows_out < (1LL << 31) && N >= 1 && (N + 127) / 128 <= 64;    // (no CUDA call here: the sizing pass also runs without a GPU)
 }
 
 inline void launch_fb2(const Fb2Params& p0, cudaStream_t stream) {

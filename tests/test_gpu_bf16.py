@@ -385,3 +385,50 @@ def test_bf16_first_block_fused_backward(N, B, kt, kind, cuda_device):
     for k in ("tmp_conv1.causal_conv.weight", "tmp_conv1.causal_conv.bias"):
         e_fused, e_plain = rel_l2(fused[k], p64["b." + k].grad), rel_l2(plain[k], p64["b." + k].grad)
         assert e_fused < GRAD_TOL and e_fused < 1.5 * e_plain + 1e-2, (k, e_fused, e_plain)
+
+
+@pytest.mark.parametrize("N,B,T,kind", [(228, 5, 12, "cheb_graph_conv"), (41, 3, 12, "cheb_graph_conv"), (207, 2, 8, "graph_conv"),
+                                         (325, 3, 12, "cheb_graph_conv"), (228, 150, 7, "cheb_graph_conv")])
+def test_bf16_second_conv_fused_backward(N, B, T, kind, cuda_device):
+    """Blocks of the default architecture (16 -> 64 GLU channels, Kt = 3, no dropout): the LayerNorm backward, the GLU
+    backward and the data / weight / bias gradients of the second temporal conv run as ONE tcgen05 kernel
+    (csrc/umma_fb2.cuh) behind ln_bwd_sums_pg_kernel.  Checked against the fp64 oracle of the block on every parameter
+    gradient and on dx: ragged vertex tiles (N = 228, 325, 41), 1..3 tiles, more samples than CTAs per tile (B = 150: several
+    items per CTA, the accumulator rings wrap), T2 from 3 to 8.  With dropout active in training the block must take the
+    unfused path (the mask is applied there) and still agree with itself run to run."""
+    from stgcn_b200 import layers, _lib as L
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(N + B + T)
+    torch.manual_seed(N + B + T)
+    gso = O.synthetic_gso(N, seed=N)
+    blk = layers.STConvBlock(3, 3, N, 64, [64, 16, 64], "glu", kind, gso.to(dev), True, 0.0).to(dev)
+    blk.train()
+    x = torch.randn(B, 64, T, N, generator=gen)
+    dy = torch.randn(B, 64, T - 4, N, generator=gen)
+    xg = x.to(dev).requires_grad_(True)
+    L.profile_begin()
+    blk(xg).backward(dy.to(dev).bfloat16())
+    prof = L.profile_end()
+    assert any("umma_fb2_kernel" in k for k in prof), sorted(prof)
+    assert any("ln_bwd_sums_pg_kernel" in k for k in prof)
+    assert not any("ln_gate_bwd_kernel" in k for k in prof)
+    got = {k: p.grad.detach().float().cpu() for k, p in blk.named_parameters() if p.grad is not None}
+    got["dx"] = xg.grad.detach().float().cpu()
+    p64 = {"b." + k: v.detach().double().cpu().requires_grad_(True) for k, v in blk.state_dict().items()}
+    x64 = x.double().requires_grad_(True)
+    O.st_conv_block(x64, p64, "b.", gso.double(), 3, [64, 16, 64], "glu", kind).backward(dy.double())
+    ref = {k: p64["b." + k].grad for k in got if k != "dx"}
+    ref["dx"] = x64.grad
+    for k in got:
+        assert ref[k] is not None, k
+        assert rel_l2(got[k], ref[k].float()) < GRAD_TOL, (k, rel_l2(got[k], ref[k].float()))
+    # the tensors the fused kernel produces itself, tighter: second conv weight / bias, LayerNorm weight / bias
+    for k in ("tmp_conv2.causal_conv.weight", "tmp_conv2.causal_conv.bias", "tc2_ln.weight", "tc2_ln.bias"):
+        assert rel_l2(got[k], ref[k].float()) < 3e-2, (k, rel_l2(got[k], ref[k].float()))
+    # dropout in training: unfused path
+    blk_d = layers.STConvBlock(3, 3, N, 64, [64, 16, 64], "glu", kind, gso.to(dev), True, 0.5).to(dev)
+    blk_d.train()
+    L.profile_begin()
+    blk_d(x.to(dev).requires_grad_(True)).backward(dy.to(dev).bfloat16())
+    prof_d = L.profile_end()
+    assert not any("umma_fb2_kernel" in k for k in prof_d), sorted(prof_d)
