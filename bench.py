@@ -710,10 +710,10 @@ def _kernel_work(key, n, B, kind, ks, esize, blocks=BLOCKS, kt=3, n_his=12):
         tin, tout = (d["T0"], d["T1"]) if op == "tc1" else (d["T1"], d["T2"])
         W = 2 * cout
         gemm = 2.0 * W * cin * d["kt"] * rows(tout)
-        if "umma_fb0_kernel<FIRST>" in kern:    # align data gradient + GLU backward + first-conv weight gradient: reads the
+        if "umma_fb0_kernel" in kern and cin == 1:    # align data gradient + GLU backward + first-conv weight gradient: reads the
             c2 = d["c2"]                         # 16-channel gradient and the model input, writes only the weight gradient
             return gemm + 2.0 * c2 * cout * rows(tout), (rows(tout) * c2 + rows(tin) * cin) * e
-        if "umma_fb0_kernel<GATE>" in kern:     # align data gradient + q-only GLU backward: dX0, Q, H in; dZ out
+        if "umma_fb0_kernel" in kern:     # align data gradient + q-only GLU backward: dX0, Q, H in; dZ out
             c2 = d["c2"]
             return 2.0 * c2 * cout * rows(tout), rows(tout) * (c2 + 2 * cout + W) * e
         if "umma_fb2_kernel" in kern:           # LayerNorm bwd + GLU bwd + data gradient + weight gradient of the second conv:
