@@ -30,7 +30,7 @@ namespace stgcn {
 namespace umma {
 
 constexpr int kFb2EpiWarps = 16;
-constexpr int kFb2Threads = 64 + 32 * kFb2EpiWarps;      // warp 0 H2 producer, warp 1 MMA issuer, 16 epilogue warps
+constexpr int kFb2Threads = 64 + 32 * kFb2EpiWarps + 128; // warp 0 H2 producer, warp 1 MMA issuer, 16 E1 warps, 4 E2 warps
 constexpr int kFb2HStages = 8;                           // H2 slices in flight (4 KB each)
 constexpr int kFb2NZ = 3;                                // dZ tiles in shared memory
 constexpr int kFb2NX = 6;                                // data-gradient accumulators X_tau (16 columns each) in tensor memory
@@ -58,7 +58,8 @@ constexpr uint32_t kFb2Wd = kFb2HRing + kFb2HStages * 4096;         // 2 x [48 r
 constexpr uint32_t kFb2Wres = kFb2Wd + 2 * 6144;                    // [16 rows][16] identity for the residual: 512 -> 2048
 constexpr uint32_t kFb2Ones = kFb2Wres + 2048;                      // [16 rows][16] ones: 512 -> 1024
 constexpr uint32_t kFb2Dz = kFb2Ones + 1024;                        // kFb2NZ x 32768 (1024-aligned)
-constexpr uint32_t kFb2Smem = kFb2Dz + kFb2NZ * 32768 + 1024;
+constexpr uint32_t kFb2Pf = kFb2Dz + kFb2NZ * 32768;                // E1 operand slots: [6 chunks][512 threads][16 B] = 49152
+constexpr uint32_t kFb2Smem = kFb2Pf + 6 * 512 * 16 + 1024;
 static_assert(kFb2Dz % 1024 == 0 && kFb2Wd % 1024 == 0, "swizzled operands need 1024-byte alignment");
 constexpr uint32_t kFb2D2Col = kFb2NX * 16;                         // 96: weight-gradient accumulators (3 taps x 16 + bias 16)
 
@@ -239,13 +240,56 @@ __global__ void __launch_bounds__(kFb2Threads, 1) umma_fb2_kernel(Fb2Params p) {
       }
       mma_commit_a(done_a);
     }
-  } else {
-    // =========================== epilogue warps ==========================
-    const int q = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter; 16-channel group
-    const int row = q * 32 + lane;
-    const int n = n0 + row;
-    const bool valid = n < p.N;                           // E2 / flush mapping: thread = TMEM lane = vertex row (or channel)
+  } else if (warp >= 2 + kFb2EpiWarps) {
+    // =========================== E2 warps: dH2 of every input step, then the weight-gradient flush =================
+    // (Four dedicated warps: with the step rotating over the E1 warp groups, one group was ~600 cycles late at every
+    // tile's rendezvous -- tile period 4400 cycles against 3300 of E1 arithmetic, profiles/r02_ab_batch_h.md.)
+    const int q = warp & 3;                               // TMEM lane quarter
+    const int row = q * 32 + lane, n = n0 + row;
+    const bool valid = n < p.N;
     const uint32_t t_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    uint32_t xi = 0, xph = 0;                             // X ring position of the current input step
+    for (int b = b0; b < p.B; b += bstep) {
+      for (int tau = 0; tau < T1; ++tau) {
+        STGCN_CSTAMP(b == b0 && tau >= 3 && tau < 7 && q == 2, 160 + 52 + (tau - 3) * 2);
+        mbar_wait_a(xfull_a + xi * 8, xph);
+        tc_fence_after();
+        uint32_t rr[16];
+        tmem_ld_32x32b_x16(t_lane + xi * 16, rr);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(xfree_a + xi * 8);
+        STGCN_CSTAMP(b == b0 && tau >= 3 && tau < 7 && q == 2, 160 + 53 + (tau - 3) * 2);
+        if (valid) {
+          float acc[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(rr[e]);
+          uint4* dst = reinterpret_cast<uint4*>(p.dh2 + (((long long)b * T1 + tau) * p.N + n) * kFb2Ci);
+          dst[0] = pack8_bf16(acc); dst[1] = pack8_bf16(acc + 8);
+        }
+        if (++xi == kFb2NX) { xi = 0; xph ^= 1; }
+      }
+    }
+    // ---- weight-gradient flush: G[o][(j, c)] -> dwt[(j * 16 + c) * 128 + o], bias row behind
+    if (b0 < p.B) {
+      mbar_wait_a(done_a, 0);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < kFb2Kt; ++j) {
+        uint32_t rr[16];
+        tmem_ld_32x32b_x16(t_lane + kFb2D2Col + j * 16, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) atomicAdd(p.dwt + (j * 16 + c) * kFb2W + row, __uint_as_float(rr[c]));
+      }
+      uint32_t rb[8];
+      tmem_ld_32x32b_x8(t_lane + kFb2D2Col + 48, rb);
+      tmem_ld_wait();
+      atomicAdd(p.dwt + 48 * kFb2W + row, __uint_as_float(rb[0]));
+    }
+  } else {
+    // =========================== E1 warps ==========================
     // E1 mapping: COALESCED.  The dY / H3 / Q rows of a tile are 128 contiguous 128-byte rows, so warp w takes rows
     // w*8 .. w*8+7 and lane l the 16-byte chunk (l & 7) of rows w*8 + (l >> 3) and + 4: every LDG.128 of a warp reads 512
     // contiguous bytes.  (With the TMEM-style mapping -- one row per thread -- every warp-wide load touched 32 different
@@ -265,52 +309,68 @@ __global__ void __launch_bounds__(kFb2Threads, 1) umma_fb2_kernel(Fb2Params p) {
     // staging offsets of this thread's two 16-byte chunks inside a [128 rows][128 B] 128B-swizzled sub-tile
     const uint32_t so[2] = {(uint32_t)er[0] * 128u + (((uint32_t)c8 ^ ((uint32_t)er[0] & 7u)) << 4),
                             (uint32_t)er[1] * 128u + (((uint32_t)c8 ^ ((uint32_t)er[1] & 7u)) << 4)};
-    // operands of the NEXT tile are requested while the current one is computed (their L2 / HBM round trip would sit
-    // in front of every tile's arithmetic otherwise)
-    uint4 dn[2], hn[2], qn[2];
+    // The operands of the NEXT tile are requested while the current one is computed -- by cp.async into a private
+    // shared-memory slot per thread, not into registers: with 24 prefetch registers live across the arithmetic the
+    // compiler (80-96 registers per thread at this CTA size) sank the loads to the end of the tile and the first use
+    // of the loaded values was the kernel's top stall (ncu source page, profiles/r02_ab_batch_h.md).
+    const int et = (warp - 2) * 32 + lane;                // 0..511
+    const uint32_t pf_s = smem_s + kFb2Pf + (uint32_t)et * 16u;      // chunk k of this thread at + k * 8192
     float sc[4];                                          // mean, rstd, s1, s2 of the next tile's (b, t) group
     auto fetch = [&](int b, int t) {
-      dn[0] = dn[1] = hn[0] = hn[1] = qn[0] = qn[1] = make_uint4(0, 0, 0, 0);
       sc[0] = sc[1] = sc[2] = sc[3] = 0.f;
-      if (b >= p.B) return;
-      const long long g = (long long)b * T2 + t;
-      sc[0] = p.mean[g]; sc[1] = p.rstd[g];
-      for (int k = 0; k < p.n_parts; ++k) { sc[2] += p.sums[k * p.part_stride + 2 * g]; sc[3] += p.sums[k * p.part_stride + 2 * g + 1]; }
+      if (b < p.B) {
+        const long long g = (long long)b * T2 + t;
+        sc[0] = p.mean[g]; sc[1] = p.rstd[g];
+        for (int k = 0; k < p.n_parts; ++k) { sc[2] += p.sums[k * p.part_stride + 2 * g]; sc[3] += p.sums[k * p.part_stride + 2 * g + 1]; }
+#pragma unroll
+        for (int r2 = 0; r2 < 2; ++r2) {
+          const bool ok = ev[r2];
+          const long long off = ok ? (g * p.N + n0 + er[r2]) * kFb2Co + c8 * 8 : 0;
+          const uint32_t nb = ok ? 16u : 0u;              // rows past N: zero fill
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pf_s + (uint32_t)(r2 * 3 + 0) * 8192u), "l"(p.dy + off), "r"(nb) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pf_s + (uint32_t)(r2 * 3 + 1) * 8192u), "l"(p.h3 + off), "r"(nb) : "memory");
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(pf_s + (uint32_t)(r2 * 3 + 2) * 8192u), "l"(p.q + off), "r"(nb) : "memory");
+        }
+      }
+      cp_async_commit();
+    };
+    auto take = [&](uint4 (&dv)[2], uint4 (&hv)[2], uint4 (&qv)[2]) {      // this thread's own slots: no cross-thread hazard
+      cp_async_wait<0>();
 #pragma unroll
       for (int r2 = 0; r2 < 2; ++r2) {
-        if (!ev[r2]) continue;
-        const long long off = (g * p.N + n0 + er[r2]) * kFb2Co + c8 * 8;
-        dn[r2] = *reinterpret_cast<const uint4*>(p.dy + off);
-        hn[r2] = *reinterpret_cast<const uint4*>(p.h3 + off);
-        qn[r2] = *reinterpret_cast<const uint4*>(p.q + off);
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dv[r2].x), "=r"(dv[r2].y), "=r"(dv[r2].z), "=r"(dv[r2].w) : "r"(pf_s + (uint32_t)(r2 * 3 + 0) * 8192u) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(hv[r2].x), "=r"(hv[r2].y), "=r"(hv[r2].z), "=r"(hv[r2].w) : "r"(pf_s + (uint32_t)(r2 * 3 + 1) * 8192u) : "memory");
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[r2].x), "=r"(qv[r2].y), "=r"(qv[r2].z), "=r"(qv[r2].w) : "r"(pf_s + (uint32_t)(r2 * 3 + 2) * 8192u) : "memory");
       }
     };
     uint32_t gt = 0;                                      // tiles done by this CTA (all warps count alike)
-    uint32_t e2cnt = 0;                                   // E2 steps done
     fetch(b0, 0);
     for (int b = b0; b < p.B; b += bstep) {
-      for (int i = 0; i < T2 + 3; ++i) {
-        if (i < T2) {
+      for (int i = 0; i < T2; ++i) {
+        {
           STGCN_CSTAMP(b == b0 && i >= 4 && i < 7 && warp == 2, 160 + 24 + (i - 4) * 8);
           STGCN_CSTAMP(b == b0 && i >= 4 && i < 7 && warp == 17, 160 + 48 + (i - 4));
           // ---------------- E1: dZ tile of output step i
-          const uint4 dv[2] = {dn[0], dn[1]}, hv[2] = {hn[0], hn[1]}, qv[2] = {qn[0], qn[1]};
+          uint4 dv[2], hv[2], qv[2];
+          take(dv, hv, qv);
           const float mu = sc[0], rs = sc[1], s1 = sc[2], s2 = sc[3];
-          if (i + 1 < T2) fetch(b, i + 1); else fetch(b + bstep, 0);
+          if (i + 1 < T2) fetch(b, i + 1); else fetch(b + bstep, 0);      // the slots are free again: values are in registers
           uint4 pu[2], pq[2];                                 // packed dP / dQ of this thread's 2 x 8 channels
           const float c1 = -mu * rs;                          // xhat = fma(h, rs, c1)
 #pragma unroll
           for (int r2 = 0; r2 < 2; ++r2) {
             float df[8], hf[8], qf[8], du[8], dq[8];
             unpack8_bf16(dv[r2], df); unpack8_bf16(hv[r2], hf); unpack8_bf16(qv[r2], qf);
-            const float rsv = ev[r2] ? rs : 0.f;              // rows past N produce a zero dZ row
+            const float hrs = ev[r2] ? 0.5f * rs : 0.f;       // rows past N produce a zero dZ row; the 0.5 of the sigmoid rides here
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
+              // sigma(q) = 0.5 + 0.5 th, th = tanh(q / 2):  dP = dH3 sigma = hu + hu th,  dQ = dH3 h (1 - sigma) = hu h - hu h th
               const float xh = fmaf(hf[e], rs, c1);
-              const float u = rsv * fmaf(-xh, s2, fmaf(df[e], gw[r2][e], -s1));      // dH3
-              const float sg = sigmoid_tanh_(qf[e]);
-              du[e] = u * sg;
-              dq[e] = u * hf[e] * (1.f - sg);
+              const float hu = hrs * fmaf(-xh, s2, fmaf(df[e], gw[r2][e], -s1));     // dH3 / 2
+              const float th = tanh_approx(0.5f * qf[e]);
+              const float huh = hu * hf[e];
+              du[e] = fmaf(hu, th, hu);
+              dq[e] = fmaf(-huh, th, huh);
             }
             pu[r2] = pack8_bf16(du); pq[r2] = pack8_bf16(dq);
           }
@@ -330,49 +390,7 @@ __global__ void __launch_bounds__(kFb2Threads, 1) umma_fb2_kernel(Fb2Params p) {
           STGCN_CSTAMP(b == b0 && i >= 4 && i < 7 && warp == 2, 160 + 27 + (i - 4) * 8);
           ++gt;
         }
-        // ---------------- E2 (one step behind): dH2 of input step tau = i - 1, by one warp group in turn
-        const int tau = i - 1;
-        if (tau >= 0 && tau < T1) {
-          if ((int)(e2cnt & 3) == grp) {
-            STGCN_CSTAMP(b == b0 && tau >= 3 && tau < 7 && q == 0, 160 + 52 + (tau - 3) * 2);
-            const uint32_t xi = e2cnt % kFb2NX, xu = e2cnt / kFb2NX;     // e2cnt = global input-step counter = X ring position
-            mbar_wait_a(xfull_a + xi * 8, xu & 1);
-            tc_fence_after();
-            uint32_t rr[16];
-            tmem_ld_32x32b_x16(t_lane + xi * 16, rr);
-            tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_a(xfree_a + xi * 8);
-            STGCN_CSTAMP(b == b0 && tau >= 3 && tau < 7 && q == 0, 160 + 53 + (tau - 3) * 2);
-            if (valid) {
-              float acc[16];
-#pragma unroll
-              for (int e = 0; e < 16; ++e) acc[e] = __uint_as_float(rr[e]);
-              uint4* dst = reinterpret_cast<uint4*>(p.dh2 + (((long long)b * T1 + tau) * p.N + n) * kFb2Ci);
-              dst[0] = pack8_bf16(acc); dst[1] = pack8_bf16(acc + 8);
-            }
-          }
-          ++e2cnt;
-        }
       }
-    }
-    // ---- weight-gradient flush: G[o][(j, c)] -> dwt[(j * 16 + c) * 128 + o], bias row behind
-    if (grp == 0 && b0 < p.B) {
-      mbar_wait_a(done_a, 0);
-      tc_fence_after();
-#pragma unroll
-      for (int j = 0; j < kFb2Kt; ++j) {
-        uint32_t rr[16];
-        tmem_ld_32x32b_x16(t_lane + kFb2D2Col + j * 16, rr);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) atomicAdd(p.dwt + (j * 16 + c) * kFb2W + row, __uint_as_float(rr[c]));
-      }
-      uint32_t rb[8];
-      tmem_ld_32x32b_x8(t_lane + kFb2D2Col + 48, rb);
-      tmem_ld_wait();
-      atomicAdd(p.dwt + 48 * kFb2W + row, __uint_as_float(rb[0]));
     }
   }
   tc_fence_before();
