@@ -201,10 +201,12 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // The per-row operands of tile i + 1 (x taps, or the Q / H1 chunks) are requested while tile i is being computed:
     // issued at the top of their own tile their L2 / HBM round trip (~1 us) sat in front of every tile's arithmetic
     // (2.4 us per tile against ~0.9 us of epilogue issue time, profiles/r02_ab_batch_f.md).
-    float xn0 = 0.f, xn1 = 0.f, xn2 = 0.f;
+    // raw bf16 bits: converting inside fetch() put a USE right behind each load, and the in-order warp stalled there for the
+    // whole round trip (11 % of this kernel's stall samples on that one convert, profiles/r02_ab_batch_h.md)
+    unsigned short xn0 = 0, xn1 = 0, xn2 = 0;
     uint4 qn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, hn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
     auto fetch = [&](int i) {
-      xn0 = xn1 = xn2 = 0.f;
+      xn0 = xn1 = xn2 = 0;
       qn[0] = qn[1] = hn[0] = hn[1] = make_uint4(0, 0, 0, 0);
       if (i >= n_my) return;
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
@@ -212,16 +214,17 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (MODE == FB_FIRST) {
         long long in0; int t_unused;
         simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
-        xn0 = simt::ldf(p.x + in0);
-        xn1 = simt::ldf(p.x + in0 + p.N);
-        if (p.Kt > 2) xn2 = simt::ldf(p.x + in0 + 2LL * p.N);
+        const unsigned short* xs = reinterpret_cast<const unsigned short*>(p.x);
+        xn0 = xs[in0];
+        xn1 = xs[in0 + p.N];
+        if (p.Kt > 2) xn2 = xs[in0 + 2LL * p.N];
       }
     };
     fetch(0);
     for (int i = 0; i < n_my; ++i) {
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
       const bool valid = r < p.rows;
-      const float x0 = xn0, x1 = xn1, x2 = xn2;
+      const float x0 = __uint_as_float((uint32_t)xn0 << 16), x1 = __uint_as_float((uint32_t)xn1 << 16), x2 = __uint_as_float((uint32_t)xn2 << 16);
       uint4 qv[2] = {qn[0], qn[1]}, hv[2] = {hn[0], hn[1]};
       fetch(i + 1);
       if (MODE == FB_GATE) {
