@@ -7,20 +7,25 @@
 // and reads only the 16-channel gradient dX0 (19 MB) and the 3 MB input:
 //
 //   per tile of 128 flat rows r = (b, t, n):
-//     MMA 1   D1[128 r x 64]   = dX0 tile [128 x 16] (K-major, cp.async producer)  x  Wa^T [64 x 16] (resident)
-//     epilogue (16 warps)      dH1 = D1 (TMEM -> registers);  P, Q recomputed from the Kt taps of x (Kt FMAs each);
-//                              dU = dH1 * s,  dQ = dH1 * (P + res) * s (1 - s),  s = sigmoid(Q)
-//                              -> bf16 dZ tile [128 r][128 o] in shared memory (MN-major A operand, 128B swizzle),
-//                                 x-window tile [128 r][16] = (x_t .. x_{t+Kt-1}, 1, 0 ...) (MN-major B operand)
-//     MMA 2   D2[128 o x 16]  += dZ^T . x-window          (K = 128 rows; accumulates over ALL tiles of the CTA in TMEM)
-//   end:      D2 columns 0..Kt-1 = dW taps, column Kt = bias gradient -> fp32 atomics into dwt[(k) * 128 + o].
+//     producer warp            dX0 tile [128 x 16] by cp.async; window tile xw [128 r][16] = (x_t, x_t+1, x_t+2, x_t, x_t+1,
+//                              x_t+2, 1, 1, x_res, 0 ...) built from the input taps (32-byte rows, 32B swizzle)
+//     MMA 1   D1[128 r x 64]   = dX0 tile (K-major)  x  Wa^T [64 x 16] (resident)
+//     MMA 0   D0[128 r x 128]  = xw (K-major A)  x  [w_hi | w_lo | b_hi, b_lo | res] [128 o x 16]: the pre-activations
+//                              P | Q with bias and zero-padded residual, fp32-exact weights through the hi / lo split
+//     epilogue (16 warps)      dH1, P, Q from tensor memory;  dU = dH1 * s,  dQ = dH1 * P * s (1 - s),  s = sigmoid(Q)
+//                              -> bf16 dZ tile [128 r][128 o] in shared memory (MN-major A operand, 128B swizzle)
+//     MMA 2   D2[128 o x 16]  += dZ^T . xw (the same tile, MN-major B)   (K = 128 rows; accumulates over ALL tiles of the
+//                              CTA in TMEM)
+//   end:      D2 columns 0..Kt-1 = dW taps, column 6 = bias gradient -> fp32 atomics into dwt[(k) * 128 + o].
+//   (Up to GPU call AA the epilogue threads recomputed P, Q themselves from the taps -- 6 FMA + 2 LDS.128 per element,
+//   40 % of their instructions: 72 us instead of 58, profiles/r02_ab_batch_h.md.)
 //
 // The block-0 input needs no data gradient (it is the model input), so dZ never reaches HBM.
 // Serves the default architecture's first block: c_in = 1, 64 GLU channels, 16 graph-conv channels, Kt in {2, 3}.
 //
 // MODE 1 (FB_GATE) -- the same front end for the temporal convs of the LATER blocks (c_in >= 16, GLU with the q-only saved
-// state): MMA 1 as above, then the epilogue reads the saved gate half Q and the layer output H1 (16-byte loads),
-// dU = dH1 * s, dQ = dH1 * H1 * (1 - s), and writes dZ = (dU | dQ) [rows, 128] to HBM for the data-gradient and
+// state): MMA 1 as above; the saved gate half Q and the layer output H1 arrive by TMA into 128B-swizzled tiles, the epilogue
+// forms dU = dH1 * s, dQ = dH1 * H1 * (1 - s) and the dZ = (dU | dQ) tile leaves by TMA store for the data-gradient and
 // weight-gradient kernels.  Replaces lowrank_expand_kernel + gate_vec_kernel (33 + 51 us at B = 256: dH1 written and read
 // back at 64 channels).
 #pragma once
@@ -34,6 +39,11 @@ constexpr int kFb0Threads = 64 + 32 * kFb0EpiWarps;      // warp 0 producer, war
 constexpr int kFb0Stages = 8;                            // dX0 tiles in flight (4 KB each)
 
 enum { FB_FIRST = 0, FB_GATE = 1 };
+// FB_FIRST: the pre-activations P, Q of the tile are not recomputed by the epilogue threads (6 FMA + 2 LDS.128 per element
+// were 40 % of their instructions: 72 -> 58 us): a producer-built window tile [x_t, x_t+1, x_t+2, x_t, x_t+1, x_t+2, 1, 1,
+// x_res, 0 ...] times [w_hi | w_lo | b_hi, b_lo | res] is one more tcgen05.mma (K = 16, N = 128, fp32-exact weights
+// through the hi / lo split) into tensor memory, and the same tile is the MN-major B operand of the weight-gradient MMA
+// (taps in columns 0..2, bias in column 6).
 struct Fb0Params {
   const bf16* dst0;        // [rows, 16] gradient w.r.t. the aligned (16-channel) graph-conv input
   const bf16* wa;          // [64][16] K-major: wa[j * 16 + o] = align_w[o][j]
@@ -52,7 +62,7 @@ struct Fb0Params {
 // shared-memory map (offsets from the 1024-aligned base)
 constexpr uint32_t kFb0ARing = 0;                                   // kFb0Stages x 4096
 constexpr uint32_t kFb0Wa = kFb0ARing + kFb0Stages * 4096;          // 2048
-constexpr uint32_t kFb0Wpq = kFb0Wa + 2048;                         // float4 [2][64] = 2048
+constexpr uint32_t kFb0Wpq = kFb0Wa + 2048;                         // (unused since the P / Q recompute moved to the tensor pipe)
 constexpr int kFb0ND1 = 3;                                          // dH1 accumulators in TMEM (64 columns each); 3 x 64 + 16 fit a 256-column
                                                                     // allocation, which leaves room for a weight-gradient kernel of the helper stream on the same SM
 constexpr int kFb0NZ = 3;                                           // dZ / x-window tile pairs in shared memory
@@ -63,6 +73,10 @@ constexpr uint32_t kFb0Smem = kFb0Dz + kFb0NZ * 32768 + 1024;
 constexpr int kFb0NQH = 2;
 constexpr uint32_t kFb0QH = kFb0Dz + kFb0NZ * 32768;
 constexpr uint32_t kFb0SmemGate = kFb0QH + kFb0NQH * 32768 + 1024;
+// FB_FIRST (same allocation): the [128 o][16] weight tile and a ring of window tiles live where FB_GATE keeps Q / H1
+constexpr int kFb0NXw = 4;
+constexpr uint32_t kFb0Wtc = kFb0QH, kFb0Xw = kFb0QH + 4096;
+constexpr uint32_t kFb0D0Col = 256;                                 // FB_FIRST: P | Q accumulators, 2 x 128 columns
 constexpr uint32_t kFb0D2Col = kFb0ND1 * 64;                        // TMEM column of the weight-gradient accumulator
 // (the first version double-buffered both: 2.4 us per 128-row tile against ~0.9 us of epilogue issue time -- every tile
 // waited for the previous tile's MMA 2 and the next tile's MMA 1 in turn; profiles/r02_ab_batch_c.md)
@@ -74,8 +88,10 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t a_full[kFb0Stages], a_empty[kFb0Stages], d1_full[kFb0ND1], d1_empty[kFb0ND1], dz_full[kFb0NZ], dz_empty[kFb0NZ], done,
-      qh_full[kFb0NQH], qh_empty[kFb0NQH];
+      qh_full[kFb0NQH], qh_empty[kFb0NQH], xw_full[kFb0NXw], xw_empty[kFb0NXw];
   __shared__ uint32_t tmem_base_s;
+  constexpr bool kFirst = MODE != FB_GATE, kTC = kFirst;
+  constexpr uint32_t kTmemCols = kTC ? 512 : 256;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // ---- one-time staging: Wa^T (K-major, 32-byte rows, 32B swizzle) and the per-channel (w_0..w_2, bias) quads
@@ -83,14 +99,22 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int j = threadIdx.x >> 1, h = threadIdx.x & 1;
     const uint4 v = *reinterpret_cast<const uint4*>(p.wa + j * 16 + h * 8);
     *reinterpret_cast<uint4*>(smem + kFb0Wa + j * 32 + ((h ^ ((j >> 2) & 1)) << 4)) = v;
-  } else if (MODE == FB_FIRST && threadIdx.x < 256) {
-    const int o = threadIdx.x - 128;                    // pre-activation channel: 0..63 = P half, 64..127 = Q half
-    float4 w;
-    w.x = p.wt[o];
-    w.y = p.wt[128 + o];
-    w.z = p.Kt > 2 ? p.wt[256 + o] : 0.f;
-    w.w = p.bias[o];
-    reinterpret_cast<float4*>(smem + kFb0Wpq)[o] = w;
+  } else if (kTC && threadIdx.x < 256) {
+    const int o = threadIdx.x - 128;
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+    for (int k = 0; k < 3; ++k) {
+      const float w = k < p.Kt ? p.wt[k * 128 + o] : 0.f;
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      v[k] = hi; v[3 + k] = w - hi;
+    }
+    const float b = p.bias[o], bh = __bfloat162float(__float2bfloat16_rn(b));
+    v[6] = bh; v[7] = b - bh;
+    v[8] = (o == 0 && p.explicit_res) ? 1.f : 0.f;
+    const int sw = (o >> 2) & 1;
+    *reinterpret_cast<uint4*>(smem + kFb0Wtc + o * 32 + ((0 ^ sw) << 4)) = pack8_bf16(v);
+    *reinterpret_cast<uint4*>(smem + kFb0Wtc + o * 32 + ((1 ^ sw) << 4)) = pack8_bf16(v + 8);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kFb0Stages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
@@ -98,9 +122,10 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     for (int i = 0; i < kFb0NZ; ++i) { mbar_init(&dz_full[i], kFb0EpiWarps); mbar_init(&dz_empty[i], 1); }
     mbar_init(&done, 1);
     for (int i = 0; i < kFb0NQH; ++i) { mbar_init(&qh_full[i], 1); mbar_init(&qh_empty[i], kFb0EpiWarps); }
+    for (int i = 0; i < kFb0NXw; ++i) { mbar_init(&xw_full[i], 1); mbar_init(&xw_empty[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 256);          // D1: kFb0ND1 x 64 columns, D2: 16 columns
+  if (warp == 1) tmem_alloc(&tmem_base_s, kTmemCols);    // D1: kFb0ND1 x 64 columns, D2: 16 columns (FB_FIRST: + 2 x 128)
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -111,6 +136,23 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0) {
     // =========================== producer: dX0 tiles by cp.async ================================
     int pending = -1;
+    unsigned short xnx[4][3];                             // FB_FIRST: input taps of the next tile's rows lane + 32 c
+    auto load_taps = [&](int i) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        xnx[c][0] = xnx[c][1] = xnx[c][2] = 0;
+        if (i >= n_my) continue;
+        const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + lane + 32 * c;
+        if (r >= p.rows) continue;
+        long long in0; int t_unused;
+        simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
+        const unsigned short* xs = reinterpret_cast<const unsigned short*>(p.x);
+        xnx[c][0] = xs[in0];
+        xnx[c][1] = xs[in0 + p.N];
+        if (p.Kt > 2) xnx[c][2] = xs[in0 + 2LL * p.N];
+      }
+    };
+    if (kTC) load_taps(0);
     for (int i = 0; i < n_my; ++i) {
       const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
       const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1;
@@ -121,6 +163,32 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive_expect_tx(&qh_full[s2], 32768);
         tma_load_2d(smem + kFb0QH + s2 * 32768, &tmQ, &qh_full[s2], 0, (int)r0);
         tma_load_2d(smem + kFb0QH + s2 * 32768 + 16384, &tmH, &qh_full[s2], 0, (int)r0);
+      }
+      if (kTC) {
+        // window tile of this tile's rows; the taps of the NEXT tile are requested first (raw bits, no use behind the load)
+        unsigned short xc[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { xc[c][0] = xnx[c][0]; xc[c][1] = xnx[c][1]; xc[c][2] = xnx[c][2]; }
+        load_taps(i + 1);
+        const uint32_t sx = i % kFb0NXw, phx = (i / kFb0NXw) & 1;
+        mbar_wait(&xw_empty[sx], phx ^ 1);
+        uint8_t* xd = smem + kFb0Xw + sx * 4096;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int row = lane + 32 * c;
+          uint4 a = make_uint4(0, 0, 0, 0), b = make_uint4(0, 0, 0, 0);
+          if (r0 + row < p.rows) {
+            const uint32_t x0 = xc[c][0], x1 = xc[c][1], x2 = xc[c][2];
+            a = make_uint4(x0 | (x1 << 16), x2 | (x0 << 16), x1 | (x2 << 16), 0x3F803F80u);
+            b.x = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0u;
+          }
+          const int sw = (row >> 2) & 1;
+          *reinterpret_cast<uint4*>(xd + row * 32 + ((0 ^ sw) << 4)) = a;
+          *reinterpret_cast<uint4*>(xd + row * 32 + ((1 ^ sw) << 4)) = b;
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&xw_full[sx]);
       }
       __syncwarp();
       mbar_wait(&a_empty[s], ph ^ 1);
@@ -160,16 +228,24 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t s = i % kFb0Stages, ph = (i / kFb0Stages) & 1, ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
         mbar_wait(&a_full[s], ph);
         mbar_wait(&d1_empty[ab], aph ^ 1);
+        if (kTC) {
+          mbar_wait(&xw_full[i % kFb0NXw], (i / kFb0NXw) & 1);
+          // P | Q slot i & 1 was last read by the epilogue of tile i - 2 (its d1_empty arrival comes after those loads)
+          if (i >= 2) mbar_wait(&d1_empty[(i - 2) % kFb0ND1], ((i - 2) / kFb0ND1) & 1);
+        }
         tc_fence_after();
         mma_bf16_ss(tmem_base + ab * 64, desc_at(pk32, smem_u32(smem + kFb0ARing + s * 4096)), desc_at(pk32, wa_s), idesc1, 0);
+        if (kTC)
+          mma_bf16_ss(tmem_base + kFb0D0Col + (i & 1) * 128, desc_at(pk32, smem_u32(smem + kFb0Xw + (i % kFb0NXw) * 4096)),
+                      desc_at(pk32, smem_u32(smem + kFb0Wtc)), make_idesc_bf16(128, 128, 0, 0), 0);
         mma_commit(&d1_full[ab]);
         mma_commit(&a_empty[s]);
       };
       int next1 = 0;                                      // MMA 1 runs up to kFb0ND1 - 1 tiles ahead of MMA 2
       for (int i = 0; i < n_my; ++i) {
-        for (; next1 < n_my && next1 < i + kFb0ND1; ++next1) mma1(next1);
+        for (; next1 < n_my && next1 < i + (kTC ? 2 : kFb0ND1); ++next1) mma1(next1);
         const uint32_t zb = i % kFb0NZ, zph = (i / kFb0NZ) & 1;
-        if (MODE != FB_FIRST) {
+        if (!kFirst) {
           // FB_GATE: the finished dZ tile leaves through two TMA stores (P half | Q half); the buffer is free once read
           mbar_wait(&dz_full[zb], zph);
           const long long r0 = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128;
@@ -182,51 +258,27 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         mbar_wait(&dz_full[zb], zph);
         tc_fence_after();
-        uint64_t da = desc_at(pdz, smem_u32(smem + kFb0Dz + zb * 32768)), db = desc_at(px3, smem_u32(smem + kFb0X3 + zb * 4096));
+        uint64_t da = desc_at(pdz, smem_u32(smem + kFb0Dz + zb * 32768)),
+                 db = desc_at(px3, smem_u32(smem + kFb0Xw + (i % kFb0NXw) * 4096));
 #pragma unroll
         for (int k = 0; k < 8; ++k) {                     // 16 rows per instruction
           mma_bf16_ss(tmem_base + kFb0D2Col, da, db, idesc2, (i != 0 || k != 0) ? 1u : 0u);
           da += 2048 >> 4; db += 512 >> 4;
         }
         mma_commit(&dz_empty[zb]);
+        if (kTC) mma_commit(&xw_empty[i % kFb0NXw]);
       }
-      if (MODE != FB_FIRST) tma_store_wait_all<0>();
+      if (!kFirst) tma_store_wait_all<0>();
       mma_commit(&done);
     }
   } else {
     // =========================== epilogue warps ==========================
     const int q = warp & 3, grp = (warp - 2) >> 2;        // TMEM lane quarter; 16-channel group
     const int row = q * 32 + lane, c0 = grp * 16;
-    const float4* wpq = reinterpret_cast<const float4*>(smem + kFb0Wpq);
-    // The per-row operands of tile i + 1 (x taps, or the Q / H1 chunks) are requested while tile i is being computed:
-    // issued at the top of their own tile their L2 / HBM round trip (~1 us) sat in front of every tile's arithmetic
-    // (2.4 us per tile against ~0.9 us of epilogue issue time, profiles/r02_ab_batch_f.md).
-    // raw bf16 bits: converting inside fetch() put a USE right behind each load, and the in-order warp stalled there for the
-    // whole round trip (11 % of this kernel's stall samples on that one convert, profiles/r02_ab_batch_h.md)
-    unsigned short xn0 = 0, xn1 = 0, xn2 = 0;
-    uint4 qn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)}, hn[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-    auto fetch = [&](int i) {
-      xn0 = xn1 = xn2 = 0;
-      qn[0] = qn[1] = hn[0] = hn[1] = make_uint4(0, 0, 0, 0);
-      if (i >= n_my) return;
-      const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
-      if (r >= p.rows) return;
-      if (MODE == FB_FIRST) {
-        long long in0; int t_unused;
-        simt::row_decode(r, p.T_out * p.N, p.N, (long long)p.T_in * p.N, in0, t_unused);
-        const unsigned short* xs = reinterpret_cast<const unsigned short*>(p.x);
-        xn0 = xs[in0];
-        xn1 = xs[in0 + p.N];
-        if (p.Kt > 2) xn2 = xs[in0 + 2LL * p.N];
-      }
-    };
-    fetch(0);
     for (int i = 0; i < n_my; ++i) {
       const long long r = ((long long)blockIdx.x + (long long)i * gridDim.x) * 128 + row;
       const bool valid = r < p.rows;
-      const float x0 = __uint_as_float((uint32_t)xn0 << 16), x1 = __uint_as_float((uint32_t)xn1 << 16), x2 = __uint_as_float((uint32_t)xn2 << 16);
-      uint4 qv[2] = {qn[0], qn[1]}, hv[2] = {hn[0], hn[1]};
-      fetch(i + 1);
+      uint4 qv[2], hv[2];
       if (MODE == FB_GATE) {
         // Q / H1 chunks of this thread's row from the TMA-staged tiles (one row per thread straight from global memory
         // touched 32 different 128-byte lines per warp-wide load: ~4000 L1 wavefront cycles per tile with the dZ stores,
@@ -242,25 +294,26 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         __syncwarp();
         if (lane == 0) mbar_arrive(&qh_empty[s2]);
       }
-      const float xres = p.explicit_res ? (p.Kt > 2 ? x2 : x1) : 0.f;      // zero-padded residual: channel 0 only
       const uint32_t ab = i % kFb0ND1, aph = (i / kFb0ND1) & 1;
       mbar_wait(&d1_full[ab], aph);
       tc_fence_after();
-      uint32_t rr[16];
+      uint32_t rr[16], rp[16], rq[16];
       tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + ab * 64 + c0, rr);
+      if (kTC) {
+        const uint32_t d0 = tmem_base + ((uint32_t)(q * 32) << 16) + kFb0D0Col + (i & 1) * 128;
+        tmem_ld_32x32b_x16(d0 + c0, rp);
+        tmem_ld_32x32b_x16(d0 + 64 + c0, rq);
+      }
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&d1_empty[ab]);
       float du[16], dq[16];
-      if (MODE == FB_FIRST) {
+      if (kTC) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float4 wp = wpq[c0 + e], wq = wpq[64 + c0 + e];
-          float u = fmaf(x0, wp.x, fmaf(x1, wp.y, fmaf(x2, wp.z, wp.w)));
-          const float g = fmaf(x0, wq.x, fmaf(x1, wq.y, fmaf(x2, wq.z, wq.w)));
-          if (c0 + e == 0) u += xres;
-          const float s = sigmoid_tanh_(g);
+        for (int e = 0; e < 16; ++e) {                    // P (bias and residual included) and Q straight from tensor memory
+          const float u = __uint_as_float(rp[e]);
+          const float s = sigmoid_tanh_(__uint_as_float(rq[e]));
           const float dh = valid ? __uint_as_float(rr[e]) : 0.f;
           du[e] = dh * s;
           dq[e] = dh * u * s * (1.f - s);
@@ -284,20 +337,12 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       stage_store8_s(dzs, row, c0 + 8, pack8_bf16(du + 8));
       stage_store8_s(dzs + 16384u, row, c0, pack8_bf16(dq));
       stage_store8_s(dzs + 16384u, row, c0 + 8, pack8_bf16(dq + 8));
-      if (MODE == FB_FIRST && grp == 0) {
-        float xw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (valid) { xw[0] = x0; xw[1] = x1; if (p.Kt > 2) xw[2] = x2; xw[p.Kt > 2 ? 3 : 2] = 1.f; }
-        uint8_t* x3 = smem + kFb0X3 + zb * 4096 + row * 32;
-        const int sw = (row >> 2) & 1;
-        *reinterpret_cast<uint4*>(x3 + ((0 ^ sw) << 4)) = pack8_bf16(xw);
-        *reinterpret_cast<uint4*>(x3 + ((1 ^ sw) << 4)) = make_uint4(0, 0, 0, 0);
-      }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&dz_full[zb]);
     }
     // ---- flush: D2[o][k] -> dwt[k * 128 + o]
-    if (MODE == FB_FIRST && grp == 0 && n_my > 0) {
+    if (kFirst && grp == 0 && n_my > 0) {
       mbar_wait(&done, 0);
       tc_fence_after();
       uint32_t rr[16];
@@ -305,12 +350,12 @@ umma_fb0_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld_wait();
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (k <= p.Kt) atomicAdd(p.dwt + k * 128 + row, __uint_as_float(rr[k]));
+        if (k <= p.Kt) atomicAdd(p.dwt + k * 128 + row, __uint_as_float(rr[(kTC && k == p.Kt) ? 6 : k]));     // bias column 6
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 256);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // shapes this kernel serves (all three datasets' first block in the default architecture)
@@ -325,8 +370,8 @@ inline void launch_fb0(const bf16* dst0, const bf16* wa, const bf16* x, const fl
   p.n_tiles = (int)((rows + 127) / 128); p.Kt = Kt; p.T_out = T_out; p.T_in = T_in; p.N = N; p.explicit_res = explicit_res;
   const int grid = p.n_tiles < sm_count() ? p.n_tiles : sm_count();
   CUtensorMap none{};                                     // FB_FIRST touches no tensor map
-  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0Smem));
-  STGCN_LAUNCH_NAMED("umma_fb0_kernel<FIRST>", umma_fb0_kernel<FB_FIRST>, grid, kFb0Threads, kFb0Smem, stream, none, none, none, p);
+  STGCN_CUDA(cudaFuncSetAttribute(umma_fb0_kernel<FB_FIRST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFb0SmemGate));
+  STGCN_LAUNCH_NAMED("umma_fb0_kernel<FIRST>", umma_fb0_kernel<FB_FIRST>, grid, kFb0Threads, kFb0SmemGate, stream, none, none, none, p);
 }
 
 // later blocks: dZ = GLU'(dX0 . Wa; Q, H1) for a 64-channel GLU conv in front of a 64 -> 16 align conv (q-only saved state)

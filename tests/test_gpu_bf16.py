@@ -388,7 +388,7 @@ def test_bf16_first_block_fused_backward(N, B, kt, kind, cuda_device):
 
 
 @pytest.mark.parametrize("N,B,T,kind", [(228, 5, 12, "cheb_graph_conv"), (41, 3, 12, "cheb_graph_conv"), (207, 2, 8, "graph_conv"),
-                                         (325, 3, 12, "cheb_graph_conv"), (228, 150, 7, "cheb_graph_conv")])
+                                         (325, 3, 12, "cheb_graph_conv"), (228, 150, 7, "cheb_graph_conv"), (100, 2, 5, "cheb_graph_conv")])
 def test_bf16_second_conv_fused_backward(N, B, T, kind, cuda_device):
     """Blocks of the default architecture (16 -> 64 GLU channels, Kt = 3, no dropout): the LayerNorm backward, the GLU
     backward and the data / weight / bias gradients of the second temporal conv run as ONE tcgen05 kernel
