@@ -347,7 +347,8 @@ class Runner:
                 self.reduce_mode = "ncclAvg on the flat gradient buffer the backward kernels write, right behind the graph replay"
         self.x_dev, self.y_dev = torch.empty_like(self.xs[0]), torch.empty_like(self.ys[0])
         self.prefetcher = None
-        if self.graphed is not None and os.environ.get("STGCN_BENCH_NO_PREFETCH") is None:
+        # (single-process runs only: the multi-GPU legs keep the copy-in-front path they were validated with)
+        if self.graphed is not None and world == 1 and os.environ.get("STGCN_BENCH_NO_PREFETCH") is None:
             from stgcn_b200.data import HostBatchPrefetcher
             self.prefetcher = HostBatchPrefetcher(self.xs[0], self.ys[0], dev)
 
